@@ -1,0 +1,167 @@
+/*
+ * plume_b200 -- C ABI of the B200-native (sm_100a) UNet smoke-plume segmenter hot path.
+ *
+ * Boundary note.  The reference project (gridl/kcl-ltss-bioatm) names a UNet in README.md:1-4 and
+ * reserves src/models/train_model.py / predict_model.py for it (README.md:44-47), but src/models/ is
+ * empty (src/models/__init__.py, 0 bytes).  There is therefore no reference FFI to replace: every
+ * entry point below is the operator a `src/models` implementation needs, and the host side in
+ * src/models/ binds them through ctypes.  Conventions:
+ *   - extern "C", plain pointers and ints; the caller (PyTorch) owns every buffer;
+ *   - all device work is enqueued on the caller's stream, no internal synchronisation;
+ *   - return 0 on success, a negative code otherwise; plume_last_error() holds the message
+ *     (thread-local).  Nothing is swallowed and there is no CPU fallback (the reference's scripts
+ *     use `except: continue`, e.g. src/features/plume_identifier_gaussian_profile.py:120-121);
+ *   - activations are NHWC bf16.  An activation argument is (pointer to channel 0 of pixel 0,
+ *     ld = pixel stride in elements), so a channel slice of a wider buffer (the skip-concat buffer)
+ *     is passed without a copy.  Channel offsets and strides must be multiples of 8 (16 bytes).
+ *   - 3x3 weights are KRSC ([Cout][3][3][Cin]); transposed-conv weights are [2*2][Cout][Cin].
+ */
+#ifndef PLUME_B200_H_
+#define PLUME_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* plume_stream_t; /* cudaStream_t */
+
+const char* plume_version(void);
+const char* plume_last_error(void);
+/* Diagnostic word written by a kernel whose bounded barrier wait expired (0 = none). */
+int plume_debug_word(void);
+int plume_num_sms(void);
+
+/* ---- tensor-core implicit GEMM (tcgen05 / TMEM / TMA) -------------------------------------- */
+
+/* y = act(conv3x3(x, w) * scale + shift); optional per-channel sum / sum-of-squares of the bf16
+ * outputs accumulated (atomically) into stat_sum / stat_sq (fp32[Cout], caller zeroes them).
+ * Cin and Cout must be multiples of 64.  scale/shift may be NULL (1 / 0). */
+int plume_conv3x3_fwd(const void* x, int ldx, const void* w_krsc_bf16, const float* scale,
+                      const float* shift, int relu, void* y, int ldy, float* stat_sum,
+                      float* stat_sq, int N, int H, int W, int Cin, int Cout, plume_stream_t stream);
+
+/* dx = conv3x3(dy, w_dgrad) with w_dgrad[ci][r][s][co] = w[co][2-r][2-s][ci] (plume_pack_conv3x3). */
+int plume_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad_bf16, void* dx, int lddx, int N,
+                        int H, int W, int Cin, int Cout, plume_stream_t stream);
+
+/* Split count and fp32 workspace bytes for a weight-gradient problem (taps = 9 or 4). */
+int plume_wgrad_splits(int N, int H, int W, int taps, int Cin, int Cout);
+size_t plume_wgrad_workspace_bytes(int N, int H, int W, int taps, int Cin, int Cout);
+
+/* dw[co][r][s][ci] (fp32) = sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  Cin is 64 or a multiple
+ * of 128, Cout a multiple of 64.  `accumulate` != 0 adds into dw. */
+int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_krsc,
+                        int accumulate, void* workspace, size_t workspace_bytes, int N, int H, int W,
+                        int Cin, int Cout, plume_stream_t stream);
+
+/* Transposed conv 2x2 stride 2 written into a channel slice of the concat buffer:
+ * u[n, 2h+i, 2w+j, co] = sum_ci x[n,h,w,ci] * w[(i*2+j)][co][ci] + bias[co];  x is N x H x W. */
+int plume_convT2x2_concat_fwd(const void* x, int ldx, const void* w_ijoc_bf16, const float* bias,
+                              void* u, int ldu, int N, int H, int W, int Cin, int Cout,
+                              plume_stream_t stream);
+/* dx[n,h,w,ci] = sum_{ij,co} du[n,2h+i,2w+j,co] * w[ij][co][ci]; w_dgrad is [Cin][4][Cout]. */
+int plume_convT2x2_dgrad(const void* du, int lddu, const void* w_dgrad_bf16, void* dx, int lddx, int N,
+                         int H, int W, int Cin, int Cout, plume_stream_t stream);
+/* dw[ij][co][ci] (fp32) = sum_pixels du[n,2h+i,2w+j,co] * x[n,h,w,ci].  Cin multiple of 128. */
+int plume_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float* dw_ijoc,
+                         int accumulate, void* workspace, size_t workspace_bytes, int N, int H, int W,
+                         int Cin, int Cout, plume_stream_t stream);
+
+/* ---- weight packing (fp32 master -> bf16 operand layouts) ---------------------------------- */
+int plume_pack_conv3x3(const float* w_krsc, void* w_fwd_bf16, void* w_dgrad_bf16, int Cout, int Cin,
+                       plume_stream_t stream);
+int plume_pack_convT2x2(const float* w_ijoc, void* w_fwd_bf16, void* w_dgrad_bf16, int Cout, int Cin,
+                        plume_stream_t stream);
+
+/* ---- bandwidth kernels ----------------------------------------------------------------------- */
+
+/* out[p][0:Cd] = concat(in[p][0:Cs], zeros) ; bf16, Cs and Cd multiples of 8. */
+int plume_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels,
+                       plume_stream_t stream);
+
+/* BatchNorm (training) from accumulated sums: mean/var over `count` values per channel, updates the
+ * running statistics (unbiased variance, PyTorch convention) and emits the fused scale = gamma*invstd,
+ * shift = beta - mean*scale used by the apply kernels, plus mean / invstd for the backward pass. */
+int plume_bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+                      const float* beta, float eps, float momentum, float* running_mean,
+                      float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                      int C, plume_stream_t stream);
+/* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = (bias - mean)*scale + beta. */
+int plume_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, const float* conv_bias, float eps, float* scale,
+                       float* shift, int C, plume_stream_t stream);
+
+/* a = relu?(y*scale + shift) per channel. */
+int plume_scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                          void* a, int lda, long long pixels, int C, plume_stream_t stream);
+/* Same, fused with the 2x2/stride-2 max pool: writes the full-resolution activation (the skip half
+ * of the concat buffer), the pooled activation and the argmax position (uint8 in 0..3, = i*2+j). */
+int plume_scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift,
+                               int relu, void* skip, int ldskip, void* pooled, int ldpooled,
+                               uint8_t* argmax, int N, int H, int W, int C, plume_stream_t stream);
+/* Plain max pool with argmax, and its backward. */
+int plume_maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H,
+                         int W, int C, plume_stream_t stream);
+/* dx[n,2h+i,2w+j,c] = (argmax==i*2+j ? dy[n,h,w,c] : 0) + (dskip ? dskip[...] : 0);  H, W are the
+ * full-resolution extents. */
+int plume_maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
+                         int lddskip, void* dx, int lddx, int N, int H, int W, int C,
+                         plume_stream_t stream);
+
+/* BatchNorm+ReLU backward.  Pass 1 reduces, per channel, sum(g) and sum(g*xhat) with
+ * g = da * [scale*y+shift > 0] (or g = da when relu == 0), xhat = (y-mean)*invstd.
+ * Pass 2 writes dy = scale * (g - sum_g/count - xhat*sum_gx/count) and accumulates sum(dy) (the conv
+ * bias gradient); dgamma = sum_gx, dbeta = sum_g. */
+int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, int relu,
+                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream);
+int plume_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
+                       long long pixels, int C, plume_stream_t stream);
+/* ReLU(+bias) backward for norm == "none": dy = da * [a > 0]; accumulates sum(dy) per channel. */
+int plume_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy,
+                   float* sum_dy, long long pixels, int C, plume_stream_t stream);
+/* out[c] += sum_p x[p][c] (fp32; caller zeroes `out`). */
+int plume_channel_sum(const void* x, int ldx, float* out, long long pixels, int C,
+                      plume_stream_t stream);
+
+/* 1x1 head + sigmoid + BCE/Dice.  logits[p] = sum_c feat[p][c]*w[c] + b (fp32).
+ * sums[0..3] += {sum BCE, sum p*t, sum p, sum t} (caller zeroes sums).  C is a multiple of 8, <= 512. */
+int plume_head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream);
+/* loss = bce_weight * BCE_mean + dice_weight * (1 - (2*S_pt + eps)/(S_p + S_t + eps)); written to
+ * loss_out[0] (and its parts to [1], [2]). */
+int plume_head_loss(const float* sums, long long pixels, float bce_weight, float dice_weight,
+                    float dice_eps, float* loss_out, plume_stream_t stream);
+/* dfeat[p][c] = dlogit[p]*w[c]; dw[c] += sum_p dlogit[p]*feat[p][c]; db += sum_p dlogit[p]
+ * (fp32 accumulators, caller zeroes).  grad_scale multiplies the loss gradient (1/world for DP). */
+int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logits,
+                   const uint8_t* target, const float* sums, float bce_weight, float dice_weight,
+                   float dice_eps, float grad_scale, void* dfeat, int lddf, float* dw, float* db,
+                   long long pixels, int C, plume_stream_t stream);
+
+/* Fused Adam over one flat fp32 parameter buffer (PyTorch semantics, no weight decay / amsgrad):
+ * m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+int plume_adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
+               float beta2, float eps, int step, float grad_scale, plume_stream_t stream);
+
+/* ---- tiled large-scene inference -------------------------------------------------------------- */
+/* Cut `count` tiles of T x T (NHWC bf16, Cd channels, zero padded past Cs and past the scene edge)
+ * out of a scene [Hs][Ws][Cs] bf16; tile k covers origin (ys[k], xs[k]) given as int32 device arrays. */
+int plume_extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
+                        int count, int T, void* tiles, int Cd, plume_stream_t stream);
+/* Overlap-stitch by centre crop: each tile contributes the pixels at least `margin` away from its
+ * border (or up to the scene edge), thresholded: mask = logit >= logit_threshold (uint8 0/1).
+ * Optionally also writes the stitched probabilities (fp32, may be NULL). */
+int plume_stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T,
+                           int margin, float logit_threshold, uint8_t* mask, float* prob, int Hs,
+                           int Ws, plume_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLUME_B200_H_ */

@@ -1,0 +1,313 @@
+// C ABI (include/plume_b200.h): argument checking, view construction, error reporting.
+// Every entry point enqueues on the caller's stream and returns; errors never cross as exceptions.
+#include "../../include/plume_b200.h"
+
+#include "bandwidth.cuh"
+#include "igemm.cuh"
+
+#include <string>
+
+namespace plume {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace plume
+
+using namespace plume;
+
+namespace {
+inline cudaStream_t S(plume_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+// Strided NHWC view of C channels with pixel stride ld (elements).
+ActView view(const void* ptr, int ld, int N, int H, int W, int C) {
+  ActView v;
+  v.ptr = ptr;
+  v.C = C; v.W = W; v.H = H; v.N = N;
+  v.pix_stride = ld;
+  v.row_stride = 1ll * W * ld;
+  v.img_stride = 1ll * H * W * ld;
+  return v;
+}
+// The (i,j) phase of a 2x-upsampled buffer [N][2H][2W][ld] seen as an N x H x W image.
+ActView phase_view(const void* ptr, int ld, int N, int H, int W, int C, int i, int j) {
+  ActView v;
+  v.ptr = static_cast<const char*>(ptr) + (1ll * i * (2 * W) + j) * ld * 2;
+  v.C = C; v.W = W; v.H = H; v.N = N;
+  v.pix_stride = 2ll * ld;
+  v.row_stride = 2ll * (2 * W) * ld;
+  v.img_stride = 1ll * (2 * H) * (2 * W) * ld;
+  return v;
+}
+bool bad_ld(int ld, int C) { return ld < C || (ld % 8) != 0; }
+#define PLUME_CHECK(cond, msg) \
+  do {                         \
+    if (!(cond)) {             \
+      set_error(msg);          \
+      return -1;               \
+    }                          \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+const char* plume_version(void) { return "plume_b200 0.1 (sm_100a; tcgen05+TMA implicit GEMM)"; }
+const char* plume_last_error(void) { return g_last_error.c_str(); }
+int plume_debug_word(void) { return read_debug_word(); }
+int plume_num_sms(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+int plume_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale, const float* shift,
+                      int relu, void* y, int ldy, float* stat_sum, float* stat_sq, int N, int H, int W,
+                      int Cin, int Cout, plume_stream_t stream) {
+  PLUME_CHECK(x && w && y, "conv3x3_fwd: null pointer");
+  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(ldy, Cout), "conv3x3_fwd: bad pixel stride");
+  PLUME_CHECK((stat_sum == nullptr) == (stat_sq == nullptr), "conv3x3_fwd: stat_sum/stat_sq mismatch");
+  FwdDesc d{};
+  d.in[0] = view(x, ldx, N, H, W, Cin);
+  d.num_in_views = 1;
+  d.num_taps = 9;
+  d.Cin = Cin;
+  d.wmat = w;
+  d.out[0] = view(y, ldy, N, H, W, Cout);
+  d.num_out_views = 1;
+  d.cout_per_view = Cout;
+  d.scale = scale; d.shift = shift; d.relu = relu;
+  d.stat_sum = stat_sum; d.stat_sq = stat_sq;
+  d.stream = S(stream);
+  return launch_igemm_fwd(d);
+}
+
+int plume_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                        int W, int Cin, int Cout, plume_stream_t stream) {
+  PLUME_CHECK(dy && w_dgrad && dx, "conv3x3_dgrad: null pointer");
+  PLUME_CHECK(!bad_ld(lddy, Cout) && !bad_ld(lddx, Cin), "conv3x3_dgrad: bad pixel stride");
+  FwdDesc d{};
+  d.in[0] = view(dy, lddy, N, H, W, Cout);
+  d.num_in_views = 1;
+  d.num_taps = 9;
+  d.Cin = Cout;
+  d.wmat = w_dgrad;
+  d.out[0] = view(dx, lddx, N, H, W, Cin);
+  d.num_out_views = 1;
+  d.cout_per_view = Cin;
+  d.stream = S(stream);
+  return launch_igemm_fwd(d);
+}
+
+int plume_wgrad_splits(int N, int H, int W, int taps, int Cin, int Cout) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (taps != 9 && taps != 4)) return 0;
+  return wgrad_plan(N, H, W, taps, Cin, Cout);
+}
+size_t plume_wgrad_workspace_bytes(int N, int H, int W, int taps, int Cin, int Cout) {
+  const int splits = plume_wgrad_splits(N, H, W, taps, Cin, Cout);
+  return static_cast<size_t>(splits) * taps * Cin * Cout * sizeof(float);
+}
+
+int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw, int accumulate,
+                        void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
+                        plume_stream_t stream) {
+  PLUME_CHECK(x && dy && dw && workspace, "conv3x3_wgrad: null pointer");
+  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(lddy, Cout), "conv3x3_wgrad: bad pixel stride");
+  PLUME_CHECK(workspace_bytes >= plume_wgrad_workspace_bytes(N, H, W, 9, Cin, Cout),
+              "conv3x3_wgrad: workspace too small (plume_wgrad_workspace_bytes)");
+  WgradDesc d{};
+  d.x = view(x, ldx, N, H, W, Cin);
+  d.dy[0] = view(dy, lddy, N, H, W, Cout);
+  d.num_dy_views = 1;
+  d.num_taps = 9;
+  d.Cin = Cin; d.Cout = Cout;
+  d.partial = static_cast<float*>(workspace);
+  d.splits = wgrad_plan(N, H, W, 9, Cin, Cout);
+  d.stream = S(stream);
+  if (int r = launch_igemm_wgrad(d)) return r;
+  // dw[co][t][ci]
+  return wgrad_reduce(d.partial, d.splits, 9, Cin, Cout, 9ll * Cin, Cin, dw, accumulate, S(stream));
+}
+
+int plume_convT2x2_concat_fwd(const void* x, int ldx, const void* w, const float* bias, void* u, int ldu,
+                              int N, int H, int W, int Cin, int Cout, plume_stream_t stream) {
+  PLUME_CHECK(x && w && u, "convT2x2_fwd: null pointer");
+  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(ldu, Cout), "convT2x2_fwd: bad pixel stride");
+  FwdDesc d{};
+  d.in[0] = view(x, ldx, N, H, W, Cin);
+  d.num_in_views = 1;
+  d.num_taps = 1;
+  d.Cin = Cin;
+  d.wmat = w;
+  for (int ij = 0; ij < 4; ++ij) d.out[ij] = phase_view(u, ldu, N, H, W, Cout, ij >> 1, ij & 1);
+  d.num_out_views = 4;
+  d.cout_per_view = Cout;
+  d.shift = bias;
+  d.stream = S(stream);
+  return launch_igemm_fwd(d);
+}
+
+int plume_convT2x2_dgrad(const void* du, int lddu, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                         int W, int Cin, int Cout, plume_stream_t stream) {
+  PLUME_CHECK(du && w_dgrad && dx, "convT2x2_dgrad: null pointer");
+  PLUME_CHECK(!bad_ld(lddu, Cout) && !bad_ld(lddx, Cin), "convT2x2_dgrad: bad pixel stride");
+  FwdDesc d{};
+  for (int ij = 0; ij < 4; ++ij) d.in[ij] = phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1);
+  d.num_in_views = 4;
+  d.num_taps = 4;
+  d.Cin = Cout;
+  d.wmat = w_dgrad;
+  d.out[0] = view(dx, lddx, N, H, W, Cin);
+  d.num_out_views = 1;
+  d.cout_per_view = Cin;
+  d.stream = S(stream);
+  return launch_igemm_fwd(d);
+}
+
+int plume_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float* dw, int accumulate,
+                         void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
+                         plume_stream_t stream) {
+  PLUME_CHECK(x && du && dw && workspace, "convT2x2_wgrad: null pointer");
+  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(lddu, Cout), "convT2x2_wgrad: bad pixel stride");
+  PLUME_CHECK(workspace_bytes >= plume_wgrad_workspace_bytes(N, H, W, 4, Cin, Cout),
+              "convT2x2_wgrad: workspace too small (plume_wgrad_workspace_bytes)");
+  WgradDesc d{};
+  d.x = view(x, ldx, N, H, W, Cin);
+  for (int ij = 0; ij < 4; ++ij) d.dy[ij] = phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1);
+  d.num_dy_views = 4;
+  d.num_taps = 4;
+  d.Cin = Cin; d.Cout = Cout;
+  d.partial = static_cast<float*>(workspace);
+  d.splits = wgrad_plan(N, H, W, 4, Cin, Cout);
+  d.stream = S(stream);
+  if (int r = launch_igemm_wgrad(d)) return r;
+  // dw[ij][co][ci]
+  return wgrad_reduce(d.partial, d.splits, 4, Cin, Cout, Cin, 1ll * Cout * Cin, dw, accumulate,
+                      S(stream));
+}
+
+int plume_pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, plume_stream_t stream) {
+  PLUME_CHECK(w, "pack_conv3x3: null pointer");
+  return pack_conv3x3(w, wf, wd, Cout, Cin, S(stream));
+}
+int plume_pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, plume_stream_t stream) {
+  PLUME_CHECK(w, "pack_convT2x2: null pointer");
+  return pack_convT2x2(w, wf, wd, Cout, Cin, S(stream));
+}
+
+int plume_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels,
+                       plume_stream_t stream) {
+  PLUME_CHECK(in && out, "pad_channels: null pointer");
+  return pad_channels(in, Cs, out, Cd, pixels, S(stream));
+}
+
+int plume_bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+                      const float* beta, float eps, float momentum, float* running_mean,
+                      float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
+                      plume_stream_t stream) {
+  PLUME_CHECK(sum && sq && scale && shift, "bn_finalize: null pointer");
+  return bn_finalize(sum, sq, count, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                     shift, mean, invstd, C, S(stream));
+}
+int plume_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, const float* conv_bias, float eps, float* scale,
+                       float* shift, int C, plume_stream_t stream) {
+  PLUME_CHECK(running_mean && running_var && scale && shift, "bn_fold_eval: null pointer");
+  return bn_fold_eval(gamma, beta, running_mean, running_var, conv_bias, eps, scale, shift, C,
+                      S(stream));
+}
+
+int plume_scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                          void* a, int lda, long long pixels, int C, plume_stream_t stream) {
+  PLUME_CHECK(y && a && scale && shift, "scale_shift_act: null pointer");
+  PLUME_CHECK(y != a, "scale_shift_act: in-place operation is not supported");
+  return scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, S(stream));
+}
+int plume_scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                               void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax,
+                               int N, int H, int W, int C, plume_stream_t stream) {
+  PLUME_CHECK(y && pooled && argmax && scale && shift, "scale_shift_act_pool: null pointer");
+  return scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H,
+                              W, C, S(stream));
+}
+int plume_maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
+                         int C, plume_stream_t stream) {
+  PLUME_CHECK(x && y && argmax, "maxpool2x2_fwd: null pointer");
+  return maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, S(stream));
+}
+int plume_maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
+                         int lddskip, void* dx, int lddx, int N, int H, int W, int C,
+                         plume_stream_t stream) {
+  PLUME_CHECK(dy && argmax && dx, "maxpool2x2_bwd: null pointer");
+  return maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, S(stream));
+}
+
+int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, int relu,
+                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream) {
+  PLUME_CHECK(da && y && scale && shift && mean && invstd && sum_g && sum_gx,
+              "bn_bwd_reduce: null pointer");
+  return bn_bwd_reduce(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C,
+                       S(stream));
+}
+int plume_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
+                       long long pixels, int C, plume_stream_t stream) {
+  PLUME_CHECK(da && y && scale && shift && mean && invstd && sum_g && sum_gx && dy,
+              "bn_bwd_apply: null pointer");
+  return bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy,
+                      sum_dy, pixels, C, S(stream));
+}
+int plume_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
+                   long long pixels, int C, plume_stream_t stream) {
+  PLUME_CHECK(da && a && dy, "relu_bwd: null pointer");
+  return relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, S(stream));
+}
+int plume_channel_sum(const void* x, int ldx, float* out, long long pixels, int C,
+                      plume_stream_t stream) {
+  PLUME_CHECK(x && out, "channel_sum: null pointer");
+  return channel_sum(x, ldx, out, pixels, C, S(stream));
+}
+
+int plume_head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream) {
+  PLUME_CHECK(feat && w && logits, "head_fwd: null pointer");
+  PLUME_CHECK(!target || sums, "head_fwd: target given without sums");
+  return head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, S(stream));
+}
+int plume_head_loss(const float* sums, long long pixels, float bce_weight, float dice_weight,
+                    float dice_eps, float* loss_out, plume_stream_t stream) {
+  PLUME_CHECK(sums && loss_out, "head_loss: null pointer");
+  return head_loss(sums, pixels, bce_weight, dice_weight, dice_eps, loss_out, S(stream));
+}
+int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                   const float* sums, float bce_weight, float dice_weight, float dice_eps,
+                   float grad_scale, void* dfeat, int lddf, float* dw, float* db, long long pixels,
+                   int C, plume_stream_t stream) {
+  PLUME_CHECK(feat && w && logits && target && sums && dfeat && dw && db, "head_bwd: null pointer");
+  return head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale,
+                  dfeat, lddf, dw, db, pixels, C, S(stream));
+}
+
+int plume_adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
+               float beta2, float eps, int step, float grad_scale, plume_stream_t stream) {
+  PLUME_CHECK(param && grad && m && v, "adam: null pointer");
+  PLUME_CHECK((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+               reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+              "adam: buffers must be 16-byte aligned");
+  return adam(param, grad, m, v, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
+}
+
+int plume_extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
+                        int count, int T, void* tiles, int Cd, plume_stream_t stream) {
+  PLUME_CHECK(scene && ys && xs && tiles, "extract_tiles: null pointer");
+  return extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, S(stream));
+}
+int plume_stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T,
+                           int margin, float logit_threshold, uint8_t* mask, float* prob, int Hs, int Ws,
+                           plume_stream_t stream) {
+  PLUME_CHECK(logits && ys && xs && mask, "stitch_threshold: null pointer");
+  return stitch_threshold(logits, ys, xs, count, T, margin, logit_threshold, mask, prob, Hs, Ws,
+                          S(stream));
+}
+
+}  // extern "C"

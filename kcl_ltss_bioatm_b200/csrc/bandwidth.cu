@@ -1,0 +1,1042 @@
+// HBM-bandwidth kernels of the UNet hot path: BatchNorm apply / backward, 2x2 max pool (+argmax),
+// 1x1 head + sigmoid + BCE/Dice, fused Adam, weight packing, split-K reduction, tile cut / stitch.
+// All activation traffic is 128-bit vectorised (8 bf16), coalesced along the NHWC channel dimension;
+// grids are sized in multiples of the SM count and walk the data with a grid-stride loop in which a
+// thread keeps the same 8 channels, so per-channel parameters live in registers.
+//
+// No reference counterpart: the reference repository has no model code.
+#include "bandwidth.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace plume {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
+
+// Grid for `work` 16-byte vectors where the loop step (grid*256) must be a multiple of `cv`, the number
+// of vectors per pixel, so that a thread's channel group is loop-invariant.
+int grid_for(long long work, int cv, int blocks_per_sm = 8) {
+  const int g = cv / gcd_int(cv, kThreads);
+  long long need = (work + kThreads - 1) / kThreads;
+  long long cap = 1ll * sm_count() * blocks_per_sm;
+  long long grid = std::max(1ll, std::min(need, cap));
+  grid = (grid + g - 1) / g * g;
+  return static_cast<int>(grid);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+struct alignas(16) BF8 {
+  uint32_t u[4];
+};
+__device__ __forceinline__ BF8 ld_bf8(const __nv_bfloat16* p) {
+  BF8 r;
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  r.u[0] = v.x; r.u[1] = v.y; r.u[2] = v.z; r.u[3] = v.w;
+  return r;
+}
+__device__ __forceinline__ BF8 ld_bf8_stream(const __nv_bfloat16* p) {
+  BF8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.u[0]), "=r"(r.u[1]), "=r"(r.u[2]), "=r"(r.u[3])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_bf8(__nv_bfloat16* p, const BF8& v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(v.u[0], v.u[1], v.u[2], v.u[3]);
+}
+__device__ __forceinline__ void unpack8(const BF8& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16x2(v.u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ BF8 pack8(const float (&f)[8]) {
+  BF8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ void ld_f8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Block-level accumulation of K per-thread partial sums per channel into global fp32 arrays.
+// Threads with the same channel group first combine in shared memory, then one atomic per channel.
+template <int K>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[K][8], int cv_idx, int CV,
+                                                     float* const (&out)[K], float* s_acc) {
+  // s_acc: K * min(CV,256) * 8 floats, zeroed here
+  const int span = min(CV, kThreads);
+  for (int i = threadIdx.x; i < K * span * 8; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  const int slot = cv_idx % span;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[(k * span + slot) * 8 + e], acc[k][e]);
+  __syncthreads();
+  // which global channel does smem slot s map to?  slot = cv % span and cv = (tid + const) % CV with
+  // the loop-invariant mapping, so slot s holds channel group (cv0 - cv0 % span) + s where cv0 is this
+  // block's first channel group; when CV <= 256, span == CV and the group is simply s.
+  const int cv_block_base = cv_idx - slot;  // identical for all threads of the block (see grid_for)
+  for (int i = threadIdx.x; i < K * span * 8; i += kThreads) {
+    const int k = i / (span * 8);
+    const int r = i % (span * 8);
+    const float v = s_acc[i];
+    if (v != 0.f) atomicAdd(out[k] + cv_block_base * 8 + r, v);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// pad_channels
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ in, int cvs,
+                                    __nv_bfloat16* __restrict__ out, int cvd, long long total) {
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const long long p = i / cvd;
+    const int cv = static_cast<int>(i % cvd);
+    BF8 v;
+    v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
+    if (cv < cvs) v = ld_bf8_stream(in + (p * cvs + cv) * 8);
+    st_bf8(out + i * 8, v);
+  }
+}
+
+int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, cudaStream_t s) {
+  if (Cs % 8 || Cd % 8 || Cs > Cd || Cs <= 0) {
+    set_error("pad_channels: channel counts must be multiples of 8 with Cs <= Cd");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const long long total = pixels * (Cd / 8);
+  const int grid = grid_for(total, 1);
+  pad_channels_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(in), Cs / 8,
+                                                static_cast<__nv_bfloat16*>(out), Cd / 8, total);
+  return check_launch("pad_channels");
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm finalize / fold
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* sum, const float* sq, float inv_count,
+                                   float unbias, const float* gamma, const float* beta, float eps,
+                                   float momentum, float* running_mean, float* running_var,
+                                   float* scale, float* shift, float* mean_out, float* invstd_out,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sum[c] * inv_count;
+  float var = sq[c] * inv_count - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (invstd_out) invstd_out[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+  if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+}
+
+int bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+                const float* beta, float eps, float momentum, float* running_mean,
+                float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
+                cudaStream_t s) {
+  if (count <= 0 || C <= 0) {
+    set_error("bn_finalize: empty batch");
+    return -1;
+  }
+  const float unbias = count > 1 ? static_cast<float>(count) / static_cast<float>(count - 1) : 1.f;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sq, 1.f / static_cast<float>(count), unbias,
+                                                     gamma, beta, eps, momentum, running_mean,
+                                                     running_var, scale, shift, mean, invstd, C);
+  return check_launch("bn_finalize");
+}
+
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm,
+                               const float* rv, const float* bias, float eps, float* scale,
+                               float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = ((bias ? bias[c] : 0.f) - rm[c]) * sc + (beta ? beta[c] : 0.f);
+}
+
+int bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                 const float* bias, float eps, float* scale, float* shift, int C, cudaStream_t s) {
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, bias, eps, scale, shift, C);
+  return check_launch("bn_fold_eval");
+}
+
+// ------------------------------------------------------------------------------------------------
+// scale/shift/act (BN apply + ReLU)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    scale_shift_act_kernel(const __nv_bfloat16* __restrict__ y, long long ldy,
+                           const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                           __nv_bfloat16* __restrict__ a, long long lda, long long pixels, int CV) {
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float sc[8], sh[8];
+  ld_f8(scale + cv * 8, sc);
+  ld_f8(shift + cv * 8, sh);
+  long long p = i0 / CV;
+  // two pixels in flight per iteration
+  for (; p + pstep < pixels; p += 2 * pstep) {
+    const BF8 v0 = ld_bf8_stream(y + p * ldy + cv * 8);
+    const BF8 v1 = ld_bf8_stream(y + (p + pstep) * ldy + cv * 8);
+    float f0[8], f1[8];
+    unpack8(v0, f0);
+    unpack8(v1, f1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f0[e] = fmaf(f0[e], sc[e], sh[e]);
+      f1[e] = fmaf(f1[e], sc[e], sh[e]);
+      if (relu) {
+        f0[e] = fmaxf(f0[e], 0.f);
+        f1[e] = fmaxf(f1[e], 0.f);
+      }
+    }
+    st_bf8(a + p * lda + cv * 8, pack8(f0));
+    st_bf8(a + (p + pstep) * lda + cv * 8, pack8(f1));
+  }
+  if (p < pixels) {
+    const BF8 v0 = ld_bf8_stream(y + p * ldy + cv * 8);
+    float f0[8];
+    unpack8(v0, f0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f0[e] = fmaf(f0[e], sc[e], sh[e]);
+      if (relu) f0[e] = fmaxf(f0[e], 0.f);
+    }
+    st_bf8(a + p * lda + cv * 8, pack8(f0));
+  }
+}
+
+int scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu, void* a,
+                    int lda, long long pixels, int C, cudaStream_t s) {
+  if (C % 8 || ldy % 8 || lda % 8 || C <= 0) {
+    set_error("scale_shift_act: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV);
+  scale_shift_act_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), ldy, scale,
+                                                   shift, relu, static_cast<__nv_bfloat16*>(a), lda,
+                                                   pixels, CV);
+  return check_launch("scale_shift_act");
+}
+
+// ------------------------------------------------------------------------------------------------
+// scale/shift/act fused with 2x2 max pool (+argmax), and the plain pool
+// ------------------------------------------------------------------------------------------------
+template <bool kAct, bool kSkip>
+__global__ void __launch_bounds__(kThreads)
+    act_pool_kernel(const __nv_bfloat16* __restrict__ y, long long ldy,
+                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                    __nv_bfloat16* __restrict__ skip, long long ldskip,
+                    __nv_bfloat16* __restrict__ pooled, long long ldpooled,
+                    uint8_t* __restrict__ argmax, int N, int Ho, int Wo, int CV) {
+  // one thread per (pooled pixel, channel group)
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  const long long opix = 1ll * N * Ho * Wo;
+  float sc[8], sh[8];
+  if (kAct) {
+    ld_f8(scale + cv * 8, sc);
+    ld_f8(shift + cv * 8, sh);
+  }
+  const int W = 2 * Wo;
+  for (long long op = i0 / CV; op < opix; op += pstep) {
+    const int wo = static_cast<int>(op % Wo);
+    const long long t = op / Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const long long ip = (n * (2 * Ho) + 2 * ho) * W + 2 * wo;  // top-left input pixel
+    BF8 v[4];
+    v[0] = ld_bf8_stream(y + ip * ldy + cv * 8);
+    v[1] = ld_bf8_stream(y + (ip + 1) * ldy + cv * 8);
+    v[2] = ld_bf8_stream(y + (ip + W) * ldy + cv * 8);
+    v[3] = ld_bf8_stream(y + (ip + W + 1) * ldy + cv * 8);
+    float f[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unpack8(v[k], f[k]);
+      if (kAct) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[k][e] = fmaf(f[k][e], sc[e], sh[e]);
+          if (relu) f[k][e] = fmaxf(f[k][e], 0.f);
+        }
+        v[k] = pack8(f[k]);
+        unpack8(v[k], f[k]);  // pool the rounded values (what the next layer reads)
+      }
+    }
+    if (kSkip) {
+      st_bf8(skip + ip * ldskip + cv * 8, v[0]);
+      st_bf8(skip + (ip + 1) * ldskip + cv * 8, v[1]);
+      st_bf8(skip + (ip + W) * ldskip + cv * 8, v[2]);
+      st_bf8(skip + (ip + W + 1) * ldskip + cv * 8, v[3]);
+    }
+    float best[8];
+    uint32_t idx_lo = 0, idx_hi = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float b = f[0][e];
+      uint32_t bi = 0;
+      if (f[1][e] > b) { b = f[1][e]; bi = 1; }
+      if (f[2][e] > b) { b = f[2][e]; bi = 2; }
+      if (f[3][e] > b) { b = f[3][e]; bi = 3; }
+      best[e] = b;
+      if (e < 4) idx_lo |= bi << (8 * e);
+      else idx_hi |= bi << (8 * (e - 4));
+    }
+    st_bf8(pooled + op * ldpooled + cv * 8, pack8(best));
+    *reinterpret_cast<uint2*>(argmax + (op * CV + cv) * 8) = make_uint2(idx_lo, idx_hi);
+  }
+}
+
+static int pool_common(bool act, bool with_skip, const void* y, int ldy, const float* scale,
+                       const float* shift, int relu, void* skip, int ldskip, void* pooled,
+                       int ldpooled, uint8_t* argmax, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8 || ldy % 8 || ldpooled % 8 || (with_skip && ldskip % 8) || C <= 0) {
+    set_error("maxpool: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if ((H & 1) || (W & 1)) {
+    set_error("maxpool: H and W must be even");
+    return -1;
+  }
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  const int CV = C / 8;
+  const long long work = 1ll * N * (H / 2) * (W / 2) * CV;
+  const int grid = grid_for(work, CV);
+  auto yy = static_cast<const __nv_bfloat16*>(y);
+  auto sk = static_cast<__nv_bfloat16*>(skip);
+  auto po = static_cast<__nv_bfloat16*>(pooled);
+  if (act && with_skip)
+    act_pool_kernel<true, true><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip, po,
+                                                          ldpooled, argmax, N, H / 2, W / 2, CV);
+  else if (act)
+    act_pool_kernel<true, false><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip,
+                                                           po, ldpooled, argmax, N, H / 2, W / 2, CV);
+  else
+    act_pool_kernel<false, false><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip,
+                                                            po, ldpooled, argmax, N, H / 2, W / 2, CV);
+  return check_launch("maxpool2x2");
+}
+
+int scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                         void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax, int N,
+                         int H, int W, int C, cudaStream_t s) {
+  return pool_common(true, skip != nullptr, y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled,
+                     argmax, N, H, W, C, s);
+}
+int maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
+                   int C, cudaStream_t s) {
+  return pool_common(false, false, x, ldx, nullptr, nullptr, 0, nullptr, 0, y, ldy, argmax, N, H, W, C,
+                     s);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                       const uint8_t* __restrict__ argmax, const __nv_bfloat16* __restrict__ dskip,
+                       long long lddskip, __nv_bfloat16* __restrict__ dx, long long lddx, int N, int Ho,
+                       int Wo, int CV) {
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  const long long opix = 1ll * N * Ho * Wo;
+  const int W = 2 * Wo;
+  for (long long op = i0 / CV; op < opix; op += pstep) {
+    const int wo = static_cast<int>(op % Wo);
+    const long long t = op / Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const long long ip = (n * (2 * Ho) + 2 * ho) * W + 2 * wo;
+    float g[8];
+    unpack8(ld_bf8_stream(dy + op * lddy + cv * 8), g);
+    const uint2 am = *reinterpret_cast<const uint2*>(argmax + (op * CV + cv) * 8);
+    const long long off[4] = {ip, ip + 1, ip + W, ip + W + 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+      if (dskip) {
+        unpack8(ld_bf8_stream(dskip + off[k] * lddskip + cv * 8), o);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t bi = ((e < 4 ? am.x : am.y) >> (8 * (e & 3))) & 0xffu;
+        if (bi == static_cast<uint32_t>(k)) o[e] += g[e];
+      }
+      st_bf8(dx + off[k] * lddx + cv * 8, pack8(o));
+    }
+  }
+}
+
+int maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
+                   void* dx, int lddx, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8 || lddy % 8 || lddx % 8 || (dskip && lddskip % 8) || C <= 0) {
+    set_error("maxpool_bwd: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if ((H & 1) || (W & 1)) {
+    set_error("maxpool_bwd: H and W must be even");
+    return -1;
+  }
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  const int CV = C / 8;
+  const long long work = 1ll * N * (H / 2) * (W / 2) * CV;
+  const int grid = grid_for(work, CV);
+  maxpool_bwd_kernel<<<grid, kThreads, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(dy), lddy, argmax, static_cast<const __nv_bfloat16*>(dskip),
+      lddskip, static_cast<__nv_bfloat16*>(dx), lddx, N, H / 2, W / 2, CV);
+  return check_launch("maxpool2x2_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, long long ldda,
+                         const __nv_bfloat16* __restrict__ y, long long ldy,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                         float* sum_g, float* sum_gx, long long pixels, int CV) {
+  extern __shared__ float s_acc[];
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float sc[8], sh[8], mu[8], is[8];
+  ld_f8(scale + cv * 8, sc);
+  ld_f8(shift + cv * 8, sh);
+  ld_f8(mean + cv * 8, mu);
+  ld_f8(invstd + cv * 8, is);
+  float acc[2][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+  for (long long p = i0 / CV; p < pixels; p += pstep) {
+    float g[8], yy[8];
+    unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
+    unpack8(ld_bf8_stream(y + p * ldy + cv * 8), yy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
+      acc[0][e] += gg;
+      acc[1][e] = fmaf(gg, (yy[e] - mu[e]) * is[e], acc[1][e]);
+    }
+  }
+  float* const outs[2] = {sum_g, sum_gx};
+  block_channel_reduce<2>(acc, cv, CV, outs, s_acc);
+}
+
+int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                  const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
+                  float* sum_gx, long long pixels, int C, cudaStream_t s) {
+  if (C % 8 || ldda % 8 || ldy % 8 || C <= 0) {
+    set_error("bn_bwd_reduce: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV, 4);
+  const size_t smem = 2ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  bn_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(
+      static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
+      shift, mean, invstd, relu, sum_g, sum_gx, pixels, CV);
+  return check_launch("bn_bwd_reduce");
+}
+
+__global__ void __launch_bounds__(kThreads)
+    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, long long ldda,
+                        const __nv_bfloat16* __restrict__ y, long long ldy,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                        const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                        float inv_count, __nv_bfloat16* __restrict__ dy, long long lddy, float* sum_dy,
+                        long long pixels, int CV) {
+  extern __shared__ float s_acc[];
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float sc[8], sh[8], mu[8], is[8], mg[8], mgx[8];
+  ld_f8(scale + cv * 8, sc);
+  ld_f8(shift + cv * 8, sh);
+  ld_f8(mean + cv * 8, mu);
+  ld_f8(invstd + cv * 8, is);
+  ld_f8(sum_g + cv * 8, mg);
+  ld_f8(sum_gx + cv * 8, mgx);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mg[e] *= inv_count;
+    mgx[e] *= inv_count;
+  }
+  float acc[1][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
+  for (long long p = i0 / CV; p < pixels; p += pstep) {
+    float g[8], yy[8], o[8];
+    unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
+    unpack8(ld_bf8_stream(y + p * ldy + cv * 8), yy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
+      const float xhat = (yy[e] - mu[e]) * is[e];
+      o[e] = sc[e] * (gg - mg[e] - xhat * mgx[e]);
+    }
+    const BF8 ov = pack8(o);
+    st_bf8(dy + p * lddy + cv * 8, ov);
+    if (sum_dy) {
+      float r[8];
+      unpack8(ov, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[0][e] += r[e];
+    }
+  }
+  if (sum_dy) {
+    float* const outs[1] = {sum_dy};
+    block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+  }
+}
+
+int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                 const float* shift, const float* mean, const float* invstd, int relu,
+                 const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
+                 long long pixels, int C, cudaStream_t s) {
+  if (C % 8 || ldda % 8 || ldy % 8 || lddy % 8 || C <= 0) {
+    set_error("bn_bwd_apply: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV, 4);
+  const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  bn_bwd_apply_kernel<<<grid, kThreads, smem, s>>>(
+      static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
+      shift, mean, invstd, relu, sum_g, sum_gx, 1.f / static_cast<float>(pixels),
+      static_cast<__nv_bfloat16*>(dy), lddy, sum_dy, pixels, CV);
+  return check_launch("bn_bwd_apply");
+}
+
+__global__ void __launch_bounds__(kThreads)
+    relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, long long ldda,
+                    const __nv_bfloat16* __restrict__ a, long long lda,
+                    __nv_bfloat16* __restrict__ dy, long long lddy, float* sum_dy, long long pixels,
+                    int CV) {
+  extern __shared__ float s_acc[];
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float acc[1][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
+  for (long long p = i0 / CV; p < pixels; p += pstep) {
+    float g[8], aa[8];
+    unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
+    unpack8(ld_bf8_stream(a + p * lda + cv * 8), aa);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g[e] = aa[e] > 0.f ? g[e] : 0.f;
+      acc[0][e] += g[e];
+    }
+    st_bf8(dy + p * lddy + cv * 8, pack8(g));
+  }
+  if (sum_dy) {
+    float* const outs[1] = {sum_dy};
+    block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+  }
+}
+
+int relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
+             long long pixels, int C, cudaStream_t s) {
+  if (C % 8 || ldda % 8 || lda % 8 || lddy % 8 || C <= 0) {
+    set_error("relu_bwd: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV, 4);
+  const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  relu_bwd_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(da), ldda,
+                                               static_cast<const __nv_bfloat16*>(a), lda,
+                                               static_cast<__nv_bfloat16*>(dy), lddy, sum_dy, pixels,
+                                               CV);
+  return check_launch("relu_bwd");
+}
+
+__global__ void __launch_bounds__(kThreads)
+    channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* out,
+                       long long pixels, int CV) {
+  extern __shared__ float s_acc[];
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float acc[1][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
+  for (long long p = i0 / CV; p < pixels; p += pstep) {
+    float f[8];
+    unpack8(ld_bf8_stream(x + p * ldx + cv * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] += f[e];
+  }
+  float* const outs[1] = {out};
+  block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+}
+
+int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cudaStream_t s) {
+  if (C % 8 || ldx % 8 || C <= 0) {
+    set_error("channel_sum: channels/strides must be multiples of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV, 4);
+  const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  channel_sum_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, out,
+                                                  pixels, CV);
+  return check_launch("channel_sum");
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 head + sigmoid + BCE / Dice
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// CV (= C/8, a power of two <= 32) consecutive lanes share one pixel.
+__global__ void __launch_bounds__(kThreads)
+    head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, long long ldf,
+                    const float* __restrict__ w, const float* __restrict__ b,
+                    const uint8_t* __restrict__ target, float* __restrict__ logits, float* sums,
+                    long long pixels, int CV) {
+  __shared__ float s_red[4][kThreads / 32];
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float wv[8];
+  ld_f8(w + cv * 8, wv);
+  const float bias = b ? __ldg(b) : 0.f;
+  float a_bce = 0.f, a_pt = 0.f, a_p = 0.f, a_t = 0.f;
+  // every lane of a pixel group runs the same trip count, so the shuffles below are convergent
+  const long long p0 = i0 / CV;
+  const long long iters = (pixels + pstep - 1) / pstep;
+  for (long long it = 0; it < iters; ++it) {
+    const long long p = p0 + it * pstep;
+    float dot = 0.f;
+    if (p < pixels) {
+      float f[8];
+      unpack8(ld_bf8_stream(feat + p * ldf + cv * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot = fmaf(f[e], wv[e], dot);
+    }
+    for (int o = CV >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (cv == 0 && p < pixels) {
+      const float z = dot + bias;
+      logits[p] = z;
+      if (target) {
+        const float t = target[p] ? 1.f : 0.f;
+        const float pr = sigmoidf_(z);
+        a_bce += fmaxf(z, 0.f) - z * t + log1pf(__expf(-fabsf(z)));
+        a_pt += pr * t;
+        a_p += pr;
+        a_t += t;
+      }
+    }
+  }
+  if (!target) return;
+  a_bce = warp_sum(a_bce);
+  a_pt = warp_sum(a_pt);
+  a_p = warp_sum(a_p);
+  a_t = warp_sum(a_t);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_red[0][warp] = a_bce;
+    s_red[1][warp] = a_pt;
+    s_red[2][warp] = a_p;
+    s_red[3][warp] = a_t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float v = 0.f;
+    for (int k = 0; k < kThreads / 32; ++k) v += s_red[threadIdx.x][k];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+static bool head_cv_ok(int C) {
+  const int CV = C / 8;
+  return C % 8 == 0 && CV >= 1 && CV <= 32 && (CV & (CV - 1)) == 0;
+}
+
+int head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+             float* logits, float* sums, long long pixels, int C, cudaStream_t s) {
+  if (!head_cv_ok(C) || ldf % 8) {
+    set_error("head_fwd: C must be 8*2^k <= 256 and ld a multiple of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV, 4);
+  head_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), ldf, w, b, target,
+                                            logits, sums, pixels, CV);
+  return check_launch("head_fwd");
+}
+
+__global__ void head_loss_kernel(const float* sums, float inv_pixels, float bce_w, float dice_w,
+                                 float eps, float* out) {
+  const float bce = sums[0] * inv_pixels;
+  const float dice = 1.f - (2.f * sums[1] + eps) / (sums[2] + sums[3] + eps);
+  out[0] = bce_w * bce + dice_w * dice;
+  out[1] = bce;
+  out[2] = dice;
+}
+
+int head_loss(const float* sums, long long pixels, float bce_w, float dice_w, float eps, float* out,
+              cudaStream_t s) {
+  if (pixels <= 0) {
+    set_error("head_loss: empty batch");
+    return -1;
+  }
+  head_loss_kernel<<<1, 1, 0, s>>>(sums, 1.f / static_cast<float>(pixels), bce_w, dice_w, eps, out);
+  return check_launch("head_loss");
+}
+
+__global__ void __launch_bounds__(kThreads)
+    head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, long long ldf,
+                    const float* __restrict__ w, const float* __restrict__ logits,
+                    const uint8_t* __restrict__ target, const float* __restrict__ sums, float inv_pixels,
+                    float bce_w, float dice_w, float eps, float grad_scale,
+                    __nv_bfloat16* __restrict__ dfeat, long long lddf, float* dw, float* db,
+                    long long pixels, int CV) {
+  extern __shared__ float s_acc[];
+  __shared__ float s_db[kThreads / 32];
+  const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
+  const int cv = static_cast<int>(i0 % CV);
+  const long long pstep = (1ll * gridDim.x * kThreads) / CV;
+  float wv[8];
+  ld_f8(w + cv * 8, wv);
+  // d(dice)/dp_i = -(2 t_i (S+eps) - (2I+eps)) / (S+eps)^2,  S = sum p + sum t, I = sum p t
+  const float I2 = 2.f * sums[1] + eps;
+  const float S = sums[2] + sums[3] + eps;
+  const float invS2 = 1.f / (S * S);
+  float acc[1][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
+  float a_db = 0.f;
+  for (long long p = i0 / CV; p < pixels; p += pstep) {
+    const float z = __ldg(logits + p);
+    const float t = target[p] ? 1.f : 0.f;
+    const float pr = sigmoidf_(z);
+    const float ddice = -(2.f * t * S - I2) * invS2;
+    const float dz = grad_scale * (bce_w * (pr - t) * inv_pixels + dice_w * ddice * pr * (1.f - pr));
+    float f[8], o[8];
+    unpack8(ld_bf8_stream(feat + p * ldf + cv * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = dz * wv[e];
+      acc[0][e] = fmaf(dz, f[e], acc[0][e]);
+    }
+    st_bf8(dfeat + p * lddf + cv * 8, pack8(o));
+    if (cv == 0) a_db += dz;
+  }
+  float* const outs[1] = {dw};
+  block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+  a_db = warp_sum(a_db);
+  if ((threadIdx.x & 31) == 0) s_db[threadIdx.x >> 5] = a_db;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int k = 0; k < kThreads / 32; ++k) v += s_db[k];
+    atomicAdd(db, v);
+  }
+}
+
+int head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+             const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
+             int lddf, float* dw, float* db, long long pixels, int C, cudaStream_t s) {
+  if (!head_cv_ok(C) || ldf % 8 || lddf % 8) {
+    set_error("head_bwd: C must be 8*2^k <= 256 and strides multiples of 8");
+    return -1;
+  }
+  if (pixels <= 0) return 0;
+  const int CV = C / 8;
+  const int grid = grid_for(pixels * CV, CV, 4);
+  const size_t smem = 1ull * CV * 8 * sizeof(float);
+  head_bwd_kernel<<<grid, kThreads, smem, s>>>(
+      static_cast<const __nv_bfloat16*>(feat), ldf, w, logits, target, sums,
+      1.f / static_cast<float>(pixels), bce_w, dice_w, eps, grad_scale,
+      static_cast<__nv_bfloat16*>(dfeat), lddf, dw, db, pixels, CV);
+  return check_launch("head_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                float* __restrict__ v, long long n4, long long n, float lr_t, float beta1, float beta2,
+                float eps, float inv_bc2_sqrt, float gscale) {
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4 p = reinterpret_cast<float4*>(param)[i];
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = reinterpret_cast<float*>(&p);
+    const float* gp = reinterpret_cast<const float*>(&g);
+    float* mp = reinterpret_cast<float*>(&mm);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ge = gp[e] * gscale;
+      mp[e] = beta1 * mp[e] + (1.f - beta1) * ge;
+      vp[e] = beta2 * vp[e] + (1.f - beta2) * ge * ge;
+      pp[e] -= lr_t * mp[e] / (sqrtf(vp[e]) * inv_bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(param)[i] = p;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (n not a multiple of 4)
+  const long long tail0 = n4 * 4;
+  const long long ti = tail0 + 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti < n) {
+    const float ge = grad[ti] * gscale;
+    const float me = beta1 * m[ti] + (1.f - beta1) * ge;
+    const float ve = beta2 * v[ti] + (1.f - beta2) * ge * ge;
+    m[ti] = me;
+    v[ti] = ve;
+    param[ti] -= lr_t * me / (sqrtf(ve) * inv_bc2_sqrt + eps);
+  }
+}
+
+int adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
+         float beta2, float eps, int step, float grad_scale, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (step < 1) {
+    set_error("adam: step must be >= 1");
+    return -1;
+  }
+  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
+  const float lr_t = static_cast<float>(lr / bc1);
+  const float inv_bc2_sqrt = static_cast<float>(1.0 / std::sqrt(bc2));
+  const long long n4 = n / 4;
+  const int grid = grid_for(std::max(n4, 1ll), 1);
+  adam_kernel<<<grid, kThreads, 0, s>>>(param, grad, m, v, n4, n, lr_t, beta1, beta2, eps,
+                                        inv_bc2_sqrt, grad_scale);
+  return check_launch("adam");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+  // w, wf: [co][t][ci];  wd: [ci][8-t][co]
+  const long long total = 1ll * Cout * 9 * Cin;
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int ci = static_cast<int>(i % Cin);
+    const int t = static_cast<int>((i / Cin) % 9);
+    const int co = static_cast<int>(i / (9ll * Cin));
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) wf[i] = v;
+    if (wd) wd[(1ll * ci * 9 + (8 - t)) * Cout + co] = v;
+  }
+}
+
+int pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s) {
+  const long long total = 1ll * Cout * 9 * Cin;
+  if (total <= 0) return 0;
+  const int grid = grid_for(total, 1);
+  pack_conv3x3_kernel<<<grid, kThreads, 0, s>>>(w, static_cast<__nv_bfloat16*>(wf),
+                                                static_cast<__nv_bfloat16*>(wd), Cout, Cin);
+  return check_launch("pack_conv3x3");
+}
+
+__global__ void pack_convT_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+  // w, wf: [ij][co][ci];  wd: [ci][ij][co]
+  const long long total = 4ll * Cout * Cin;
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int ci = static_cast<int>(i % Cin);
+    const int co = static_cast<int>((i / Cin) % Cout);
+    const int ij = static_cast<int>(i / (1ll * Cin * Cout));
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) wf[i] = v;
+    if (wd) wd[(1ll * ci * 4 + ij) * Cout + co] = v;
+  }
+}
+
+int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s) {
+  const long long total = 4ll * Cout * Cin;
+  if (total <= 0) return 0;
+  const int grid = grid_for(total, 1);
+  pack_convT_kernel<<<grid, kThreads, 0, s>>>(w, static_cast<__nv_bfloat16*>(wf),
+                                              static_cast<__nv_bfloat16*>(wd), Cout, Cin);
+  return check_launch("pack_convT2x2");
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-K reduction of the weight gradient: partial[split][t*Cin+ci][co] -> dw[co*s_co + t*s_t + ci]
+// ------------------------------------------------------------------------------------------------
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows, int Cout,
+                                    int Cin, long long s_co, long long s_t, float* __restrict__ dw,
+                                    int accumulate) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const long long split_stride = 1ll * rows * Cout;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k;
+    float acc = 0.f;
+    if (r < rows && c0 + tx < Cout) {
+      const float* src = partial + 1ll * r * Cout + c0 + tx;
+      for (int sp = 0; sp < splits; ++sp) acc += src[sp * split_stride];
+    }
+    tile[ty + 8 * k][tx] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co = c0 + ty + 8 * k;
+    const int r = r0 + tx;
+    if (r < rows && co < Cout) {
+      const int t = r / Cin, ci = r % Cin;
+      const long long o = co * s_co + t * s_t + ci;
+      const float v = tile[tx][ty + 8 * k];
+      dw[o] = accumulate ? dw[o] + v : v;
+    }
+  }
+}
+
+int wgrad_reduce(const float* partial, int splits, int taps, int Cin, int Cout, long long s_co,
+                 long long s_t, float* dw, int accumulate, cudaStream_t s) {
+  const int rows = taps * Cin;
+  dim3 grid((Cout + 31) / 32, (rows + 31) / 32);
+  dim3 block(32, 8);
+  wgrad_reduce_kernel<<<grid, block, 0, s>>>(partial, splits, rows, Cout, Cin, s_co, s_t, dw,
+                                             accumulate);
+  return check_launch("wgrad_reduce");
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiled inference: cut tiles out of a scene, stitch logits back by centre crop + threshold
+// ------------------------------------------------------------------------------------------------
+__global__ void extract_tiles_kernel(const __nv_bfloat16* __restrict__ scene, int Hs, int Ws, int cvs,
+                                     const int* __restrict__ ys, const int* __restrict__ xs, int T,
+                                     __nv_bfloat16* __restrict__ tiles, int cvd, long long total) {
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int cv = static_cast<int>(i % cvd);
+    long long t = i / cvd;
+    const int x = static_cast<int>(t % T);
+    t /= T;
+    const int y = static_cast<int>(t % T);
+    const int k = static_cast<int>(t / T);
+    const int sy = ys[k] + y, sx = xs[k] + x;
+    BF8 v;
+    v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
+    if (cv < cvs && sy >= 0 && sy < Hs && sx >= 0 && sx < Ws)
+      v = ld_bf8(scene + ((1ll * sy * Ws + sx) * cvs + cv) * 8);
+    st_bf8(tiles + i * 8, v);
+  }
+}
+
+int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs, int count,
+                  int T, void* tiles, int Cd, cudaStream_t s) {
+  if (Cs % 8 || Cd % 8 || Cs > Cd || Cs <= 0) {
+    set_error("extract_tiles: channel counts must be multiples of 8 with Cs <= Cd");
+    return -1;
+  }
+  if (count <= 0) return 0;
+  const long long total = 1ll * count * T * T * (Cd / 8);
+  const int grid = grid_for(total, 1);
+  extract_tiles_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(scene), Hs, Ws,
+                                                 Cs / 8, ys, xs, T, static_cast<__nv_bfloat16*>(tiles),
+                                                 Cd / 8, total);
+  return check_launch("extract_tiles");
+}
+
+__global__ void stitch_kernel(const float* __restrict__ logits, const int* __restrict__ ys,
+                              const int* __restrict__ xs, int T, int margin, float thr,
+                              uint8_t* __restrict__ mask, float* __restrict__ prob, int Hs, int Ws,
+                              long long total) {
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int x = static_cast<int>(i % T);
+    const long long t = i / T;
+    const int y = static_cast<int>(t % T);
+    const int k = static_cast<int>(t / T);
+    const int y0 = ys[k], x0 = xs[k];
+    const int sy = y0 + y, sx = x0 + x;
+    if (sy < 0 || sy >= Hs || sx < 0 || sx >= Ws) continue;
+    // a tile owns its interior; a border strip is owned only where the tile touches the scene edge
+    const bool own_y = (y >= margin || y0 <= 0) && (y < T - margin || y0 + T >= Hs);
+    const bool own_x = (x >= margin || x0 <= 0) && (x < T - margin || x0 + T >= Ws);
+    if (!(own_y && own_x)) continue;
+    const float z = logits[i];
+    mask[1ll * sy * Ws + sx] = z >= thr ? 1 : 0;
+    if (prob) prob[1ll * sy * Ws + sx] = 1.f / (1.f + __expf(-z));
+  }
+}
+
+int stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T, int margin,
+                     float thr, uint8_t* mask, float* prob, int Hs, int Ws, cudaStream_t s) {
+  if (count <= 0) return 0;
+  if (margin < 0 || 2 * margin >= T) {
+    set_error("stitch_threshold: margin must satisfy 0 <= 2*margin < T");
+    return -1;
+  }
+  const long long total = 1ll * count * T * T;
+  const int grid = grid_for(total, 1);
+  stitch_kernel<<<grid, kThreads, 0, s>>>(logits, ys, xs, T, margin, thr, mask, prob, Hs, Ws, total);
+  return check_launch("stitch_threshold");
+}
+
+}  // namespace plume

@@ -1,0 +1,715 @@
+// Implicit-GEMM convolution kernels for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+//  * igemm_fwd_kernel  : pixels x out-channels GEMM, K = taps x in-channels, both operands K-major.
+//                        A tiles are 4-D TMA boxes of the NHWC activation (halo/padding comes from
+//                        TMA out-of-bounds zero fill, one load per filter tap); B tiles are 2-D boxes
+//                        of the packed weight matrix.  Persistent CTAs, warp-specialised:
+//                        warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+//                        warps4-7 = epilogue (TMEM -> regs -> scale/shift/ReLU -> bf16 -> swizzled smem
+//                        -> TMA store; optional per-channel sum / sum-of-squares for BatchNorm).
+//                        Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//  * igemm_wgrad_kernel: in-channels x out-channels GEMM per filter tap, K = pixels.  Both operands are
+//                        MN-major (channels are the contiguous dimension of NHWC), so the same TMA boxes
+//                        feed the MMA without a transpose.  Split-K over pixel tiles, fp32 partials.
+//
+// No reference counterpart: the reference repository has no model code.
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace plume {
+
+__device__ int g_dbg_word = 0;
+
+int read_debug_word() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_dbg_word, sizeof(int));
+  return v;
+}
+
+struct TmapPack4 {
+  CUtensorMap m[4];
+};
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// Spatial box of `target` pixels (a power of two) for an image of W x H: as square as the image allows.
+static void pick_box(int W, int H, int target, int max_w, int* bw, int* bh, int* bn) {
+  int w = std::min(pow2_floor(W), max_w);
+  w = std::min(w, target);
+  int h = std::min(pow2_floor(H), target / w);
+  *bw = w;
+  *bh = h;
+  *bn = target / (w * h);
+}
+
+// =================================================================================================
+// Forward kernel
+// =================================================================================================
+struct FwdParams {
+  int tiles_w, tiles_h, tiles_n;  // spatial tiling of the GEMM M dimension
+  int TW, TH, TN;                 // box extents, TW*TH*TN == 128
+  int W, H, N;                    // output extents (row-valid mask)
+  int n_tiles;                    // tiles along GEMM N
+  int num_taps, per_tap_view;     // per_tap_view: tap t reads input view t (no spatial shift)
+  int kb_per_tap;                 // Cin / 64
+  int k_per_tap;                  // Cin
+  int cout_per_view;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+template <int BLOCK_N, int STAGES, int STAGING>
+struct FwdSmem {
+  static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 bf16 (one 128-B swizzle row each)
+  static constexpr int B_BYTES = BLOCK_N * 128;  // BLOCK_N out-channels x 64 bf16
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = 128 * 128;    // 128 pixels x 64 bf16 outputs
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_PARAM = OFF_STG + STAGING * STG_BYTES;  // scale|shift|sum|sq, BLOCK_N each
+  static constexpr int OFF_BAR = OFF_PARAM + 4 * BLOCK_N * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEMPTR + 16 + 1024;  // + slack for the 1024-B alignment
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
+};
+
+// 32 accumulator columns of one pixel row -> scale/shift/ReLU -> bf16 -> four 16-byte chunks of the
+// 128-byte-swizzled staging row (chunk index XOR row%8, the layout the TMA store expects).
+__device__ __forceinline__ void epi_store_half(const uint32_t (&v)[32], int jbase, const float* sc,
+                                               const float* sh, int relu, bool valid, uint8_t* stg,
+                                               int row) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = fmaf(__uint_as_float(v[j * 8 + e]), sc[j * 8 + e], sh[j * 8 + e]);
+      if (relu) t = fmaxf(t, 0.0f);
+      y[e] = valid ? t : 0.0f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(y[0], y[1]);
+    o.y = pack_bf16x2(y[2], y[3]);
+    o.z = pack_bf16x2(y[4], y[5]);
+    o.w = pack_bf16x2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(stg + row * 128 + (((jbase + j) ^ (row & 7)) << 4)) = o;
+  }
+}
+
+template <int BLOCK_N, int STAGES, int STAGING>
+__global__ void __launch_bounds__(256, 1)
+    igemm_fwd_kernel(const __grid_constant__ TmapPack4 amaps,
+                     const __grid_constant__ CUtensorMap bmap,
+                     const __grid_constant__ TmapPack4 omaps, const FwdParams p) {
+  using L = FwdSmem<BLOCK_N, STAGES, STAGING>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - raw_addr);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar0 = sbase + L::OFF_BAR;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_TMEMPTR);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amaps.m[0]);
+    tma_prefetch_desc(&bmap);
+    tma_prefetch_desc(&omaps.m[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(sbase + L::OFF_TMEMPTR, 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int kiters = p.num_taps * p.kb_per_tap;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int w0 = (m_tile % p.tiles_w) * p.TW;
+        const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          int dw = 0, dh = 0, av = 0;
+          if (p.per_tap_view) {
+            av = tap;
+          } else if (p.num_taps == 9) {
+            dh = tap / 3 - 1;
+            dw = tap % 3 - 1;
+          }
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1, 1, &g_dbg_word);
+            const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
+            const uint32_t b_addr = a_addr + L::A_BYTES;
+            mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+            tma_load_4d(a_addr, &amaps.m[av], full_bar(stage), kb * 64, w0 + dw, h0 + dh, n0);
+            tma_load_2d(b_addr, &bmap, full_bar(stage), tap * p.k_per_tap + kb * 64,
+                        n_tile * BLOCK_N);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const int acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2, &g_dbg_word);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(full_bar(stage), phase, 3, &g_dbg_word);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kit | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    float* s_scale = reinterpret_cast<float*>(gbase + L::OFF_PARAM);
+    float* s_shift = s_scale + BLOCK_N;
+    float* s_sum = s_shift + BLOCK_N;
+    float* s_sq = s_sum + BLOCK_N;
+    const bool do_stats = p.stat_sum != nullptr;
+    int it = 0;
+    int chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int w0 = (m_tile % p.tiles_w) * p.TW;
+      const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
+      const int acc = it & 1;
+      const int acc_phase = (it >> 1) & 1;
+      const int col0 = n_tile * BLOCK_N;
+      const int ov = col0 / p.cout_per_view;
+      const int ch0 = col0 % p.cout_per_view;
+
+      for (int c = et; c < BLOCK_N; c += 128) {
+        s_scale[c] = p.scale ? p.scale[ch0 + c] : 1.0f;
+        s_shift[c] = p.shift ? p.shift[ch0 + c] : 0.0f;
+        s_sum[c] = 0.0f;
+        s_sq[c] = 0.0f;
+      }
+      const int pw = row % p.TW;
+      const int ph = (row / p.TW) % p.TH;
+      const int pn = row / (p.TW * p.TH);
+      const bool valid = (w0 + pw < p.W) && (h0 + ph < p.H) && (n0 + pn < p.N);
+
+      mbar_wait(tfull_bar(acc), acc_phase, 4, &g_dbg_word);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_ctr) {
+        uint32_t v0[32], v1[32];
+        {
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + chunk * 64;
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32, v1);
+          tmem_ld_wait();
+        }
+        if (chunk == BLOCK_N / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));  // accumulator drained: MMA may overwrite it
+        }
+        const int sb = (STAGING == 2) ? (chunk_ctr & 1) : 0;
+        if (et == 0) tma_store_wait_read<STAGING - 1>();  // staging buffer `sb` no longer being read
+        named_bar_sync(1, 128);
+
+        uint8_t* stg = gbase + L::OFF_STG + sb * L::STG_BYTES;
+        epi_store_half(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg, row);
+        epi_store_half(v1, 4, s_scale + chunk * 64 + 32, s_shift + chunk * 64 + 32, p.relu, valid,
+                       stg, row);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&omaps.m[ov], sbase + L::OFF_STG + sb * L::STG_BYTES, ch0 + chunk * 64, w0, h0,
+                       n0);
+          tma_store_commit();
+        }
+        if (do_stats) {
+          // column sums of the rounded outputs: lane <-> channel pair, warp <-> 32-row group
+          const int j = lane >> 2, wsub = lane & 3;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = q * 32 + rr;
+            const uint32_t u =
+                *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((j ^ (r & 7)) << 4) + wsub * 4);
+            const float2 f = unpack_bf16x2(u);
+            s0 += f.x;
+            s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0);
+            q1 = fmaf(f.y, f.y, q1);
+          }
+          atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
+          atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
+          atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
+          atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
+        }
+      }
+      if (do_stats) {
+        named_bar_sync(1, 128);
+        for (int c = et; c < BLOCK_N; c += 128) {
+          atomicAdd(p.stat_sum + ch0 + c, s_sum[c]);
+          atomicAdd(p.stat_sq + ch0 + c, s_sq[c]);
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+}
+
+template <int BLOCK_N, int STAGES, int STAGING>
+static int launch_fwd_inst(const TmapPack4& amaps, const CUtensorMap& bmap, const TmapPack4& omaps,
+                           const FwdParams& p, int total_tiles, cudaStream_t stream) {
+  using L = FwdSmem<BLOCK_N, STAGES, STAGING>;
+  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES, STAGING>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(igemm_fwd): ") + cudaGetErrorString(attr_err));
+    return -2;
+  }
+  const int grid = std::min(total_tiles, num_sms());
+  kern<<<grid, 256, L::TOTAL, stream>>>(amaps, bmap, omaps, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("igemm_fwd launch: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+int launch_igemm_fwd(const FwdDesc& d) {
+  if (d.Cin % 64 != 0 || d.Cin <= 0) {
+    set_error("igemm_fwd: input channels must be a positive multiple of 64");
+    return -1;
+  }
+  if (d.cout_per_view % 64 != 0 || d.cout_per_view <= 0) {
+    set_error("igemm_fwd: output channels must be a positive multiple of 64");
+    return -1;
+  }
+  const int W = d.in[0].W, H = d.in[0].H, N = d.in[0].N;
+  if (W <= 0 || H <= 0 || N <= 0) {
+    set_error("igemm_fwd: empty input");
+    return -1;
+  }
+  for (int i = 0; i < d.num_out_views; ++i)
+    if (d.out[i].W != W || d.out[i].H != H || d.out[i].N != N) {
+      set_error("igemm_fwd: output view extents differ from the input extents");
+      return -1;
+    }
+  int bw, bh, bn;
+  pick_box(W, H, 128, 16, &bw, &bh, &bn);
+  const int block_n = (d.cout_per_view % 256 == 0) ? 256 : (d.cout_per_view % 128 == 0 ? 128 : 64);
+
+  TmapPack4 amaps, omaps;
+  CUtensorMap bmap;
+  for (int i = 0; i < 4; ++i) {
+    const ActView& v = d.in[i < d.num_in_views ? i : 0];
+    if (v.C != d.Cin) {
+      set_error("igemm_fwd: input view channel count != Cin");
+      return -1;
+    }
+    if (make_act_map(&amaps.m[i], v, 64, bw, bh, bn)) return -1;
+    const ActView& o = d.out[i < d.num_out_views ? i : 0];
+    if (o.C != d.cout_per_view) {
+      set_error("igemm_fwd: output view channel count != cout_per_view");
+      return -1;
+    }
+    if (make_act_map(&omaps.m[i], o, 64, bw, bh, bn)) return -1;
+  }
+  const long long n_total = static_cast<long long>(d.num_out_views) * d.cout_per_view;
+  const long long k_total = static_cast<long long>(d.num_taps) * d.Cin;
+  if (make_mat_map(&bmap, d.wmat, n_total, k_total, 64, block_n)) return -1;
+
+  FwdParams p;
+  p.TW = bw; p.TH = bh; p.TN = bn;
+  p.W = W; p.H = H; p.N = N;
+  p.tiles_w = (W + bw - 1) / bw;
+  p.tiles_h = (H + bh - 1) / bh;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.n_tiles = static_cast<int>(n_total / block_n);
+  p.num_taps = d.num_taps;
+  p.per_tap_view = d.num_in_views > 1 ? 1 : 0;
+  p.kb_per_tap = d.Cin / 64;
+  p.k_per_tap = d.Cin;
+  p.cout_per_view = d.cout_per_view;
+  p.scale = d.scale;
+  p.shift = d.shift;
+  p.relu = d.relu;
+  p.stat_sum = d.stat_sum;
+  p.stat_sq = d.stat_sq;
+  const long long total = 1ll * p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  if (total > 0x7fffffffll) {
+    set_error("igemm_fwd: too many tiles");
+    return -1;
+  }
+  switch (block_n) {
+    case 256: return launch_fwd_inst<256, 4, 1>(amaps, bmap, omaps, p, (int)total, d.stream);
+    case 128: return launch_fwd_inst<128, 5, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+    default:  return launch_fwd_inst<64, 6, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+  }
+}
+
+// =================================================================================================
+// Weight-gradient kernel
+// =================================================================================================
+struct WgradParams {
+  int tiles_w, tiles_h, tiles_n;  // pixel tiling (64 pixels per K block)
+  int PW, PH, PN;
+  int num_taps, per_tap_dy;       // per_tap_dy: tap t reads dY view t and X is unshifted (convT)
+  int cin, cout;
+  int pair_taps;                  // cin == 64: an M tile stacks two taps
+  int ci_tiles;                   // cin / 128 when !pair_taps
+  int m_units, n_tiles;
+  int splits, ktiles_per_split;
+  float* partial;
+};
+
+template <int BLOCK_N, int STAGES>
+struct WgSmem {
+  static constexpr int A_BYTES = 2 * 64 * 128;              // two boxes of 64 pixels x 64 channels
+  static constexpr int B_BYTES = (BLOCK_N / 64) * 64 * 128; // BLOCK_N/64 such boxes
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 1;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEMPTR + 16 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+    igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap,
+                       const __grid_constant__ TmapPack4 dymaps, const WgradParams p) {
+  using L = WgSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - raw_addr);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + L::OFF_BAR;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_TMEMPTR);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&dymaps.m[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(sbase + L::OFF_TMEMPTR, BLOCK_N < 32 ? 32 : BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // ---- work decomposition: blockIdx.x = (m unit, n tile), blockIdx.y = K split
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int unit = blockIdx.x / p.n_tiles;
+  const int split = blockIdx.y;
+  int tapA, tapB, cA0, cA1, row_base;
+  if (p.pair_taps) {
+    tapA = 2 * unit;
+    tapB = min(2 * unit + 1, p.num_taps - 1);
+    cA0 = 0;
+    cA1 = 0;
+    row_base = tapA * 64;
+  } else {
+    tapA = tapB = unit / p.ci_tiles;
+    cA0 = (unit % p.ci_tiles) * 128;
+    cA1 = cA0 + 64;
+    row_base = tapA * p.cin + cA0;
+  }
+  const int total_ktiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int kt_begin = split * p.ktiles_per_split;
+  const int kt_end = min(kt_begin + p.ktiles_per_split, total_ktiles);
+  const int nk = kt_end - kt_begin;  // host guarantees nk >= 1
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int dwA = 0, dhA = 0, dwB = 0, dhB = 0;
+      if (!p.per_tap_dy && p.num_taps == 9) {
+        dhA = tapA / 3 - 1; dwA = tapA % 3 - 1;
+        dhB = tapB / 3 - 1; dwB = tapB % 3 - 1;
+      }
+      const int dyv = p.per_tap_dy ? tapA : 0;
+      int stage = 0, phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        const int w0 = (kt % p.tiles_w) * p.PW;
+        const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.PH;
+        const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.PN;
+        mbar_wait(empty_bar(stage), phase ^ 1, 5, &g_dbg_word);
+        const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+        mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+        tma_load_4d(a_addr, &xmap, full_bar(stage), cA0, w0 + dwA, h0 + dhA, n0);
+        tma_load_4d(a_addr + 8192, &xmap, full_bar(stage), cA1, w0 + dwB, h0 + dhB, n0);
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b)
+          tma_load_4d(b_addr + b * 8192, &dymaps.m[dyv], full_bar(stage),
+                      n_tile * BLOCK_N + b * 64, w0, h0, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; ++i) {
+        mbar_wait(full_bar(stage), phase, 6, &g_dbg_word);
+        tc_fence_after();
+        const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // MN-major: 16 pixels (two 8-pixel atoms, SBO = 1024 B apart) per MMA; 64-channel groups
+          // are LBO = 8192 B apart (one TMA box each).
+          const uint64_t adesc = umma_desc_sw128(a_addr + k * 2048, 8192, 1024);
+          const uint64_t bdesc = umma_desc_sw128(b_addr + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int grow = row_base + row;
+    const bool row_ok = grow < p.num_taps * p.cin && (!p.pair_taps || row < 64 || tapB != tapA);
+    mbar_wait(tfull_bar, 0, 7, &g_dbg_word);
+    tc_fence_after();
+    float* dst = p.partial +
+                 (static_cast<size_t>(split) * p.num_taps * p.cin + grow) * p.cout + n_tile * BLOCK_N;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          *reinterpret_cast<float4*>(dst + c + 4 * j) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+}
+
+static void wgrad_geometry(int N, int H, int W, int* bw, int* bh, int* bn, int* ktiles) {
+  pick_box(W, H, 64, 16, bw, bh, bn);
+  const int tw = (W + *bw - 1) / *bw, th = (H + *bh - 1) / *bh, tn = (N + *bn - 1) / *bn;
+  *ktiles = tw * th * tn;
+}
+
+static int wgrad_block_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
+
+int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout) {
+  int bw, bh, bn, ktiles;
+  wgrad_geometry(N, H, W, &bw, &bh, &bn, &ktiles);
+  const int block_n = wgrad_block_n(Cout);
+  const int m_units = (Cin == 64) ? (num_taps + 1) / 2 : num_taps * (Cin / 128);
+  const int ctas = m_units * (Cout / block_n);
+  // aim for ~2 waves of CTAs, but keep at least 8 K tiles (512 pixels) per split
+  int want = std::max(1, (2 * 148 + ctas - 1) / ctas);
+  want = std::min(want, std::max(1, ktiles / 8));
+  const int per = (ktiles + want - 1) / want;
+  return (ktiles + per - 1) / per;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad_inst(const CUtensorMap& xmap, const TmapPack4& dymaps, const WgradParams& p,
+                             cudaStream_t stream) {
+  using L = WgSmem<BLOCK_N, STAGES>;
+  auto kern = igemm_wgrad_kernel<BLOCK_N, STAGES>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(igemm_wgrad): ") + cudaGetErrorString(attr_err));
+    return -2;
+  }
+  dim3 grid(p.m_units * p.n_tiles, p.splits);
+  kern<<<grid, 256, L::TOTAL, stream>>>(xmap, dymaps, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("igemm_wgrad launch: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+int launch_igemm_wgrad(const WgradDesc& d) {
+  if (d.Cin == 64 && d.num_dy_views > 1) {
+    set_error("igemm_wgrad: per-tap dY views need Cin to be a multiple of 128");
+    return -1;
+  }
+  if (!(d.Cin == 64 || d.Cin % 128 == 0) || d.Cin <= 0) {
+    set_error("igemm_wgrad: input channels must be 64 or a multiple of 128");
+    return -1;
+  }
+  if (d.Cout % 64 != 0 || d.Cout <= 0) {
+    set_error("igemm_wgrad: output channels must be a positive multiple of 64");
+    return -1;
+  }
+  const int W = d.x.W, H = d.x.H, N = d.x.N;
+  if (W <= 0 || H <= 0 || N <= 0) {
+    set_error("igemm_wgrad: empty input");
+    return -1;
+  }
+  int bw, bh, bn, ktiles;
+  wgrad_geometry(N, H, W, &bw, &bh, &bn, &ktiles);
+  const int block_n = wgrad_block_n(d.Cout);
+
+  CUtensorMap xmap;
+  TmapPack4 dymaps;
+  if (d.x.C != d.Cin) {
+    set_error("igemm_wgrad: x view channel count != Cin");
+    return -1;
+  }
+  if (make_act_map(&xmap, d.x, 64, bw, bh, bn)) return -1;
+  for (int i = 0; i < 4; ++i) {
+    const ActView& v = d.dy[i < d.num_dy_views ? i : 0];
+    if (v.C != d.Cout || v.W != W || v.H != H || v.N != N) {
+      set_error("igemm_wgrad: dy view extents do not match");
+      return -1;
+    }
+    if (make_act_map(&dymaps.m[i], v, 64, bw, bh, bn)) return -1;
+  }
+  WgradParams p;
+  p.PW = bw; p.PH = bh; p.PN = bn;
+  p.tiles_w = (W + bw - 1) / bw;
+  p.tiles_h = (H + bh - 1) / bh;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.num_taps = d.num_taps;
+  p.per_tap_dy = d.num_dy_views > 1 ? 1 : 0;
+  p.cin = d.Cin;
+  p.cout = d.Cout;
+  p.pair_taps = d.Cin == 64 ? 1 : 0;
+  p.ci_tiles = d.Cin / 128;
+  p.m_units = p.pair_taps ? (d.num_taps + 1) / 2 : d.num_taps * p.ci_tiles;
+  p.n_tiles = d.Cout / block_n;
+  p.splits = d.splits;
+  p.ktiles_per_split = (ktiles + d.splits - 1) / d.splits;
+  if (d.splits < 1 || 1ll * (d.splits - 1) * p.ktiles_per_split >= ktiles) {
+    set_error("igemm_wgrad: invalid split count (use plume_wgrad_splits)");
+    return -1;
+  }
+  p.partial = d.partial;
+  switch (block_n) {
+    case 256: return launch_wgrad_inst<256, 4>(xmap, dymaps, p, d.stream);
+    case 128: return launch_wgrad_inst<128, 6>(xmap, dymaps, p, d.stream);
+    default:  return launch_wgrad_inst<64, 8>(xmap, dymaps, p, d.stream);
+  }
+}
+
+}  // namespace plume

@@ -1,0 +1,51 @@
+// Internal C++ interface of the tensor-core implicit-GEMM kernels (igemm.cu).
+#pragma once
+#include "tmap.cuh"
+
+namespace plume {
+
+// Forward-type implicit GEMM:  OUT[pixel, n] = epilogue( sum_{tap, c} IN_tap[pixel + shift(tap), c] * Wmat[n, tap*Cin + c] )
+//   conv3x3 fwd   : 9 taps, shifts (-1..1)^2 on one input view, one output view
+//   conv3x3 dgrad : same kernel on dY with the rotated/transposed weight matrix
+//   convT2x2 fwd  : 1 tap, four strided output views (one per (i,j)), Wmat rows = (ij, co)
+//   convT2x2 dgrad: 4 taps, each reading its own strided view of dU, no shift
+struct FwdDesc {
+  ActView in[4];
+  int num_in_views;   // 1, or 4 when every tap reads its own view
+  int num_taps;       // 9, 4 or 1
+  int Cin;            // channels per tap (multiple of 64)
+  const void* wmat;   // bf16 [Ntotal][num_taps*Cin]
+  ActView out[4];
+  int num_out_views;  // 1, or 4 (convT fwd)
+  int cout_per_view;  // multiple of 64
+  const float* scale; // per output channel (index = n % cout_per_view), may be null (=1)
+  const float* shift; // per output channel, may be null (=0)
+  int relu;
+  float* stat_sum;    // optional per-channel sum / sum of squares of the bf16 outputs
+  float* stat_sq;
+  cudaStream_t stream;
+};
+int launch_igemm_fwd(const FwdDesc& d);
+
+// Weight-gradient implicit GEMM:
+//   partial[split][tap*Cin + ci][co] = sum_{pixels in split} X_tap[pixel + shift(tap), ci] * DY_tap[pixel, co]
+//   conv3x3 : X shifted per tap, one dY view
+//   convT2x2: X unshifted, dY view per tap (the four strided views of dU)
+struct WgradDesc {
+  ActView x;
+  ActView dy[4];
+  int num_dy_views;   // 1 (conv3x3) or 4 (convT)
+  int num_taps;       // 9 or 4
+  int Cin;            // 64, or a multiple of 128
+  int Cout;           // multiple of 64
+  float* partial;     // fp32 [splits][num_taps*Cin][Cout]
+  int splits;         // from wgrad_plan()
+  cudaStream_t stream;
+};
+// Chooses the K split for a problem; returns the number of splits (>=1).
+int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout);
+int launch_igemm_wgrad(const WgradDesc& d);
+
+int read_debug_word();  // last watchdog tag written by a trapped kernel (0 if none)
+
+}  // namespace plume

@@ -1,0 +1,277 @@
+"""Operator layer over the C ABI: one method per entry point of ``include/plume_b200.h``.
+
+Tensors are torch CUDA tensors in NHWC; bf16 activations may be channel slices of a wider buffer
+(``concat[..., :C]``) -- the pixel stride is read from ``stride(2)``.  Outputs are preallocated by the
+caller (nothing is allocated per call except the growable weight-gradient workspace), so a whole
+step is a fixed sequence of launches on the current stream.
+
+The same method names and argument meaning are implemented on CPU in ``oracle/ops_ref.py``; that class
+is test infrastructure (the checker), never imported from here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib as _lib
+from .lib import check, current_stream, ptr
+
+
+def _act(t: torch.Tensor, name: str):
+    """(pointer, pixel stride, N, H, W, C) of an NHWC bf16 activation view."""
+    if t.dtype != torch.bfloat16 or t.dim() != 4:
+        raise TypeError(f"{name}: expected a 4-D bf16 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
+    if not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    ld = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
+    ok = (sc == 1 or c == 1) and ld >= c and ld % 8 == 0
+    ok = ok and (w == 1 or sw == ld) and (h == 1 or sh == w * ld) and (n == 1 or sn == h * w * ld)
+    if not ok:
+        raise ValueError(f"{name}: not a dense-pixel NHWC view: shape {tuple(t.shape)} strides {t.stride()}")
+    return ptr(t), int(ld), int(n), int(h), int(w), int(c)
+
+
+def _f32(t, name: str, numel: int | None = None):
+    if t is None:
+        return ptr(None)
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise TypeError(f"{name}: expected a contiguous fp32 CUDA tensor")
+    if numel is not None and t.numel() < numel:
+        raise ValueError(f"{name}: needs {numel} elements, has {t.numel()}")
+    return ptr(t)
+
+
+class CudaOps:
+    """Launches the sm_100a kernels.  Fails loudly when the library or a GPU is missing."""
+
+    name = "b200"
+
+    def __init__(self) -> None:
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.PlumeError("CUDA device required: the B200 path has no CPU fallback")
+        self._ws: torch.Tensor | None = None
+        self.launches = 0  # kernels of ours enqueued so far (bench.py reports the per-step count)
+
+    # ------------------------------------------------------------------ helpers
+    def _workspace(self, nbytes: int, device) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        return self._ws
+
+    # ------------------------------------------------------------------ tensor-core GEMMs
+    def conv3x3_fwd(self, x, w_fwd, scale, shift, relu, y, stat_sum=None, stat_sq=None):
+        xp, ldx, n, h, w, cin = _act(x, "x")
+        yp, ldy, n2, h2, w2, cout = _act(y, "y")
+        assert (n, h, w) == (n2, h2, w2)
+        assert w_fwd.dtype == torch.bfloat16 and w_fwd.numel() == cout * 9 * cin and w_fwd.is_contiguous()
+        check(self.lib.plume_conv3x3_fwd(xp, ldx, ptr(w_fwd), _f32(scale, "scale", cout),
+                                         _f32(shift, "shift", cout), int(bool(relu)), yp, ldy,
+                                         _f32(stat_sum, "stat_sum", cout), _f32(stat_sq, "stat_sq", cout),
+                                         n, h, w, cin, cout, current_stream()), "plume_conv3x3_fwd")
+        self.launches += 1
+
+    def conv3x3_dgrad(self, dy, w_dgrad, dx):
+        dyp, lddy, n, h, w, cout = _act(dy, "dy")
+        dxp, lddx, n2, h2, w2, cin = _act(dx, "dx")
+        assert (n, h, w) == (n2, h2, w2)
+        assert w_dgrad.dtype == torch.bfloat16 and w_dgrad.numel() == cout * 9 * cin
+        check(self.lib.plume_conv3x3_dgrad(dyp, lddy, ptr(w_dgrad), dxp, lddx, n, h, w, cin, cout,
+                                           current_stream()), "plume_conv3x3_dgrad")
+        self.launches += 1
+
+    def conv3x3_wgrad(self, x, dy, dw, accumulate=False):
+        xp, ldx, n, h, w, cin = _act(x, "x")
+        dyp, lddy, n2, h2, w2, cout = _act(dy, "dy")
+        assert (n, h, w) == (n2, h2, w2)
+        nbytes = self.lib.plume_wgrad_workspace_bytes(n, h, w, 9, cin, cout)
+        ws = self._workspace(nbytes, x.device)
+        check(self.lib.plume_conv3x3_wgrad(xp, ldx, dyp, lddy, _f32(dw, "dw", cout * 9 * cin),
+                                           int(bool(accumulate)), ptr(ws), ws.numel(), n, h, w, cin, cout,
+                                           current_stream()), "plume_conv3x3_wgrad")
+        self.launches += 2
+
+    def convT_fwd(self, x, w_fwd, bias, u):
+        xp, ldx, n, h, w, cin = _act(x, "x")
+        up, ldu, n2, h2, w2, cout = _act(u, "u")
+        assert (n2, h2, w2) == (n, 2 * h, 2 * w)
+        assert w_fwd.dtype == torch.bfloat16 and w_fwd.numel() == 4 * cout * cin
+        check(self.lib.plume_convT2x2_concat_fwd(xp, ldx, ptr(w_fwd), _f32(bias, "bias", cout), up, ldu,
+                                                 n, h, w, cin, cout, current_stream()),
+              "plume_convT2x2_concat_fwd")
+        self.launches += 1
+
+    def convT_dgrad(self, du, w_dgrad, dx):
+        dup, lddu, n2, h2, w2, cout = _act(du, "du")
+        dxp, lddx, n, h, w, cin = _act(dx, "dx")
+        assert (n2, h2, w2) == (n, 2 * h, 2 * w)
+        check(self.lib.plume_convT2x2_dgrad(dup, lddu, ptr(w_dgrad), dxp, lddx, n, h, w, cin, cout,
+                                            current_stream()), "plume_convT2x2_dgrad")
+        self.launches += 1
+
+    def convT_wgrad(self, x, du, dw, accumulate=False):
+        xp, ldx, n, h, w, cin = _act(x, "x")
+        dup, lddu, n2, h2, w2, cout = _act(du, "du")
+        assert (n2, h2, w2) == (n, 2 * h, 2 * w)
+        nbytes = self.lib.plume_wgrad_workspace_bytes(n, h, w, 4, cin, cout)
+        ws = self._workspace(nbytes, x.device)
+        check(self.lib.plume_convT2x2_wgrad(xp, ldx, dup, lddu, _f32(dw, "dw", 4 * cout * cin),
+                                            int(bool(accumulate)), ptr(ws), ws.numel(), n, h, w, cin, cout,
+                                            current_stream()), "plume_convT2x2_wgrad")
+        self.launches += 2
+
+    # ------------------------------------------------------------------ packing
+    def pack_conv3x3(self, w, wf, wd):
+        cout, _, _, cin = w.shape
+        check(self.lib.plume_pack_conv3x3(_f32(w, "w"), ptr(wf), ptr(wd), cout, cin, current_stream()),
+              "plume_pack_conv3x3")
+        self.launches += 1
+
+    def pack_convT(self, w, wf, wd):
+        _, cout, cin = w.shape
+        check(self.lib.plume_pack_convT2x2(_f32(w, "w"), ptr(wf), ptr(wd), cout, cin, current_stream()),
+              "plume_pack_convT2x2")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ bandwidth kernels
+    def pad_channels(self, x, out):
+        assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype == torch.bfloat16
+        pixels = x.numel() // x.shape[-1]
+        check(self.lib.plume_pad_channels(ptr(x), x.shape[-1], ptr(out), out.shape[-1], pixels,
+                                          current_stream()), "plume_pad_channels")
+        self.launches += 1
+
+    def bn_finalize(self, ssum, ssq, count, gamma, beta, eps, momentum, running_mean, running_var,
+                    scale, shift, mean, invstd):
+        c = ssum.numel()
+        check(self.lib.plume_bn_finalize(_f32(ssum, "sum"), _f32(ssq, "sq"), int(count), _f32(gamma, "gamma"),
+                                         _f32(beta, "beta"), float(eps), float(momentum),
+                                         _f32(running_mean, "rm"), _f32(running_var, "rv"),
+                                         _f32(scale, "scale"), _f32(shift, "shift"), _f32(mean, "mean"),
+                                         _f32(invstd, "invstd"), c, current_stream()), "plume_bn_finalize")
+        self.launches += 1
+
+    def bn_fold_eval(self, gamma, beta, running_mean, running_var, conv_bias, eps, scale, shift):
+        c = scale.numel()
+        check(self.lib.plume_bn_fold_eval(_f32(gamma, "gamma"), _f32(beta, "beta"), _f32(running_mean, "rm"),
+                                          _f32(running_var, "rv"), _f32(conv_bias, "bias"), float(eps),
+                                          _f32(scale, "scale"), _f32(shift, "shift"), c, current_stream()),
+              "plume_bn_fold_eval")
+        self.launches += 1
+
+    def scale_shift_act(self, y, scale, shift, relu, a):
+        yp, ldy, n, h, w, c = _act(y, "y")
+        ap, lda, *_ = _act(a, "a")
+        check(self.lib.plume_scale_shift_act(yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c),
+                                             int(bool(relu)), ap, lda, n * h * w, c, current_stream()),
+              "plume_scale_shift_act")
+        self.launches += 1
+
+    def scale_shift_act_pool(self, y, scale, shift, relu, skip, pooled, argmax):
+        yp, ldy, n, h, w, c = _act(y, "y")
+        sp, lds = (ptr(None), 0)
+        if skip is not None:
+            sp, lds, *_ = _act(skip, "skip")
+        pp, ldp, n2, h2, w2, _ = _act(pooled, "pooled")
+        assert (n2, h2, w2) == (n, h // 2, w // 2) and argmax.dtype == torch.uint8 and argmax.is_contiguous()
+        check(self.lib.plume_scale_shift_act_pool(yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c),
+                                                  int(bool(relu)), sp, lds, pp, ldp, ptr(argmax), n, h, w, c,
+                                                  current_stream()), "plume_scale_shift_act_pool")
+        self.launches += 1
+
+    def maxpool_fwd(self, x, y, argmax):
+        xp, ldx, n, h, w, c = _act(x, "x")
+        yp, ldy, *_ = _act(y, "y")
+        check(self.lib.plume_maxpool2x2_fwd(xp, ldx, yp, ldy, ptr(argmax), n, h, w, c, current_stream()),
+              "plume_maxpool2x2_fwd")
+        self.launches += 1
+
+    def maxpool_bwd(self, dy, argmax, dskip, dx):
+        dyp, lddy, *_ = _act(dy, "dy")
+        dxp, lddx, n, h, w, c = _act(dx, "dx")
+        sp, lds = (ptr(None), 0)
+        if dskip is not None:
+            sp, lds, *_ = _act(dskip, "dskip")
+        check(self.lib.plume_maxpool2x2_bwd(dyp, lddy, ptr(argmax), sp, lds, dxp, lddx, n, h, w, c,
+                                            current_stream()), "plume_maxpool2x2_bwd")
+        self.launches += 1
+
+    def bn_bwd_reduce(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx):
+        dap, ldda, n, h, w, c = _act(da, "da")
+        yp, ldy, *_ = _act(y, "y")
+        check(self.lib.plume_bn_bwd_reduce(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
+                                           _f32(mean, "mean"), _f32(invstd, "invstd"), int(bool(relu)),
+                                           _f32(sum_g, "sum_g", c), _f32(sum_gx, "sum_gx", c), n * h * w, c,
+                                           current_stream()), "plume_bn_bwd_reduce")
+        self.launches += 1
+
+    def bn_bwd_apply(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, sum_dy):
+        dap, ldda, n, h, w, c = _act(da, "da")
+        yp, ldy, *_ = _act(y, "y")
+        dyp, lddy, *_ = _act(dy, "dy")
+        check(self.lib.plume_bn_bwd_apply(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
+                                          _f32(mean, "mean"), _f32(invstd, "invstd"), int(bool(relu)),
+                                          _f32(sum_g, "sum_g"), _f32(sum_gx, "sum_gx"), dyp, lddy,
+                                          _f32(sum_dy, "sum_dy"), n * h * w, c, current_stream()),
+              "plume_bn_bwd_apply")
+        self.launches += 1
+
+    def relu_bwd(self, da, a, dy, sum_dy):
+        dap, ldda, n, h, w, c = _act(da, "da")
+        ap, lda, *_ = _act(a, "a")
+        dyp, lddy, *_ = _act(dy, "dy")
+        check(self.lib.plume_relu_bwd(dap, ldda, ap, lda, dyp, lddy, _f32(sum_dy, "sum_dy"), n * h * w, c,
+                                      current_stream()), "plume_relu_bwd")
+        self.launches += 1
+
+    def channel_sum(self, x, out):
+        xp, ldx, n, h, w, c = _act(x, "x")
+        check(self.lib.plume_channel_sum(xp, ldx, _f32(out, "out", c), n * h * w, c, current_stream()),
+              "plume_channel_sum")
+        self.launches += 1
+
+    def head_fwd(self, feat, w, b, target, logits, sums):
+        fp, ldf, n, h, wd, c = _act(feat, "feat")
+        check(self.lib.plume_head_fwd(fp, ldf, _f32(w, "w", c), _f32(b, "b", 1), ptr(target),
+                                      _f32(logits, "logits", n * h * wd), _f32(sums, "sums"), n * h * wd, c,
+                                      current_stream()), "plume_head_fwd")
+        self.launches += 1
+
+    def head_loss(self, sums, pixels, bce_w, dice_w, eps, loss_out):
+        check(self.lib.plume_head_loss(_f32(sums, "sums", 4), int(pixels), float(bce_w), float(dice_w),
+                                       float(eps), _f32(loss_out, "loss", 3), current_stream()),
+              "plume_head_loss")
+        self.launches += 1
+
+    def head_bwd(self, feat, w, logits, target, sums, bce_w, dice_w, eps, grad_scale, dfeat, dw, db):
+        fp, ldf, n, h, wd, c = _act(feat, "feat")
+        dfp, lddf, *_ = _act(dfeat, "dfeat")
+        check(self.lib.plume_head_bwd(fp, ldf, _f32(w, "w", c), _f32(logits, "logits"), ptr(target),
+                                      _f32(sums, "sums", 4), float(bce_w), float(dice_w), float(eps),
+                                      float(grad_scale), dfp, lddf, _f32(dw, "dw", c), _f32(db, "db", 1),
+                                      n * h * wd, c, current_stream()), "plume_head_bwd")
+        self.launches += 1
+
+    def adam(self, param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+        n = param.numel()
+        check(self.lib.plume_adam(_f32(param, "param"), _f32(grad, "grad", n), _f32(m, "m", n),
+                                  _f32(v, "v", n), n, float(lr), float(beta1), float(beta2), float(eps),
+                                  int(step), float(grad_scale), current_stream()), "plume_adam")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ tiled inference
+    def extract_tiles(self, scene, ys, xs, tile, tiles):
+        hs, ws, cs = scene.shape
+        count = ys.numel()
+        assert tiles.shape[0] >= count and tiles.is_contiguous() and scene.is_contiguous()
+        check(self.lib.plume_extract_tiles(ptr(scene), hs, ws, cs, ptr(ys), ptr(xs), count, tile, ptr(tiles),
+                                           tiles.shape[-1], current_stream()), "plume_extract_tiles")
+        self.launches += 1
+
+    def stitch_threshold(self, logits, ys, xs, tile, margin, logit_threshold, mask, prob=None):
+        hs, ws = mask.shape
+        check(self.lib.plume_stitch_threshold(_f32(logits, "logits"), ptr(ys), ptr(xs), ys.numel(), tile,
+                                              margin, float(logit_threshold), ptr(mask), _f32(prob, "prob"),
+                                              hs, ws, current_stream()), "plume_stitch_threshold")
+        self.launches += 1
