@@ -817,7 +817,7 @@ int head_bwd(const void* feat, int ldf, const float* w, const float* logits, con
 __global__ void __launch_bounds__(kThreads)
     adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                 float* __restrict__ v, long long n4, long long n, float lr_t, float beta1, float beta2,
-                float eps, float inv_bc2_sqrt, float gscale) {
+                float omb1, float omb2, float eps, float inv_bc2_sqrt, float gscale) {
   const long long step = 1ll * gridDim.x * blockDim.x;
   for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
     float4 p = reinterpret_cast<float4*>(param)[i];
@@ -831,8 +831,8 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float ge = gp[e] * gscale;
-      mp[e] = beta1 * mp[e] + (1.f - beta1) * ge;
-      vp[e] = beta2 * vp[e] + (1.f - beta2) * ge * ge;
+      mp[e] = beta1 * mp[e] + omb1 * ge;
+      vp[e] = beta2 * vp[e] + omb2 * ge * ge;
       pp[e] -= lr_t * mp[e] / (sqrtf(vp[e]) * inv_bc2_sqrt + eps);
     }
     reinterpret_cast<float4*>(param)[i] = p;
@@ -844,8 +844,8 @@ __global__ void __launch_bounds__(kThreads)
   const long long ti = tail0 + 1ll * blockIdx.x * blockDim.x + threadIdx.x;
   if (ti < n) {
     const float ge = grad[ti] * gscale;
-    const float me = beta1 * m[ti] + (1.f - beta1) * ge;
-    const float ve = beta2 * v[ti] + (1.f - beta2) * ge * ge;
+    const float me = beta1 * m[ti] + omb1 * ge;
+    const float ve = beta2 * v[ti] + omb2 * ge * ge;
     m[ti] = me;
     v[ti] = ve;
     param[ti] -= lr_t * me / (sqrtf(ve) * inv_bc2_sqrt + eps);
@@ -865,7 +865,10 @@ int adam(float* param, const float* grad, float* m, float* v, long long n, float
   const float inv_bc2_sqrt = static_cast<float>(1.0 / std::sqrt(bc2));
   const long long n4 = n / 4;
   const int grid = grid_for(std::max(n4, 1ll), 1);
-  adam_kernel<<<grid, kThreads, 0, s>>>(param, grad, m, v, n4, n, lr_t, beta1, beta2, eps,
+  // (1 - beta) is formed in double like torch.optim.Adam does, then rounded once
+  const float omb1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+  const float omb2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+  adam_kernel<<<grid, kThreads, 0, s>>>(param, grad, m, v, n4, n, lr_t, beta1, beta2, omb1, omb2, eps,
                                         inv_bc2_sqrt, grad_scale);
   return check_launch("adam");
 }

@@ -29,7 +29,10 @@ class RefOps:
 
     name = "ref"
 
-    def __init__(self) -> None:
+    def __init__(self, act_dtype: torch.dtype = torch.bfloat16) -> None:
+        # act_dtype=torch.float32 removes every bf16 rounding point: the host schedule can then be
+        # checked against autograd to fp32 accuracy (tests/test_host_logic.py)
+        self.act_dtype = act_dtype
         self.launches = 0
 
     # ---- 3x3 convolution (weights KRSC = [Cout][3][3][Cin]) ------------------------------------
@@ -43,7 +46,7 @@ class RefOps:
             o = o + shift.view(1, -1, 1, 1)
         if relu:
             o = o.relu()
-        y.copy_(_nhwc(o).to(torch.bfloat16))
+        y.copy_(_nhwc(o).to(self.act_dtype))
         if stat_sum is not None:
             yr = y.float()
             stat_sum += yr.sum(dim=(0, 1, 2))
@@ -53,7 +56,7 @@ class RefOps:
         # w_dgrad[ci][r][s][co] = w[co][2-r][2-s][ci]: a plain 3x3 correlation of dy with it is dgrad
         cin, cout = dx.shape[-1], dy.shape[-1]
         w = w_dgrad.float().view(cin, 3, 3, cout).permute(0, 3, 1, 2)
-        dx.copy_(_nhwc(F.conv2d(_nchw(dy), w, padding=1)).to(torch.bfloat16))
+        dx.copy_(_nhwc(F.conv2d(_nchw(dy), w, padding=1)).to(self.act_dtype))
 
     def conv3x3_wgrad(self, x, dy, dw, accumulate=False):
         cout, cin = dy.shape[-1], x.shape[-1]
@@ -69,12 +72,12 @@ class RefOps:
         cout, cin = u.shape[-1], x.shape[-1]
         w = w_fwd.float().view(2, 2, cout, cin).permute(3, 2, 0, 1)  # [Cin][Cout][i][j]
         o = F.conv_transpose2d(_nchw(x), w, bias=bias, stride=2)
-        u.copy_(_nhwc(o).to(torch.bfloat16))
+        u.copy_(_nhwc(o).to(self.act_dtype))
 
     def convT_dgrad(self, du, w_dgrad, dx):
         cin, cout = dx.shape[-1], du.shape[-1]
         w = w_dgrad.float().view(cin, 2, 2, cout).permute(0, 3, 1, 2)  # conv weight [Cin][Cout][i][j]
-        dx.copy_(_nhwc(F.conv2d(_nchw(du), w, stride=2)).to(torch.bfloat16))
+        dx.copy_(_nhwc(F.conv2d(_nchw(du), w, stride=2)).to(self.act_dtype))
 
     def convT_wgrad(self, x, du, dw, accumulate=False):
         cout, cin = du.shape[-1], x.shape[-1]
@@ -89,7 +92,7 @@ class RefOps:
 
     # ---- packing ---------------------------------------------------------------------------------
     def pack_conv3x3(self, w, wf, wd):
-        wb = w.to(torch.bfloat16)
+        wb = w.to(self.act_dtype)
         if wf is not None:
             wf.view_as(w).copy_(wb)
         if wd is not None:
@@ -97,7 +100,7 @@ class RefOps:
             wd.view(cin, 3, 3, cout).copy_(wb.flip(1, 2).permute(3, 1, 2, 0))
 
     def pack_convT(self, w, wf, wd):
-        wb = w.to(torch.bfloat16)
+        wb = w.to(self.act_dtype)
         if wf is not None:
             wf.view_as(w).copy_(wb)
         if wd is not None:
@@ -140,7 +143,7 @@ class RefOps:
         o = y.float() * scale + shift
         if relu:
             o = o.relu()
-        a.copy_(o.to(torch.bfloat16))
+        a.copy_(o.to(self.act_dtype))
 
     @staticmethod
     def _pool(v: torch.Tensor):
@@ -159,16 +162,16 @@ class RefOps:
         o = y.float() * scale + shift
         if relu:
             o = o.relu()
-        ob = o.to(torch.bfloat16)
+        ob = o.to(self.act_dtype)
         if skip is not None:
             skip.copy_(ob)
         best, idx = self._pool(ob.float())
-        pooled.copy_(best.to(torch.bfloat16))
+        pooled.copy_(best.to(self.act_dtype))
         argmax.view_as(idx).copy_(idx)
 
     def maxpool_fwd(self, x, y, argmax):
         best, idx = self._pool(x.float())
-        y.copy_(best.to(torch.bfloat16))
+        y.copy_(best.to(self.act_dtype))
         argmax.view_as(idx).copy_(idx)
 
     def maxpool_bwd(self, dy, argmax, dskip, dx):
@@ -180,7 +183,7 @@ class RefOps:
         out = out.reshape(n, h // 2, w // 2, c, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(n, h, w, c)
         if dskip is not None:
             out = out + dskip.float()
-        dx.copy_(out.to(torch.bfloat16))
+        dx.copy_(out.to(self.act_dtype))
 
     def bn_bwd_reduce(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx):
         yf = y.float()
@@ -199,14 +202,14 @@ class RefOps:
         xhat = (yf - mean) * invstd
         cnt = yf.numel() // yf.shape[-1]
         o = scale * (g - sum_g / cnt - xhat * (sum_gx / cnt))
-        ob = o.to(torch.bfloat16)
+        ob = o.to(self.act_dtype)
         dy.copy_(ob)
         if sum_dy is not None:
             sum_dy += ob.float().sum(dim=(0, 1, 2))
 
     def relu_bwd(self, da, a, dy, sum_dy):
         g = torch.where(a.float() > 0, da.float(), torch.zeros_like(da, dtype=torch.float32))
-        gb = g.to(torch.bfloat16)
+        gb = g.to(self.act_dtype)
         dy.copy_(gb)
         if sum_dy is not None:
             sum_dy += gb.float().sum(dim=(0, 1, 2))
@@ -242,7 +245,7 @@ class RefOps:
         I2 = 2 * sums[1] + eps
         ddice = -(2 * t * S - I2) / (S * S)
         dz = grad_scale * (bce_w * (p - t) / pixels + dice_w * ddice * p * (1 - p))
-        dfeat.copy_((dz.unsqueeze(-1) * w).to(torch.bfloat16))
+        dfeat.copy_((dz.unsqueeze(-1) * w).to(self.act_dtype))
         dw += (dz.unsqueeze(-1) * feat.float()).sum(dim=(0, 1, 2))
         db += dz.sum()
 

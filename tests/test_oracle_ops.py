@@ -199,9 +199,8 @@ def test_adam_matches_torch_optim():
 def test_tiles_roundtrip_covers_scene_once():
     hs, ws, T, margin = 70, 90, 32, 4
     stride = T - 2 * margin
-    ys = [max(y - margin, 0) if y else 0 for y in range(0, hs - 2 * margin, stride)]
-    ys = [y0 - margin if y0 else 0 for y0 in range(0, hs - 2 * margin, stride)]
-    xs = [x0 - margin if x0 else 0 for x0 in range(0, ws - 2 * margin, stride)]
+    ys = list(range(0, hs - 2 * margin, stride))
+    xs = list(range(0, ws - 2 * margin, stride))
     yy = torch.tensor([y for y in ys for _ in xs], dtype=torch.int32)
     xx = torch.tensor([x for _ in ys for x in xs], dtype=torch.int32)
     scene = rnd(hs, ws, 8, seed=1).to(BF)
