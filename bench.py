@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the UNet training hot path (BASELINE.json: "UNet train tiles/sec (256^2 px)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A "step" is one optimisation step (forward, backward, gradient
+all-reduce, Adam) of the default UNetSpec on this rank's 32 synthetic 256x256x8 bf16 tiles
+(BASELINE.json configs[1]); with N GPUs every rank keeps 32 tiles (weak scaling) and the value is the
+whole-job tiles/s.  `value` is timed with inputs resident in HBM; `e2e` runs the same step through the
+public Trainer API from pinned host buffers with the host->device copies and the loss read-back inside
+the timed region.  `roofline` is measured live with CUDA events around every launch of the dominant
+kernel (the tcgen05 implicit-GEMM forward kernel: conv fwd + dgrad + convT) during the timed steps.
+`--impl reference` times the CPU oracle (oracle/unet_ref.py -- the reference repository itself has no
+model code) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "unet_train_tiles_per_sec_256px"
+UNIT = "tiles/s"
+TILE, BATCH = 256, 32
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:  # noqa: BLE001  (no nvidia-smi: report nulls)
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ----------------------------------------------------------------------------------------------------
+def time_cpu_oracle(steps: int, warmup: int, tiles_per_step: int, budget_s: float):
+    """fp32 PyTorch-CPU UNet (the parity oracle) doing full training steps on `tiles_per_step` synthetic
+    256^2 tiles; stops early if the time budget is exhausted.  Returns (tiles/s, s/step, steps done)."""
+    import torch
+
+    from kcl_ltss_bioatm_b200.data import synthetic_batch
+    from kcl_ltss_bioatm_b200.spec import UNetSpec
+    from oracle.unet_ref import UNetRef, make_optimizer, plume_loss
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = UNetSpec()
+    torch.manual_seed(0)
+    model = UNetRef(spec).train()
+    opt = make_optimizer(model, spec)
+    x, t = synthetic_batch(tiles_per_step, TILE, TILE, spec.in_channels, seed=1234, dtype=torch.float32)
+    x = x.permute(0, 3, 1, 2).contiguous()
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        loss = plume_loss(model(x)[:, 0], t, spec)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        one()
+        if time.perf_counter() - t_start > budget_s / 2:
+            break
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    sec = sum(times) / len(times)
+    return tiles_per_step / sec, sec, len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # bounded sample: 2 tiles of the 32-tile batch per step keeps K+W steps within a few minutes
+    tiles = 2
+    v, sec, done, threads = time_cpu_oracle(args.steps, min(args.warmup, 2), tiles, budget_s=240.0)
+    sample = (f"{tiles} of the {BATCH} tiles per step, {done} timed full training steps "
+              f"(fwd+bwd+Adam, fp32, PyTorch CPU oracle; the reference repo has no model code)")
+    cb = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "default UNetSpec training step, 256x256x8 tiles (BASELINE.json configs[1] "
+                               "sampled at 2 tiles/step on host cores)", "tile": TILE, "tiles_per_step": tiles,
+                   "host_threads": threads},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+class GemmTimer:
+    """Wraps the tensor-core launches of CudaOps with CUDA event pairs (recorded on the launching stream)
+    and attributes algorithmic FLOPs to them."""
+
+    FWD_KERNEL = ("conv3x3_fwd", "conv3x3_dgrad", "convT_fwd", "convT_dgrad")
+    WGRAD = ("conv3x3_wgrad", "convT_wgrad")
+
+    def __init__(self, ops, logical_cin0: int, padded_cin0: int):
+        import torch
+
+        self.torch, self.ops = torch, ops
+        self.records = []  # (family, flops, ev0, ev1)
+        self.enabled = False
+        self.cin0, self.cin0_pad = logical_cin0, padded_cin0
+        for name in self.FWD_KERNEL + self.WGRAD:
+            setattr(ops, name, self._wrap(name, getattr(ops, name)))
+
+    def _flops(self, name, a):
+        # algorithmic FLOPs with LOGICAL channels (the zero padding of the first layer earns nothing)
+        def lc(c):
+            return self.cin0 if c == self.cin0_pad and self.cin0 != self.cin0_pad else c
+        if name == "conv3x3_fwd":
+            x, y = a[0], a[5]
+            return 2.0 * 9 * lc(x.shape[-1]) * y.shape[-1] * y.shape[0] * y.shape[1] * y.shape[2]
+        if name == "conv3x3_dgrad":
+            dy, dx = a[0], a[2]
+            return 2.0 * 9 * dy.shape[-1] * dx.shape[-1] * dx.shape[0] * dx.shape[1] * dx.shape[2]
+        if name == "conv3x3_wgrad":
+            x, dy = a[0], a[1]
+            return 2.0 * 9 * lc(x.shape[-1]) * dy.shape[-1] * x.shape[0] * x.shape[1] * x.shape[2]
+        if name in ("convT_fwd", "convT_wgrad"):
+            x, u = a[0], (a[3] if name == "convT_fwd" else a[1])
+            return 2.0 * 4 * x.shape[-1] * u.shape[-1] * x.shape[0] * x.shape[1] * x.shape[2]
+        if name == "convT_dgrad":
+            du, dx = a[0], a[2]
+            return 2.0 * 4 * du.shape[-1] * dx.shape[-1] * dx.shape[0] * dx.shape[1] * dx.shape[2]
+        raise KeyError(name)
+
+    def _wrap(self, name, fn):
+        fam = "fwd_kernel" if name in self.FWD_KERNEL else "wgrad_kernel"
+
+        def timed(*a, **kw):
+            if not self.enabled:
+                return fn(*a, **kw)
+            e0 = self.torch.cuda.Event(enable_timing=True)
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            self.records.append((fam, self._flops(name, a), e0, e1))
+            return r
+
+        return timed
+
+    def summary(self):
+        out = {}
+        for fam in ("fwd_kernel", "wgrad_kernel"):
+            rec = [r for r in self.records if r[0] == fam]
+            ms = sum(r[2].elapsed_time(r[3]) for r in rec)
+            fl = sum(r[1] for r in rec)
+            out[fam] = {"launches": len(rec), "ms": ms, "flops": fl,
+                        "tflops": (fl / (ms * 1e-3) / 1e12) if ms > 0 else 0.0}
+        return out
+
+
+def run_gpu(args):
+    import torch
+
+    from kcl_ltss_bioatm_b200.data import synthetic_batch
+    from kcl_ltss_bioatm_b200.spec import UNetSpec, train_flops_per_tile
+    from kcl_ltss_bioatm_b200.trainer import Trainer, init_distributed
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"metric": METRIC, "error": "no CUDA device: the B200 path has no CPU fallback"}))
+        return 2
+    rank, world, local, pg = init_distributed("cuda")
+    dev = torch.device("cuda", local)
+    spec = UNetSpec()
+    trainer = Trainer(spec, device=dev, process_group=pg, seed=0)
+    model, ops = trainer.model, trainer.model.ops
+    timer = GemmTimer(ops, spec.in_channels, spec.cin_padded)
+
+    # distinct synthetic shard per rank; host copies live in pinned memory for the end-to-end leg
+    nbuf = 2
+    host = [synthetic_batch(BATCH, TILE, TILE, spec.in_channels, seed=1234 + 97 * rank + i) for i in range(nbuf)]
+    host = [(x.pin_memory(), t.pin_memory()) for x, t in host]
+    dev_batches = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    def barrier():
+        if pg is not None:
+            import torch.distributed as dist
+            dist.barrier(group=pg)
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if pg is None:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
+        return float(t.item())
+
+    # ---------------- device-resident leg
+    for i in range(args.warmup):
+        trainer.step(*dev_batches[i % nbuf])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launches
+    timer.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        trainer.step(*dev_batches[i % nbuf])
+    e1.record()
+    barrier()
+    timer.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launches - launches0
+    loss_now = float(model.loss_out[0].item())
+    gemm = timer.summary()
+
+    # ---------------- end-to-end leg: pinned host buffers -> H2D -> step -> loss read-back, every step
+    xs = torch.empty_like(dev_batches[0][0])
+    ts = torch.empty_like(dev_batches[0][1])
+    h2d = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel()
+    d2h = 3 * 4
+    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+    for i in range(min(args.warmup, 3)):
+        xs.copy_(host[i % nbuf][0], non_blocking=True)
+        ts.copy_(host[i % nbuf][1], non_blocking=True)
+        trainer.step(xs, ts)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        xs.copy_(host[i % nbuf][0], non_blocking=True)
+        ts.copy_(host[i % nbuf][1], non_blocking=True)
+        out = trainer.step(xs, ts)
+        loss_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    if rank != 0:
+        return 0
+
+    peaks, peak_kind = load_peaks()
+    tiles = world * BATCH * args.steps
+    value = tiles / (ms_total * 1e-3)
+    e2e_value = tiles / e2e_s
+    fk = gemm["fwd_kernel"]
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    roof = {"bound": "tensor", "kernel": "igemm_fwd_kernel (conv3x3 fwd + dgrad, convT fwd + dgrad)",
+            "achieved": fk["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": fk["tflops"] / peak_tf if peak_tf else None, "traffic": None,
+            "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
+            "launches_timed": fk["launches"], "ms_per_step": fk["ms"] / max(args.steps, 1)}
+    wk = gemm["wgrad_kernel"]
+    roof_w = {"bound": "tensor", "kernel": "igemm_wgrad_kernel + split-K reduce", "achieved": wk["tflops"],
+              "peak": peak_tf, "unit": "TFLOP/s", "frac": wk["tflops"] / peak_tf if peak_tf else None,
+              "launches_timed": wk["launches"], "ms_per_step": wk["ms"] / max(args.steps, 1)}
+    step_tf = train_flops_per_tile(spec, TILE, TILE) * BATCH / (ms_total / args.steps * 1e-3) / 1e12
+
+    # ---------------- CPU baseline: config 1 on the host cores (bounded to ~20 s)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec, done, threads = time_cpu_oracle(steps=8, warmup=1, tiles_per_step=1, budget_s=25.0)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"BASELINE.json configs[0]: 1 tile of 256x256x8 per step, fp32, {done} timed full "
+                         f"training steps of the PyTorch-CPU oracle ({sec:.3f} s/step)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: default UNetSpec (in 8, base 64, depth 4, BatchNorm) "
+                               "training step, 32 tiles of 256x256 per GPU, bf16 activations / fp32 accumulate, "
+                               "Adam", "tile": TILE, "per_gpu_batch": BATCH, "global_batch": BATCH * world,
+                   "parallelism": f"dp{world}", "params": 31046401,
+                   "l2_policy": "inputs larger than L2: one step streams several GB of activations "
+                                f"({model.activation_bytes() / 1e9:.1f} GB workspace) through a 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": launches,
+        "roofline": roof, "roofline_wgrad": roof_w,
+        "step_tflops": step_tf, "step_frac_of_peak": step_tf / peak_tf if peak_tf else None,
+        "clocks": clocks, "cpu_baseline": cpu, "final_loss": loss_now,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    if args.warmup < 3:
+        args.warmup = 3
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

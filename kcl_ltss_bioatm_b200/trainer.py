@@ -1,0 +1,118 @@
+"""Training driver: data-parallel setup, micro-batching, checkpoint / resume, logging.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink; gloo on CPU for tests).  Every rank holds a
+full replica and a distinct shard of the tile batch; BatchNorm statistics stay per GPU (the
+DistributedDataParallel default), the loss is scaled by 1/world and gradient buckets are summed with
+asynchronous all-reduces launched from inside the backward pass (unet.UNetB200.backward).
+
+Checkpoint layout (defined here; the reference only reserves the directory,
+``src/config/filepaths.py:33`` ``path_to_model_folder``):
+    <dir>/<name>.pt       torch.save(state_dict) with the oracle's keys, NCHW fp32 -- loadable by
+                          ``UNetRef.load_state_dict`` and by ``UNetB200.load_state_dict``
+    <dir>/<name>.opt.pt   {"spec": UNetSpec dict, "step": int, "adam_m": flat fp32, "adam_v": flat fp32}
+Log format follows the reference's scripts (``src/features/plume_identifier_rg.py:23-25``).
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from .spec import UNetSpec
+from .unet import UNetB200
+
+LOG_FMT = "%(asctime)s - %(name)s - %(levelname)s - %(message)s"
+
+
+def init_distributed(device_type: str = "cuda"):
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK (torchrun).  Returns (rank, world, local_rank, process_group)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        if device_type == "cuda":
+            torch.cuda.set_device(local)
+        return rank, world, local, None
+    import torch.distributed as dist
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if device_type == "cuda":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    return rank, world, local, dist.group.WORLD
+
+
+class Trainer:
+    def __init__(self, spec: UNetSpec = UNetSpec(), device="cuda", process_group=None, ops=None,
+                 seed: int = 0, micro_batches: int = 1, bucket_mb: float = 25.0):
+        self.spec = spec
+        self.model = UNetB200(spec, ops=ops, device=device, seed=seed, process_group=process_group,
+                              bucket_mb=bucket_mb)
+        self.micro_batches = micro_batches
+        self.pg = process_group
+        self.log = logging.getLogger("train_model")
+        if process_group is not None:
+            import torch.distributed as dist
+
+            # replicas must start identical even if a caller seeded ranks differently
+            dist.broadcast(self.model.params, src=0, group=process_group)
+            self.model._param_version += 1
+
+    # ------------------------------------------------------------------ one optimisation step
+    def step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """x [n,h,w,c] / target [n,h,w] are this rank's shard, already on the device.  With
+        micro_batches = k the shard is processed in k slices with gradient accumulation (BatchNorm and the
+        Dice term then see one slice at a time).  Returns the device tensor [loss, bce, dice] of the last
+        slice; no host synchronisation happens here."""
+        m, k = self.model, self.micro_batches
+        if k == 1:
+            return m.train_step(x, target)
+        n = x.shape[0]
+        if n % k:
+            raise ValueError("batch must divide into micro_batches")
+        mb = n // k
+        m.train(True)
+        for i in range(k):
+            m.forward(x[i * mb:(i + 1) * mb], target[i * mb:(i + 1) * mb])
+            m.backward(accumulate=i > 0, sync=(i == k - 1), loss_scale=1.0 / k)
+        m.optimizer_step()
+        return m.loss_out
+
+    def fit(self, steps: int, batch_fn: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
+            log_every: int = 10, on_step: Optional[Callable[[int, float], None]] = None):
+        losses = []
+        for it in range(steps):
+            x, t = batch_fn(it)
+            out = self.step(x, t)
+            if log_every and (it % log_every == 0 or it == steps - 1):
+                v = out.detach().float().cpu().tolist()  # host sync only when logging
+                losses.append((it, v[0]))
+                self.log.info("step %d loss %.5f (bce %.5f dice %.5f)", it, v[0], v[1], v[2])
+                if on_step:
+                    on_step(it, v[0])
+        return losses
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, directory: str, name: str = "unet_plume") -> str:
+        os.makedirs(directory, exist_ok=True)
+        path = os.path.join(directory, f"{name}.pt")
+        torch.save(self.model.state_dict(), path)
+        opt = self.model.optimizer_state()
+        torch.save({"spec": self.spec.to_dict(), "step": opt["step"], "adam_m": opt["m"], "adam_v": opt["v"]},
+                   os.path.join(directory, f"{name}.opt.pt"))
+        return path
+
+    def load_checkpoint(self, directory: str, name: str = "unet_plume", with_optimizer: bool = True) -> None:
+        sd = torch.load(os.path.join(directory, f"{name}.pt"), map_location="cpu")
+        self.model.load_state_dict(sd)
+        opt_path = os.path.join(directory, f"{name}.opt.pt")
+        if with_optimizer and os.path.exists(opt_path):
+            st = torch.load(opt_path, map_location="cpu")
+            if UNetSpec.from_dict(st["spec"]) != self.spec:
+                raise ValueError("checkpoint was written for a different UNetSpec")
+            self.model.load_optimizer_state({"step": st["step"], "m": st["adam_m"], "v": st["adam_v"]})
