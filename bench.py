@@ -49,6 +49,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -62,7 +69,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -74,7 +81,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines
+                  if self.t0 is None or (self.t0 + 0.05 <= ts <= (self.t1 or ts) + 0.05)]
+        if not inside:  # region shorter than the sampling period: fall back to every sample taken
+            inside = [ln for (_, ln) in self.lines]
+        for ln in inside:
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -117,7 +128,7 @@ def time_cpu_oracle(steps: int, warmup: int, tiles_per_step: int, budget_s: floa
         loss = plume_loss(model(x)[:, 0], t, spec)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     t_start = time.perf_counter()
     for _ in range(warmup):
@@ -266,12 +277,13 @@ def run_gpu(args):
         return float(t.item())
 
     # ---------------- device-resident leg
-    for i in range(args.warmup):
-        trainer.step(*dev_batches[i % nbuf])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        trainer.step(*dev_batches[i % nbuf])
+    barrier()
+    sampler.mark_begin()
     launches0 = ops.launches
     timer.enabled = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,6 +292,7 @@ def run_gpu(args):
         trainer.step(*dev_batches[i % nbuf])
     e1.record()
     barrier()
+    sampler.mark_end()
     timer.enabled = False
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -360,8 +373,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

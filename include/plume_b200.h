@@ -145,9 +145,11 @@ int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logit
                    long long pixels, int C, plume_stream_t stream);
 
 /* Fused Adam over one flat fp32 parameter buffer (PyTorch semantics, no weight decay / amsgrad):
- * m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
-int plume_adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
-               float beta2, float eps, int step, float grad_scale, plume_stream_t stream);
+ * m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * Hyper-parameters are doubles so that (1-beta) and the bias corrections are formed exactly as
+ * torch.optim.Adam forms them before rounding to fp32. */
+int plume_adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
+               double beta2, double eps, int step, float grad_scale, plume_stream_t stream);
 
 /* ---- tiled large-scene inference -------------------------------------------------------------- */
 /* Cut `count` tiles of T x T (NHWC bf16, Cd channels, zero padded past Cs and past the scene edge)

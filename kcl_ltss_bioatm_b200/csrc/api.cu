@@ -288,8 +288,8 @@ int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logit
                   dfeat, lddf, dw, db, pixels, C, S(stream));
 }
 
-int plume_adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
-               float beta2, float eps, int step, float grad_scale, plume_stream_t stream) {
+int plume_adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
+               double beta2, double eps, int step, float grad_scale, plume_stream_t stream) {
   PLUME_CHECK(param && grad && m && v, "adam: null pointer");
   PLUME_CHECK((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,

@@ -852,23 +852,22 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
-int adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
-         float beta2, float eps, int step, float grad_scale, cudaStream_t s) {
+int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
+         double beta2, double eps, int step, float grad_scale, cudaStream_t s) {
   if (n <= 0) return 0;
   if (step < 1) {
     set_error("adam: step must be >= 1");
     return -1;
   }
-  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
+  const double bc1 = 1.0 - std::pow(beta1, step);
+  const double bc2 = 1.0 - std::pow(beta2, step);
   const float lr_t = static_cast<float>(lr / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / std::sqrt(bc2));
   const long long n4 = n / 4;
   const int grid = grid_for(std::max(n4, 1ll), 1);
-  // (1 - beta) is formed in double like torch.optim.Adam does, then rounded once
-  const float omb1 = static_cast<float>(1.0 - static_cast<double>(beta1));
-  const float omb2 = static_cast<float>(1.0 - static_cast<double>(beta2));
-  adam_kernel<<<grid, kThreads, 0, s>>>(param, grad, m, v, n4, n, lr_t, beta1, beta2, omb1, omb2, eps,
+  adam_kernel<<<grid, kThreads, 0, s>>>(param, grad, m, v, n4, n, lr_t, static_cast<float>(beta1),
+                                        static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
+                                        static_cast<float>(1.0 - beta2), static_cast<float>(eps),
                                         inv_bc2_sqrt, grad_scale);
   return check_launch("adam");
 }

@@ -42,8 +42,8 @@ int head_loss(const float* sums, long long pixels, float bce_w, float dice_w, fl
 int head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
              const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
              int lddf, float* dw, float* db, long long pixels, int C, cudaStream_t s);
-int adam(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
-         float beta2, float eps, int step, float grad_scale, cudaStream_t s);
+int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
+         double beta2, double eps, int step, float grad_scale, cudaStream_t s);
 int pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
 int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
 int wgrad_reduce(const float* partial, int splits, int taps, int Cin, int Cout, long long s_co,

@@ -9,12 +9,12 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplume_b200.so")
 
-_P, _I, _F, _LL = c_void_p, c_int, c_float, c_longlong
+_P, _I, _F, _LL, _D = c_void_p, c_int, c_float, c_longlong, c_double
 
 # name -> (restype, argtypes); mirrors include/plume_b200.h one to one
 SIGNATURES = {
@@ -46,7 +46,7 @@ SIGNATURES = {
     "plume_head_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P]),
     "plume_head_loss": (_I, [_P, _LL, _F, _F, _F, _P, _P]),
     "plume_head_bwd": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
-    "plume_adam": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _F, _P]),
+    "plume_adam": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P]),
     "plume_extract_tiles": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
 }
