@@ -136,6 +136,8 @@ class CudaOps:
 
     # ------------------------------------------------------------------ bandwidth kernels
     def pad_channels(self, x, out):
+        if not (x.is_cuda and out.is_cuda):
+            raise TypeError("pad_channels: expected CUDA tensors (there is no CPU path)")
         assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype == torch.bfloat16
         pixels = x.numel() // x.shape[-1]
         check(self.lib.plume_pad_channels(ptr(x), x.shape[-1], ptr(out), out.shape[-1], pixels,

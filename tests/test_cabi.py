@@ -1,0 +1,68 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports exactly what include/plume_b200.h
+declares; the ctypes prototypes cover every declared entry point; argument errors are reported through
+return codes + plume_last_error() (no compute is launched here)."""
+import os
+import re
+
+from kcl_ltss_bioatm_b200 import lib as plib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "plume_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(plume_[a-zA-Z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    handle = plib.load()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/plume_b200.h but not exported"
+
+
+def test_ctypes_signatures_cover_the_header():
+    assert sorted(plib.SIGNATURES) == declared_symbols()
+
+
+def test_version_and_error_reporting_without_gpu():
+    handle = plib.load()
+    assert b"sm_100a" in handle.plume_version()
+    # null pointers are rejected before anything touches the device
+    rc = handle.plume_pad_channels(None, 8, None, 64, 16, None)
+    assert rc != 0 and b"null" in handle.plume_last_error()
+    rc = handle.plume_adam(None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None)
+    assert rc != 0
+    # planning helpers are pure host code
+    assert handle.plume_wgrad_splits(32, 256, 256, 9, 64, 64) >= 1
+    assert handle.plume_wgrad_workspace_bytes(32, 16, 16, 9, 1024, 1024) >= 9 * 1024 * 1024 * 4
+    assert handle.plume_wgrad_splits(0, 1, 1, 9, 64, 64) == 0
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    monkeypatch.setattr(plib, "_lib", None)
+    monkeypatch.setattr(plib, "LIB_PATH", str(tmp_path / "nope.so"))
+    try:
+        plib.load()
+    except plib.PlumeError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("load() must raise when the library is absent")
+    finally:
+        monkeypatch.undo()
+        plib._lib = None
+        plib.load()
+
+
+def test_cuda_ops_refuse_to_run_without_gpu():
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from kcl_ltss_bioatm_b200.ops import CudaOps
+
+    with pytest.raises(plib.PlumeError):
+        CudaOps()

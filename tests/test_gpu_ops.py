@@ -1,0 +1,337 @@
+"""GPU parity, operator by operator: every C-ABI entry point (through ctypes) against the CPU oracle
+(oracle/ops_ref.py) on the same seeded inputs.
+
+Tolerances (written per test): bf16 outputs of a GEMM are compared to the oracle's bf16 outputs within
+2 bf16 ulps of the tensor's max (fp32 accumulation order differs); fp32 reductions within 1e-3 relative;
+integer / index / copy work (argmax, masks, packing, padding, tiles) bit-exact.
+"""
+import pytest
+import torch
+
+from oracle.ops_ref import RefOps
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from kcl_ltss_bioatm_b200.ops import CudaOps
+
+    return CudaOps(), RefOps()
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def relmax(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert torch.isfinite(got).all()
+    return ((got - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
+
+
+CONV_SHAPES = [  # N, H, W, Cin, Cout
+    (1, 16, 16, 64, 64), (2, 16, 16, 64, 128), (1, 32, 32, 128, 256), (2, 8, 8, 256, 512),
+    (3, 24, 40, 64, 64),    # ragged: partial tiles along w and h
+    (1, 4, 4, 64, 64),      # one GEMM tile spans several images (and is mostly out of bounds)
+    (5, 4, 4, 128, 64),
+    (1, 16, 16, 1024, 256), (2, 48, 24, 128, 128),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES)
+def test_conv3x3_fwd_epilogue_stats(ops, n, h, w, cin, cout):
+    cu, rf = ops
+    x = rnd(n, h, w, cin, seed=1).to(BF)
+    wt = (rnd(cout, 3, 3, cin, seed=2) / (9 * cin) ** 0.5).to(BF)
+    scale, shift = 1 + 0.1 * rnd(cout, seed=3), 0.1 * rnd(cout, seed=4)
+    for relu, stats in ((0, False), (1, True)):
+        y_ref = torch.empty(n, h, w, cout, dtype=BF)
+        ss_r, sq_r = torch.zeros(cout), torch.zeros(cout)
+        rf.conv3x3_fwd(x, wt, scale, shift, relu, y_ref, ss_r if stats else None, sq_r if stats else None)
+        y = torch.full((n, h, w, cout), float("nan"), dtype=BF, device=DEV)
+        ss, sq = torch.zeros(cout, device=DEV), torch.zeros(cout, device=DEV)
+        cu.conv3x3_fwd(x.to(DEV), wt.to(DEV), scale.to(DEV), shift.to(DEV), relu, y,
+                       ss if stats else None, sq if stats else None)
+        torch.cuda.synchronize()
+        assert relmax(y, y_ref) < 1.6e-2  # 2 bf16 ulps at the top of the range
+        if stats:
+            assert relmax(ss, ss_r) < 5e-3 and relmax(sq, sq_r) < 5e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES[:6])
+def test_conv3x3_concat_slices_and_dgrad(ops, n, h, w, cin, cout):
+    cu, rf = ops
+    x = rnd(n, h, w, cin, seed=1).to(BF)
+    wm = rnd(cout, 3, 3, cin, seed=5) / (9 * cout) ** 0.5
+    wf_r, wd_r = torch.empty(cout, 3, 3, cin, dtype=BF), torch.empty(cin, 3, 3, cout, dtype=BF)
+    rf.pack_conv3x3(wm, wf_r, wd_r)
+    wf = torch.empty(cout, 3, 3, cin, dtype=BF, device=DEV)
+    wd = torch.empty(cin, 3, 3, cout, dtype=BF, device=DEV)
+    cu.pack_conv3x3(wm.to(DEV), wf, wd)
+    torch.cuda.synchronize()
+    assert torch.equal(wf.cpu(), wf_r) and torch.equal(wd.cpu(), wd_r)  # packing is bit-exact
+    # input read from, and output written to, channel slices of wider buffers
+    xb = torch.zeros(n, h, w, cin + 64, dtype=BF, device=DEV)
+    xb[..., 64:] = x.to(DEV)
+    yb = torch.zeros(n, h, w, cout + 64, dtype=BF, device=DEV)
+    cu.conv3x3_fwd(xb[..., 64:], wf, None, None, 0, yb[..., :cout])
+    torch.cuda.synchronize()
+    y_ref = torch.empty(n, h, w, cout, dtype=BF)
+    rf.conv3x3_fwd(x, wf_r, None, None, 0, y_ref)
+    assert relmax(yb[..., :cout], y_ref) < 1.6e-2
+    assert yb[..., cout:].abs().max().item() == 0  # nothing leaks outside the slice
+    dy = rnd(n, h, w, cout, seed=6).to(BF)
+    dx_ref = torch.empty(n, h, w, cin, dtype=BF)
+    rf.conv3x3_dgrad(dy, wd_r, dx_ref)
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=BF, device=DEV)
+    cu.conv3x3_dgrad(dy.to(DEV), wd, dx)
+    torch.cuda.synchronize()
+    assert relmax(dx, dx_ref) < 1.6e-2
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (1, 16, 16, 64, 64), (2, 16, 16, 64, 128), (2, 16, 16, 128, 64), (1, 32, 32, 128, 256),
+    (4, 8, 8, 256, 128), (3, 24, 40, 64, 64), (5, 4, 4, 128, 64), (8, 64, 64, 64, 64), (2, 16, 16, 512, 256)])
+def test_conv3x3_wgrad_splitk(ops, n, h, w, cin, cout):
+    cu, rf = ops
+    x, dy = rnd(n, h, w, cin, seed=1).to(BF), rnd(n, h, w, cout, seed=2).to(BF)
+    dw_ref = torch.zeros(cout, 3, 3, cin)
+    rf.conv3x3_wgrad(x, dy, dw_ref)
+    dw = torch.full((cout, 3, 3, cin), float("nan"), device=DEV)
+    cu.conv3x3_wgrad(x.to(DEV), dy.to(DEV), dw)
+    torch.cuda.synchronize()
+    assert relmax(dw, dw_ref) < 1e-4  # fp32 accumulate of exact bf16 products: only summation order differs
+    cu.conv3x3_wgrad(x.to(DEV), dy.to(DEV), dw, accumulate=True)
+    torch.cuda.synchronize()
+    assert relmax(dw, 2 * dw_ref) < 1e-4
+
+
+def test_conv3x3_linearity_and_zero_at_full_size(ops):
+    """Size-independent properties at BASELINE configs[1] layer size (32 x 256 x 256, 64 -> 64), where the
+    CPU oracle would take too long: conv(0) == 0 exactly, conv(2x) == 2 conv(x) exactly (powers of two
+    commute with bf16 rounding), and a checksum against the oracle on one image."""
+    cu, rf = ops
+    n, h, w, c = 32, 256, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(n, h, w, c, generator=g, device=DEV).to(BF)
+    wt = (torch.randn(c, 3, 3, c, generator=g, device=DEV) / 24).to(BF)
+    y0 = torch.full((n, h, w, c), float("nan"), dtype=BF, device=DEV)
+    cu.conv3x3_fwd(torch.zeros_like(x), wt, None, None, 0, y0)
+    assert y0.abs().max().item() == 0
+    y1, y2 = torch.empty_like(y0), torch.empty_like(y0)
+    cu.conv3x3_fwd(x, wt, None, None, 0, y1)
+    cu.conv3x3_fwd(x * 2, wt, None, None, 0, y2)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y1 * 2)
+    y_ref = torch.empty(1, h, w, c, dtype=BF)
+    rf.conv3x3_fwd(x[7:8].cpu(), wt.cpu(), None, None, 0, y_ref)
+    assert relmax(y1[7:8], y_ref) < 1.6e-2
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 128, 64), (2, 8, 8, 256, 128), (2, 4, 4, 512, 256),
+                                            (3, 12, 20, 128, 64), (1, 16, 16, 1024, 512)])
+def test_convT2x2_fwd_dgrad_wgrad(ops, n, h, w, cin, cout):
+    cu, rf = ops
+    x = rnd(n, h, w, cin, seed=1).to(BF)
+    wm, bias = rnd(4, cout, cin, seed=2) / cin ** 0.5, 0.1 * rnd(cout, seed=3)
+    wf_r, wd_r = torch.empty(4, cout, cin, dtype=BF), torch.empty(cin, 4, cout, dtype=BF)
+    rf.pack_convT(wm, wf_r, wd_r)
+    wf, wd = torch.empty(4, cout, cin, dtype=BF, device=DEV), torch.empty(cin, 4, cout, dtype=BF, device=DEV)
+    cu.pack_convT(wm.to(DEV), wf, wd)
+    torch.cuda.synchronize()
+    assert torch.equal(wf.cpu(), wf_r) and torch.equal(wd.cpu(), wd_r)
+    cat_r = torch.zeros(n, 2 * h, 2 * w, 2 * cout, dtype=BF)
+    rf.convT_fwd(x, wf_r, bias, cat_r[..., cout:])
+    cat = torch.zeros(n, 2 * h, 2 * w, 2 * cout, dtype=BF, device=DEV)
+    cu.convT_fwd(x.to(DEV), wf, bias.to(DEV), cat[..., cout:])
+    torch.cuda.synchronize()
+    assert relmax(cat, cat_r) < 1.6e-2 and cat[..., :cout].abs().max().item() == 0
+    du = rnd(n, 2 * h, 2 * w, 2 * cout, seed=4).to(BF)
+    dud = du.to(DEV)
+    dx_ref = torch.empty(n, h, w, cin, dtype=BF)
+    rf.convT_dgrad(du[..., cout:], wd_r, dx_ref)
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=BF, device=DEV)
+    cu.convT_dgrad(dud[..., cout:], wd, dx)
+    dw_ref = torch.zeros(4, cout, cin)
+    rf.convT_wgrad(x, du[..., cout:], dw_ref)
+    dw = torch.full((4, cout, cin), float("nan"), device=DEV)
+    cu.convT_wgrad(x.to(DEV), dud[..., cout:], dw)
+    torch.cuda.synchronize()
+    assert relmax(dx, dx_ref) < 1.6e-2
+    assert relmax(dw, dw_ref) < 1e-4
+
+
+@pytest.mark.parametrize("n,h,w,c,ld", [(2, 16, 16, 64, 64), (3, 8, 12, 128, 256), (1, 4, 4, 1024, 1024),
+                                        (2, 6, 10, 192, 192), (1, 2, 2, 4096, 4096)])
+def test_bn_pool_relu_kernels(ops, n, h, w, c, ld):
+    cu, rf = ops
+    ybuf = rnd(n, h, w, ld, seed=1).to(BF)
+    y, yd = ybuf[..., ld - c:], ybuf.to(DEV)[..., ld - c:]
+    scale, shift = 1 + 0.2 * rnd(c, seed=2), 0.3 * rnd(c, seed=3)
+    a_ref = torch.empty(n, h, w, c, dtype=BF)
+    rf.scale_shift_act(y, scale, shift, 1, a_ref)
+    a = torch.empty(n, h, w, c, dtype=BF, device=DEV)
+    cu.scale_shift_act(yd, scale.to(DEV), shift.to(DEV), 1, a)
+    torch.cuda.synchronize()
+    assert relmax(a, a_ref) < 4e-3  # fma vs mul+add: at most 1 bf16 ulp apart
+    skip_r = torch.zeros(n, h, w, 2 * c, dtype=BF)
+    pooled_r = torch.empty(n, h // 2, w // 2, c, dtype=BF)
+    am_r = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8)
+    rf.scale_shift_act_pool(y, scale, shift, 1, skip_r[..., :c], pooled_r, am_r)
+    skip = torch.zeros(n, h, w, 2 * c, dtype=BF, device=DEV)
+    pooled = torch.empty(n, h // 2, w // 2, c, dtype=BF, device=DEV)
+    am = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=DEV)
+    cu.scale_shift_act_pool(yd, scale.to(DEV), shift.to(DEV), 1, skip[..., :c], pooled, am)
+    torch.cuda.synchronize()
+    assert relmax(skip, skip_r) < 4e-3 and relmax(pooled, pooled_r) < 4e-3
+    # plain pool on identical inputs: values and argmax indices bit-exact (first maximum wins ties)
+    p2, am2 = torch.empty_like(pooled), torch.empty_like(am)
+    cu.maxpool_fwd(skip[..., :c], p2, am2)
+    p2_r, am2_r = torch.empty_like(pooled_r), torch.empty_like(am_r)
+    rf.maxpool_fwd(skip.cpu()[..., :c], p2_r, am2_r)
+    torch.cuda.synchronize()
+    assert torch.equal(p2.cpu(), p2_r) and torch.equal(am2.cpu(), am2_r)
+    assert torch.equal(pooled, p2) and torch.equal(am, am2)  # fused and plain pool agree exactly
+    dyp = rnd(n, h // 2, w // 2, c, seed=5).to(BF)
+    dcat = rnd(n, h, w, 2 * c, seed=6).to(BF)
+    dx_r = torch.empty(n, h, w, c, dtype=BF)
+    dx = torch.empty(n, h, w, c, dtype=BF, device=DEV)
+    rf.maxpool_bwd(dyp, am2_r, None, dx_r)
+    cu.maxpool_bwd(dyp.to(DEV), am2, None, dx)
+    torch.cuda.synchronize()
+    assert torch.equal(dx.cpu(), dx_r)
+    rf.maxpool_bwd(dyp, am2_r, dcat[..., :c], dx_r)
+    cu.maxpool_bwd(dyp.to(DEV), am2, dcat.to(DEV)[..., :c], dx)
+    torch.cuda.synchronize()
+    assert relmax(dx, dx_r) < 4e-3
+    # BatchNorm finalize / fold / backward
+    cnt = n * h * w
+    ss, sq = y.float().sum((0, 1, 2)), (y.float() ** 2).sum((0, 1, 2))
+    gamma, beta = 1 + 0.1 * rnd(c, seed=7), 0.1 * rnd(c, seed=8)
+    outs_r = [torch.zeros(c) for _ in range(4)]
+    rm_r, rv_r = torch.zeros(c), torch.ones(c)
+    rf.bn_finalize(ss, sq, cnt, gamma, beta, 1e-5, 0.1, rm_r, rv_r, *outs_r)
+    outs = [torch.zeros(c, device=DEV) for _ in range(4)]
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    cu.bn_finalize(ss.to(DEV), sq.to(DEV), cnt, gamma.to(DEV), beta.to(DEV), 1e-5, 0.1, rm, rv, *outs)
+    torch.cuda.synchronize()
+    for o, o_r in zip(outs + [rm, rv], outs_r + [rm_r, rv_r]):
+        assert relmax(o, o_r) < 1e-4
+    fs_r, fh_r = torch.zeros(c), torch.zeros(c)
+    rf.bn_fold_eval(gamma, beta, rm_r, rv_r, shift, 1e-5, fs_r, fh_r)
+    fs, fh = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    cu.bn_fold_eval(gamma.to(DEV), beta.to(DEV), rm, rv, shift.to(DEV), 1e-5, fs, fh)
+    torch.cuda.synchronize()
+    assert relmax(fs, fs_r) < 1e-4 and relmax(fh, fh_r) < 1e-4
+    da = rnd(n, h, w, c, seed=9).to(BF)
+    dad = da.to(DEV)
+    coef_d = [t.to(DEV) for t in outs_r]
+    sg_r, sgx_r = torch.zeros(c), torch.zeros(c)
+    rf.bn_bwd_reduce(da, y, *outs_r, 1, sg_r, sgx_r)
+    sg, sgx = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    cu.bn_bwd_reduce(dad, yd, *coef_d, 1, sg, sgx)
+    torch.cuda.synchronize()
+    assert relmax(sg, sg_r) < 2e-3 and relmax(sgx, sgx_r) < 2e-3
+    dy_r, sdy_r = torch.empty(n, h, w, c, dtype=BF), torch.zeros(c)
+    rf.bn_bwd_apply(da, y, *outs_r, 1, sg_r, sgx_r, dy_r, sdy_r)
+    dyo, sdy = torch.empty(n, h, w, c, dtype=BF, device=DEV), torch.zeros(c, device=DEV)
+    cu.bn_bwd_apply(dad, yd, *coef_d, 1, sg_r.to(DEV), sgx_r.to(DEV), dyo, sdy)
+    torch.cuda.synchronize()
+    assert relmax(dyo, dy_r) < 4e-3
+    assert (sdy.cpu() - sdy_r).abs().max().item() < 2e-2 * dy_r.float().abs().max().item() * cnt ** 0.5
+    rdy_r, rs_r = torch.empty(n, h, w, c, dtype=BF), torch.zeros(c)
+    rf.relu_bwd(da, a_ref, rdy_r, rs_r)
+    rdy, rs = torch.empty(n, h, w, c, dtype=BF, device=DEV), torch.zeros(c, device=DEV)
+    cu.relu_bwd(dad, a_ref.to(DEV), rdy, rs)
+    cs_r, cs = torch.zeros(c), torch.zeros(c, device=DEV)
+    rf.channel_sum(y, cs_r)
+    cu.channel_sum(yd, cs)
+    torch.cuda.synchronize()
+    assert torch.equal(rdy.cpu(), rdy_r) and relmax(rs, rs_r) < 1e-3 and relmax(cs, cs_r) < 1e-3
+
+
+def test_pad_channels_and_empty_inputs(ops):
+    cu, rf = ops
+    xin = rnd(2, 8, 8, 8, seed=1).to(BF)
+    out = torch.full((2, 8, 8, 64), float("nan"), dtype=BF, device=DEV)
+    cu.pad_channels(xin.to(DEV), out)
+    out_r = torch.empty(2, 8, 8, 64, dtype=BF)
+    rf.pad_channels(xin, out_r)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), out_r)
+    # zero-pixel launches are no-ops, not errors
+    lib = cu.lib
+    from kcl_ltss_bioatm_b200.lib import ptr
+
+    assert lib.plume_pad_channels(ptr(xin.to(DEV)), 8, ptr(out), 64, 0, None) == 0
+    # misuse is reported, not swallowed
+    assert lib.plume_pad_channels(ptr(out), 64, ptr(out), 8, 10, None) != 0
+    assert b"multiples of 8" in lib.plume_last_error() or b"Cs <= Cd" in lib.plume_last_error()
+    z = torch.zeros(1, 8, 8, 72, dtype=BF, device=DEV)
+    with pytest.raises(Exception):
+        cu.conv3x3_fwd(z, torch.zeros(64 * 9 * 72, dtype=BF, device=DEV), None, None, 0,
+                       torch.zeros(1, 8, 8, 64, dtype=BF, device=DEV))  # Cin not a multiple of 64
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 8, 24, 128), (3, 4, 4, 64), (32, 64, 64, 64)])
+def test_head_loss_fwd_bwd(ops, n, h, w, c):
+    cu, rf = ops
+    feat = rnd(n, h, w, c, seed=1).to(BF)
+    wv, b = rnd(c, seed=2) / c ** 0.5, torch.tensor([0.05])
+    tgt = (rnd(n, h, w, seed=3) > 0.8).to(torch.uint8)
+    lg_r, sums_r, loss_r = torch.zeros(n, h, w), torch.zeros(4), torch.zeros(3)
+    rf.head_fwd(feat, wv, b, tgt, lg_r, sums_r)
+    rf.head_loss(sums_r, n * h * w, 1.0, 1.0, 1.0, loss_r)
+    lg, sums, loss = (torch.zeros(n, h, w, device=DEV), torch.zeros(4, device=DEV), torch.zeros(3, device=DEV))
+    cu.head_fwd(feat.to(DEV), wv.to(DEV), b.to(DEV), tgt.to(DEV), lg, sums)
+    cu.head_loss(sums, n * h * w, 1.0, 1.0, 1.0, loss)
+    torch.cuda.synchronize()
+    assert relmax(lg, lg_r) < 1e-5 and relmax(sums, sums_r) < 1e-4 and relmax(loss, loss_r) < 1e-4
+    df_r, dw_r, db_r = torch.empty(n, h, w, c, dtype=BF), torch.zeros(c), torch.zeros(1)
+    rf.head_bwd(feat, wv, lg_r, tgt, sums_r, 1.0, 1.0, 1.0, 0.5, df_r, dw_r, db_r)
+    df, dw, db = (torch.empty(n, h, w, c, dtype=BF, device=DEV), torch.zeros(c, device=DEV),
+                  torch.zeros(1, device=DEV))
+    cu.head_bwd(feat.to(DEV), wv.to(DEV), lg_r.to(DEV), tgt.to(DEV), sums_r.to(DEV), 1.0, 1.0, 1.0, 0.5, df, dw, db)
+    torch.cuda.synchronize()
+    assert relmax(df, df_r) < 8e-3 and relmax(dw, dw_r) < 1e-3 and relmax(db, db_r) < 1e-3
+
+
+@pytest.mark.parametrize("n", [1 << 20, 12345, 3])
+def test_adam_three_steps(ops, n):
+    cu, rf = ops
+    p, g = rnd(n, seed=1), rnd(n, seed=2)
+    m, v = torch.zeros(n), torch.zeros(n)
+    pd, gd, md, vd = p.to(DEV), g.to(DEV), m.to(DEV), v.to(DEV)
+    for step in (1, 2, 3):
+        rf.adam(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step, 0.5)
+        cu.adam(pd, gd, md, vd, 1e-3, 0.9, 0.999, 1e-8, step, 0.5)
+    torch.cuda.synchronize()
+    assert relmax(pd, p) < 1e-6 and relmax(md, m) < 1e-6 and relmax(vd, v) < 1e-6
+
+
+def test_tiles_extract_stitch_bit_exact(ops):
+    cu, rf = ops
+    from kcl_ltss_bioatm_b200.predict import tile_grid
+
+    hs, ws, cs, T, margin = 100, 130, 8, 64, 8
+    scene = rnd(hs, ws, cs, seed=1).to(BF)
+    ys_l, xs_l = tile_grid(hs, ws, T, margin)
+    ys, xs = torch.tensor(ys_l, dtype=torch.int32), torch.tensor(xs_l, dtype=torch.int32)
+    k = ys.numel()
+    tiles_r = torch.empty(k, T, T, 64, dtype=BF)
+    rf.extract_tiles(scene, ys, xs, T, tiles_r)
+    tiles = torch.full((k, T, T, 64), float("nan"), dtype=BF, device=DEV)
+    cu.extract_tiles(scene.to(DEV), ys.to(DEV), xs.to(DEV), T, tiles)
+    torch.cuda.synchronize()
+    assert torch.equal(tiles.cpu(), tiles_r)
+    logits = rnd(k, T, T, seed=2)
+    mask_r, prob_r = torch.full((hs, ws), 7, dtype=torch.uint8), torch.zeros(hs, ws)
+    rf.stitch_threshold(logits, ys, xs, T, margin, 0.0, mask_r, prob_r)
+    mask, prob = torch.full((hs, ws), 7, dtype=torch.uint8, device=DEV), torch.zeros(hs, ws, device=DEV)
+    cu.stitch_threshold(logits.to(DEV), ys.to(DEV), xs.to(DEV), T, margin, 0.0, mask, prob)
+    torch.cuda.synchronize()
+    assert (mask_r != 7).all()                     # every scene pixel owned by exactly one tile
+    assert torch.equal(mask.cpu(), mask_r) and relmax(prob, prob_r) < 1e-5
