@@ -457,7 +457,29 @@ __global__ void __launch_bounds__(kThreads)
   float acc[2][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
-  for (long long p = i0 / CV; p < pixels; p += pstep) {
+  constexpr int U = 4;  // pixels in flight per thread: 8 independent 16-byte loads cover the HBM latency
+  long long p = i0 / CV;
+  for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
+    BF8 gv[U], yv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      gv[u] = ld_bf8_stream(da + (p + u * pstep) * ldda + cv * 8);
+      yv[u] = ld_bf8_stream(y + (p + u * pstep) * ldy + cv * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float g[8], yy[8];
+      unpack8(gv[u], g);
+      unpack8(yv[u], yy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
+        acc[0][e] += gg;
+        acc[1][e] = fmaf(gg, (yy[e] - mu[e]) * is[e], acc[1][e]);
+      }
+    }
+  }
+  for (; p < pixels; p += pstep) {
     float g[8], yy[8];
     unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
     unpack8(ld_bf8_stream(y + p * ldy + cv * 8), yy);
@@ -516,10 +538,10 @@ __global__ void __launch_bounds__(kThreads)
   float acc[1][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
-  for (long long p = i0 / CV; p < pixels; p += pstep) {
+  auto one = [&](const BF8& gvv, const BF8& yvv, long long pp) {
     float g[8], yy[8], o[8];
-    unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
-    unpack8(ld_bf8_stream(y + p * ldy + cv * 8), yy);
+    unpack8(gvv, g);
+    unpack8(yvv, yy);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
@@ -527,14 +549,28 @@ __global__ void __launch_bounds__(kThreads)
       o[e] = sc[e] * (gg - mg[e] - xhat * mgx[e]);
     }
     const BF8 ov = pack8(o);
-    st_bf8(dy + p * lddy + cv * 8, ov);
+    st_bf8(dy + pp * lddy + cv * 8, ov);
     if (sum_dy) {
       float r[8];
       unpack8(ov, r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[0][e] += r[e];
     }
+  };
+  constexpr int U = 4;
+  long long p = i0 / CV;
+  for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
+    BF8 gv[U], yv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      gv[u] = ld_bf8_stream(da + (p + u * pstep) * ldda + cv * 8);
+      yv[u] = ld_bf8_stream(y + (p + u * pstep) * ldy + cv * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(gv[u], yv[u], p + u * pstep);
   }
+  for (; p < pixels; p += pstep)
+    one(ld_bf8_stream(da + p * ldda + cv * 8), ld_bf8_stream(y + p * ldy + cv * 8), p);
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
     block_channel_reduce<1>(acc, cv, CV, outs, s_acc);

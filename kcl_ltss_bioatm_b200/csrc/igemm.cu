@@ -17,6 +17,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace plume {
@@ -360,6 +361,382 @@ static int launch_fwd_inst(const TmapPack4& amaps, const CUtensorMap& bmap, cons
   return 0;
 }
 
+// =================================================================================================
+// 3x3 convolution kernel with halo reuse ("conv3"): the forward kernel above reloads the activation
+// tile once per filter tap, which makes the narrow layers (64 / 128 output channels) L2-bound
+// (profiles/: 3.6 GB of L2->SM traffic for a 268 MB input).  Here an M tile is 8 (w) x 16 (h) pixels,
+// so each group of 8 consecutive GEMM rows (one 1024-byte swizzle atom) is one image row of the tile.
+// One TMA box of 8 x 18 pixels (one halo row above and below) then serves the three vertical taps:
+// tap dh simply starts the UMMA descriptor (1 + dh) atoms further.  Horizontal taps still need their
+// own boxes (a one-pixel shift moves pixels across atoms).  A traffic drops from 9 x 16 KB to
+// 3 x 18 KB per 64 input channels.  When the whole weight slice [BLOCK_N][9*Cin] fits in shared memory
+// it is loaded once per CTA and stays resident; otherwise weight tiles flow through their own ring.
+// =================================================================================================
+struct Conv3Params {
+  int tiles_w, tiles_h;           // per image; tile = 8 x 16 pixels
+  int W, H, N;
+  int n_tiles;                    // tiles along GEMM N
+  int kb;                         // Cin / 64
+  int cin;
+  int a_slots, b_slots;           // ring depths (b_slots == 0: weights resident)
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+constexpr int kHaloBytes = 18 * 1024;  // 8 w x 18 h pixels x 64 channels bf16
+constexpr int kMaxSlots = 8;
+
+template <int BLOCK_N, int STAGING>
+__global__ void __launch_bounds__(256, 1)
+    igemm_conv3_kernel(const __grid_constant__ CUtensorMap amap,
+                       const __grid_constant__ CUtensorMap bmap,
+                       const __grid_constant__ CUtensorMap omap, const Conv3Params p) {
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STG_BYTES = 128 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - raw_addr);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const bool resident = p.b_slots == 0;
+  const int b_tiles = resident ? 9 * p.kb : p.b_slots;
+  const uint32_t off_a = 0;
+  const uint32_t off_b = off_a + p.a_slots * kHaloBytes;
+  const uint32_t off_stg = off_b + b_tiles * B_BYTES;
+  const uint32_t off_param = off_stg + STAGING * STG_BYTES;
+  const uint32_t off_bar = off_param + 4 * BLOCK_N * 4;
+  const uint32_t bar0 = sbase + off_bar;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * kMaxSlots + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (3 * kMaxSlots + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (4 * kMaxSlots + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (4 * kMaxSlots + 2 + a); };
+  const uint32_t bres_full = bar0 + 8u * (4 * kMaxSlots + 4);
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 5));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&bmap);
+    tma_prefetch_desc(&omap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxSlots; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    mbar_init(bres_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = tiles_img * p.N;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      if (resident) {
+        // n_tiles == 1 in this mode: the CTA's weight slice never changes
+        mbar_expect_tx(bres_full, static_cast<uint32_t>(b_tiles) * B_BYTES);
+        for (int t = 0; t < 9; ++t)
+          for (int kb = 0; kb < p.kb; ++kb)
+            tma_load_2d(sbase + off_b + (t * p.kb + kb) * B_BYTES, &bmap, bres_full,
+                        t * p.cin + kb * 64, 0);
+      }
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_img;
+        const int rem = m_tile % tiles_img;
+        const int w0 = (rem % p.tiles_w) * 8;
+        const int h0 = (rem / p.tiles_w) * 16;
+        for (int kb = 0; kb < p.kb; ++kb) {
+          for (int dwi = 0; dwi < 3; ++dwi) {
+            mbar_wait(a_empty(sa), pa ^ 1, 1, &g_dbg_word);
+            mbar_expect_tx(a_full(sa), kHaloBytes);
+            tma_load_4d(sbase + off_a + sa * kHaloBytes, &amap, a_full(sa), kb * 64, w0 + dwi - 1,
+                        h0 - 1, img);
+            if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+            if (!resident) {
+              for (int dhi = 0; dhi < 3; ++dhi) {
+                mbar_wait(b_empty(sb), pb ^ 1, 8, &g_dbg_word);
+                mbar_expect_tx(b_full(sb), B_BYTES);
+                tma_load_2d(sbase + off_b + sb * B_BYTES, &bmap, b_full(sb),
+                            (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N);
+                if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      if (resident) {
+        mbar_wait(bres_full, 0, 9, &g_dbg_word);
+        tc_fence_after();
+      }
+      int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const int acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2, &g_dbg_word);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.kb; ++kb) {
+          for (int dwi = 0; dwi < 3; ++dwi) {
+            mbar_wait(a_full(sa), pa, 3, &g_dbg_word);
+            tc_fence_after();
+            const uint32_t a_slot = sbase + off_a + sa * kHaloBytes;
+#pragma unroll 1
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              uint32_t b_addr;
+              if (resident) {
+                b_addr = sbase + off_b + ((dhi * 3 + dwi) * p.kb + kb) * B_BYTES;
+              } else {
+                mbar_wait(b_full(sb), pb, 10, &g_dbg_word);
+                tc_fence_after();
+                b_addr = sbase + off_b + sb * B_BYTES;
+              }
+              const uint32_t a_addr = a_slot + dhi * 1024;  // vertical tap = atom offset in the halo
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                          umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accumulate);
+                accumulate = 1;
+              }
+              if (!resident) {
+                umma_commit(b_empty(sb));
+                if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+              }
+            }
+            umma_commit(a_empty(sa));
+            if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    float* s_scale = reinterpret_cast<float*>(gbase + off_param);
+    float* s_shift = s_scale + BLOCK_N;
+    float* s_sum = s_shift + BLOCK_N;
+    float* s_sq = s_sum + BLOCK_N;
+    const bool do_stats = p.stat_sum != nullptr;
+    int it = 0, chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_img;
+      const int rem = m_tile % tiles_img;
+      const int w0 = (rem % p.tiles_w) * 8;
+      const int h0 = (rem / p.tiles_w) * 16;
+      const int acc = it & 1;
+      const int acc_phase = (it >> 1) & 1;
+      const int ch0 = n_tile * BLOCK_N;
+      for (int c = et; c < BLOCK_N; c += 128) {
+        s_scale[c] = p.scale ? p.scale[ch0 + c] : 1.0f;
+        s_shift[c] = p.shift ? p.shift[ch0 + c] : 0.0f;
+        s_sum[c] = 0.0f;
+        s_sq[c] = 0.0f;
+      }
+      const bool valid = (w0 + (row & 7) < p.W) && (h0 + (row >> 3) < p.H);
+      mbar_wait(tfull_bar(acc), acc_phase, 4, &g_dbg_word);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_ctr) {
+        uint32_t v0[32], v1[32];
+        {
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + chunk * 64;
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32, v1);
+          tmem_ld_wait();
+        }
+        if (chunk == BLOCK_N / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        const int sbuf = (STAGING == 2) ? (chunk_ctr & 1) : 0;
+        if (et == 0) tma_store_wait_read<STAGING - 1>();
+        named_bar_sync(1, 128);
+        uint8_t* stg = gbase + off_stg + sbuf * STG_BYTES;
+        epi_store_half(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg, row);
+        epi_store_half(v1, 4, s_scale + chunk * 64 + 32, s_shift + chunk * 64 + 32, p.relu, valid,
+                       stg, row);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&omap, sbase + off_stg + sbuf * STG_BYTES, ch0 + chunk * 64, w0, h0, img);
+          tma_store_commit();
+        }
+        if (do_stats) {
+          const int j = lane >> 2, wsub = lane & 3;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = q * 32 + rr;
+            const uint32_t u =
+                *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((j ^ (r & 7)) << 4) + wsub * 4);
+            const float2 f = unpack_bf16x2(u);
+            s0 += f.x;
+            s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0);
+            q1 = fmaf(f.y, f.y, q1);
+          }
+          atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
+          atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
+          atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
+          atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
+        }
+      }
+      if (do_stats) {
+        named_bar_sync(1, 128);
+        for (int c = et; c < BLOCK_N; c += 128) {
+          atomicAdd(p.stat_sum + ch0 + c, s_sum[c]);
+          atomicAdd(p.stat_sq + ch0 + c, s_sq[c]);
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+}
+
+static size_t conv3_smem_bytes(int block_n, int staging, int a_slots, int b_tiles) {
+  return static_cast<size_t>(a_slots) * kHaloBytes + static_cast<size_t>(b_tiles) * block_n * 128 +
+         static_cast<size_t>(staging) * 16384 + 4 * block_n * 4 + 8 * (4 * kMaxSlots + 5) + 16 + 1024;
+}
+
+template <int BLOCK_N, int STAGING>
+static int launch_conv3_inst(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
+                             const Conv3Params& p, size_t smem, int total_tiles, cudaStream_t stream) {
+  auto kern = igemm_conv3_kernel<BLOCK_N, STAGING>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(igemm_conv3): ") + cudaGetErrorString(attr_err));
+    return -2;
+  }
+  const int grid = std::min(total_tiles, num_sms());
+  kern<<<grid, 256, smem, stream>>>(amap, bmap, omap, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("igemm_conv3 launch: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+// conv3x3 fwd / dgrad through the halo-reuse kernel.  Returns 1 if the shape is not eligible (caller
+// falls back to the generic forward kernel), 0 on success, < 0 on error.
+static int try_launch_conv3(const FwdDesc& d) {
+  static const bool disabled = getenv("PLUME_DISABLE_CONV3") != nullptr;
+  if (disabled) return 1;
+  if (d.num_taps != 9 || d.num_in_views != 1 || d.num_out_views != 1) return 1;
+  const int W = d.in[0].W, H = d.in[0].H, N = d.in[0].N;
+  if (H < 16 || W < 8) return 1;
+  const int cout = d.cout_per_view;
+  const int block_n = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  const int n_tiles = cout / block_n;
+  const int kb = d.Cin / 64;
+  const int staging_hi = block_n == 256 ? 1 : 2;
+  const size_t limit = 232448;
+
+  Conv3Params p;
+  p.tiles_w = (W + 7) / 8;
+  p.tiles_h = (H + 15) / 16;
+  p.W = W; p.H = H; p.N = N;
+  p.n_tiles = n_tiles;
+  p.kb = kb;
+  p.cin = d.Cin;
+  p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
+  p.stat_sum = d.stat_sum; p.stat_sq = d.stat_sq;
+
+  // resident weights when the whole [block_n][9*Cin] slice fits beside >= 3 halo slots
+  int staging = staging_hi;
+  bool resident = false;
+  if (n_tiles == 1) {
+    for (int st = staging_hi; st >= 1 && !resident; --st) {
+      if (conv3_smem_bytes(block_n, st, 3, 9 * kb) <= limit) {
+        resident = true;
+        staging = st;
+      }
+    }
+  }
+  if (resident) {
+    p.b_slots = 0;
+    p.a_slots = 3;
+    while (p.a_slots < 6 && conv3_smem_bytes(block_n, staging, p.a_slots + 1, 9 * kb) <= limit)
+      ++p.a_slots;
+  } else {
+    p.a_slots = block_n == 256 ? 3 : 4;
+    p.b_slots = block_n == 256 ? 4 : (block_n == 128 ? 6 : 8);
+  }
+  const size_t smem = conv3_smem_bytes(block_n, staging, p.a_slots, resident ? 9 * kb : p.b_slots);
+  if (smem > limit) return 1;
+
+  CUtensorMap amap, bmap, omap;
+  if (d.in[0].C != d.Cin || d.out[0].C != cout) {
+    set_error("igemm_conv3: view channel counts do not match");
+    return -1;
+  }
+  if (make_act_map(&amap, d.in[0], 64, 8, 18, 1)) return -1;
+  if (make_act_map(&omap, d.out[0], 64, 8, 16, 1)) return -1;
+  if (make_mat_map(&bmap, d.wmat, cout, 9ll * d.Cin, 64, block_n)) return -1;
+  const long long total = 1ll * p.tiles_w * p.tiles_h * N * n_tiles;
+  if (total > 0x7fffffffll) {
+    set_error("igemm_conv3: too many tiles");
+    return -1;
+  }
+  switch (block_n) {
+    case 256:
+      return launch_conv3_inst<256, 1>(amap, bmap, omap, p, smem, (int)total, d.stream);
+    case 128:
+      return staging == 2 ? launch_conv3_inst<128, 2>(amap, bmap, omap, p, smem, (int)total, d.stream)
+                          : launch_conv3_inst<128, 1>(amap, bmap, omap, p, smem, (int)total, d.stream);
+    default:
+      return staging == 2 ? launch_conv3_inst<64, 2>(amap, bmap, omap, p, smem, (int)total, d.stream)
+                          : launch_conv3_inst<64, 1>(amap, bmap, omap, p, smem, (int)total, d.stream);
+  }
+}
+
 int launch_igemm_fwd(const FwdDesc& d) {
   if (d.Cin % 64 != 0 || d.Cin <= 0) {
     set_error("igemm_fwd: input channels must be a positive multiple of 64");
@@ -379,6 +756,10 @@ int launch_igemm_fwd(const FwdDesc& d) {
       set_error("igemm_fwd: output view extents differ from the input extents");
       return -1;
     }
+  {
+    const int r = try_launch_conv3(d);
+    if (r <= 0) return r;
+  }
   int bw, bh, bn;
   pick_box(W, H, 128, 16, &bw, &bh, &bn);
   const int block_n = (d.cout_per_view % 256 == 0) ? 256 : (d.cout_per_view % 128 == 0 ? 128 : 64);
@@ -611,17 +992,278 @@ static void wgrad_geometry(int N, int H, int W, int* bw, int* bh, int* bn, int* 
 
 static int wgrad_block_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
 
-int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout) {
-  int bw, bh, bn, ktiles;
-  wgrad_geometry(N, H, W, &bw, &bh, &bn, &ktiles);
-  const int block_n = wgrad_block_n(Cout);
-  const int m_units = (Cin == 64) ? (num_taps + 1) / 2 : num_taps * (Cin / 128);
-  const int ctas = m_units * (Cout / block_n);
-  // aim for ~2 waves of CTAs, but keep at least 8 K tiles (512 pixels) per split
+// One place decides which weight-gradient kernel runs and how K is split, so that the workspace size
+// reported through the C ABI always matches what the launcher does.
+struct WgradConfig {
+  bool halo;        // igemm_wgrad3_kernel (3x3, halo reuse) vs the generic igemm_wgrad_kernel
+  int block_n;
+  int ctas_mn;      // CTAs per split
+  int ktiles;       // 64-pixel K tiles
+  int splits, ktiles_per_split;
+};
+
+static int split_for(int ctas, int ktiles, int min_ktiles, int* per_out) {
+  // aim for ~2 waves of CTAs, but keep at least `min_ktiles` K tiles per split
   int want = std::max(1, (2 * 148 + ctas - 1) / ctas);
-  want = std::min(want, std::max(1, ktiles / 8));
+  want = std::min(want, std::max(1, ktiles / min_ktiles));
   const int per = (ktiles + want - 1) / want;
+  *per_out = per;
   return (ktiles + per - 1) / per;
+}
+
+static WgradConfig wgrad_config(int N, int H, int W, int num_taps, int Cin, int Cout, int dy_views) {
+  static const bool no_halo = getenv("PLUME_DISABLE_WGRAD3") != nullptr;
+  WgradConfig c;
+  c.halo = !no_halo && num_taps == 9 && dy_views == 1 && H >= 8 && W >= 8 &&
+           (Cin == 64 || Cin % 128 == 0);
+  if (c.halo) {
+    // Cin == 64: one CTA covers all nine taps (five 128-row blocks of TMEM, 64 columns each)
+    // otherwise : one CTA covers the three vertical taps of one horizontal tap for 128 input channels
+    c.block_n = (Cin == 64) ? 64 : (Cout % 128 == 0 ? 128 : 64);
+    const int units = (Cin == 64) ? 1 : 3 * (Cin / 128);
+    c.ctas_mn = units * (Cout / c.block_n);
+    c.ktiles = ((W + 7) / 8) * ((H + 7) / 8) * N;
+    c.splits = split_for(c.ctas_mn, c.ktiles, 16, &c.ktiles_per_split);
+  } else {
+    int bw, bh, bn;
+    wgrad_geometry(N, H, W, &bw, &bh, &bn, &c.ktiles);
+    c.block_n = wgrad_block_n(Cout);
+    const int m_units = (Cin == 64) ? (num_taps + 1) / 2 : num_taps * (Cin / 128);
+    c.ctas_mn = m_units * (Cout / c.block_n);
+    c.splits = split_for(c.ctas_mn, c.ktiles, 8, &c.ktiles_per_split);
+  }
+  return c;
+}
+
+int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout) {
+  return wgrad_config(N, H, W, num_taps, Cin, Cout, num_taps == 9 ? 1 : 4).splits;
+}
+
+// =================================================================================================
+// 3x3 weight gradient with halo reuse ("wgrad3").  K tile = 8 (w) x 8 (h) pixels; with MN-major
+// operands an 8-pixel image row of the tile is one 1024-byte atom, so one X box of 8 x 10 pixels
+// feeds the three vertical taps (descriptor start moved by (1+dh) atoms) and dY is loaded once per
+// K tile instead of once per tap.  Accumulators for all taps of the CTA live side by side in TMEM:
+//   Cin == 64 : 9 taps x 64 rows = five 128-row blocks (tap pairs), 3 X boxes (dw = -1,0,1) per K tile
+//   Cin >= 128: 3 vertical taps x 128 rows = three blocks for one dw and one 128-channel slice
+// =================================================================================================
+struct Wgrad3Params {
+  int tiles_w, tiles_h, N;        // K tiling: 8 x 8 pixel tiles per image
+  int cin, cout;
+  int mode9;                      // 1: Cin == 64, all nine taps in one CTA
+  int ci_blocks;                  // Cin / 128 (mode9 == 0)
+  int n_tiles;
+  int splits, ktiles_per_split;
+  int stages;
+  float* partial;                 // [splits][9*Cin][Cout]
+};
+
+constexpr int kXBox = 10 * 1024;  // 8 w x 10 h pixels x 64 channels
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+    igemm_wgrad3_kernel(const __grid_constant__ CUtensorMap xmap,
+                        const __grid_constant__ CUtensorMap dymap, const Wgrad3Params p) {
+  constexpr int DY_BYTES = (BLOCK_N / 64) * 8192;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - raw_addr);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const int x_bytes = p.mode9 ? 3 * kXBox : 2 * kXBox;
+  const int stage_bytes = x_bytes + DY_BYTES;
+  const uint32_t off_bar = p.stages * stage_bytes;
+  const uint32_t bar0 = sbase + off_bar;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * kMaxSlots);
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (2 * kMaxSlots + 1));
+  const int nblocks = p.mode9 ? 5 : 3;
+  const uint32_t tmem_cols = (nblocks * BLOCK_N <= 256) ? 256u : 512u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&dymap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxSlots; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // work item: blockIdx.x = (unit, n tile), blockIdx.y = K split
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int unit = blockIdx.x / p.n_tiles;
+  const int split = blockIdx.y;
+  const int dwi = p.mode9 ? 0 : unit / p.ci_blocks;   // horizontal tap of this CTA (mode 3)
+  const int cb = p.mode9 ? 0 : unit % p.ci_blocks;    // 128-channel slice of this CTA (mode 3)
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int total_ktiles = tiles_img * p.N;
+  const int kt_begin = split * p.ktiles_per_split;
+  const int kt_end = min(kt_begin + p.ktiles_per_split, total_ktiles);
+  const int nk = kt_end - kt_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        const int img = kt / tiles_img;
+        const int rem = kt % tiles_img;
+        const int w0 = (rem % p.tiles_w) * 8;
+        const int h0 = (rem / p.tiles_w) * 8;
+        mbar_wait(empty_bar(stage), phase ^ 1, 5, &g_dbg_word);
+        const uint32_t x_addr = sbase + stage * stage_bytes;
+        const uint32_t dy_addr = x_addr + x_bytes;
+        mbar_expect_tx(full_bar(stage), stage_bytes);
+        if (p.mode9) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            tma_load_4d(x_addr + d * kXBox, &xmap, full_bar(stage), 0, w0 + d - 1, h0 - 1, img);
+        } else {
+          tma_load_4d(x_addr, &xmap, full_bar(stage), cb * 128, w0 + dwi - 1, h0 - 1, img);
+          tma_load_4d(x_addr + kXBox, &xmap, full_bar(stage), cb * 128 + 64, w0 + dwi - 1, h0 - 1,
+                      img);
+        }
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b)
+          tma_load_4d(dy_addr + b * 8192, &dymap, full_bar(stage), n_tile * BLOCK_N + b * 64, w0, h0,
+                      img);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; ++i) {
+        mbar_wait(full_bar(stage), phase, 6, &g_dbg_word);
+        tc_fence_after();
+        const uint32_t x_addr = sbase + stage * stage_bytes;
+        const uint32_t dy_addr = x_addr + x_bytes;
+        for (int blk = 0; blk < nblocks; ++blk) {
+          uint32_t a_start, a_lbo;
+          if (p.mode9) {
+            // rows 0-63: tap 2*blk, rows 64-127: tap 2*blk+1, taps ordered (dw major, dh minor)
+            const int t0 = 2 * blk;
+            a_start = x_addr + (t0 / 3) * kXBox + (t0 % 3) * 1024;
+            a_lbo = (blk == 1) ? static_cast<uint32_t>(kXBox - 2048) : 1024u;
+          } else {
+            a_start = x_addr + blk * 1024;   // blk == vertical tap; two 64-channel boxes kXBox apart
+            a_lbo = kXBox;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tmem_base + blk * BLOCK_N, umma_desc_sw128(a_start + k * 2048, a_lbo, 1024),
+                      umma_desc_sw128(dy_addr + k * 2048, 8192, 1024), idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    mbar_wait(tfull_bar, 0, 7, &g_dbg_word);
+    tc_fence_after();
+    for (int blk = 0; blk < nblocks; ++blk) {
+      int wt, ci;  // weight tap index (r*3+s) and input channel of this TMEM lane
+      bool ok = true;
+      if (p.mode9) {
+        const int t = 2 * blk + (row >> 6);  // (dw major, dh minor)
+        ok = t < 9;
+        wt = (t % 3) * 3 + (t / 3);
+        ci = row & 63;
+      } else {
+        wt = blk * 3 + dwi;
+        ci = cb * 128 + row;
+      }
+      float* dst = p.partial +
+                   (static_cast<size_t>(split) * 9 * p.cin + static_cast<size_t>(wt) * p.cin + ci) *
+                       p.cout +
+                   n_tile * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * BLOCK_N + c, v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            *reinterpret_cast<float4*>(dst + c + 4 * j) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+template <int BLOCK_N>
+static int launch_wgrad3_inst(const CUtensorMap& xmap, const CUtensorMap& dymap, const Wgrad3Params& p,
+                              size_t smem, int ctas_mn, cudaStream_t stream) {
+  auto kern = igemm_wgrad3_kernel<BLOCK_N>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(igemm_wgrad3): ") + cudaGetErrorString(attr_err));
+    return -2;
+  }
+  dim3 grid(ctas_mn, p.splits);
+  kern<<<grid, 256, smem, stream>>>(xmap, dymap, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("igemm_wgrad3 launch: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
+  const int W = d.x.W, H = d.x.H, N = d.x.N;
+  Wgrad3Params p;
+  p.tiles_w = (W + 7) / 8;
+  p.tiles_h = (H + 7) / 8;
+  p.N = N;
+  p.cin = d.Cin;
+  p.cout = d.Cout;
+  p.mode9 = d.Cin == 64 ? 1 : 0;
+  p.ci_blocks = d.Cin / 128;
+  p.n_tiles = d.Cout / c.block_n;
+  p.splits = c.splits;
+  p.ktiles_per_split = c.ktiles_per_split;
+  p.partial = d.partial;
+  const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (c.block_n / 64) * 8192;
+  const int overhead = 8 * (2 * kMaxSlots + 1) + 16 + 1024;
+  p.stages = std::min(kMaxSlots, (232448 - overhead) / stage_bytes);
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + overhead;
+  CUtensorMap xmap, dymap;
+  if (make_act_map(&xmap, d.x, 64, 8, 10, 1)) return -1;
+  if (make_act_map(&dymap, d.dy[0], 64, 8, 8, 1)) return -1;
+  if (c.block_n == 128) return launch_wgrad3_inst<128>(xmap, dymap, p, smem, c.ctas_mn, d.stream);
+  return launch_wgrad3_inst<64>(xmap, dymap, p, smem, c.ctas_mn, d.stream);
 }
 
 template <int BLOCK_N, int STAGES>
@@ -666,23 +1308,32 @@ int launch_igemm_wgrad(const WgradDesc& d) {
     set_error("igemm_wgrad: empty input");
     return -1;
   }
-  int bw, bh, bn, ktiles;
-  wgrad_geometry(N, H, W, &bw, &bh, &bn, &ktiles);
-  const int block_n = wgrad_block_n(d.Cout);
-
-  CUtensorMap xmap;
-  TmapPack4 dymaps;
   if (d.x.C != d.Cin) {
     set_error("igemm_wgrad: x view channel count != Cin");
     return -1;
   }
-  if (make_act_map(&xmap, d.x, 64, bw, bh, bn)) return -1;
-  for (int i = 0; i < 4; ++i) {
-    const ActView& v = d.dy[i < d.num_dy_views ? i : 0];
+  for (int i = 0; i < d.num_dy_views; ++i) {
+    const ActView& v = d.dy[i];
     if (v.C != d.Cout || v.W != W || v.H != H || v.N != N) {
       set_error("igemm_wgrad: dy view extents do not match");
       return -1;
     }
+  }
+  const WgradConfig c = wgrad_config(N, H, W, d.num_taps, d.Cin, d.Cout, d.num_dy_views);
+  if (d.splits != c.splits) {
+    set_error("igemm_wgrad: invalid split count (use plume_wgrad_splits)");
+    return -1;
+  }
+  if (c.halo) return launch_wgrad3(d, c);
+
+  int bw, bh, bn, ktiles;
+  wgrad_geometry(N, H, W, &bw, &bh, &bn, &ktiles);
+  const int block_n = c.block_n;
+  CUtensorMap xmap;
+  TmapPack4 dymaps;
+  if (make_act_map(&xmap, d.x, 64, bw, bh, bn)) return -1;
+  for (int i = 0; i < 4; ++i) {
+    const ActView& v = d.dy[i < d.num_dy_views ? i : 0];
     if (make_act_map(&dymaps.m[i], v, 64, bw, bh, bn)) return -1;
   }
   WgradParams p;
@@ -698,12 +1349,8 @@ int launch_igemm_wgrad(const WgradDesc& d) {
   p.ci_tiles = d.Cin / 128;
   p.m_units = p.pair_taps ? (d.num_taps + 1) / 2 : d.num_taps * p.ci_tiles;
   p.n_tiles = d.Cout / block_n;
-  p.splits = d.splits;
-  p.ktiles_per_split = (ktiles + d.splits - 1) / d.splits;
-  if (d.splits < 1 || 1ll * (d.splits - 1) * p.ktiles_per_split >= ktiles) {
-    set_error("igemm_wgrad: invalid split count (use plume_wgrad_splits)");
-    return -1;
-  }
+  p.splits = c.splits;
+  p.ktiles_per_split = c.ktiles_per_split;
   p.partial = d.partial;
   switch (block_n) {
     case 256: return launch_wgrad_inst<256, 4>(xmap, dymaps, p, d.stream);
