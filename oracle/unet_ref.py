@@ -99,3 +99,26 @@ def predict_mask(model: nn.Module, x: torch.Tensor, spec: UNetSpec) -> torch.Ten
         logits = model(x)[:, 0]
     model.train(was)
     return (torch.sigmoid(logits) >= spec.mask_threshold).to(torch.uint8)
+
+
+def with_bf16_storage(model: nn.Module) -> nn.Module:
+    """Copy of `model` that rounds to bf16 exactly where a bf16-storage implementation must: the GEMM
+    weights, every conv / transposed-conv output and every BatchNorm output (ReLU and max-pool commute
+    with rounding).  Arithmetic stays fp32.  The gap between this and the fp32 model is the error floor of
+    ANY bf16-activation implementation of the network; the gap between this and the CUDA path is what the
+    kernels themselves add."""
+    import copy
+
+    m2 = copy.deepcopy(model)
+
+    def _round(_m, _i, out):
+        return out.to(torch.bfloat16).float()
+
+    for name, mod in m2.named_modules():
+        if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+            if name != "head":
+                mod.weight.data = mod.weight.data.to(torch.bfloat16).float()
+                mod.register_forward_hook(_round)
+        elif isinstance(mod, nn.BatchNorm2d):
+            mod.register_forward_hook(_round)
+    return m2
