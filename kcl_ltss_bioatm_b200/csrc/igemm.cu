@@ -213,16 +213,17 @@ __global__ void __launch_bounds__(256, 1)
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2, &g_dbg_word);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(full_bar(stage), phase, 3, &g_dbg_word);
           tc_fence_after();
-          const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + L::A_BYTES;
+          const uint32_t a_lo = umma_desc_lo(sbase + stage * L::STAGE_BYTES, 16);
+          const uint32_t b_lo = a_lo + (L::A_BYTES >> 4);
+          constexpr uint32_t hi = umma_desc_hi_sw128(1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kit | k) != 0 ? 1u : 0u);
+            umma_bf16_lohi(d_tmem, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
+            accumulate = 1;
           }
           umma_commit(empty_bar(stage));  // slot reusable once these MMAs have read it
           if (++stage == STAGES) {
@@ -513,27 +514,29 @@ __global__ void __launch_bounds__(256, 1)
           for (int dwi = 0; dwi < 3; ++dwi) {
             mbar_wait(a_full(sa), pa, 3, &g_dbg_word);
             tc_fence_after();
-            const uint32_t a_slot = sbase + off_a + sa * kHaloBytes;
-#pragma unroll 1
+            constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+            const uint32_t a_lo = umma_desc_lo(sbase + off_a + sa * kHaloBytes, 16);
+            // resident weights: tile (tap, kb) at ((dh*3+dw)*KB + kb) * B_BYTES
+            uint32_t b_lo = umma_desc_lo(sbase + off_b + (dwi * p.kb + kb) * B_BYTES, 16);
+            const uint32_t b_step = 3 * p.kb * (B_BYTES >> 4);
+#pragma unroll
             for (int dhi = 0; dhi < 3; ++dhi) {
-              uint32_t b_addr;
-              if (resident) {
-                b_addr = sbase + off_b + ((dhi * 3 + dwi) * p.kb + kb) * B_BYTES;
-              } else {
+              if (!resident) {
                 mbar_wait(b_full(sb), pb, 10, &g_dbg_word);
                 tc_fence_after();
-                b_addr = sbase + off_b + sb * B_BYTES;
+                b_lo = umma_desc_lo(sbase + off_b + sb * B_BYTES, 16);
               }
-              const uint32_t a_addr = a_slot + dhi * 1024;  // vertical tap = atom offset in the halo
+              // vertical tap = one 1024-byte atom (64 descriptor units) further into the halo
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                          umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, accumulate);
+                umma_bf16_lohi(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
                 accumulate = 1;
               }
               if (!resident) {
                 umma_commit(b_empty(sb));
                 if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+              } else {
+                b_lo += b_step;
               }
             }
             umma_commit(a_empty(sa));
@@ -939,14 +942,13 @@ __global__ void __launch_bounds__(256, 1)
         tc_fence_after();
         const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
         const uint32_t b_addr = a_addr + L::A_BYTES;
+        // MN-major: 16 pixels (two 8-pixel atoms, SBO = 1024 B apart) per MMA; 64-channel groups
+        // are LBO = 8192 B apart (one TMA box each); a K step is 2048 B = 128 descriptor units.
+        constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+        const uint32_t a_lo = umma_desc_lo(a_addr, 8192), b_lo = umma_desc_lo(b_addr, 8192);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // MN-major: 16 pixels (two 8-pixel atoms, SBO = 1024 B apart) per MMA; 64-channel groups
-          // are LBO = 8192 B apart (one TMA box each).
-          const uint64_t adesc = umma_desc_sw128(a_addr + k * 2048, 8192, 1024);
-          const uint64_t bdesc = umma_desc_sw128(b_addr + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_lohi(tmem_base, a_lo + 128 * k, hi, b_lo + 128 * k, hi, idesc, (i | k) != 0 ? 1u : 0u);
         umma_commit(empty_bar(stage));
         if (++stage == STAGES) {
           stage = 0;
@@ -1154,21 +1156,31 @@ __global__ void __launch_bounds__(256, 1)
         tc_fence_after();
         const uint32_t x_addr = sbase + stage * stage_bytes;
         const uint32_t dy_addr = x_addr + x_bytes;
-        for (int blk = 0; blk < nblocks; ++blk) {
-          uint32_t a_start, a_lbo;
-          if (p.mode9) {
-            // rows 0-63: tap 2*blk, rows 64-127: tap 2*blk+1, taps ordered (dw major, dh minor)
-            const int t0 = 2 * blk;
-            a_start = x_addr + (t0 / 3) * kXBox + (t0 % 3) * 1024;
-            a_lbo = (blk == 1) ? static_cast<uint32_t>(kXBox - 2048) : 1024u;
-          } else {
-            a_start = x_addr + blk * 1024;   // blk == vertical tap; two 64-channel boxes kXBox apart
-            a_lbo = kXBox;
-          }
+        constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+        const uint32_t b_lo = umma_desc_lo(dy_addr, 8192);
+        const uint32_t accflag = i != 0 ? 1u : 0u;
+        if (p.mode9) {
+          // rows 0-63: tap 2*blk, rows 64-127: tap 2*blk+1, taps ordered (dw major, dh minor):
+          // tap t lives at box (t/3) of the stage, atom (t%3); LBO = distance between the two taps
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_base + blk * BLOCK_N, umma_desc_sw128(a_start + k * 2048, a_lbo, 1024),
-                      umma_desc_sw128(dy_addr + k * 2048, 8192, 1024), idesc, (i | k) != 0 ? 1u : 0u);
+          for (int blk = 0; blk < 5; ++blk) {
+            const int t0 = 2 * blk;
+            const uint32_t a_lo = umma_desc_lo(x_addr + (t0 / 3) * kXBox + (t0 % 3) * 1024,
+                                               blk == 1 ? (kXBox - 2048) : 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lohi(tmem_base + blk * BLOCK_N, a_lo + 128 * k, hi, b_lo + 128 * k, hi, idesc,
+                             k == 0 ? accflag : 1u);
+          }
+        } else {
+          // blk == vertical tap; the two 64-channel boxes are kXBox apart
+#pragma unroll
+          for (int blk = 0; blk < 3; ++blk) {
+            const uint32_t a_lo = umma_desc_lo(x_addr + blk * 1024, kXBox);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lohi(tmem_base + blk * BLOCK_N, a_lo + 128 * k, hi, b_lo + 128 * k, hi, idesc,
+                             k == 0 ? accflag : 1u);
           }
         }
         umma_commit(empty_bar(stage));
