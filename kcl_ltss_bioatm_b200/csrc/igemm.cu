@@ -373,6 +373,26 @@ static int launch_fwd_inst(const TmapPack4& amaps, const CUtensorMap& bmap, cons
 // 3 x 18 KB per 64 input channels.  When the whole weight slice [BLOCK_N][9*Cin] fits in shared memory
 // it is loaded once per CTA and stays resident; otherwise weight tiles flow through their own ring.
 // =================================================================================================
+// Division by a runtime constant without the ~20-instruction integer divide (tile decoding runs in
+// every epilogue thread once per tile).  Granlund-Montgomery round-up method, exact for all 32-bit n.
+struct FastDiv {
+  uint32_t mul, sh1, sh2, d;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l > 1 ? l - 1 : 0;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.mul, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 struct Conv3Params {
   int tiles_w, tiles_h;           // per image; tile = 8 x 16 pixels
   int W, H, N;
@@ -380,6 +400,7 @@ struct Conv3Params {
   int kb;                         // Cin / 64
   int cin;
   int a_slots, b_slots;           // ring depths (b_slots == 0: weights resident)
+  FastDiv div_ntiles, div_tiles_img, div_tiles_w;
   const float* scale;
   const float* shift;
   int relu;
@@ -389,9 +410,33 @@ struct Conv3Params {
 
 constexpr int kHaloBytes = 18 * 1024;  // 8 w x 18 h pixels x 64 channels bf16
 constexpr int kMaxSlots = 8;
+constexpr int kConv3Threads = 384;     // 4 control warps + two epilogue warpgroups
 
-template <int BLOCK_N, int STAGING>
-__global__ void __launch_bounds__(256, 1)
+// One 32-column half of a 64-channel chunk: scale/shift (+ReLU) -> bf16 -> swizzled staging row.
+template <bool RELU, bool MASK>
+__device__ __forceinline__ void epi_half(const uint32_t (&v)[32], int jbase, const float* sc,
+                                         const float* sh, bool valid, uint8_t* stg, int row) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = fmaf(__uint_as_float(v[j * 8 + e]), sc[j * 8 + e], sh[j * 8 + e]);
+      if (RELU) t = fmaxf(t, 0.0f);
+      y[e] = t;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(y[0], y[1]);
+    o.y = pack_bf16x2(y[2], y[3]);
+    o.z = pack_bf16x2(y[4], y[5]);
+    o.w = pack_bf16x2(y[6], y[7]);
+    if (MASK && !valid) o = make_uint4(0u, 0u, 0u, 0u);  // rows outside the image must not reach the stats
+    *reinterpret_cast<uint4*>(stg + row * 128 + (((jbase + j) ^ (row & 7)) << 4)) = o;
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kConv3Threads, 1)
     igemm_conv3_kernel(const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap bmap,
                        const __grid_constant__ CUtensorMap omap, const Conv3Params p) {
@@ -409,9 +454,9 @@ __global__ void __launch_bounds__(256, 1)
   const int b_tiles = resident ? 9 * p.kb : p.b_slots;
   const uint32_t off_a = 0;
   const uint32_t off_b = off_a + p.a_slots * kHaloBytes;
-  const uint32_t off_stg = off_b + b_tiles * B_BYTES;
-  const uint32_t off_param = off_stg + STAGING * STG_BYTES;
-  const uint32_t off_bar = off_param + 4 * BLOCK_N * 4;
+  const uint32_t off_stg = off_b + b_tiles * B_BYTES;       // one staging buffer per epilogue warpgroup
+  const uint32_t off_param = off_stg + 2 * STG_BYTES;       // per warpgroup: scale|shift|sum|sq
+  const uint32_t off_bar = off_param + 2 * 4 * BLOCK_N * 4;
   const uint32_t bar0 = sbase + off_bar;
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };
@@ -452,8 +497,18 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int tiles_img = p.tiles_w * p.tiles_h;
-  const int m_tiles = tiles_img * p.N;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = tiles_img * p.N * p.n_tiles;
+
+  // tile -> (n tile, image, w0, h0) without integer divides
+  auto decode = [&](int tile, int& n_tile, int& img, int& w0, int& h0) {
+    const uint32_t m_tile = fdiv(tile, p.div_ntiles);
+    n_tile = tile - m_tile * p.n_tiles;
+    img = fdiv(m_tile, p.div_tiles_img);
+    const uint32_t rem = m_tile - img * tiles_img;
+    const uint32_t ty = fdiv(rem, p.div_tiles_w);
+    w0 = (rem - ty * p.tiles_w) * 8;
+    h0 = ty * 16;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
@@ -468,12 +523,8 @@ __global__ void __launch_bounds__(256, 1)
       }
       int sa = 0, pa = 0, sb = 0, pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int img = m_tile / tiles_img;
-        const int rem = m_tile % tiles_img;
-        const int w0 = (rem % p.tiles_w) * 8;
-        const int h0 = (rem / p.tiles_w) * 16;
+        int n_tile, img, w0, h0;
+        decode(tile, n_tile, img, w0, h0);
         for (int kb = 0; kb < p.kb; ++kb) {
           for (int dwi = 0; dwi < 3; ++dwi) {
             mbar_wait(a_empty(sa), pa ^ 1, 1, &g_dbg_word);
@@ -498,6 +549,7 @@ __global__ void __launch_bounds__(256, 1)
     // ------------------------------------------------------------------ MMA issuer (one lane)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       if (resident) {
         mbar_wait(bres_full, 0, 9, &g_dbg_word);
         tc_fence_after();
@@ -514,7 +566,6 @@ __global__ void __launch_bounds__(256, 1)
           for (int dwi = 0; dwi < 3; ++dwi) {
             mbar_wait(a_full(sa), pa, 3, &g_dbg_word);
             tc_fence_after();
-            constexpr uint32_t hi = umma_desc_hi_sw128(1024);
             const uint32_t a_lo = umma_desc_lo(sbase + off_a + sa * kHaloBytes, 16);
             // resident weights: tile (tap, kb) at ((dh*3+dw)*KB + kb) * B_BYTES
             uint32_t b_lo = umma_desc_lo(sbase + off_b + (dwi * p.kb + kb) * B_BYTES, 16);
@@ -547,63 +598,89 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int q = warp - 4;
+    // ------------------------------------------------------------------ epilogue: two warpgroups,
+    // warpgroup g drains accumulator g (tiles it = g, g+2, ...), so each has two tile times per tile.
+    // A lone warp per scheduler runs ~4 cycles per dependent instruction; ~1000 instructions per tile
+    // made a single warpgroup the bottleneck of the 64-/128-channel layers.
+    const int g = (warp - 4) >> 2;
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;
-    float* s_scale = reinterpret_cast<float*>(gbase + off_param);
+    const int et = threadIdx.x - 128 - g * 128;
+    const uint32_t bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
+    float* s_scale = reinterpret_cast<float*>(gbase + off_param) + g * 4 * BLOCK_N;
     float* s_shift = s_scale + BLOCK_N;
     float* s_sum = s_shift + BLOCK_N;
     float* s_sq = s_sum + BLOCK_N;
+    uint8_t* stg = gbase + off_stg + g * STG_BYTES;
+    const uint32_t stg_s = sbase + off_stg + g * STG_BYTES;
     const bool do_stats = p.stat_sum != nullptr;
-    int it = 0, chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
-      const int img = m_tile / tiles_img;
-      const int rem = m_tile % tiles_img;
-      const int w0 = (rem % p.tiles_w) * 8;
-      const int h0 = (rem / p.tiles_w) * 16;
-      const int acc = it & 1;
+    const bool relu = p.relu != 0;
+    int last_n_tile = -1;
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+      int n_tile, img, w0, h0;
+      decode(tile, n_tile, img, w0, h0);
       const int acc_phase = (it >> 1) & 1;
       const int ch0 = n_tile * BLOCK_N;
-      for (int c = et; c < BLOCK_N; c += 128) {
-        s_scale[c] = p.scale ? p.scale[ch0 + c] : 1.0f;
-        s_shift[c] = p.shift ? p.shift[ch0 + c] : 0.0f;
-        s_sum[c] = 0.0f;
-        s_sq[c] = 0.0f;
+      if (n_tile != last_n_tile) {  // per-channel parameters change only with the N tile
+        for (int c = et; c < BLOCK_N; c += 128) {
+          s_scale[c] = p.scale ? p.scale[ch0 + c] : 1.0f;
+          s_shift[c] = p.shift ? p.shift[ch0 + c] : 0.0f;
+        }
+        last_n_tile = n_tile;
       }
+      if (do_stats)
+        for (int c = et; c < BLOCK_N; c += 128) {
+          s_sum[c] = 0.0f;
+          s_sq[c] = 0.0f;
+        }
+      const bool full_tile = (w0 + 8 <= p.W) && (h0 + 16 <= p.H);
       const bool valid = (w0 + (row & 7) < p.W) && (h0 + (row >> 3) < p.H);
-      mbar_wait(tfull_bar(acc), acc_phase, 4, &g_dbg_word);
+      mbar_wait(tfull_bar(g), acc_phase, 4, &g_dbg_word);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_ctr) {
+      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
         uint32_t v0[32], v1[32];
         {
           const uint32_t taddr =
-              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + chunk * 64;
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BLOCK_N + chunk * 64;
           tmem_ld_32x32b_x32(taddr, v0);
           tmem_ld_32x32b_x32(taddr + 32, v1);
           tmem_ld_wait();
         }
         if (chunk == BLOCK_N / 64 - 1) {
           tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
+          mbar_arrive(tempty_bar(g));
         }
-        const int sbuf = (STAGING == 2) ? (chunk_ctr & 1) : 0;
-        if (et == 0) tma_store_wait_read<STAGING - 1>();
-        named_bar_sync(1, 128);
-        uint8_t* stg = gbase + off_stg + sbuf * STG_BYTES;
-        epi_store_half(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg, row);
-        epi_store_half(v1, 4, s_scale + chunk * 64 + 32, s_shift + chunk * 64 + 32, p.relu, valid,
-                       stg, row);
+        if (et == 0) tma_store_wait_read<0>();  // the previous store has finished reading the buffer
+        named_bar_sync(bar_a, 128);
+        const float* sc = s_scale + chunk * 64;
+        const float* sh = s_shift + chunk * 64;
+        if (full_tile) {
+          if (relu) {
+            epi_half<true, false>(v0, 0, sc, sh, true, stg, row);
+            epi_half<true, false>(v1, 4, sc + 32, sh + 32, true, stg, row);
+          } else {
+            epi_half<false, false>(v0, 0, sc, sh, true, stg, row);
+            epi_half<false, false>(v1, 4, sc + 32, sh + 32, true, stg, row);
+          }
+        } else {
+          if (relu) {
+            epi_half<true, true>(v0, 0, sc, sh, valid, stg, row);
+            epi_half<true, true>(v1, 4, sc + 32, sh + 32, valid, stg, row);
+          } else {
+            epi_half<false, true>(v0, 0, sc, sh, valid, stg, row);
+            epi_half<false, true>(v1, 4, sc + 32, sh + 32, valid, stg, row);
+          }
+        }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(bar_b, 128);
         if (et == 0) {
-          tma_store_4d(&omap, sbase + off_stg + sbuf * STG_BYTES, ch0 + chunk * 64, w0, h0, img);
+          tma_store_4d(&omap, stg_s, ch0 + chunk * 64, w0, h0, img);
           tma_store_commit();
         }
         if (do_stats) {
+          // column sums of the rounded outputs: lane <-> channel pair, warp <-> 32-row group
           const int j = lane >> 2, wsub = lane & 3;
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
@@ -624,7 +701,7 @@ __global__ void __launch_bounds__(256, 1)
         }
       }
       if (do_stats) {
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_a, 128);
         for (int c = et; c < BLOCK_N; c += 128) {
           atomicAdd(p.stat_sum + ch0 + c, s_sum[c]);
           atomicAdd(p.stat_sq + ch0 + c, s_sq[c]);
@@ -639,15 +716,15 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
-static size_t conv3_smem_bytes(int block_n, int staging, int a_slots, int b_tiles) {
+static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles) {
   return static_cast<size_t>(a_slots) * kHaloBytes + static_cast<size_t>(b_tiles) * block_n * 128 +
-         static_cast<size_t>(staging) * 16384 + 4 * block_n * 4 + 8 * (4 * kMaxSlots + 5) + 16 + 1024;
+         2 * 16384 + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 5) + 16 + 1024;
 }
 
-template <int BLOCK_N, int STAGING>
+template <int BLOCK_N>
 static int launch_conv3_inst(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
                              const Conv3Params& p, size_t smem, int total_tiles, cudaStream_t stream) {
-  auto kern = igemm_conv3_kernel<BLOCK_N, STAGING>;
+  auto kern = igemm_conv3_kernel<BLOCK_N>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -658,7 +735,7 @@ static int launch_conv3_inst(const CUtensorMap& amap, const CUtensorMap& bmap, c
     return -2;
   }
   const int grid = std::min(total_tiles, num_sms());
-  kern<<<grid, 256, smem, stream>>>(amap, bmap, omap, p);
+  kern<<<grid, kConv3Threads, smem, stream>>>(amap, bmap, omap, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error(std::string("igemm_conv3 launch: ") + cudaGetErrorString(e));
@@ -679,7 +756,6 @@ static int try_launch_conv3(const FwdDesc& d) {
   const int block_n = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
   const int n_tiles = cout / block_n;
   const int kb = d.Cin / 64;
-  const int staging_hi = block_n == 256 ? 1 : 2;
   const size_t limit = 232448;
 
   Conv3Params p;
@@ -689,30 +765,24 @@ static int try_launch_conv3(const FwdDesc& d) {
   p.n_tiles = n_tiles;
   p.kb = kb;
   p.cin = d.Cin;
+  p.div_ntiles = make_fastdiv(n_tiles);
+  p.div_tiles_img = make_fastdiv(p.tiles_w * p.tiles_h);
+  p.div_tiles_w = make_fastdiv(p.tiles_w);
   p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
   p.stat_sum = d.stat_sum; p.stat_sq = d.stat_sq;
 
-  // resident weights when the whole [block_n][9*Cin] slice fits beside >= 3 halo slots
-  int staging = staging_hi;
-  bool resident = false;
-  if (n_tiles == 1) {
-    for (int st = staging_hi; st >= 1 && !resident; --st) {
-      if (conv3_smem_bytes(block_n, st, 3, 9 * kb) <= limit) {
-        resident = true;
-        staging = st;
-      }
-    }
-  }
+  // weights stay resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (each slot is
+  // 12 MMAs of work; fewer slots cannot cover the TMA latency)
+  const bool resident = n_tiles == 1 && conv3_smem_bytes(block_n, 4, 9 * kb) <= limit;
   if (resident) {
     p.b_slots = 0;
-    p.a_slots = 3;
-    while (p.a_slots < 6 && conv3_smem_bytes(block_n, staging, p.a_slots + 1, 9 * kb) <= limit)
-      ++p.a_slots;
+    p.a_slots = 4;
+    while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, 9 * kb) <= limit) ++p.a_slots;
   } else {
     p.a_slots = block_n == 256 ? 3 : 4;
     p.b_slots = block_n == 256 ? 4 : (block_n == 128 ? 6 : 8);
   }
-  const size_t smem = conv3_smem_bytes(block_n, staging, p.a_slots, resident ? 9 * kb : p.b_slots);
+  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, resident ? 9 * kb : p.b_slots);
   if (smem > limit) return 1;
 
   CUtensorMap amap, bmap, omap;
@@ -729,14 +799,9 @@ static int try_launch_conv3(const FwdDesc& d) {
     return -1;
   }
   switch (block_n) {
-    case 256:
-      return launch_conv3_inst<256, 1>(amap, bmap, omap, p, smem, (int)total, d.stream);
-    case 128:
-      return staging == 2 ? launch_conv3_inst<128, 2>(amap, bmap, omap, p, smem, (int)total, d.stream)
-                          : launch_conv3_inst<128, 1>(amap, bmap, omap, p, smem, (int)total, d.stream);
-    default:
-      return staging == 2 ? launch_conv3_inst<64, 2>(amap, bmap, omap, p, smem, (int)total, d.stream)
-                          : launch_conv3_inst<64, 1>(amap, bmap, omap, p, smem, (int)total, d.stream);
+    case 256: return launch_conv3_inst<256>(amap, bmap, omap, p, smem, (int)total, d.stream);
+    case 128: return launch_conv3_inst<128>(amap, bmap, omap, p, smem, (int)total, d.stream);
+    default:  return launch_conv3_inst<64>(amap, bmap, omap, p, smem, (int)total, d.stream);
   }
 }
 
