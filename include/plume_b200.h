@@ -33,6 +33,9 @@ const char* plume_last_error(void);
 /* Diagnostic word written by a kernel whose bounded barrier wait expired (0 = none). */
 int plume_debug_word(void);
 int plume_num_sms(void);
+/* Diagnostics: device buffer [num_sms][8] of int64 that the conv3x3 kernel fills with per-CTA cycle
+ * counters of its producer / MMA / epilogue roles (NULL = off, the default). */
+void plume_debug_set_prof(long long* buf);
 
 /* ---- tensor-core implicit GEMM (tcgen05 / TMEM / TMA) -------------------------------------- */
 

@@ -52,6 +52,7 @@ extern "C" {
 const char* plume_version(void) { return "plume_b200 0.1 (sm_100a; tcgen05+TMA implicit GEMM)"; }
 const char* plume_last_error(void) { return g_last_error.c_str(); }
 int plume_debug_word(void) { return read_debug_word(); }
+void plume_debug_set_prof(long long* buf) { set_prof_buffer(buf); }
 int plume_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -24,6 +24,9 @@ namespace plume {
 
 __device__ int g_dbg_word = 0;
 
+static long long* g_prof_buf = nullptr;
+void set_prof_buffer(long long* buf) { g_prof_buf = buf; }
+
 int read_debug_word() {
   int v = 0;
   cudaMemcpyFromSymbol(&v, g_dbg_word, sizeof(int));
@@ -406,11 +409,13 @@ struct Conv3Params {
   int relu;
   float* stat_sum;
   float* stat_sq;
+  long long* prof;                // optional [grid][8] cycle counters (plume_debug_set_prof)
+  int dbg_mode;                   // diagnostics (PLUME_CONV3_DBG): 1 = skip epilogue work, 2 = no TMA loads
 };
 
 constexpr int kHaloBytes = 18 * 1024;  // 8 w x 18 h pixels x 64 channels bf16
 constexpr int kMaxSlots = 8;
-constexpr int kConv3Threads = 384;     // 4 control warps + two epilogue warpgroups
+constexpr int kConv3Threads = 416;     // 8 epilogue warps + 5 single-thread role warps
 
 // One 32-column half of a 64-channel chunk: scale/shift (+ReLU) -> bf16 -> swizzled staging row.
 template <bool RELU, bool MASK>
@@ -435,13 +440,41 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], int jbase, con
   }
 }
 
-template <int BLOCK_N>
+// Spin on a shared-memory counter published by a relay thread (see the kernel comment).
+__device__ __forceinline__ void wait_counter(const volatile uint32_t* ctr, uint32_t need, int tag) {
+  if (*ctr >= need) return;
+  long long t0 = clock64();
+  while (*ctr < need) {
+    if (clock64() - t0 > PLUME_WATCHDOG_CYCLES) {
+      atomicExch(&g_dbg_word, 0x7100 | tag);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// Warp roles (the warp arbiter prefers higher warp ids within a scheduler, so the single-thread roles sit
+// above the epilogue warps):
+//   0-7  epilogue, two warpgroups; warpgroup g drains TMEM accumulator g
+//   8    TMEM allocator, then relay for "accumulator drained" barriers
+//   9    TMA producer
+//   10   barrier init, then relay for "halo slot full" barriers
+//   11   MMA issuer
+//   12   relay for "weight tile full" barriers (ring mode)
+// Relays: an mbarrier probe costs the thread that executes it 100-300 cycles and the tensor pipe buffers
+// only about one MMA beyond the running one, so any barrier wait in the MMA thread drains the pipe
+// (scripts/bench_mma2.cu: 48 -> 73-130 cycles per N=64 MMA).  The relay threads do the mbarrier waits
+// and publish monotonically increasing counters in shared memory; the MMA thread only polls those
+// (one LDS, ~30 cycles) between MMA groups.  The counters order nothing by themselves: the data was
+// written by TMA before the mbarrier completed, which the relay observed before bumping the counter.
+template <int BLOCK_N, bool RESIDENT>
 __global__ void __launch_bounds__(kConv3Threads, 1)
     igemm_conv3_kernel(const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap bmap,
                        const __grid_constant__ CUtensorMap omap, const Conv3Params p) {
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STG_BYTES = 128 * 128;
+  constexpr int kWarpAlloc = 8, kWarpProducer = 9, kWarpInit = 10, kWarpMma = 11, kWarpRelayB = 12;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
@@ -450,8 +483,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
-  const bool resident = p.b_slots == 0;
-  const int b_tiles = resident ? 9 * p.kb : p.b_slots;
+  const int b_tiles = RESIDENT ? 9 * p.kb : p.b_slots;
   const uint32_t off_a = 0;
   const uint32_t off_b = off_a + p.a_slots * kHaloBytes;
   const uint32_t off_stg = off_b + b_tiles * B_BYTES;       // one staging buffer per epilogue warpgroup
@@ -467,13 +499,15 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   const uint32_t bres_full = bar0 + 8u * (4 * kMaxSlots + 4);
   volatile uint32_t* tmem_ptr_smem =
       reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 5));
+  // relay counters: [0] halo slots ready, [1] weight tiles ready, [2] accumulators drained
+  volatile uint32_t* ctr = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 6));
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&amap);
     tma_prefetch_desc(&bmap);
     tma_prefetch_desc(&omap);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpInit && lane == 0) {
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(a_full(s), 1);
       mbar_init(a_empty(s), 1);
@@ -485,9 +519,12 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       mbar_init(tempty_bar(a), 128);
     }
     mbar_init(bres_full, 1);
+    ctr[0] = 0;
+    ctr[1] = 0;
+    ctr[2] = 2;  // both accumulators start drained
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     tmem_alloc(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * BLOCK_N);
     tmem_relinquish();
   }
@@ -498,6 +535,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
 
   const int tiles_img = p.tiles_w * p.tiles_h;
   const int total_tiles = tiles_img * p.N * p.n_tiles;
+  const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int slots_per_tile = 3 * p.kb;  // halo slots (and, in ring mode, weight triples) per tile
 
   // tile -> (n tile, image, w0, h0) without integer divides
   auto decode = [&](int tile, int& n_tile, int& img, int& w0, int& h0) {
@@ -510,10 +550,10 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     h0 = ty * 16;
   };
 
-  if (warp == 0) {
+  if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
-      if (resident) {
+      if (RESIDENT) {
         // n_tiles == 1 in this mode: the CTA's weight slice never changes
         mbar_expect_tx(bres_full, static_cast<uint32_t>(b_tiles) * B_BYTES);
         for (int t = 0; t < 9; ++t)
@@ -522,19 +562,22 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
                         t * p.cin + kb * 64, 0);
       }
       int sa = 0, pa = 0, sb = 0, pb = 0;
+      long long t_wait = 0, t_begin = clock64();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_tile, img, w0, h0;
         decode(tile, n_tile, img, w0, h0);
         for (int kb = 0; kb < p.kb; ++kb) {
           for (int dwi = 0; dwi < 3; ++dwi) {
-            mbar_wait(a_empty(sa), pa ^ 1, 1, &g_dbg_word);
+            const long long tw0 = p.prof ? clock64() : 0;
+            mbar_wait_relaxed(a_empty(sa), pa ^ 1, 1, &g_dbg_word);
+            if (p.prof) t_wait += clock64() - tw0;
             mbar_expect_tx(a_full(sa), kHaloBytes);
             tma_load_4d(sbase + off_a + sa * kHaloBytes, &amap, a_full(sa), kb * 64, w0 + dwi - 1,
                         h0 - 1, img);
             if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
-            if (!resident) {
+            if (!RESIDENT) {
               for (int dhi = 0; dhi < 3; ++dhi) {
-                mbar_wait(b_empty(sb), pb ^ 1, 8, &g_dbg_word);
+                mbar_wait_relaxed(b_empty(sb), pb ^ 1, 8, &g_dbg_word);
                 mbar_expect_tx(b_full(sb), B_BYTES);
                 tma_load_2d(sbase + off_b + sb * B_BYTES, &bmap, b_full(sb),
                             (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N);
@@ -544,38 +587,78 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
           }
         }
       }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin;  // producer: total
+        p.prof[blockIdx.x * 8 + 1] = t_wait;               // producer: waiting for a free halo slot
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpInit) {
+    // ------------------------------------------------------------------ relay: halo slots full
+    if (lane == 0) {
+      int sa = 0, pa = 0;
+      const uint32_t n = static_cast<uint32_t>(my_tiles) * slots_per_tile;
+      for (uint32_t i = 0; i < n; ++i) {
+        mbar_wait(a_full(sa), pa, 11, &g_dbg_word);
+        ctr[0] = i + 1;
+        if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == kWarpRelayB) {
+    // ------------------------------------------------------------------ relay: weight tiles full
+    if (lane == 0) {
+      if (RESIDENT) {
+        mbar_wait(bres_full, 0, 9, &g_dbg_word);
+        ctr[1] = 1;
+      } else {
+        int sb = 0, pb = 0;
+        const uint32_t n = static_cast<uint32_t>(my_tiles) * slots_per_tile * 3;
+        for (uint32_t i = 0; i < n; ++i) {
+          mbar_wait(b_full(sb), pb, 12, &g_dbg_word);
+          ctr[1] = i + 1;
+          if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kWarpAlloc) {
+    // ------------------------------------------------------------------ relay: accumulators drained
+    if (lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        // tile `it` may start once the epilogue drained the previous user of accumulator it & 1
+        mbar_wait(tempty_bar(it & 1), ((it >> 1) & 1) ^ 1, 13, &g_dbg_word);
+        if (it >= 2) ctr[2] = it + 1;
+      }
+    }
+  } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (one lane)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
-      if (resident) {
-        mbar_wait(bres_full, 0, 9, &g_dbg_word);
+      const long long t_begin = clock64();
+      const uint32_t a_lo_base = umma_desc_lo(sbase + off_a, 16);
+      const uint32_t b_lo_base = umma_desc_lo(sbase + off_b, 16);
+      constexpr uint32_t kHaloUnits = kHaloBytes >> 4, kBUnits = B_BYTES >> 4;
+      const uint32_t b_tap_step = 3 * p.kb * kBUnits;  // resident: next vertical tap
+      if (RESIDENT) wait_counter(ctr + 1, 1, 1);
+      uint32_t a_cnt = 0, b_cnt = 0;
+      int sa = 0, sb = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        wait_counter(ctr + 2, it + 1, 2);
         tc_fence_after();
-      }
-      int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const int acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2, &g_dbg_word);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
         uint32_t accumulate = 0;
         for (int kb = 0; kb < p.kb; ++kb) {
+#pragma unroll 1
           for (int dwi = 0; dwi < 3; ++dwi) {
-            mbar_wait(a_full(sa), pa, 3, &g_dbg_word);
-            tc_fence_after();
-            const uint32_t a_lo = umma_desc_lo(sbase + off_a + sa * kHaloBytes, 16);
-            // resident weights: tile (tap, kb) at ((dh*3+dw)*KB + kb) * B_BYTES
-            uint32_t b_lo = umma_desc_lo(sbase + off_b + (dwi * p.kb + kb) * B_BYTES, 16);
-            const uint32_t b_step = 3 * p.kb * (B_BYTES >> 4);
+            wait_counter(ctr + 0, ++a_cnt, 3);
+            if (RESIDENT) tc_fence_after();
+            const uint32_t a_lo = a_lo_base + sa * kHaloUnits;
+            uint32_t b_lo = b_lo_base + (dwi * p.kb + kb) * kBUnits;
 #pragma unroll
             for (int dhi = 0; dhi < 3; ++dhi) {
-              if (!resident) {
-                mbar_wait(b_full(sb), pb, 10, &g_dbg_word);
+              if (!RESIDENT) {
+                wait_counter(ctr + 1, ++b_cnt, 4);
                 tc_fence_after();
-                b_lo = umma_desc_lo(sbase + off_b + sb * B_BYTES, 16);
+                b_lo = b_lo_base + sb * kBUnits;
               }
               // vertical tap = one 1024-byte atom (64 descriptor units) further into the halo
 #pragma unroll
@@ -583,29 +666,28 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
                 umma_bf16_lohi(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
                 accumulate = 1;
               }
-              if (!resident) {
+              if (!RESIDENT) {
                 umma_commit(b_empty(sb));
-                if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+                if (++sb == p.b_slots) sb = 0;
               } else {
-                b_lo += b_step;
+                b_lo += b_tap_step;
               }
             }
             umma_commit(a_empty(sa));
-            if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+            if (++sa == p.a_slots) sa = 0;
           }
         }
-        umma_commit(tfull_bar(acc));
+        umma_commit(tfull_bar(it & 1));
       }
+      if (p.prof) p.prof[blockIdx.x * 8 + 2] = clock64() - t_begin;  // MMA issuer: total
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue: two warpgroups,
     // warpgroup g drains accumulator g (tiles it = g, g+2, ...), so each has two tile times per tile.
-    // A lone warp per scheduler runs ~4 cycles per dependent instruction; ~1000 instructions per tile
-    // made a single warpgroup the bottleneck of the 64-/128-channel layers.
-    const int g = (warp - 4) >> 2;
+    const int g = warp >> 2;
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128 - g * 128;
+    const int et = threadIdx.x - g * 128;
     const uint32_t bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
     float* s_scale = reinterpret_cast<float*>(gbase + off_param) + g * 4 * BLOCK_N;
     float* s_shift = s_scale + BLOCK_N;
@@ -617,6 +699,8 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     const bool relu = p.relu != 0;
     int last_n_tile = -1;
     int it = g;
+    long long t_epi_wait = 0;
+    const long long t_epi_begin = clock64();
     for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
       int n_tile, img, w0, h0;
       decode(tile, n_tile, img, w0, h0);
@@ -636,7 +720,11 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
         }
       const bool full_tile = (w0 + 8 <= p.W) && (h0 + 16 <= p.H);
       const bool valid = (w0 + (row & 7) < p.W) && (h0 + (row >> 3) < p.H);
-      mbar_wait(tfull_bar(g), acc_phase, 4, &g_dbg_word);
+      {
+        const long long tw0 = p.prof ? clock64() : 0;
+        mbar_wait_relaxed(tfull_bar(g), acc_phase, 4, &g_dbg_word);
+        if (p.prof && et == 0) t_epi_wait += clock64() - tw0;
+      }
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
@@ -709,22 +797,26 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       }
     }
     if (et == 0) tma_store_wait_all<0>();
+    if (p.prof && et == 0 && g == 0) {
+      p.prof[blockIdx.x * 8 + 6] = clock64() - t_epi_begin;  // epilogue warpgroup 0: total
+      p.prof[blockIdx.x * 8 + 7] = t_epi_wait;               // waiting for a finished accumulator
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
 static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles) {
   return static_cast<size_t>(a_slots) * kHaloBytes + static_cast<size_t>(b_tiles) * block_n * 128 +
-         2 * 16384 + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 5) + 16 + 1024;
+         2 * 16384 + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RESIDENT>
 static int launch_conv3_inst(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
                              const Conv3Params& p, size_t smem, int total_tiles, cudaStream_t stream) {
-  auto kern = igemm_conv3_kernel<BLOCK_N>;
+  auto kern = igemm_conv3_kernel<BLOCK_N, RESIDENT>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -770,6 +862,11 @@ static int try_launch_conv3(const FwdDesc& d) {
   p.div_tiles_w = make_fastdiv(p.tiles_w);
   p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
   p.stat_sum = d.stat_sum; p.stat_sq = d.stat_sq;
+  p.prof = g_prof_buf;
+  {
+    static const int dbg = getenv("PLUME_CONV3_DBG") ? atoi(getenv("PLUME_CONV3_DBG")) : 0;
+    p.dbg_mode = dbg;
+  }
 
   // weights stay resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (each slot is
   // 12 MMAs of work; fewer slots cannot cover the TMA latency)
@@ -798,10 +895,15 @@ static int try_launch_conv3(const FwdDesc& d) {
     set_error("igemm_conv3: too many tiles");
     return -1;
   }
+  const int tt = static_cast<int>(total);
+  if (resident) {
+    if (block_n == 128) return launch_conv3_inst<128, true>(amap, bmap, omap, p, smem, tt, d.stream);
+    return launch_conv3_inst<64, true>(amap, bmap, omap, p, smem, tt, d.stream);
+  }
   switch (block_n) {
-    case 256: return launch_conv3_inst<256>(amap, bmap, omap, p, smem, (int)total, d.stream);
-    case 128: return launch_conv3_inst<128>(amap, bmap, omap, p, smem, (int)total, d.stream);
-    default:  return launch_conv3_inst<64>(amap, bmap, omap, p, smem, (int)total, d.stream);
+    case 256: return launch_conv3_inst<256, false>(amap, bmap, omap, p, smem, tt, d.stream);
+    case 128: return launch_conv3_inst<128, false>(amap, bmap, omap, p, smem, tt, d.stream);
+    default:  return launch_conv3_inst<64, false>(amap, bmap, omap, p, smem, tt, d.stream);
   }
 }
 

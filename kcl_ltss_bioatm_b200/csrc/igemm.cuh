@@ -46,6 +46,8 @@ struct WgradDesc {
 int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout);
 int launch_igemm_wgrad(const WgradDesc& d);
 
-int read_debug_word();  // last watchdog tag written by a trapped kernel (0 if none)
+int read_debug_word();
+// Diagnostics: when set, conv3 launches write per-CTA cycle counters ([grid][8] int64) there.
+void set_prof_buffer(long long* buf);  // last watchdog tag written by a trapped kernel (0 if none)
 
 }  // namespace plume

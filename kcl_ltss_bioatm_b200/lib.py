@@ -22,6 +22,7 @@ SIGNATURES = {
     "plume_last_error": (c_char_p, []),
     "plume_debug_word": (_I, []),
     "plume_num_sms": (_I, []),
+    "plume_debug_set_prof": (None, [_P]),
     "plume_conv3x3_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "plume_conv3x3_dgrad": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "plume_wgrad_splits": (_I, [_I, _I, _I, _I, _I, _I]),
