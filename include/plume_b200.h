@@ -50,12 +50,16 @@ int plume_conv3x3_fwd(const void* x, int ldx, const void* w_krsc_bf16, const flo
 int plume_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad_bf16, void* dx, int lddx, int N,
                         int H, int W, int Cin, int Cout, plume_stream_t stream);
 
-/* Split count and fp32 workspace bytes for a weight-gradient problem (taps = 9 or 4). */
+/* K-split count the weight-gradient kernel will use (taps = 9 or 4) -- informational.  The partial
+ * sums of the splits are added into dw with fp32 atomic reductions, so no workspace is needed:
+ * plume_wgrad_workspace_bytes() returns 0 and the workspace arguments below may be NULL / 0 (they are
+ * kept so that a deterministic two-pass reduction can return without an ABI change). */
 int plume_wgrad_splits(int N, int H, int W, int taps, int Cin, int Cout);
 size_t plume_wgrad_workspace_bytes(int N, int H, int W, int taps, int Cin, int Cout);
 
 /* dw[co][r][s][ci] (fp32) = sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  Cin is 64 or a multiple
- * of 128, Cout a multiple of 64.  `accumulate` != 0 adds into dw. */
+ * of 128, Cout a multiple of 64.  `accumulate` != 0 adds into dw; 0 zeroes dw first (on the stream).
+ * The summation order over pixels is not fixed (atomics): results are reproducible to fp32 rounding. */
 int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_krsc,
                         int accumulate, void* workspace, size_t workspace_bytes, int N, int H, int W,
                         int Cin, int Cout, plume_stream_t stream);

@@ -103,29 +103,31 @@ int plume_wgrad_splits(int N, int H, int W, int taps, int Cin, int Cout) {
   return wgrad_plan(N, H, W, taps, Cin, Cout);
 }
 size_t plume_wgrad_workspace_bytes(int N, int H, int W, int taps, int Cin, int Cout) {
-  const int splits = plume_wgrad_splits(N, H, W, taps, Cin, Cout);
-  return static_cast<size_t>(splits) * taps * Cin * Cout * sizeof(float);
+  (void)N; (void)H; (void)W; (void)taps; (void)Cin; (void)Cout;
+  return 0;  // split-K partial sums are reduced with fp32 atomics; no workspace is needed any more
 }
 
 int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw, int accumulate,
                         void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
                         plume_stream_t stream) {
-  PLUME_CHECK(x && dy && dw && workspace, "conv3x3_wgrad: null pointer");
+  (void)workspace; (void)workspace_bytes;
+  PLUME_CHECK(x && dy && dw, "conv3x3_wgrad: null pointer");
   PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(lddy, Cout), "conv3x3_wgrad: bad pixel stride");
-  PLUME_CHECK(workspace_bytes >= plume_wgrad_workspace_bytes(N, H, W, 9, Cin, Cout),
-              "conv3x3_wgrad: workspace too small (plume_wgrad_workspace_bytes)");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 9ull * Cin * Cout, S(stream));
+    PLUME_CHECK(e == cudaSuccess, "conv3x3_wgrad: cudaMemsetAsync failed");
+  }
   WgradDesc d{};
   d.x = view(x, ldx, N, H, W, Cin);
   d.dy[0] = view(dy, lddy, N, H, W, Cout);
   d.num_dy_views = 1;
   d.num_taps = 9;
   d.Cin = Cin; d.Cout = Cout;
-  d.partial = static_cast<float*>(workspace);
-  d.splits = wgrad_plan(N, H, W, 9, Cin, Cout);
+  d.dw = dw;            // dw[co][t][ci]
+  d.s_co = 9ll * Cin;
+  d.s_t = Cin;
   d.stream = S(stream);
-  if (int r = launch_igemm_wgrad(d)) return r;
-  // dw[co][t][ci]
-  return wgrad_reduce(d.partial, d.splits, 9, Cin, Cout, 9ll * Cin, Cin, dw, accumulate, S(stream));
+  return launch_igemm_wgrad(d);
 }
 
 int plume_convT2x2_concat_fwd(const void* x, int ldx, const void* w, const float* bias, void* u, int ldu,
@@ -166,23 +168,24 @@ int plume_convT2x2_dgrad(const void* du, int lddu, const void* w_dgrad, void* dx
 int plume_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float* dw, int accumulate,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
                          plume_stream_t stream) {
-  PLUME_CHECK(x && du && dw && workspace, "convT2x2_wgrad: null pointer");
+  (void)workspace; (void)workspace_bytes;
+  PLUME_CHECK(x && du && dw, "convT2x2_wgrad: null pointer");
   PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(lddu, Cout), "convT2x2_wgrad: bad pixel stride");
-  PLUME_CHECK(workspace_bytes >= plume_wgrad_workspace_bytes(N, H, W, 4, Cin, Cout),
-              "convT2x2_wgrad: workspace too small (plume_wgrad_workspace_bytes)");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 4ull * Cin * Cout, S(stream));
+    PLUME_CHECK(e == cudaSuccess, "convT2x2_wgrad: cudaMemsetAsync failed");
+  }
   WgradDesc d{};
   d.x = view(x, ldx, N, H, W, Cin);
   for (int ij = 0; ij < 4; ++ij) d.dy[ij] = phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1);
   d.num_dy_views = 4;
   d.num_taps = 4;
   d.Cin = Cin; d.Cout = Cout;
-  d.partial = static_cast<float*>(workspace);
-  d.splits = wgrad_plan(N, H, W, 4, Cin, Cout);
+  d.dw = dw;            // dw[ij][co][ci]
+  d.s_co = Cin;
+  d.s_t = 1ll * Cout * Cin;
   d.stream = S(stream);
-  if (int r = launch_igemm_wgrad(d)) return r;
-  // dw[ij][co][ci]
-  return wgrad_reduce(d.partial, d.splits, 4, Cin, Cout, Cin, 1ll * Cout * Cin, dw, accumulate,
-                      S(stream));
+  return launch_igemm_wgrad(d);
 }
 
 int plume_pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, plume_stream_t stream) {

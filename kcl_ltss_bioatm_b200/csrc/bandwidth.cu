@@ -960,50 +960,6 @@ int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStr
 }
 
 // ------------------------------------------------------------------------------------------------
-// split-K reduction of the weight gradient: partial[split][t*Cin+ci][co] -> dw[co*s_co + t*s_t + ci]
-// ------------------------------------------------------------------------------------------------
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows, int Cout,
-                                    int Cin, long long s_co, long long s_t, float* __restrict__ dw,
-                                    int accumulate) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const long long split_stride = 1ll * rows * Cout;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int r = r0 + ty + 8 * k;
-    float acc = 0.f;
-    if (r < rows && c0 + tx < Cout) {
-      const float* src = partial + 1ll * r * Cout + c0 + tx;
-      for (int sp = 0; sp < splits; ++sp) acc += src[sp * split_stride];
-    }
-    tile[ty + 8 * k][tx] = acc;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int co = c0 + ty + 8 * k;
-    const int r = r0 + tx;
-    if (r < rows && co < Cout) {
-      const int t = r / Cin, ci = r % Cin;
-      const long long o = co * s_co + t * s_t + ci;
-      const float v = tile[tx][ty + 8 * k];
-      dw[o] = accumulate ? dw[o] + v : v;
-    }
-  }
-}
-
-int wgrad_reduce(const float* partial, int splits, int taps, int Cin, int Cout, long long s_co,
-                 long long s_t, float* dw, int accumulate, cudaStream_t s) {
-  const int rows = taps * Cin;
-  dim3 grid((Cout + 31) / 32, (rows + 31) / 32);
-  dim3 block(32, 8);
-  wgrad_reduce_kernel<<<grid, block, 0, s>>>(partial, splits, rows, Cout, Cin, s_co, s_t, dw,
-                                             accumulate);
-  return check_launch("wgrad_reduce");
-}
-
-// ------------------------------------------------------------------------------------------------
 // tiled inference: cut tiles out of a scene, stitch logits back by centre crop + threshold
 // ------------------------------------------------------------------------------------------------
 __global__ void extract_tiles_kernel(const __nv_bfloat16* __restrict__ scene, int Hs, int Ws, int cvs,

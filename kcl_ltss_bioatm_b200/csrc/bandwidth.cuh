@@ -46,8 +46,6 @@ int adam(float* param, const float* grad, float* m, float* v, long long n, doubl
          double beta2, double eps, int step, float grad_scale, cudaStream_t s);
 int pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
 int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
-int wgrad_reduce(const float* partial, int splits, int taps, int Cin, int Cout, long long s_co,
-                 long long s_t, float* dw, int accumulate, cudaStream_t s);
 int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs, int count,
                   int T, void* tiles, int Cd, cudaStream_t s);
 int stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T, int margin,

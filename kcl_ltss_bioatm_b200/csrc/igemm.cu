@@ -10,7 +10,8 @@
 //                        Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //  * igemm_wgrad_kernel: in-channels x out-channels GEMM per filter tap, K = pixels.  Both operands are
 //                        MN-major (channels are the contiguous dimension of NHWC), so the same TMA boxes
-//                        feed the MMA without a transpose.  Split-K over pixel tiles, fp32 partials.
+//                        feed the MMA without a transpose.  Split-K over pixel tiles; the partial sums are
+//                        added into dW with fp32 reductions (RED.ADD) from the epilogue.
 //
 // No reference counterpart: the reference repository has no model code.
 #include "igemm.cuh"
@@ -995,7 +996,8 @@ struct WgradParams {
   int ci_tiles;                   // cin / 128 when !pair_taps
   int m_units, n_tiles;
   int splits, ktiles_per_split;
-  float* partial;
+  float* dw;                      // fp32 weight gradient, element (tap t, ci, co) at co*s_co + t*s_t + ci
+  long long s_co, s_t;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -1129,10 +1131,12 @@ __global__ void __launch_bounds__(256, 1)
     const int row = q * 32 + lane;
     const int grow = row_base + row;
     const bool row_ok = grow < p.num_taps * p.cin && (!p.pair_taps || row < 64 || tapB != tapA);
-    mbar_wait(tfull_bar, 0, 7, &g_dbg_word);
+    mbar_wait_relaxed(tfull_bar, 0, 7, &g_dbg_word);
     tc_fence_after();
-    float* dst = p.partial +
-                 (static_cast<size_t>(split) * p.num_taps * p.cin + grow) * p.cout + n_tile * BLOCK_N;
+    // split-K partial sums are added straight into dW with fp32 reductions (RED.ADD): consecutive lanes are
+    // consecutive input channels = consecutive addresses, so every warp instruction is one 128-byte line
+    const int t = grow / p.cin, ci = grow - t * p.cin;
+    float* dst = p.dw + t * p.s_t + ci + static_cast<long long>(n_tile * BLOCK_N) * p.s_co;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t v[32];
@@ -1140,11 +1144,7 @@ __global__ void __launch_bounds__(256, 1)
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          *reinterpret_cast<float4*>(dst + c + 4 * j) = o;
-        }
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * p.s_co, __uint_as_float(v[j]));
       }
     }
   }
@@ -1224,16 +1224,20 @@ struct Wgrad3Params {
   int n_tiles;
   int splits, ktiles_per_split;
   int stages;
-  float* partial;                 // [splits][9*Cin][Cout]
+  float* dw;                      // fp32, element (tap t, ci, co) at co*s_co + t*s_t + ci
+  long long s_co, s_t;
 };
 
 constexpr int kXBox = 10 * 1024;  // 8 w x 10 h pixels x 64 channels
 
+// Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4 TMEM allocator, 5 TMA producer,
+// 6 barrier init then relay ("stage full" barriers -> shared-memory counter), 7 MMA issuer.
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
     igemm_wgrad3_kernel(const __grid_constant__ CUtensorMap xmap,
                         const __grid_constant__ CUtensorMap dymap, const Wgrad3Params p) {
   constexpr int DY_BYTES = (BLOCK_N / 64) * 8192;
+  constexpr int kWarpAlloc = 4, kWarpProducer = 5, kWarpRelay = 6, kWarpMma = 7;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
@@ -1250,22 +1254,24 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t tfull_bar = bar0 + 8u * (2 * kMaxSlots);
   volatile uint32_t* tmem_ptr_smem =
       reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (2 * kMaxSlots + 1));
+  volatile uint32_t* ctr = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (2 * kMaxSlots + 2));
   const int nblocks = p.mode9 ? 5 : 3;
   const uint32_t tmem_cols = (nblocks * BLOCK_N <= 256) ? 256u : 512u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&xmap);
     tma_prefetch_desc(&dymap);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpRelay && lane == 0) {
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
+    ctr[0] = 0;
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     tmem_alloc(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
     tmem_relinquish();
   }
@@ -1286,7 +1292,7 @@ __global__ void __launch_bounds__(256, 1)
   const int kt_end = min(kt_begin + p.ktiles_per_split, total_ktiles);
   const int nk = kt_end - kt_begin;
 
-  if (warp == 0) {
+  if (warp == kWarpProducer) {
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int kt = kt_begin; kt < kt_end; ++kt) {
@@ -1294,7 +1300,7 @@ __global__ void __launch_bounds__(256, 1)
         const int rem = kt % tiles_img;
         const int w0 = (rem % p.tiles_w) * 8;
         const int h0 = (rem / p.tiles_w) * 8;
-        mbar_wait(empty_bar(stage), phase ^ 1, 5, &g_dbg_word);
+        mbar_wait_relaxed(empty_bar(stage), phase ^ 1, 5, &g_dbg_word);
         const uint32_t x_addr = sbase + stage * stage_bytes;
         const uint32_t dy_addr = x_addr + x_bytes;
         mbar_expect_tx(full_bar(stage), stage_bytes);
@@ -1314,17 +1320,25 @@ __global__ void __launch_bounds__(256, 1)
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpRelay) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
       int stage = 0, phase = 0;
       for (int i = 0; i < nk; ++i) {
         mbar_wait(full_bar(stage), phase, 6, &g_dbg_word);
+        ctr[0] = i + 1;
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+      int stage = 0;
+      for (int i = 0; i < nk; ++i) {
+        wait_counter(ctr, i + 1, 6);
         tc_fence_after();
         const uint32_t x_addr = sbase + stage * stage_bytes;
-        const uint32_t dy_addr = x_addr + x_bytes;
-        constexpr uint32_t hi = umma_desc_hi_sw128(1024);
-        const uint32_t b_lo = umma_desc_lo(dy_addr, 8192);
+        const uint32_t b_lo = umma_desc_lo(x_addr + x_bytes, 8192);
         const uint32_t accflag = i != 0 ? 1u : 0u;
         if (p.mode9) {
           // rows 0-63: tap 2*blk, rows 64-127: tap 2*blk+1, taps ordered (dw major, dh minor):
@@ -1351,14 +1365,14 @@ __global__ void __launch_bounds__(256, 1)
           }
         }
         umma_commit(empty_bar(stage));
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) stage = 0;
       }
       umma_commit(tfull_bar);
     }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
+  } else if (warp < 4) {
+    const int q = warp;
     const int row = q * 32 + lane;
-    mbar_wait(tfull_bar, 0, 7, &g_dbg_word);
+    mbar_wait_relaxed(tfull_bar, 0, 7, &g_dbg_word);
     tc_fence_after();
     for (int blk = 0; blk < nblocks; ++blk) {
       int wt, ci;  // weight tap index (r*3+s) and input channel of this TMEM lane
@@ -1372,10 +1386,8 @@ __global__ void __launch_bounds__(256, 1)
         wt = blk * 3 + dwi;
         ci = cb * 128 + row;
       }
-      float* dst = p.partial +
-                   (static_cast<size_t>(split) * 9 * p.cin + static_cast<size_t>(wt) * p.cin + ci) *
-                       p.cout +
-                   n_tile * BLOCK_N;
+      // fp32 reductions straight into dW: lanes = consecutive ci = one 128-byte line per instruction
+      float* dst = p.dw + wt * p.s_t + ci + static_cast<long long>(n_tile * BLOCK_N) * p.s_co;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
@@ -1383,18 +1395,14 @@ __global__ void __launch_bounds__(256, 1)
         tmem_ld_wait();
         if (ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            *reinterpret_cast<float4*>(dst + c + 4 * j) = o;
-          }
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * p.s_co, __uint_as_float(v[j]));
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == kWarpAlloc) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 template <int BLOCK_N>
@@ -1433,9 +1441,11 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   p.n_tiles = d.Cout / c.block_n;
   p.splits = c.splits;
   p.ktiles_per_split = c.ktiles_per_split;
-  p.partial = d.partial;
+  p.dw = d.dw;
+  p.s_co = d.s_co;
+  p.s_t = d.s_t;
   const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (c.block_n / 64) * 8192;
-  const int overhead = 8 * (2 * kMaxSlots + 1) + 16 + 1024;
+  const int overhead = 8 * (2 * kMaxSlots + 3) + 16 + 1024;
   p.stages = std::min(kMaxSlots, (232448 - overhead) / stage_bytes);
   const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + overhead;
   CUtensorMap xmap, dymap;
@@ -1499,10 +1509,6 @@ int launch_igemm_wgrad(const WgradDesc& d) {
     }
   }
   const WgradConfig c = wgrad_config(N, H, W, d.num_taps, d.Cin, d.Cout, d.num_dy_views);
-  if (d.splits != c.splits) {
-    set_error("igemm_wgrad: invalid split count (use plume_wgrad_splits)");
-    return -1;
-  }
   if (c.halo) return launch_wgrad3(d, c);
 
   int bw, bh, bn, ktiles;
@@ -1530,7 +1536,9 @@ int launch_igemm_wgrad(const WgradDesc& d) {
   p.n_tiles = d.Cout / block_n;
   p.splits = c.splits;
   p.ktiles_per_split = c.ktiles_per_split;
-  p.partial = d.partial;
+  p.dw = d.dw;
+  p.s_co = d.s_co;
+  p.s_t = d.s_t;
   switch (block_n) {
     case 256: return launch_wgrad_inst<256, 4>(xmap, dymaps, p, d.stream);
     case 128: return launch_wgrad_inst<128, 6>(xmap, dymaps, p, d.stream);

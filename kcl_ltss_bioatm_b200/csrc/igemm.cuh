@@ -28,7 +28,7 @@ struct FwdDesc {
 int launch_igemm_fwd(const FwdDesc& d);
 
 // Weight-gradient implicit GEMM:
-//   partial[split][tap*Cin + ci][co] = sum_{pixels in split} X_tap[pixel + shift(tap), ci] * DY_tap[pixel, co]
+//   dw[co*s_co + tap*s_t + ci] += sum_{pixels} X_tap[pixel + shift(tap), ci] * DY_tap[pixel, co]   (fp32 atomics)
 //   conv3x3 : X shifted per tap, one dY view
 //   convT2x2: X unshifted, dY view per tap (the four strided views of dU)
 struct WgradDesc {
@@ -38,8 +38,8 @@ struct WgradDesc {
   int num_taps;       // 9 or 4
   int Cin;            // 64, or a multiple of 128
   int Cout;           // multiple of 64
-  float* partial;     // fp32 [splits][num_taps*Cin][Cout]
-  int splits;         // from wgrad_plan()
+  float* dw;          // fp32 gradient, accumulated into (caller zeroes it for a plain assignment)
+  long long s_co, s_t;
   cudaStream_t stream;
 };
 // Chooses the K split for a problem; returns the number of splits (>=1).

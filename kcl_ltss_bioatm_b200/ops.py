@@ -85,12 +85,10 @@ class CudaOps:
         xp, ldx, n, h, w, cin = _act(x, "x")
         dyp, lddy, n2, h2, w2, cout = _act(dy, "dy")
         assert (n, h, w) == (n2, h2, w2)
-        nbytes = self.lib.plume_wgrad_workspace_bytes(n, h, w, 9, cin, cout)
-        ws = self._workspace(nbytes, x.device)
         check(self.lib.plume_conv3x3_wgrad(xp, ldx, dyp, lddy, _f32(dw, "dw", cout * 9 * cin),
-                                           int(bool(accumulate)), ptr(ws), ws.numel(), n, h, w, cin, cout,
+                                           int(bool(accumulate)), ptr(None), 0, n, h, w, cin, cout,
                                            current_stream()), "plume_conv3x3_wgrad")
-        self.launches += 2
+        self.launches += 1
 
     def convT_fwd(self, x, w_fwd, bias, u):
         xp, ldx, n, h, w, cin = _act(x, "x")
@@ -114,12 +112,10 @@ class CudaOps:
         xp, ldx, n, h, w, cin = _act(x, "x")
         dup, lddu, n2, h2, w2, cout = _act(du, "du")
         assert (n2, h2, w2) == (n, 2 * h, 2 * w)
-        nbytes = self.lib.plume_wgrad_workspace_bytes(n, h, w, 4, cin, cout)
-        ws = self._workspace(nbytes, x.device)
         check(self.lib.plume_convT2x2_wgrad(xp, ldx, dup, lddu, _f32(dw, "dw", 4 * cout * cin),
-                                            int(bool(accumulate)), ptr(ws), ws.numel(), n, h, w, cin, cout,
+                                            int(bool(accumulate)), ptr(None), 0, n, h, w, cin, cout,
                                             current_stream()), "plume_convT2x2_wgrad")
-        self.launches += 2
+        self.launches += 1
 
     # ------------------------------------------------------------------ packing
     def pack_conv3x3(self, w, wf, wd):

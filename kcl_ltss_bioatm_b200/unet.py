@@ -459,7 +459,8 @@ class UNetB200:
                              g_y, self.g(f"{name}.bias"))
         else:
             ops.relu_bwd(g_a, a, g_y, self.g(f"{name}.bias"))
-        ops.conv3x3_wgrad(x_in, g_y, self.g(f"{name}.weight"), acc)
+        # the flat gradient buffer was zeroed (or holds the previous micro-batches), so always accumulate
+        ops.conv3x3_wgrad(x_in, g_y, self.g(f"{name}.weight"), True)
         if g_in is not None:
             ops.conv3x3_dgrad(g_y, self.wd(name), g_in)
 
@@ -492,7 +493,7 @@ class UNetB200:
             x_up = b.ba2 if l == d - 1 else b.da2[l + 1]
             g_up = b.bg_a if l == d - 1 else b.g_a[l + 1]
             ops.channel_sum(du, self.g(f"up{l}.bias"))
-            ops.convT_wgrad(x_up, du, self.g(f"up{l}.weight"), acc)
+            ops.convT_wgrad(x_up, du, self.g(f"up{l}.weight"), True)
             ops.convT_dgrad(du, self.wd(f"up{l}"), g_up)
             self._grads_ready(f"up{l}.bias")
         self._conv_block_bwd("bottleneck.conv2", b.ba1, b.by2, b.ba2, b.bg_a, b.bg_y, b.bg_a, acc)
