@@ -416,7 +416,7 @@ struct Conv3Params {
 
 constexpr int kHaloBytes = 18 * 1024;  // 8 w x 18 h pixels x 64 channels bf16
 constexpr int kMaxSlots = 8;
-constexpr int kConv3Threads = 416;     // 8 epilogue warps + 5 single-thread role warps
+constexpr int kConv3Threads = 448;     // 8 epilogue warps + 6 single-thread role warps
 
 // One 32-column half of a 64-channel chunk: scale/shift (+ReLU) -> bf16 -> swizzled staging row.
 template <bool RELU, bool MASK>
@@ -456,26 +456,45 @@ __device__ __forceinline__ void wait_counter(const volatile uint32_t* ctr, uint3
 
 // Warp roles (the warp arbiter prefers higher warp ids within a scheduler, so the single-thread roles sit
 // above the epilogue warps):
-//   0-7  epilogue, two warpgroups; warpgroup g drains TMEM accumulator g
-//   8    TMEM allocator, then relay for "accumulator drained" barriers
-//   9    TMA producer
-//   10   barrier init, then relay for "halo slot full" barriers
-//   11   MMA issuer
-//   12   relay for "weight tile full" barriers (ring mode)
-// Relays: an mbarrier probe costs the thread that executes it 100-300 cycles and the tensor pipe buffers
-// only about one MMA beyond the running one, so any barrier wait in the MMA thread drains the pipe
-// (scripts/bench_mma2.cu: 48 -> 73-130 cycles per N=64 MMA).  The relay threads do the mbarrier waits
-// and publish monotonically increasing counters in shared memory; the MMA thread only polls those
-// (one LDS, ~30 cycles) between MMA groups.  The counters order nothing by themselves: the data was
-// written by TMA before the mbarrier completed, which the relay observed before bumping the counter.
-template <int BLOCK_N, bool RESIDENT>
+//   0-7   epilogue, two warpgroups; warpgroup g drains TMEM accumulator g
+//   8     TMEM allocator, then relay for "accumulator drained" barriers
+//   9     TMA producer
+//   10    barrier init, then relay for "halo slot full" barriers
+//   11,13 MMA issuers (two threads that alternate MMA groups)
+//   12    relay for "weight slot full" barriers (ring mode)
+//
+// What limits small-N MMAs is the issuing thread, not the tensor pipe (scripts/bench_mma*.cu): the pipe
+// buffers about one MMA beyond the running one, and every observation of shared state by the issuing
+// thread -- an mbarrier probe, even a plain shared-memory load -- costs it ~300 cycles, a tcgen05.commit
+// ~80.  Measured cycles per M=128 MMA at N = 64 / 128: 48 / 64 with nothing in between, 83 / 108 with one
+// poll + commit per 12 (4) MMAs.  Hence:
+//   * relay threads do the mbarrier waits and publish monotonically increasing counters in shared
+//     memory (the data was written by TMA before the mbarrier completed, which the relay observed before
+//     bumping the counter, which the issuer reads before issuing);
+//   * MMAs are issued in groups of TPG taps (12 MMAs, or 4 for 256-wide tiles whose weight tiles are too
+//     big to be grouped) and TWO issuer threads alternate groups: while one polls / commits, the other's
+//     MMAs keep the pipe full (55.6 / 64.1 cycles per MMA in the micro-benchmark).  All MMAs of a tile
+//     accumulate into the same TMEM tile, which is order-independent except for the zeroing first MMA:
+//     the thread that owns a tile's first group publishes ctr[3] after issuing it and the other thread
+//     waits for that before touching the tile.
+//
+// MODE 0: weights resident in shared memory (whole [BLOCK_N][9*Cin] slice), group = one halo slot
+// MODE 1: weight ring of "triples" (the three vertical taps of one halo slot share a barrier)
+// MODE 2: weight ring of single tiles (BLOCK_N = 256), group = one tap
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kConv3Threads, 1)
     igemm_conv3_kernel(const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap bmap,
                        const __grid_constant__ CUtensorMap omap, const Conv3Params p) {
+  constexpr bool RESIDENT = MODE == 0;
+  constexpr int TPG = MODE == 2 ? 1 : 3;   // taps per MMA group
+  constexpr int GPS = 3 / TPG;             // groups per halo slot
+  constexpr uint32_t ISSUERS = MODE == 2 ? 1 : 2;  // 512-cycle groups of N=256 MMAs hide a single issuer's sync
   constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int BSLOT_BYTES = TPG * B_BYTES;
   constexpr int STG_BYTES = 128 * 128;
-  constexpr int kWarpAlloc = 8, kWarpProducer = 9, kWarpInit = 10, kWarpMma = 11, kWarpRelayB = 12;
+  constexpr int kWarpAlloc = 8, kWarpProducer = 9, kWarpInit = 10, kWarpMma0 = 11, kWarpRelayB = 12,
+                kWarpMma1 = 13;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
@@ -484,10 +503,10 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
-  const int b_tiles = RESIDENT ? 9 * p.kb : p.b_slots;
+  const uint32_t b_region = RESIDENT ? 9u * p.kb * B_BYTES : static_cast<uint32_t>(p.b_slots) * BSLOT_BYTES;
   const uint32_t off_a = 0;
   const uint32_t off_b = off_a + p.a_slots * kHaloBytes;
-  const uint32_t off_stg = off_b + b_tiles * B_BYTES;       // one staging buffer per epilogue warpgroup
+  const uint32_t off_stg = off_b + b_region;                // one staging buffer per epilogue warpgroup
   const uint32_t off_param = off_stg + 2 * STG_BYTES;       // per warpgroup: scale|shift|sum|sq
   const uint32_t off_bar = off_param + 2 * 4 * BLOCK_N * 4;
   const uint32_t bar0 = sbase + off_bar;
@@ -500,7 +519,8 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   const uint32_t bres_full = bar0 + 8u * (4 * kMaxSlots + 4);
   volatile uint32_t* tmem_ptr_smem =
       reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 5));
-  // relay counters: [0] halo slots ready, [1] weight tiles ready, [2] accumulators drained
+  // relay counters: [0] halo slots landed, [1] weight slots landed, [2] accumulators drained,
+  // [3] tiles whose first MMA group has been issued
   volatile uint32_t* ctr = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 6));
 
   if (warp == kWarpProducer && lane == 0) {
@@ -511,18 +531,19 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   if (warp == kWarpInit && lane == 0) {
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_empty(s), 1);
+      mbar_init(a_empty(s), GPS);  // every MMA group that read the slot commits once
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
+      mbar_init(tfull_bar(a), ISSUERS);  // every issuer commits after its last group of the tile
       mbar_init(tempty_bar(a), 128);
     }
     mbar_init(bres_full, 1);
     ctr[0] = 0;
     ctr[1] = 0;
     ctr[2] = 2;  // both accumulators start drained
+    ctr[3] = 0;
     fence_mbar_init();
   }
   if (warp == kWarpAlloc) {
@@ -538,7 +559,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   const int total_tiles = tiles_img * p.N * p.n_tiles;
   const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
-  const int slots_per_tile = 3 * p.kb;  // halo slots (and, in ring mode, weight triples) per tile
+  const int slots_per_tile = 3 * p.kb;  // halo slots per tile
 
   // tile -> (n tile, image, w0, h0) without integer divides
   auto decode = [&](int tile, int& n_tile, int& img, int& w0, int& h0) {
@@ -556,7 +577,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     if (lane == 0) {
       if (RESIDENT) {
         // n_tiles == 1 in this mode: the CTA's weight slice never changes
-        mbar_expect_tx(bres_full, static_cast<uint32_t>(b_tiles) * B_BYTES);
+        mbar_expect_tx(bres_full, b_region);
         for (int t = 0; t < 9; ++t)
           for (int kb = 0; kb < p.kb; ++kb)
             tma_load_2d(sbase + off_b + (t * p.kb + kb) * B_BYTES, &bmap, bres_full,
@@ -577,11 +598,16 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
                         h0 - 1, img);
             if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
             if (!RESIDENT) {
-              for (int dhi = 0; dhi < 3; ++dhi) {
+#pragma unroll
+              for (int g = 0; g < GPS; ++g) {
                 mbar_wait_relaxed(b_empty(sb), pb ^ 1, 8, &g_dbg_word);
-                mbar_expect_tx(b_full(sb), B_BYTES);
-                tma_load_2d(sbase + off_b + sb * B_BYTES, &bmap, b_full(sb),
-                            (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N);
+                mbar_expect_tx(b_full(sb), BSLOT_BYTES);
+#pragma unroll
+                for (int t = 0; t < TPG; ++t) {
+                  const int dhi = g * TPG + t;
+                  tma_load_2d(sbase + off_b + sb * BSLOT_BYTES + t * B_BYTES, &bmap, b_full(sb),
+                              (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N);
+                }
                 if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
               }
             }
@@ -605,14 +631,14 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       }
     }
   } else if (warp == kWarpRelayB) {
-    // ------------------------------------------------------------------ relay: weight tiles full
+    // ------------------------------------------------------------------ relay: weight slots full
     if (lane == 0) {
       if (RESIDENT) {
         mbar_wait(bres_full, 0, 9, &g_dbg_word);
         ctr[1] = 1;
       } else {
         int sb = 0, pb = 0;
-        const uint32_t n = static_cast<uint32_t>(my_tiles) * slots_per_tile * 3;
+        const uint32_t n = static_cast<uint32_t>(my_tiles) * slots_per_tile * GPS;
         for (uint32_t i = 0; i < n; ++i) {
           mbar_wait(b_full(sb), pb, 12, &g_dbg_word);
           ctr[1] = i + 1;
@@ -629,9 +655,10 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
         if (it >= 2) ctr[2] = it + 1;
       }
     }
-  } else if (warp == kWarpMma) {
-    // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
+  } else if (warp == kWarpMma0 || warp == kWarpMma1) {
+    // ------------------------------------------------------------------ MMA issuers (one lane each)
+    if (lane == 0 && (warp == kWarpMma0 || ISSUERS == 2)) {
+      const uint32_t me = warp == kWarpMma0 ? 0u : 1u;
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       const long long t_begin = clock64();
@@ -640,47 +667,63 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       constexpr uint32_t kHaloUnits = kHaloBytes >> 4, kBUnits = B_BYTES >> 4;
       const uint32_t b_tap_step = 3 * p.kb * kBUnits;  // resident: next vertical tap
       if (RESIDENT) wait_counter(ctr + 1, 1, 1);
-      uint32_t a_cnt = 0, b_cnt = 0;
+      uint32_t G = 0;   // global group index; this thread owns the groups with (G & 1) == me
+      uint32_t A = 0;   // global halo-slot index
       int sa = 0, sb = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        wait_counter(ctr + 2, it + 1, 2);
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
-        uint32_t accumulate = 0;
+        const uint32_t first_G = G;
+        bool entered = false;  // has this thread synchronised with the start of tile `it` yet?
         for (int kb = 0; kb < p.kb; ++kb) {
 #pragma unroll 1
-          for (int dwi = 0; dwi < 3; ++dwi) {
-            wait_counter(ctr + 0, ++a_cnt, 3);
-            if (RESIDENT) tc_fence_after();
+          for (int dwi = 0; dwi < 3; ++dwi, ++A) {
             const uint32_t a_lo = a_lo_base + sa * kHaloUnits;
-            uint32_t b_lo = b_lo_base + (dwi * p.kb + kb) * kBUnits;
 #pragma unroll
-            for (int dhi = 0; dhi < 3; ++dhi) {
-              if (!RESIDENT) {
-                wait_counter(ctr + 1, ++b_cnt, 4);
+            for (int g = 0; g < GPS; ++g, ++G) {
+              if (ISSUERS == 1 || (G & 1u) == me) {
+                uint32_t accumulate = 1;
+                if (!entered) {
+                  if (G == first_G) {
+                    wait_counter(ctr + 2, it + 1, 2);   // accumulator drained by the epilogue
+                    accumulate = 0;                      // this group zeroes the accumulator
+                  } else {
+                    wait_counter(ctr + 3, it + 1, 5);   // the other issuer has issued the zeroing group
+                  }
+                  entered = true;
+                }
+                wait_counter(ctr + 0, A + 1, 3);
+                uint32_t b_lo;
+                if (RESIDENT) {
+                  b_lo = b_lo_base + (dwi * p.kb + kb) * kBUnits;
+                } else {
+                  wait_counter(ctr + 1, G + 1, 4);
+                  b_lo = b_lo_base + sb * (BSLOT_BYTES >> 4);
+                }
                 tc_fence_after();
-                b_lo = b_lo_base + sb * kBUnits;
-              }
-              // vertical tap = one 1024-byte atom (64 descriptor units) further into the halo
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_lohi(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
-                accumulate = 1;
+                for (int t = 0; t < TPG; ++t) {
+                  const int dhi = g * TPG + t;   // vertical tap = one 1024-byte atom further into the halo
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    umma_bf16_lohi(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                  b_lo += RESIDENT ? b_tap_step : kBUnits;
+                }
+                if (!RESIDENT) umma_commit(b_empty(sb));
+                umma_commit(a_empty(sa));
+                if (G == first_G) ctr[3] = it + 1;
               }
               if (!RESIDENT) {
-                umma_commit(b_empty(sb));
                 if (++sb == p.b_slots) sb = 0;
-              } else {
-                b_lo += b_tap_step;
               }
             }
-            umma_commit(a_empty(sa));
             if (++sa == p.a_slots) sa = 0;
           }
         }
-        umma_commit(tfull_bar(it & 1));
+        umma_commit(tfull_bar(it & 1));   // arrives once this thread's MMAs of the tile are complete
       }
-      if (p.prof) p.prof[blockIdx.x * 8 + 2] = clock64() - t_begin;  // MMA issuer: total
+      if (p.prof && me == 0) p.prof[blockIdx.x * 8 + 2] = clock64() - t_begin;  // MMA issuer: total
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue: two warpgroups,
@@ -814,10 +857,10 @@ static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles) {
          2 * 16384 + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
 }
 
-template <int BLOCK_N, bool RESIDENT>
+template <int BLOCK_N, int MODE>
 static int launch_conv3_inst(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
                              const Conv3Params& p, size_t smem, int total_tiles, cudaStream_t stream) {
-  auto kern = igemm_conv3_kernel<BLOCK_N, RESIDENT>;
+  auto kern = igemm_conv3_kernel<BLOCK_N, MODE>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -864,23 +907,30 @@ static int try_launch_conv3(const FwdDesc& d) {
   p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
   p.stat_sum = d.stat_sum; p.stat_sq = d.stat_sq;
   p.prof = g_prof_buf;
-  {
-    static const int dbg = getenv("PLUME_CONV3_DBG") ? atoi(getenv("PLUME_CONV3_DBG")) : 0;
-    p.dbg_mode = dbg;
-  }
+  p.dbg_mode = 0;
 
-  // weights stay resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (each slot is
-  // 12 MMAs of work; fewer slots cannot cover the TMA latency)
-  const bool resident = n_tiles == 1 && conv3_smem_bytes(block_n, 4, 9 * kb) <= limit;
-  if (resident) {
+  // mode 0: weights resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (a slot is
+  //         12 MMAs of work; fewer cannot cover the TMA latency)
+  // mode 1: weight triples (block_n <= 128), mode 2: single weight tiles (block_n == 256)
+  int mode, b_tiles;
+  if (n_tiles == 1 && block_n <= 128 && conv3_smem_bytes(block_n, 4, 9 * kb) <= limit) {
+    mode = 0;
     p.b_slots = 0;
+    b_tiles = 9 * kb;
     p.a_slots = 4;
-    while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, 9 * kb) <= limit) ++p.a_slots;
+  } else if (block_n <= 128) {
+    mode = 1;
+    p.b_slots = block_n == 128 ? 2 : 4;   // triples of 48 KB / 24 KB
+    b_tiles = 3 * p.b_slots;
+    p.a_slots = 3;
   } else {
-    p.a_slots = block_n == 256 ? 3 : 4;
-    p.b_slots = block_n == 256 ? 4 : (block_n == 128 ? 6 : 8);
+    mode = 2;
+    p.b_slots = 4;
+    b_tiles = 4;
+    p.a_slots = 3;
   }
-  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, resident ? 9 * kb : p.b_slots);
+  while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles) <= limit) ++p.a_slots;
+  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles);
   if (smem > limit) return 1;
 
   CUtensorMap amap, bmap, omap;
@@ -897,15 +947,15 @@ static int try_launch_conv3(const FwdDesc& d) {
     return -1;
   }
   const int tt = static_cast<int>(total);
-  if (resident) {
-    if (block_n == 128) return launch_conv3_inst<128, true>(amap, bmap, omap, p, smem, tt, d.stream);
-    return launch_conv3_inst<64, true>(amap, bmap, omap, p, smem, tt, d.stream);
+  if (mode == 0) {
+    if (block_n == 128) return launch_conv3_inst<128, 0>(amap, bmap, omap, p, smem, tt, d.stream);
+    return launch_conv3_inst<64, 0>(amap, bmap, omap, p, smem, tt, d.stream);
   }
-  switch (block_n) {
-    case 256: return launch_conv3_inst<256, false>(amap, bmap, omap, p, smem, tt, d.stream);
-    case 128: return launch_conv3_inst<128, false>(amap, bmap, omap, p, smem, tt, d.stream);
-    default:  return launch_conv3_inst<64, false>(amap, bmap, omap, p, smem, tt, d.stream);
+  if (mode == 1) {
+    if (block_n == 128) return launch_conv3_inst<128, 1>(amap, bmap, omap, p, smem, tt, d.stream);
+    return launch_conv3_inst<64, 1>(amap, bmap, omap, p, smem, tt, d.stream);
   }
+  return launch_conv3_inst<256, 2>(amap, bmap, omap, p, smem, tt, d.stream);
 }
 
 int launch_igemm_fwd(const FwdDesc& d) {
