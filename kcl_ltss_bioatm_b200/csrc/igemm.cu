@@ -473,10 +473,9 @@ __device__ __forceinline__ void wait_counter(const volatile uint32_t* ctr, uint3
 //     bumping the counter, which the issuer reads before issuing);
 //   * MMAs are issued in groups of TPG taps (12 MMAs, or 4 for 256-wide tiles whose weight tiles are too
 //     big to be grouped) and TWO issuer threads alternate groups: while one polls / commits, the other's
-//     MMAs keep the pipe full (55.6 / 64.1 cycles per MMA in the micro-benchmark).  All MMAs of a tile
-//     accumulate into the same TMEM tile, which is order-independent except for the zeroing first MMA:
-//     the thread that owns a tile's first group publishes ctr[3] after issuing it and the other thread
-//     waits for that before touching the tile.
+//     MMAs keep the pipe full (55.6 / 64.1 cycles per MMA in the micro-benchmark).  Each issuer
+//     accumulates into its OWN TMEM tile (its groups in a fixed order) and the epilogue adds the two
+//     partial accumulators, so results do not depend on how the two instruction streams interleave.
 //
 // MODE 0: weights resident in shared memory (whole [BLOCK_N][9*Cin] slice), group = one halo slot
 // MODE 1: weight ring of "triples" (the three vertical taps of one halo slot share a barrier)
@@ -519,8 +518,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   const uint32_t bres_full = bar0 + 8u * (4 * kMaxSlots + 4);
   volatile uint32_t* tmem_ptr_smem =
       reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 5));
-  // relay counters: [0] halo slots landed, [1] weight slots landed, [2] accumulators drained,
-  // [3] tiles whose first MMA group has been issued
+  // relay counters: [0] halo slots landed, [1] weight slots landed, [2] accumulators drained
   volatile uint32_t* ctr = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (4 * kMaxSlots + 6));
 
   if (warp == kWarpProducer && lane == 0) {
@@ -543,11 +541,10 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     ctr[0] = 0;
     ctr[1] = 0;
     ctr[2] = 2;  // both accumulators start drained
-    ctr[3] = 0;
     fence_mbar_init();
   }
   if (warp == kWarpAlloc) {
-    tmem_alloc(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * BLOCK_N);
+    tmem_alloc(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * ISSUERS * BLOCK_N);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -671,9 +668,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       uint32_t A = 0;   // global halo-slot index
       int sa = 0, sb = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t d_tmem = tmem_base + (it & 1) * BLOCK_N;
-        const uint32_t first_G = G;
-        bool entered = false;  // has this thread synchronised with the start of tile `it` yet?
+        // accumulator (tile parity, issuer): each issuer owns one TMEM tile per tile parity
+        const uint32_t d_tmem = tmem_base + ((it & 1) * ISSUERS + me) * BLOCK_N;
+        bool entered = false;  // has this thread started accumulating tile `it` yet?
         for (int kb = 0; kb < p.kb; ++kb) {
 #pragma unroll 1
           for (int dwi = 0; dwi < 3; ++dwi, ++A) {
@@ -683,12 +680,8 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
               if (ISSUERS == 1 || (G & 1u) == me) {
                 uint32_t accumulate = 1;
                 if (!entered) {
-                  if (G == first_G) {
-                    wait_counter(ctr + 2, it + 1, 2);   // accumulator drained by the epilogue
-                    accumulate = 0;                      // this group zeroes the accumulator
-                  } else {
-                    wait_counter(ctr + 3, it + 1, 5);   // the other issuer has issued the zeroing group
-                  }
+                  wait_counter(ctr + 2, it + 1, 2);   // accumulators of this parity drained by the epilogue
+                  accumulate = 0;                      // this thread's first group zeroes its accumulator
                   entered = true;
                 }
                 wait_counter(ctr + 0, A + 1, 3);
@@ -712,7 +705,6 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
                 }
                 if (!RESIDENT) umma_commit(b_empty(sb));
                 umma_commit(a_empty(sa));
-                if (G == first_G) ctr[3] = it + 1;
               }
               if (!RESIDENT) {
                 if (++sb == p.b_slots) sb = 0;
@@ -774,11 +766,24 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
         uint32_t v0[32], v1[32];
         {
-          const uint32_t taddr =
-              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BLOCK_N + chunk * 64;
+          // the issuers' partial accumulators of this tile parity sit side by side; add them in a fixed order
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 g * ISSUERS * BLOCK_N + chunk * 64;
           tmem_ld_32x32b_x32(taddr, v0);
           tmem_ld_32x32b_x32(taddr + 32, v1);
-          tmem_ld_wait();
+          if (ISSUERS == 2) {
+            uint32_t w0r[32];
+            tmem_ld_32x32b_x32(taddr + BLOCK_N, w0r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v0[e] = __float_as_uint(__uint_as_float(v0[e]) + __uint_as_float(w0r[e]));
+            tmem_ld_32x32b_x32(taddr + BLOCK_N + 32, w0r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v1[e] = __float_as_uint(__uint_as_float(v1[e]) + __uint_as_float(w0r[e]));
+          } else {
+            tmem_ld_wait();
+          }
         }
         if (chunk == BLOCK_N / 64 - 1) {
           tc_fence_before();
@@ -849,7 +854,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 2 * ISSUERS * BLOCK_N);
 }
 
 static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles) {
