@@ -239,7 +239,32 @@ class GemmTimer:
         return out
 
 
+class StdoutToStderr:
+    """Everything other than the final JSON line goes to stderr, including what native libraries print on
+    file descriptor 1 (NCCL prints its version banner there)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_gpu(args):
+    with StdoutToStderr():
+        rc, line = _run_gpu(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return rc
+
+
+def _run_gpu(args):
     import torch
 
     from kcl_ltss_bioatm_b200.data import synthetic_batch
@@ -247,8 +272,7 @@ def run_gpu(args):
     from kcl_ltss_bioatm_b200.trainer import Trainer, init_distributed
 
     if not torch.cuda.is_available():
-        print(json.dumps({"metric": METRIC, "error": "no CUDA device: the B200 path has no CPU fallback"}))
-        return 2
+        return 2, {"metric": METRIC, "error": "no CUDA device: the B200 path has no CPU fallback"}
     rank, world, local, pg = init_distributed("cuda")
     dev = torch.device("cuda", local)
     spec = UNetSpec()
@@ -321,8 +345,12 @@ def run_gpu(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
 
+    if pg is not None:
+        import torch.distributed as dist
+        dist.barrier(group=pg)
+        dist.destroy_process_group()
     if rank != 0:
-        return 0
+        return 0, None
 
     peaks, peak_kind = load_peaks()
     tiles = world * BATCH * args.steps
@@ -366,8 +394,7 @@ def run_gpu(args):
         "step_tflops": step_tf, "step_frac_of_peak": step_tf / peak_tf if peak_tf else None,
         "clocks": clocks, "cpu_baseline": cpu, "final_loss": loss_now,
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return 0, line
 
 
 def main():

@@ -695,29 +695,39 @@ __global__ void __launch_bounds__(kThreads)
   ld_f8(w + cv * 8, wv);
   const float bias = b ? __ldg(b) : 0.f;
   float a_bce = 0.f, a_pt = 0.f, a_p = 0.f, a_t = 0.f;
-  // every lane of a pixel group runs the same trip count, so the shuffles below are convergent
+  // every lane of a pixel group runs the same trip count, so the shuffles below are convergent;
+  // four pixels are in flight per thread to cover the HBM latency
+  constexpr int U = 4;
   const long long p0 = i0 / CV;
   const long long iters = (pixels + pstep - 1) / pstep;
-  for (long long it = 0; it < iters; ++it) {
-    const long long p = p0 + it * pstep;
-    float dot = 0.f;
-    if (p < pixels) {
+  for (long long it = 0; it < iters; it += U) {
+    BF8 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + (it + u) * pstep;
+      if (it + u < iters && p < pixels) v[u] = ld_bf8_stream(feat + p * ldf + cv * 8);
+      else v[u].u[0] = v[u].u[1] = v[u].u[2] = v[u].u[3] = 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + (it + u) * pstep;
       float f[8];
-      unpack8(ld_bf8_stream(feat + p * ldf + cv * 8), f);
+      unpack8(v[u], f);
+      float dot = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) dot = fmaf(f[e], wv[e], dot);
-    }
-    for (int o = CV >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (cv == 0 && p < pixels) {
-      const float z = dot + bias;
-      logits[p] = z;
-      if (target) {
-        const float t = target[p] ? 1.f : 0.f;
-        const float pr = sigmoidf_(z);
-        a_bce += fmaxf(z, 0.f) - z * t + log1pf(__expf(-fabsf(z)));
-        a_pt += pr * t;
-        a_p += pr;
-        a_t += t;
+      for (int o = CV >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (cv == 0 && it + u < iters && p < pixels) {
+        const float z = dot + bias;
+        logits[p] = z;
+        if (target) {
+          const float t = target[p] ? 1.f : 0.f;
+          const float pr = sigmoidf_(z);
+          a_bce += fmaxf(z, 0.f) - z * t + log1pf(__expf(-fabsf(z)));
+          a_pt += pr * t;
+          a_p += pr;
+          a_t += t;
+        }
       }
     }
   }
@@ -801,14 +811,12 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   float a_db = 0.f;
-  for (long long p = i0 / CV; p < pixels; p += pstep) {
-    const float z = __ldg(logits + p);
-    const float t = target[p] ? 1.f : 0.f;
+  auto one = [&](long long p, const BF8& fv, float z, float t) {
     const float pr = sigmoidf_(z);
     const float ddice = -(2.f * t * S - I2) * invS2;
     const float dz = grad_scale * (bce_w * (pr - t) * inv_pixels + dice_w * ddice * pr * (1.f - pr));
     float f[8], o[8];
-    unpack8(ld_bf8_stream(feat + p * ldf + cv * 8), f);
+    unpack8(fv, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       o[e] = dz * wv[e];
@@ -816,7 +824,23 @@ __global__ void __launch_bounds__(kThreads)
     }
     st_bf8(dfeat + p * lddf + cv * 8, pack8(o));
     if (cv == 0) a_db += dz;
+  };
+  constexpr int U = 4;
+  long long p = i0 / CV;
+  for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
+    BF8 fv[U];
+    float zz[U], tt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      fv[u] = ld_bf8_stream(feat + (p + u * pstep) * ldf + cv * 8);
+      zz[u] = __ldg(logits + p + u * pstep);
+      tt[u] = target[p + u * pstep] ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(p + u * pstep, fv[u], zz[u], tt[u]);
   }
+  for (; p < pixels; p += pstep)
+    one(p, ld_bf8_stream(feat + p * ldf + cv * 8), __ldg(logits + p), target[p] ? 1.f : 0.f);
   float* const outs[1] = {dw};
   block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
   a_db = warp_sum(a_db);
@@ -911,27 +935,42 @@ int adam(float* param, const float* grad, float* m, float* v, long long n, doubl
 // ------------------------------------------------------------------------------------------------
 // weight packing
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
-  // w, wf: [co][t][ci];  wd: [ci][8-t][co]
-  const long long total = 1ll * Cout * 9 * Cin;
-  const long long step = 1ll * gridDim.x * blockDim.x;
-  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const int ci = static_cast<int>(i % Cin);
-    const int t = static_cast<int>((i / Cin) % 9);
-    const int co = static_cast<int>(i / (9ll * Cin));
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
-    if (wf) wf[i] = v;
-    if (wd) wd[(1ll * ci * 9 + (8 - t)) * Cout + co] = v;
+// w, wf: [co][t][ci] (ci contiguous);  wd: [ci][8-t][co] (co contiguous).  One block transposes a
+// 32 (co) x 32 (ci) tile of one tap through shared memory so that both the fp32 reads and the two bf16
+// writes are coalesced.
+__global__ void __launch_bounds__(256)
+    pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                        __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co = co0 + ty + 8 * k, ci = ci0 + tx;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      const long long i = (1ll * co * 9 + t) * Cin + ci;
+      v = w[i];
+      if (wf) wf[i] = __float2bfloat16_rn(v);
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  if (!wd) return;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ci = ci0 + ty + 8 * k, co = co0 + tx;
+    if (co < Cout && ci < Cin)
+      wd[(1ll * ci * 9 + (8 - t)) * Cout + co] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
   }
 }
 
 int pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s) {
-  const long long total = 1ll * Cout * 9 * Cin;
-  if (total <= 0) return 0;
-  const int grid = grid_for(total, 1);
-  pack_conv3x3_kernel<<<grid, kThreads, 0, s>>>(w, static_cast<__nv_bfloat16*>(wf),
-                                                static_cast<__nv_bfloat16*>(wd), Cout, Cin);
+  if (Cout <= 0 || Cin <= 0) return 0;
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, 9);
+  pack_conv3x3_kernel<<<grid, 256, 0, s>>>(w, static_cast<__nv_bfloat16*>(wf),
+                                           static_cast<__nv_bfloat16*>(wd), Cout, Cin);
   return check_launch("pack_conv3x3");
 }
 

@@ -491,7 +491,11 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   constexpr uint32_t ISSUERS = MODE == 2 ? 1 : 2;  // 512-cycle groups of N=256 MMAs hide a single issuer's sync
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int BSLOT_BYTES = TPG * B_BYTES;
-  constexpr int STG_BYTES = 128 * 128;
+  // 128-wide tiles in triple mode need a third weight slot more than a full staging tile: stage 64 rows
+  // (half a tile) at a time there
+  constexpr bool HALF_STAGE = (BLOCK_N == 128 && MODE == 1);
+  constexpr int STG_ROWS = HALF_STAGE ? 64 : 128;
+  constexpr int STG_BYTES = STG_ROWS * 128;
   constexpr int kWarpAlloc = 8, kWarpProducer = 9, kWarpInit = 10, kWarpMma0 = 11, kWarpRelayB = 12,
                 kWarpMma1 = 13;
   extern __shared__ uint8_t smem_raw[];
@@ -789,52 +793,60 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
           tc_fence_before();
           mbar_arrive(tempty_bar(g));
         }
-        if (et == 0) tma_store_wait_read<0>();  // the previous store has finished reading the buffer
-        named_bar_sync(bar_a, 128);
         const float* sc = s_scale + chunk * 64;
         const float* sh = s_shift + chunk * 64;
-        if (full_tile) {
-          if (relu) {
-            epi_half<true, false>(v0, 0, sc, sh, true, stg, row);
-            epi_half<true, false>(v1, 4, sc + 32, sh + 32, true, stg, row);
-          } else {
-            epi_half<false, false>(v0, 0, sc, sh, true, stg, row);
-            epi_half<false, false>(v1, 4, sc + 32, sh + 32, true, stg, row);
+#pragma unroll 1
+        for (int half = 0; half < (HALF_STAGE ? 2 : 1); ++half) {
+          if (et == 0) tma_store_wait_read<0>();  // the previous store has finished reading the buffer
+          named_bar_sync(bar_a, 128);
+          const bool mine = !HALF_STAGE || (row >> 6) == half;
+          const int srow = HALF_STAGE ? (row & 63) : row;
+          if (mine) {
+            if (full_tile) {
+              if (relu) {
+                epi_half<true, false>(v0, 0, sc, sh, true, stg, srow);
+                epi_half<true, false>(v1, 4, sc + 32, sh + 32, true, stg, srow);
+              } else {
+                epi_half<false, false>(v0, 0, sc, sh, true, stg, srow);
+                epi_half<false, false>(v1, 4, sc + 32, sh + 32, true, stg, srow);
+              }
+            } else {
+              if (relu) {
+                epi_half<true, true>(v0, 0, sc, sh, valid, stg, srow);
+                epi_half<true, true>(v1, 4, sc + 32, sh + 32, valid, stg, srow);
+              } else {
+                epi_half<false, true>(v0, 0, sc, sh, valid, stg, srow);
+                epi_half<false, true>(v1, 4, sc + 32, sh + 32, valid, stg, srow);
+              }
+            }
           }
-        } else {
-          if (relu) {
-            epi_half<true, true>(v0, 0, sc, sh, valid, stg, row);
-            epi_half<true, true>(v1, 4, sc + 32, sh + 32, valid, stg, row);
-          } else {
-            epi_half<false, true>(v0, 0, sc, sh, valid, stg, row);
-            epi_half<false, true>(v1, 4, sc + 32, sh + 32, valid, stg, row);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_b, 128);
+          if (et == 0) {
+            tma_store_4d(&omap, stg_s, ch0 + chunk * 64, w0, h0 + (HALF_STAGE ? 8 * half : 0), img);
+            tma_store_commit();
           }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_b, 128);
-        if (et == 0) {
-          tma_store_4d(&omap, stg_s, ch0 + chunk * 64, w0, h0, img);
-          tma_store_commit();
-        }
-        if (do_stats) {
-          // column sums of the rounded outputs: lane <-> channel pair, warp <-> 32-row group
-          const int j = lane >> 2, wsub = lane & 3;
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          if (do_stats) {
+            // column sums of the rounded outputs: lane <-> channel pair, warp <-> row group
+            constexpr int RPW = STG_ROWS / 4;  // staged rows per warp
+            const int j = lane >> 2, wsub = lane & 3;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r = q * 32 + rr;
-            const uint32_t u =
-                *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((j ^ (r & 7)) << 4) + wsub * 4);
-            const float2 f = unpack_bf16x2(u);
-            s0 += f.x;
-            s1 += f.y;
-            q0 = fmaf(f.x, f.x, q0);
-            q1 = fmaf(f.y, f.y, q1);
+            for (int rr = 0; rr < RPW; ++rr) {
+              const int r = q * RPW + rr;
+              const uint32_t u =
+                  *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((j ^ (r & 7)) << 4) + wsub * 4);
+              const float2 f = unpack_bf16x2(u);
+              s0 += f.x;
+              s1 += f.y;
+              q0 = fmaf(f.x, f.x, q0);
+              q1 = fmaf(f.y, f.y, q1);
+            }
+            atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
+            atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
+            atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
+            atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
           }
-          atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
-          atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
-          atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
-          atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
         }
       }
       if (do_stats) {
@@ -857,9 +869,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 2 * ISSUERS * BLOCK_N);
 }
 
-static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles) {
+static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles, bool half_stage = false) {
   return static_cast<size_t>(a_slots) * kHaloBytes + static_cast<size_t>(b_tiles) * block_n * 128 +
-         2 * 16384 + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
+         2 * (half_stage ? 8192 : 16384) + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
 }
 
 template <int BLOCK_N, int MODE>
@@ -925,7 +937,7 @@ static int try_launch_conv3(const FwdDesc& d) {
     p.a_slots = 4;
   } else if (block_n <= 128) {
     mode = 1;
-    p.b_slots = block_n == 128 ? 2 : 4;   // triples of 48 KB / 24 KB
+    p.b_slots = block_n == 128 ? 3 : 4;   // triples of 48 KB / 24 KB
     b_tiles = 3 * p.b_slots;
     p.a_slots = 3;
   } else {
@@ -934,8 +946,9 @@ static int try_launch_conv3(const FwdDesc& d) {
     b_tiles = 4;
     p.a_slots = 3;
   }
-  while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles) <= limit) ++p.a_slots;
-  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles);
+  const bool half_stage = mode == 1 && block_n == 128;  // must match HALF_STAGE in the kernel
+  while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles, half_stage) <= limit) ++p.a_slots;
+  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles, half_stage);
   if (smem > limit) return 1;
 
   CUtensorMap amap, bmap, omap;
@@ -944,7 +957,7 @@ static int try_launch_conv3(const FwdDesc& d) {
     return -1;
   }
   if (make_act_map(&amap, d.in[0], 64, 8, 18, 1)) return -1;
-  if (make_act_map(&omap, d.out[0], 64, 8, 16, 1)) return -1;
+  if (make_act_map(&omap, d.out[0], 64, 8, half_stage ? 8 : 16, 1)) return -1;
   if (make_mat_map(&bmap, d.wmat, cout, 9ll * d.Cin, 64, block_n)) return -1;
   const long long total = 1ll * p.tiles_w * p.tiles_h * N * n_tiles;
   if (total > 0x7fffffffll) {
