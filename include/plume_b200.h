@@ -158,6 +158,11 @@ int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logit
 int plume_adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
                double beta2, double eps, int step, float grad_scale, plume_stream_t stream);
 
+/* Same update with the step-dependent coefficients in device memory (for CUDA-graph replay of a whole
+ * training step): coef[8] = {lr/(1-b1^t), b1, b2, 1-b1, 1-b2, eps, 1/sqrt(1-b2^t), grad_scale}. */
+int plume_adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
+                   plume_stream_t stream);
+
 /* ---- tiled large-scene inference -------------------------------------------------------------- */
 /* Cut `count` tiles of T x T (NHWC bf16, Cd channels, zero padded past Cs and past the scene edge)
  * out of a scene [Hs][Ws][Cs] bf16; tile k covers origin (ys[k], xs[k]) given as int32 device arrays. */

@@ -301,6 +301,15 @@ int plume_adam(float* param, const float* grad, float* m, float* v, long long n,
   return adam(param, grad, m, v, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
 }
 
+int plume_adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
+                   plume_stream_t stream) {
+  PLUME_CHECK(param && grad && m && v && coef, "adam_dev: null pointer");
+  PLUME_CHECK((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+               reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+              "adam_dev: buffers must be 16-byte aligned");
+  return adam_dev(param, grad, m, v, n, coef, S(stream));
+}
+
 int plume_extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
                         int count, int T, void* tiles, int Cd, plume_stream_t stream) {
   PLUME_CHECK(scene && ys && xs && tiles, "extract_tiles: null pointer");

@@ -32,9 +32,11 @@ int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
 
 // Grid for `work` 16-byte vectors where the loop step (grid*256) must be a multiple of `cv`, the number
 // of vectors per pixel, so that a thread's channel group is loop-invariant.
-int grid_for(long long work, int cv, int blocks_per_sm = 8) {
+int grid_for(long long work, int cv, int blocks_per_sm = 8, int min_per_thread = 1) {
+  // min_per_thread > 1: kernels that end with a per-block channel reduction (shared + global atomics)
+  // should not be split so finely that the reduction dominates on small tensors
   const int g = cv / gcd_int(cv, kThreads);
-  long long need = (work + kThreads - 1) / kThreads;
+  long long need = (work + 1ll * kThreads * min_per_thread - 1) / (1ll * kThreads * min_per_thread);
   long long cap = 1ll * sm_count() * blocks_per_sm;
   long long grid = std::max(1ll, std::min(need, cap));
   grid = (grid + g - 1) / g * g;
@@ -503,7 +505,7 @@ int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float*
   }
   if (pixels <= 0) return 0;
   const int CV = C / 8;
-  const int grid = grid_for(pixels * CV, CV, 4);
+  const int grid = grid_for(pixels * CV, CV, 4, 16);
   const size_t smem = 2ull * std::min(CV, kThreads) * 8 * sizeof(float);
   bn_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(
       static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
@@ -587,7 +589,7 @@ int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* 
   }
   if (pixels <= 0) return 0;
   const int CV = C / 8;
-  const int grid = grid_for(pixels * CV, CV, 4);
+  const int grid = grid_for(pixels * CV, CV, 4, 16);
   const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
   bn_bwd_apply_kernel<<<grid, kThreads, smem, s>>>(
       static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
@@ -669,7 +671,7 @@ int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cud
   }
   if (pixels <= 0) return 0;
   const int CV = C / 8;
-  const int grid = grid_for(pixels * CV, CV, 4);
+  const int grid = grid_for(pixels * CV, CV, 4, 16);
   const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
   channel_sum_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, out,
                                                   pixels, CV);
@@ -708,25 +710,38 @@ __global__ void __launch_bounds__(kThreads)
       if (it + u < iters && p < pixels) v[u] = ld_bf8_stream(feat + p * ldf + cv * 8);
       else v[u].u[0] = v[u].u[1] = v[u].u[2] = v[u].u[3] = 0u;
     }
+    float dots[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long p = p0 + (it + u) * pstep;
       float f[8];
       unpack8(v[u], f);
       float dot = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) dot = fmaf(f[e], wv[e], dot);
       for (int o = CV >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      if (cv == 0 && it + u < iters && p < pixels) {
-        const float z = dot + bias;
-        logits[p] = z;
-        if (target) {
-          const float t = target[p] ? 1.f : 0.f;
-          const float pr = sigmoidf_(z);
-          a_bce += fmaxf(z, 0.f) - z * t + log1pf(__expf(-fabsf(z)));
-          a_pt += pr * t;
-          a_p += pr;
-          a_t += t;
+      dots[u] = dot;  // every lane of the pixel group now holds the full dot product
+    }
+    // spread the per-pixel epilogue (sigmoid / log) over the lanes of the group: lane u takes pixel u
+    // (when the group has fewer lanes than pixels in flight, lane 0 takes them in turn)
+    const int per_lane = CV >= U ? 1 : U;
+    for (int k = 0; k < per_lane; ++k) {
+      const int u = CV >= U ? cv : k;
+      if (u < U && (CV >= U || cv == 0)) {
+        float zsel = dots[0];
+#pragma unroll
+        for (int uu = 1; uu < U; ++uu) zsel = (u == uu) ? dots[uu] : zsel;
+        const long long p = p0 + (it + u) * pstep;
+        if (it + u < iters && p < pixels) {
+          const float z = zsel + bias;
+          logits[p] = z;
+          if (target) {
+            const float t = target[p] ? 1.f : 0.f;
+            const float pr = sigmoidf_(z);
+            a_bce += fmaxf(z, 0.f) - z * t + log1pf(__expf(-fabsf(z)));
+            a_pt += pr * t;
+            a_p += pr;
+            a_t += t;
+          }
         }
       }
     }
@@ -910,6 +925,55 @@ __global__ void __launch_bounds__(kThreads)
     v[ti] = ve;
     param[ti] -= lr_t * me / (sqrtf(ve) * inv_bc2_sqrt + eps);
   }
+}
+
+// Same update with the step-dependent coefficients read from device memory, so that a captured CUDA
+// graph of the whole training step can be replayed (the host refreshes the 8 floats before each replay):
+// coef = {lr/(1-b1^t), beta1, beta2, 1-beta1, 1-beta2, eps, 1/sqrt(1-b2^t), grad_scale}
+__global__ void __launch_bounds__(kThreads)
+    adam_dev_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                    float* __restrict__ v, long long n4, long long n, const float* __restrict__ coef) {
+  const float lr_t = coef[0], beta1 = coef[1], beta2 = coef[2], omb1 = coef[3], omb2 = coef[4], eps = coef[5],
+              inv_bc2_sqrt = coef[6], gscale = coef[7];
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4 p = reinterpret_cast<float4*>(param)[i];
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = reinterpret_cast<float*>(&p);
+    const float* gp = reinterpret_cast<const float*>(&g);
+    float* mp = reinterpret_cast<float*>(&mm);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ge = gp[e] * gscale;
+      mp[e] = beta1 * mp[e] + omb1 * ge;
+      vp[e] = beta2 * vp[e] + omb2 * ge * ge;
+      pp[e] -= lr_t * mp[e] / (sqrtf(vp[e]) * inv_bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(param)[i] = p;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  const long long ti = n4 * 4 + 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti < n) {
+    const float ge = grad[ti] * gscale;
+    const float me = beta1 * m[ti] + omb1 * ge;
+    const float ve = beta2 * v[ti] + omb2 * ge * ge;
+    m[ti] = me;
+    v[ti] = ve;
+    param[ti] -= lr_t * me / (sqrtf(ve) * inv_bc2_sqrt + eps);
+  }
+}
+
+int adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
+             cudaStream_t s) {
+  if (n <= 0) return 0;
+  const long long n4 = n / 4;
+  const int grid = grid_for(std::max(n4, 1ll), 1);
+  adam_dev_kernel<<<grid, kThreads, 0, s>>>(param, grad, m, v, n4, n, coef);
+  return check_launch("adam_dev");
 }
 
 int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,

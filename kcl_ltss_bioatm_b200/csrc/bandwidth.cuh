@@ -44,6 +44,8 @@ int head_bwd(const void* feat, int ldf, const float* w, const float* logits, con
              int lddf, float* dw, float* db, long long pixels, int C, cudaStream_t s);
 int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
          double beta2, double eps, int step, float grad_scale, cudaStream_t s);
+int adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
+             cudaStream_t s);
 int pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
 int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
 int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs, int count,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "plume_head_loss": (_I, [_P, _LL, _F, _F, _F, _P, _P]),
     "plume_head_bwd": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
     "plume_adam": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P]),
+    "plume_adam_dev": (_I, [_P, _P, _P, _P, _LL, _P, _P]),
     "plume_extract_tiles": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
 }

@@ -258,6 +258,13 @@ class CudaOps:
                                   int(step), float(grad_scale), current_stream()), "plume_adam")
         self.launches += 1
 
+    def adam_dev(self, param, grad, m, v, coef):
+        n = param.numel()
+        check(self.lib.plume_adam_dev(_f32(param, "param"), _f32(grad, "grad", n), _f32(m, "m", n),
+                                      _f32(v, "v", n), n, _f32(coef, "coef", 8), current_stream()),
+              "plume_adam_dev")
+        self.launches += 1
+
     # ------------------------------------------------------------------ tiled inference
     def extract_tiles(self, scene, ys, xs, tile, tiles):
         hs, ws, cs = scene.shape

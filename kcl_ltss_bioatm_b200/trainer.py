@@ -83,6 +83,64 @@ class Trainer:
         m.optimizer_step()
         return m.loss_out
 
+    # ------------------------------------------------------------------ CUDA-graph step (single GPU)
+    def step_graphed(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """Same optimisation step replayed from a captured CUDA graph (forward, backward, Adam: ~170 kernel
+        launches become one graph launch).  The batch is copied into static device buffers, the Adam
+        bias-correction coefficients into an 8-float device buffer, then the graph is replayed.  Captured
+        on first use per (N, H, W); single process only (the data-parallel all-reduce stays eager)."""
+        m = self.model
+        if self.pg is not None or self.micro_batches != 1:
+            return self.step(x, target)
+        key = tuple(x.shape)
+        g = getattr(self, "_graphs", None)
+        if g is None:
+            g = self._graphs = {}
+        if key not in g:
+            xs, ts = torch.empty_like(x), torch.empty_like(target)
+            coef = torch.zeros(8, dtype=torch.float32, device=x.device)
+            # ring of pinned staging slots for the coefficients: a slot is rewritten only after the copy that
+            # read it has executed (its event), so the host may run many steps ahead of the GPU
+            coef_host = [(torch.zeros(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+            xs.copy_(x)
+            ts.copy_(target)
+            # two eager steps on a side stream: lazy one-time work (kernel attributes, buffers) must not be
+            # captured, and they are real optimisation steps on this batch
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    m.train(True)
+                    m.forward(xs, ts)
+                    m.backward()
+                    m.step_count += 1
+                    coef.copy_(m.adam_coefficients(m.step_count).to(x.device))
+                    m.optimizer_step_dev(coef)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            m.train(True)
+            nbt = m.num_batches_tracked
+            with torch.cuda.graph(graph):
+                m.forward(xs, ts)
+                m.backward()
+                m.optimizer_step_dev(coef)
+            m.num_batches_tracked = nbt  # capture runs the Python bookkeeping once without executing kernels
+            g[key] = (graph, xs, ts, coef, coef_host, 2)
+            return m.loss_out  # the two warm-up steps already consumed this batch
+        graph, xs, ts, coef, coef_host, _ = g[key]
+        xs.copy_(x, non_blocking=True)
+        ts.copy_(target, non_blocking=True)
+        m.step_count += 1
+        if m.use_bn:
+            m.num_batches_tracked += 1
+        slot, ev = coef_host[m.step_count % len(coef_host)]
+        ev.synchronize()
+        slot.copy_(m.adam_coefficients(m.step_count))
+        coef.copy_(slot, non_blocking=True)
+        ev.record()
+        graph.replay()
+        return m.loss_out
+
     def fit(self, steps: int, batch_fn: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
             log_every: int = 10, on_step: Optional[Callable[[int, float], None]] = None):
         losses = []

@@ -568,6 +568,21 @@ class UNetB200:
                       spec.adam_eps, self.step_count)
         self._param_version += 1
 
+    def adam_coefficients(self, step: int) -> torch.Tensor:
+        """The 8 floats ``plume_adam_dev`` reads (host tensor), formed in double like torch.optim.Adam."""
+        spec = self.spec
+        b1, b2 = float(spec.betas[0]), float(spec.betas[1])
+        bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+        return torch.tensor([spec.lr / bc1, b1, b2, 1.0 - b1, 1.0 - b2, spec.adam_eps, 1.0 / math.sqrt(bc2), 1.0],
+                            dtype=torch.float32)
+
+    def optimizer_step_dev(self, coef: torch.Tensor) -> None:
+        """Adam with coefficients already in device memory (CUDA-graph capturable); the caller advances
+        ``step_count`` and refreshes `coef` before every replay."""
+        self.wait_grads()
+        self.ops.adam_dev(self.params, self.grads, self.adam_m, self.adam_v, coef)
+        self._param_version += 1
+
     def train_step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One optimisation step; returns the device tensor [loss, bce, dice] (no host sync)."""
         self.train(True)

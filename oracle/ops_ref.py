@@ -257,6 +257,13 @@ class RefOps:
         bc2 = 1 - beta2 ** step
         param.sub_((lr / bc1) * m / (v.sqrt() / (bc2 ** 0.5) + eps))
 
+    def adam_dev(self, param, grad, m, v, coef):
+        lr_t, b1, b2, omb1, omb2, eps, inv_bc2_sqrt, gs = [float(c) for c in coef.tolist()]
+        g = grad * gs
+        m.mul_(b1).add_(omb1 * g)
+        v.mul_(b2).add_(omb2 * g * g)
+        param.sub_(lr_t * m / (v.sqrt() * inv_bc2_sqrt + eps))
+
     # ---- tiled inference -----------------------------------------------------------------------------
     def extract_tiles(self, scene, ys, xs, tile, tiles):
         hs, ws, cs = scene.shape

@@ -198,6 +198,37 @@ def test_checkpoint_roundtrip_with_oracle(tmp_path):
     assert (net.predict_mask(x.to(DEV)).cpu() == m_ref).float().mean().item() >= 0.995
 
 
+def test_cuda_graph_step_matches_eager_step():
+    """The captured-graph training step (one graph launch per step) follows the eager schedule: same
+    losses and weights up to the summation order of the atomics (BatchNorm statistics, split-K)."""
+    from kcl_ltss_bioatm_b200.trainer import Trainer
+
+    spec = UNetSpec(base_filters=64, depth=2)
+    batches = [synthetic_batch(4, 32, 32, spec.in_channels, seed=50 + i) for i in range(3)]
+    batches = [(x.to(DEV), t.to(DEV)) for x, t in batches]
+    a, b = Trainer(spec, device=DEV, seed=3), Trainer(spec, device=DEV, seed=3)
+    la, lb = [], []
+    for i in range(8):
+        x, t = batches[i % 3]
+        la.append(a.step(x, t)[0].item())
+        # the first graphed call performs two eager steps on its batch while capturing: mirror that
+        if i == 0:
+            a.step(x, t)
+            b.step_graphed(x, t)
+            lb.append(la[-1])
+        else:
+            lb.append(b.step_graphed(x, t)[0].item())
+    torch.cuda.synchronize()
+    assert a.model.step_count == b.model.step_count
+    assert a.model.num_batches_tracked == b.model.num_batches_tracked
+    for u, v in zip(la[2:], lb[2:]):
+        assert abs(u - v) <= 2e-3 * abs(u), (la, lb)
+    sa, sb = a.model.state_dict(), b.model.state_dict()
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            assert (sa[k] - sb[k]).abs().max().item() <= 2e-3 * (sa[k].abs().max().item() + 1e-6), k
+
+
 def test_tiled_scene_inference_matches_oracle_tiling():
     """Overlap-stitched scene mask vs the same tiling done with the CPU oracle (operator oracle for
     cut / stitch, UNetRef for the tiles)."""
