@@ -1299,13 +1299,19 @@ struct Wgrad3Params {
 constexpr int kXBox = 10 * 1024;  // 8 w x 10 h pixels x 64 channels
 
 // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4 TMEM allocator, 5 TMA producer,
-// 6 barrier init then relay ("stage full" barriers -> shared-memory counter), 7 MMA issuer.
+// 6 barrier init then relay ("stage full" barriers -> shared-memory counter), 7 and 8 MMA issuers.
+// The two issuers alternate pipeline stages (12 or 20 MMAs each) so that one's counter poll / commit
+// overlaps the other's MMAs (see igemm_conv3_kernel).  They accumulate into the same TMEM blocks: the
+// split-K sums are combined with atomics anyway, so the order of the stages' contributions is free; only
+// the zeroing stage 0 must come first, which issuer 1 waits for (ctr[1]).
+constexpr int kWgrad3Threads = 288;
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kWgrad3Threads, 1)
     igemm_wgrad3_kernel(const __grid_constant__ CUtensorMap xmap,
                         const __grid_constant__ CUtensorMap dymap, const Wgrad3Params p) {
   constexpr int DY_BYTES = (BLOCK_N / 64) * 8192;
-  constexpr int kWarpAlloc = 4, kWarpProducer = 5, kWarpRelay = 6, kWarpMma = 7;
+  constexpr int kWarpAlloc = 4, kWarpProducer = 5, kWarpRelay = 6, kWarpMma0 = 7, kWarpMma1 = 8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
@@ -1326,28 +1332,6 @@ __global__ void __launch_bounds__(256, 1)
   const int nblocks = p.mode9 ? 5 : 3;
   const uint32_t tmem_cols = (nblocks * BLOCK_N <= 256) ? 256u : 512u;
 
-  if (warp == kWarpProducer && lane == 0) {
-    tma_prefetch_desc(&xmap);
-    tma_prefetch_desc(&dymap);
-  }
-  if (warp == kWarpRelay && lane == 0) {
-    for (int s = 0; s < kMaxSlots; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    mbar_init(tfull_bar, 1);
-    ctr[0] = 0;
-    fence_mbar_init();
-  }
-  if (warp == kWarpAlloc) {
-    tmem_alloc(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
   // work item: blockIdx.x = (unit, n tile), blockIdx.y = K split
   const int n_tile = blockIdx.x % p.n_tiles;
   const int unit = blockIdx.x / p.n_tiles;
@@ -1359,6 +1343,29 @@ __global__ void __launch_bounds__(256, 1)
   const int kt_begin = split * p.ktiles_per_split;
   const int kt_end = min(kt_begin + p.ktiles_per_split, total_ktiles);
   const int nk = kt_end - kt_begin;
+
+  if (warp == kWarpProducer && lane == 0) {
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&dymap);
+  }
+  if (warp == kWarpRelay && lane == 0) {
+    for (int s = 0; s < kMaxSlots; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, nk > 1 ? 2 : 1);  // every issuer that has a stage commits once
+    ctr[0] = 0;
+    ctr[1] = 0;
+    fence_mbar_init();
+  }
+  if (warp == kWarpAlloc) {
+    tmem_alloc(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
@@ -1397,12 +1404,14 @@ __global__ void __launch_bounds__(256, 1)
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == kWarpMma) {
-    if (lane == 0) {
+  } else if (warp == kWarpMma0 || warp == kWarpMma1) {
+    const int me = warp == kWarpMma0 ? 0 : 1;
+    if (lane == 0 && me < nk) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
-      int stage = 0;
-      for (int i = 0; i < nk; ++i) {
+      if (me == 1) wait_counter(ctr + 1, 1, 8);  // the zeroing stage has been issued
+      int stage = me % p.stages;
+      for (int i = me; i < nk; i += 2) {
         wait_counter(ctr, i + 1, 6);
         tc_fence_after();
         const uint32_t x_addr = sbase + stage * stage_bytes;
@@ -1433,7 +1442,9 @@ __global__ void __launch_bounds__(256, 1)
           }
         }
         umma_commit(empty_bar(stage));
-        if (++stage == p.stages) stage = 0;
+        if (i == 0) ctr[1] = 1;
+        stage += 2;
+        while (stage >= p.stages) stage -= p.stages;
       }
       umma_commit(tfull_bar);
     }
@@ -1487,7 +1498,7 @@ static int launch_wgrad3_inst(const CUtensorMap& xmap, const CUtensorMap& dymap,
     return -2;
   }
   dim3 grid(ctas_mn, p.splits);
-  kern<<<grid, 256, smem, stream>>>(xmap, dymap, p);
+  kern<<<grid, kWgrad3Threads, smem, stream>>>(xmap, dymap, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error(std::string("igemm_wgrad3 launch: ") + cudaGetErrorString(e));
