@@ -441,9 +441,21 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], int jbase, con
   }
 }
 
-// Spin on a shared-memory counter published by a relay thread (see the kernel comment).
+// Spin on a shared-memory counter published by a relay thread.  The load is deliberately a WEAK
+// ld.shared: a volatile / relaxed (strong) load issued behind tcgen05.mma instructions stalls the thread
+// for ~300 cycles (it appears to wait for the asynchronous MMAs in flight), which drains the tensor pipe;
+// the weak load returns in ~30 cycles (scripts/bench_mma3.cu: 83 -> 59 cycles per N=64 MMA, 108 -> 71 at
+// N=128, 133 -> 128 at N=256).  Shared memory is not cached, so a weak load in a loop still observes the
+// relay's store; what follows the wait is ordered by the control dependency on the loaded value.
+__device__ __forceinline__ uint32_t ld_counter(const volatile uint32_t* ctr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<const uint32_t*>(ctr))) : "memory");
+  return v;
+}
 __device__ __forceinline__ void wait_counter(const volatile uint32_t* ctr, uint32_t need, int tag) {
-  if (*ctr >= need) return;
+  if (ld_counter(ctr) >= need) return;  // common case: the data is already there (weak, cheap probe)
+  // not there yet: the pipe is starving anyway, so spin with strong loads (a weak load inside a loop may be
+  // kept in a register by the assembler and never observe the relay's store)
   long long t0 = clock64();
   while (*ctr < need) {
     if (clock64() - t0 > PLUME_WATCHDOG_CYCLES) {
