@@ -1504,6 +1504,10 @@ static int launch_wgrad3_inst(const CUtensorMap& xmap, const CUtensorMap& dymap,
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    // full shared-memory carve-out, so that a block of another stream's kernel fits beside this CTA
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared);
   });
   if (attr_err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(igemm_wgrad3): ") + cudaGetErrorString(attr_err));
@@ -1537,7 +1541,13 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   p.s_t = d.s_t;
   const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (c.block_n / 64) * 8192;
   const int overhead = 8 * (2 * kMaxSlots + 3) + 16 + 1024;
-  p.stages = std::min(kMaxSlots, (232448 - overhead) / stage_bytes);
+  // Leave room beside a CTA for one block of a bandwidth kernel on another stream (see unet.py).
+  static const int smem_budget = [] {
+    const char* e = getenv("PLUME_WGRAD3_SMEM");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 65536 && v <= 232448) ? v : 212992;
+  }();
+  p.stages = std::min(kMaxSlots, (smem_budget - overhead) / stage_bytes);
   const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + overhead;
   CUtensorMap xmap, dymap;
   if (make_act_map(&xmap, d.x, 64, 8, 10, 1)) return -1;

@@ -15,6 +15,7 @@ tensors, so weights round-trip with ``oracle/unet_ref.py`` and ``torch.save`` fi
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -112,6 +113,13 @@ class UNetB200:
             self.world = dist.get_world_size(process_group)
         self._buckets = self._make_buckets(bucket_mb)
         self._pending: List = []
+        # Weight-gradient kernels go to a second stream: they are tensor/L2 bound and leave registers and
+        # shared memory for one block of the (HBM bound) BatchNorm-backward kernels of the next layer, so
+        # the two overlap on the same SMs.  PLUME_NO_WGRAD_OVERLAP=1 keeps everything on one stream.
+        self.overlap_wgrad = self.device.type == "cuda" and not os.environ.get("PLUME_NO_WGRAD_OVERLAP")
+        self._side: Optional["torch.cuda.Stream"] = None   # weight gradients (lowest priority)
+        self._chain: Optional["torch.cuda.Stream"] = None  # the backward pass's critical chain (high priority)
+        self._gy_busy: Dict[int, "torch.cuda.Event"] = {}
 
         if seed is not None:
             self.init_parameters(seed)
@@ -304,7 +312,7 @@ class UNetB200:
             b.dy2.append(act(hh, ww, c) if self.use_bn else None)
             b.da2.append(act(hh, ww, c))
             b.g_a.append(act(hh, ww, c))
-            b.g_y.append(act(hh, ww, c))
+            b.g_y.append((act(hh, ww, c), act(hh, ww, c)))   # ping-pong: wgrad reads one while the next is written
             b.g_cat.append(act(hh, ww, 2 * c))
             b.g_pool.append(act(hh // 2, ww // 2, c))
         cb, hb, wb = spec.channels(d), h >> d, w >> d
@@ -313,7 +321,7 @@ class UNetB200:
         b.by2 = act(hb, wb, cb) if self.use_bn else None
         b.ba2 = act(hb, wb, cb)
         b.bg_a = act(hb, wb, cb)
-        b.bg_y = act(hb, wb, cb)
+        b.bg_y = (act(hb, wb, cb), act(hb, wb, cb))
         b.logits = torch.empty(n, h, w, dtype=torch.float32, device=dev)
         self._buf = b
         return b
@@ -325,8 +333,9 @@ class UNetB200:
         tot = 0
         for v in vars(b).values():
             for t in (v if isinstance(v, list) else [v]):
-                if isinstance(t, torch.Tensor):
-                    tot += t.numel() * t.element_size()
+                for u in (t if isinstance(t, tuple) else (t,)):
+                    if isinstance(u, torch.Tensor):
+                        tot += u.numel() * u.element_size()
         return tot
 
     # ------------------------------------------------------------------ weights -> bf16 operands
@@ -446,11 +455,34 @@ class UNetB200:
         return b.logits
 
     # ------------------------------------------------------------------ backward
+    def _on_side(self, after: Optional["torch.cuda.Event"], fn) -> Optional["torch.cuda.Event"]:
+        """Run `fn` (weight-gradient launches) on the side stream once `after` has happened; returns an event
+        that fires when they are done.  Without overlap: runs inline, returns None."""
+        if not self.overlap_wgrad:
+            fn()
+            return None
+        self._side.wait_event(after)
+        with torch.cuda.stream(self._side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        return done
+
+    def _mark(self) -> Optional["torch.cuda.Event"]:
+        if not self.overlap_wgrad:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
     def _conv_block_bwd(self, name: str, x_in, y, a, g_a, g_y, g_in, acc=False):
         """Backward of conv -> [BN] -> ReLU.  g_a: gradient w.r.t. the activated output; g_y: scratch for
         the gradient w.r.t. the raw conv output; g_in: where the input gradient goes (None = not needed)."""
         ops = self.ops
         L = self.convs[name]
+        busy = self._gy_busy.pop(g_y.data_ptr(), None)
+        if busy is not None:  # an earlier layer's weight-gradient kernel may still be reading this scratch
+            torch.cuda.current_stream(self.device).wait_event(busy)
         if self.use_bn:
             st = self._bn[name]
             dbeta, dgamma = self.g(f"{L.bn}.bias"), self.g(f"{L.bn}.weight")
@@ -459,10 +491,14 @@ class UNetB200:
                              g_y, self.g(f"{name}.bias"))
         else:
             ops.relu_bwd(g_a, a, g_y, self.g(f"{name}.bias"))
-        # the flat gradient buffer was zeroed (or holds the previous micro-batches), so always accumulate
-        ops.conv3x3_wgrad(x_in, g_y, self.g(f"{name}.weight"), True)
+        ready = self._mark()
+        # data gradient first (host launch order): it is the critical chain, the weight gradient fills in
         if g_in is not None:
             ops.conv3x3_dgrad(g_y, self.wd(name), g_in)
+        # the flat gradient buffer was zeroed (or holds the previous micro-batches), so always accumulate
+        done = self._on_side(ready, lambda: ops.conv3x3_wgrad(x_in, g_y, self.g(f"{name}.weight"), True))
+        if done is not None:
+            self._gy_busy[g_y.data_ptr()] = done
 
     def backward(self, accumulate: bool = False, sync: bool = True, loss_scale: float = 1.0) -> None:
         """Gradient of the loss computed by the last training forward (with target) into ``self.grads``.
@@ -474,12 +510,31 @@ class UNetB200:
         b = self._buf
         if b is None or b.target is None:
             raise RuntimeError("backward() needs a preceding training forward(x, target)")
-        acc = bool(accumulate)
+        if not self.overlap_wgrad:
+            self._backward_body(b, bool(accumulate), bool(sync), loss_scale)
+            return
+        # Fork: the critical chain (BN backward -> data gradient -> ...) runs on a high-priority stream and
+        # the weight gradients on a lowest-priority one, so that a bandwidth kernel of the chain is placed
+        # beside the resident weight-gradient CTAs ahead of that kernel's still-pending CTAs.
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=0)
+            self._chain = torch.cuda.Stream(device=self.device, priority=-1)
+        caller = torch.cuda.current_stream(self.device)
+        self._chain.wait_stream(caller)
+        with torch.cuda.stream(self._chain):
+            self._backward_body(b, bool(accumulate), bool(sync), loss_scale)
+        caller.wait_stream(self._chain)   # join: the optimizer / next forward see every gradient
+        caller.wait_stream(self._side)
+        self._gy_busy = {}
+
+    def _backward_body(self, b: _Buffers, acc: bool, sync: bool, loss_scale: float) -> None:
+        spec, d, ops = self.spec, self.spec.depth, self.ops
         if not acc:
             self.grads.zero_()
         self._pending = []
         self._next_bucket = 0
-        self._sync = bool(sync)
+        self._sync = sync
+        self._gy_busy = {}
         feat = b.da2[0]
         ops.head_bwd(feat, self.p("head.weight"), b.logits, b.target, self.head_sums, spec.bce_weight,
                      spec.dice_weight, spec.dice_eps, loss_scale / self.world, b.g_a[0], self.g("head.weight"),
@@ -487,26 +542,27 @@ class UNetB200:
         self._grads_ready("head.bias")
         for l in range(d):
             c = spec.channels(l)
-            self._conv_block_bwd(f"dec{l}.conv2", b.da1[l], b.dy2[l], b.da2[l], b.g_a[l], b.g_y[l], b.g_a[l], acc)
-            self._conv_block_bwd(f"dec{l}.conv1", b.cat[l], b.dy1[l], b.da1[l], b.g_a[l], b.g_y[l], b.g_cat[l], acc)
+            self._conv_block_bwd(f"dec{l}.conv2", b.da1[l], b.dy2[l], b.da2[l], b.g_a[l], b.g_y[l][0], b.g_a[l], acc)
+            self._conv_block_bwd(f"dec{l}.conv1", b.cat[l], b.dy1[l], b.da1[l], b.g_a[l], b.g_y[l][1], b.g_cat[l], acc)
             du = b.g_cat[l][..., c:]
             x_up = b.ba2 if l == d - 1 else b.da2[l + 1]
             g_up = b.bg_a if l == d - 1 else b.g_a[l + 1]
             ops.channel_sum(du, self.g(f"up{l}.bias"))
-            ops.convT_wgrad(x_up, du, self.g(f"up{l}.weight"), True)
+            ready = self._mark()
             ops.convT_dgrad(du, self.wd(f"up{l}"), g_up)
+            self._on_side(ready, lambda: ops.convT_wgrad(x_up, du, self.g(f"up{l}.weight"), True))
             self._grads_ready(f"up{l}.bias")
-        self._conv_block_bwd("bottleneck.conv2", b.ba1, b.by2, b.ba2, b.bg_a, b.bg_y, b.bg_a, acc)
-        self._conv_block_bwd("bottleneck.conv1", b.pool[d - 1], b.by1, b.ba1, b.bg_a, b.bg_y, b.g_pool[d - 1], acc)
+        self._conv_block_bwd("bottleneck.conv2", b.ba1, b.by2, b.ba2, b.bg_a, b.bg_y[0], b.bg_a, acc)
+        self._conv_block_bwd("bottleneck.conv1", b.pool[d - 1], b.by1, b.ba1, b.bg_a, b.bg_y[1], b.g_pool[d - 1], acc)
         self._grads_ready("bottleneck.conv1.bias")
         for l in reversed(range(d)):
             c = spec.channels(l)
             skip = b.cat[l][..., :c]
             ops.maxpool_bwd(b.g_pool[l], b.am[l], b.g_cat[l][..., :c], b.g_a[l])
-            self._conv_block_bwd(f"enc{l}.conv2", b.a1[l], b.y2[l], skip, b.g_a[l], b.g_y[l], b.g_a[l], acc)
+            self._conv_block_bwd(f"enc{l}.conv2", b.a1[l], b.y2[l], skip, b.g_a[l], b.g_y[l][0], b.g_a[l], acc)
             x_in = b.x_in if l == 0 else b.pool[l - 1]
             g_in = None if l == 0 else b.g_pool[l - 1]
-            self._conv_block_bwd(f"enc{l}.conv1", x_in, b.y1[l], b.a1[l], b.g_a[l], b.g_y[l], g_in, acc)
+            self._conv_block_bwd(f"enc{l}.conv1", x_in, b.y1[l], b.a1[l], b.g_a[l], b.g_y[l][1], g_in, acc)
             self._grads_ready(None if l == 0 else f"enc{l}.conv1.bias")
 
     # ------------------------------------------------------------------ data parallel buckets
@@ -550,8 +606,14 @@ class UNetB200:
             a, e = self._buckets[self._next_bucket]
             if e > upto and not (last_key is None):
                 break
-            self._pending.append(dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg,
-                                                 async_op=True))
+            if self.overlap_wgrad:
+                # the bucket's weight gradients are on the side stream, the rest on this one
+                self._side.wait_event(self._mark())
+                with torch.cuda.stream(self._side):
+                    wk = dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            else:
+                wk = dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._pending.append(wk)
             self._next_bucket += 1
 
     def wait_grads(self) -> None:
