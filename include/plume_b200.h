@@ -83,6 +83,19 @@ int plume_pack_conv3x3(const float* w_krsc, void* w_fwd_bf16, void* w_dgrad_bf16
 int plume_pack_convT2x2(const float* w_ijoc, void* w_fwd_bf16, void* w_dgrad_bf16, int Cout, int Cin,
                         plume_stream_t stream);
 
+/* All layers of a network in ONE launch.  `descs` is an array of n plume_pack_desc in DEVICE memory (the
+ * pointers inside are device pointers); `first_block` is the running sum of plume_pack_blocks() over the
+ * preceding entries and `total_blocks` the sum over all of them.  kind 0 = conv3x3 (same layouts as
+ * plume_pack_conv3x3), kind 1 = convT2x2 (plume_pack_convT2x2); w_fwd / w_dgrad may be null. */
+typedef struct plume_pack_desc {
+  const float* w;
+  void* w_fwd_bf16;
+  void* w_dgrad_bf16;
+  int kind, Cout, Cin, first_block;
+} plume_pack_desc;
+int plume_pack_blocks(int kind, int Cout, int Cin);
+int plume_pack_batch(const plume_pack_desc* descs, int n, int total_blocks, plume_stream_t stream);
+
 /* ---- bandwidth kernels ----------------------------------------------------------------------- */
 
 /* out[p][0:Cd] = concat(in[p][0:Cs], zeros) ; bf16, Cs and Cd multiples of 8. */

@@ -192,6 +192,11 @@ int plume_pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, pl
   PLUME_CHECK(w, "pack_conv3x3: null pointer");
   return pack_conv3x3(w, wf, wd, Cout, Cin, S(stream));
 }
+int plume_pack_blocks(int kind, int Cout, int Cin) { return pack_blocks(kind, Cout, Cin); }
+int plume_pack_batch(const plume_pack_desc* descs, int n, int total_blocks, plume_stream_t stream) {
+  PLUME_CHECK(descs || n <= 0, "pack_batch: null descriptor table");
+  return pack_batch(descs, n, total_blocks, S(stream));
+}
 int plume_pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, plume_stream_t stream) {
   PLUME_CHECK(w, "pack_convT2x2: null pointer");
   return pack_convT2x2(w, wf, wd, Cout, Cin, S(stream));

@@ -1062,6 +1062,59 @@ int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStr
   return check_launch("pack_convT2x2");
 }
 
+// Table-driven version: one launch packs every layer.  A block handles one 32 x 32 (co, ci) tile of one tap
+// of one layer; both layouts are a transpose of the master:
+//   conv3x3 : w[(co*9 + t)*Cin + ci]     -> wd[(ci*9 + 8-t)*Cout + co]
+//   convT2x2: w[(t*Cout + co)*Cin + ci]  -> wd[(ci*4 + t)*Cout + co]
+__global__ void __launch_bounds__(256)
+    pack_batch_kernel(const plume_pack_desc* __restrict__ descs, int n) {
+  __shared__ float tile[32][33];
+  int e = 0;
+  while (e + 1 < n && static_cast<int>(blockIdx.x) >= descs[e + 1].first_block) ++e;
+  const plume_pack_desc d = descs[e];
+  const int local = blockIdx.x - d.first_block;
+  const int tiles_ci = (d.Cin + 31) / 32, tiles_co = (d.Cout + 31) / 32;
+  const int ci0 = (local % tiles_ci) * 32;
+  const int co0 = ((local / tiles_ci) % tiles_co) * 32;
+  const int t = local / (tiles_ci * tiles_co);
+  const int taps = d.kind == 0 ? 9 : 4;
+  const float* __restrict__ w = d.w;
+  __nv_bfloat16* __restrict__ wf = static_cast<__nv_bfloat16*>(d.w_fwd_bf16);
+  __nv_bfloat16* __restrict__ wd = static_cast<__nv_bfloat16*>(d.w_dgrad_bf16);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co = co0 + ty + 8 * k, ci = ci0 + tx;
+    float v = 0.f;
+    if (co < d.Cout && ci < d.Cin) {
+      const long long i = d.kind == 0 ? (1ll * co * 9 + t) * d.Cin + ci : (1ll * t * d.Cout + co) * d.Cin + ci;
+      v = w[i];
+      if (wf) wf[i] = __float2bfloat16_rn(v);
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  if (!wd) return;
+  __syncthreads();
+  const int td = d.kind == 0 ? 8 - t : t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ci = ci0 + ty + 8 * k, co = co0 + tx;
+    if (co < d.Cout && ci < d.Cin)
+      wd[(1ll * ci * taps + td) * d.Cout + co] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+  }
+}
+
+int pack_blocks(int kind, int Cout, int Cin) {
+  if (Cout <= 0 || Cin <= 0) return 0;
+  return ((Cin + 31) / 32) * ((Cout + 31) / 32) * (kind == 0 ? 9 : 4);
+}
+
+int pack_batch(const plume_pack_desc* descs, int n, int total_blocks, cudaStream_t s) {
+  if (n <= 0 || total_blocks <= 0) return 0;
+  pack_batch_kernel<<<total_blocks, 256, 0, s>>>(descs, n);
+  return check_launch("pack_batch");
+}
+
 // ------------------------------------------------------------------------------------------------
 // tiled inference: cut tiles out of a scene, stitch logits back by centre crop + threshold
 // ------------------------------------------------------------------------------------------------

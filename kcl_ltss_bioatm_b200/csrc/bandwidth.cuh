@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <string>
 
+#include "../../include/plume_b200.h"
+
 namespace plume {
 
 void set_error(const std::string& msg);
@@ -48,6 +50,8 @@ int adam_dev(float* param, const float* grad, float* m, float* v, long long n, c
              cudaStream_t s);
 int pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
 int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
+int pack_blocks(int kind, int Cout, int Cin);
+int pack_batch(const plume_pack_desc* descs, int n, int total_blocks, cudaStream_t s);
 int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs, int count,
                   int T, void* tiles, int Cd, cudaStream_t s);
 int stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T, int margin,

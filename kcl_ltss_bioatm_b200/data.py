@@ -11,7 +11,8 @@ torch is used here as plumbing (RNG, device memory); nothing in this file is on 
 """
 from __future__ import annotations
 
-from typing import Tuple
+from collections import deque
+from typing import Iterable, Iterator, Tuple
 
 import torch
 
@@ -80,3 +81,52 @@ def synthetic_scene(h: int, w: int, channels: int, seed: int, dtype=torch.bfloat
             blk[..., b] += gains[b] * field
         out[y0:y1] = blk.to(dtype)
     return out
+
+
+class DevicePrefetcher:
+    """Iterates device copies of an iterable of pinned host batches ``(tiles, masks)``, keeping the
+    host->device copy of the next batches in flight on a copy stream while the caller trains on the current
+    one.  Every batch is copied exactly once, when it is `depth` batches ahead of use; the yielded tensors
+    are valid until the next item is requested.  On a CPU device the host batches pass through unchanged."""
+
+    def __init__(self, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], device, depth: int = 2):
+        self.batches, self.device, self.depth = batches, torch.device(device), max(1, int(depth))
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        if self.device.type != "cuda":
+            yield from self.batches
+            return
+        copy_stream = torch.cuda.Stream(device=self.device)
+        src = iter(self.batches)
+        slots, queue = [], deque()
+
+        def issue(slot, hb) -> None:
+            x, t = hb
+            if slot["x"] is None or slot["x"].shape != x.shape or slot["x"].dtype != x.dtype:
+                slot["x"] = torch.empty(x.shape, dtype=x.dtype, device=self.device)
+                slot["t"] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+            if slot["free"] is not None:
+                copy_stream.wait_event(slot["free"])  # the consumer's kernels on this slot have run
+            with torch.cuda.stream(copy_stream):
+                slot["x"].copy_(x, non_blocking=True)
+                slot["t"].copy_(t, non_blocking=True)
+                slot["ready"] = torch.cuda.Event()
+                slot["ready"].record(copy_stream)
+            queue.append(slot)
+
+        for _ in range(self.depth):
+            hb = next(src, None)
+            if hb is None:
+                break
+            slots.append({"x": None, "t": None, "free": None, "ready": None})
+            issue(slots[-1], hb)
+        while queue:
+            slot = queue.popleft()
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(slot["ready"])
+            yield slot["x"], slot["t"]
+            slot["free"] = torch.cuda.Event()
+            slot["free"].record(torch.cuda.current_stream(self.device))
+            hb = next(src, None)
+            if hb is not None:
+                issue(slot, hb)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "plume_convT2x2_wgrad": (_I, [_P, _I, _P, _I, _P, _I, _P, c_size_t, _I, _I, _I, _I, _I, _P]),
     "plume_pack_conv3x3": (_I, [_P, _P, _P, _I, _I, _P]),
     "plume_pack_convT2x2": (_I, [_P, _P, _P, _I, _I, _P]),
+    "plume_pack_blocks": (_I, [_I, _I, _I]),
+    "plume_pack_batch": (_I, [_P, _I, _I, _P]),
     "plume_pad_channels": (_I, [_P, _I, _P, _I, _LL, _P]),
     "plume_bn_finalize": (_I, [_P, _P, _LL, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
     "plume_bn_fold_eval": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _I, _P]),

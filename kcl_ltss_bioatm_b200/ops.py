@@ -130,6 +130,33 @@ class CudaOps:
               "plume_pack_convT2x2")
         self.launches += 1
 
+    def pack_batch(self, jobs):
+        """jobs: sequence of (kind, w, wf, wd) with kind "conv3x3" (w [Cout,3,3,Cin]) or "convT" (w [4,Cout,Cin]);
+        wf / wd may be None.  One launch for all of them; the descriptor table (plume_pack_desc, device
+        memory) is built once per distinct set of buffers."""
+        key = tuple((k, w.data_ptr(), ptr(wf).value, ptr(wd).value) for k, w, wf, wd in jobs)
+        cached = getattr(self, "_pack_tables", None)
+        if cached is None:
+            cached = self._pack_tables = {}
+        if key not in cached:
+            import ctypes
+            import struct
+
+            blob, first = b"", 0
+            for kind, w, wf, wd in jobs:
+                k = 0 if kind == "conv3x3" else 1
+                cout, cin = (w.shape[0], w.shape[3]) if k == 0 else (w.shape[1], w.shape[2])
+                _f32(w, "w")
+                blob += struct.pack("<QQQiiii", w.data_ptr(), ptr(wf).value or 0, ptr(wd).value or 0, k, cout, cin,
+                                    first)
+                first += self.lib.plume_pack_blocks(k, cout, cin)
+            assert ctypes.sizeof(ctypes.c_void_p) == 8 and len(blob) == 40 * len(jobs)
+            table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(jobs[0][1].device)
+            cached[key] = (table, len(jobs), first)
+        table, n, total = cached[key]
+        check(self.lib.plume_pack_batch(ptr(table), n, total, current_stream()), "plume_pack_batch")
+        self.launches += 1
+
     # ------------------------------------------------------------------ bandwidth kernels
     def pad_channels(self, x, out):
         if not (x.is_cuda and out.is_cuda):

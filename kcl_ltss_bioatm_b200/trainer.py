@@ -146,9 +146,22 @@ class Trainer:
 
     def fit(self, steps: int, batch_fn: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
             log_every: int = 10, on_step: Optional[Callable[[int, float], None]] = None):
+        """batch_fn(i) returns this rank's shard of batch i: device tensors, or (pinned) host tensors, which are
+        then copied `depth` batches ahead on a copy stream (DevicePrefetcher)."""
+        from .data import DevicePrefetcher
+
         losses = []
-        for it in range(steps):
-            x, t = batch_fn(it)
+        first = batch_fn(0)
+
+        def batches():
+            yield first
+            for it in range(1, steps):
+                yield batch_fn(it)
+
+        stream = batches()
+        if first[0].device.type == "cpu" and self.model.device.type == "cuda":
+            stream = DevicePrefetcher(stream, self.model.device)
+        for it, (x, t) in enumerate(stream):
             out = self.step(x, t)
             if log_every and (it % log_every == 0 or it == steps - 1):
                 v = out.detach().float().cpu().tolist()  # host sync only when logging

@@ -113,6 +113,7 @@ class UNetB200:
             self.world = dist.get_world_size(process_group)
         self._buckets = self._make_buckets(bucket_mb)
         self._pending: List = []
+        self._pack_jobs = None
         # Weight-gradient kernels go to a second stream: they are tensor/L2 bound and leave registers and
         # shared memory for one block of the (HBM bound) BatchNorm-backward kernels of the next layer, so
         # the two overlap on the same SMs.  PLUME_NO_WGRAD_OVERLAP=1 keeps everything on one stream.
@@ -342,11 +343,15 @@ class UNetB200:
     def pack_weights(self) -> None:
         if self._packed_version == self._param_version:
             return
-        for name, L in self.convs.items():
-            need_dgrad = name != "enc0.conv1"
-            self.ops.pack_conv3x3(self.p(f"{name}.weight"), self.wf(name), self.wd(name) if need_dgrad else None)
-        for name in self.ups:
-            self.ops.pack_convT(self.p(f"{name}.weight"), self.wf(name), self.wd(name))
+        if self._pack_jobs is None:
+            jobs = []
+            for name in self.convs:
+                need_dgrad = name != "enc0.conv1"
+                jobs.append(("conv3x3", self.p(f"{name}.weight"), self.wf(name), self.wd(name) if need_dgrad else None))
+            for name in self.ups:
+                jobs.append(("convT", self.p(f"{name}.weight"), self.wf(name), self.wd(name)))
+            self._pack_jobs = jobs
+        self.ops.pack_batch(self._pack_jobs)  # every layer in one launch
         self._packed_version = self._param_version
 
     def _fold_bn(self) -> None:

@@ -107,6 +107,10 @@ class RefOps:
             _, cout, cin = w.shape
             wd.view(cin, 4, cout).copy_(wb.permute(2, 0, 1))
 
+    def pack_batch(self, jobs):
+        for kind, w, wf, wd in jobs:
+            (self.pack_conv3x3 if kind == "conv3x3" else self.pack_convT)(w, wf, wd)
+
     # ---- bandwidth operators ----------------------------------------------------------------------
     def pad_channels(self, x, out):
         out.zero_()

@@ -335,3 +335,30 @@ def test_tiles_extract_stitch_bit_exact(ops):
     torch.cuda.synchronize()
     assert (mask_r != 7).all()                     # every scene pixel owned by exactly one tile
     assert torch.equal(mask.cpu(), mask_r) and relmax(prob, prob_r) < 1e-5
+
+
+def test_pack_batch_matches_per_layer_packing(ops):
+    """One table-driven launch for several layers == the per-layer packers (bit-exact), incl. odd sizes,
+    a layer without a dgrad layout and a transposed-conv layer."""
+    cu, rf = ops
+    jobs_r, jobs_c = [], []
+    for i, (kind, cout, cin, need_wd) in enumerate([("conv3x3", 64, 64, False), ("conv3x3", 128, 64, True),
+                                                    ("convT", 64, 128, True), ("conv3x3", 72, 40, True),
+                                                    ("convT", 40, 24, True)]):
+        if kind == "conv3x3":
+            w = rnd(cout, 3, 3, cin, seed=20 + i)
+            wf, wd = torch.empty(cout, 3, 3, cin, dtype=BF), torch.empty(cin, 3, 3, cout, dtype=BF)
+        else:
+            w = rnd(4, cout, cin, seed=20 + i)
+            wf, wd = torch.empty(4, cout, cin, dtype=BF), torch.empty(cin, 4, cout, dtype=BF)
+        jobs_r.append((kind, w, wf, wd if need_wd else None))
+        jobs_c.append((kind, w.to(DEV), torch.zeros_like(wf, device=DEV),
+                       torch.zeros_like(wd, device=DEV) if need_wd else None))
+    rf.pack_batch(jobs_r)
+    cu.pack_batch(jobs_c)
+    cu.pack_batch(jobs_c)  # cached table path
+    torch.cuda.synchronize()
+    for (_, _, wf_r, wd_r), (_, _, wf, wd) in zip(jobs_r, jobs_c):
+        assert torch.equal(wf.cpu(), wf_r)
+        if wd_r is not None:
+            assert torch.equal(wd.cpu(), wd_r)
