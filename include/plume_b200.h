@@ -41,7 +41,11 @@ void plume_debug_set_prof(long long* buf);
 
 /* y = act(conv3x3(x, w) * scale + shift); optional per-channel sum / sum-of-squares of the bf16
  * outputs accumulated (atomically) into stat_sum / stat_sq (fp32[Cout], caller zeroes them).
- * Cin and Cout must be multiples of 64.  scale/shift may be NULL (1 / 0). */
+ * Cin and Cout must be multiples of 64.  scale/shift may be NULL (1 / 0).
+ * Fewer real input channels than Cin: pass ldx < Cin (a multiple of 8).  x is then taken as dense with
+ * ldx channels per pixel and the weights' remaining input channels read as zero (TMA out-of-bounds fill)
+ * -- how the 8-band input feeds the first layer without a padded copy.  Same rule in plume_conv3x3_wgrad,
+ * where the gradient of those weight columns comes out zero. */
 int plume_conv3x3_fwd(const void* x, int ldx, const void* w_krsc_bf16, const float* scale,
                       const float* shift, int relu, void* y, int ldy, float* stat_sum,
                       float* stat_sq, int N, int H, int W, int Cin, int Cout, plume_stream_t stream);

@@ -64,10 +64,12 @@ int plume_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale,
                       int relu, void* y, int ldy, float* stat_sum, float* stat_sq, int N, int H, int W,
                       int Cin, int Cout, plume_stream_t stream) {
   PLUME_CHECK(x && w && y, "conv3x3_fwd: null pointer");
-  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(ldy, Cout), "conv3x3_fwd: bad pixel stride");
+  // ldx < Cin: x is dense with ldx channels per pixel; the weights' remaining input channels read as zero
+  const int Cx = ldx < Cin ? ldx : Cin;
+  PLUME_CHECK(Cx > 0 && !bad_ld(ldx, Cx) && !bad_ld(ldy, Cout), "conv3x3_fwd: bad pixel stride");
   PLUME_CHECK((stat_sum == nullptr) == (stat_sq == nullptr), "conv3x3_fwd: stat_sum/stat_sq mismatch");
   FwdDesc d{};
-  d.in[0] = view(x, ldx, N, H, W, Cin);
+  d.in[0] = view(x, ldx, N, H, W, Cx);
   d.num_in_views = 1;
   d.num_taps = 9;
   d.Cin = Cin;
@@ -112,13 +114,14 @@ int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float*
                         plume_stream_t stream) {
   (void)workspace; (void)workspace_bytes;
   PLUME_CHECK(x && dy && dw, "conv3x3_wgrad: null pointer");
-  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(lddy, Cout), "conv3x3_wgrad: bad pixel stride");
+  const int Cx = ldx < Cin ? ldx : Cin;  // see plume_conv3x3_fwd
+  PLUME_CHECK(Cx > 0 && !bad_ld(ldx, Cx) && !bad_ld(lddy, Cout), "conv3x3_wgrad: bad pixel stride");
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 9ull * Cin * Cout, S(stream));
     PLUME_CHECK(e == cudaSuccess, "conv3x3_wgrad: cudaMemsetAsync failed");
   }
   WgradDesc d{};
-  d.x = view(x, ldx, N, H, W, Cin);
+  d.x = view(x, ldx, N, H, W, Cx);
   d.dy[0] = view(dy, lddy, N, H, W, Cout);
   d.num_dy_views = 1;
   d.num_taps = 9;

@@ -964,7 +964,7 @@ static int try_launch_conv3(const FwdDesc& d) {
   if (smem > limit) return 1;
 
   CUtensorMap amap, bmap, omap;
-  if (d.in[0].C != d.Cin || d.out[0].C != cout) {
+  if (d.in[0].C > d.Cin || d.in[0].C % 8 || d.out[0].C != cout) {  // fewer input channels: TMA zero-fills
     set_error("igemm_conv3: view channel counts do not match");
     return -1;
   }
@@ -1019,8 +1019,8 @@ int launch_igemm_fwd(const FwdDesc& d) {
   CUtensorMap bmap;
   for (int i = 0; i < 4; ++i) {
     const ActView& v = d.in[i < d.num_in_views ? i : 0];
-    if (v.C != d.Cin) {
-      set_error("igemm_fwd: input view channel count != Cin");
+    if (v.C > d.Cin || v.C % 8) {  // fewer channels than the weights' K per tap: TMA zero-fills the rest
+      set_error("igemm_fwd: input view channel count > Cin");
       return -1;
     }
     if (make_act_map(&amaps.m[i], v, 64, bw, bh, bn)) return -1;
@@ -1598,8 +1598,8 @@ int launch_igemm_wgrad(const WgradDesc& d) {
     set_error("igemm_wgrad: empty input");
     return -1;
   }
-  if (d.x.C != d.Cin) {
-    set_error("igemm_wgrad: x view channel count != Cin");
+  if (d.x.C > d.Cin || d.x.C % 8) {  // fewer channels: TMA zero-fills, those dW columns receive zeros
+    set_error("igemm_wgrad: x view channel count > Cin");
     return -1;
   }
   for (int i = 0; i < d.num_dy_views; ++i) {

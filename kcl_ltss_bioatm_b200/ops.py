@@ -32,6 +32,15 @@ def _act(t: torch.Tensor, name: str):
     return ptr(t), int(ld), int(n), int(h), int(w), int(c)
 
 
+def _weight_cin(w_numel: int, cout: int, cin: int, ldx: int) -> int:
+    """Input channels per tap of a 3x3 weight tensor.  It may exceed the activation's channel count when
+    the activation is dense (ldx == cin): the C ABI then reads the missing channels as zero (ldx < Cin)."""
+    kcin = w_numel // (9 * cout)
+    if kcin * 9 * cout != w_numel or kcin < cin or (kcin > cin and ldx != cin):
+        raise ValueError(f"3x3 weights with {w_numel} elements do not fit Cout={cout}, Cin={cin} (ld {ldx})")
+    return kcin
+
+
 def _f32(t, name: str, numel: int | None = None):
     if t is None:
         return ptr(None)
@@ -65,11 +74,12 @@ class CudaOps:
         xp, ldx, n, h, w, cin = _act(x, "x")
         yp, ldy, n2, h2, w2, cout = _act(y, "y")
         assert (n, h, w) == (n2, h2, w2)
-        assert w_fwd.dtype == torch.bfloat16 and w_fwd.numel() == cout * 9 * cin and w_fwd.is_contiguous()
+        kcin = _weight_cin(w_fwd.numel(), cout, cin, ldx)
+        assert w_fwd.dtype == torch.bfloat16 and w_fwd.is_contiguous()
         check(self.lib.plume_conv3x3_fwd(xp, ldx, ptr(w_fwd), _f32(scale, "scale", cout),
                                          _f32(shift, "shift", cout), int(bool(relu)), yp, ldy,
                                          _f32(stat_sum, "stat_sum", cout), _f32(stat_sq, "stat_sq", cout),
-                                         n, h, w, cin, cout, current_stream()), "plume_conv3x3_fwd")
+                                         n, h, w, kcin, cout, current_stream()), "plume_conv3x3_fwd")
         self.launches += 1
 
     def conv3x3_dgrad(self, dy, w_dgrad, dx):
@@ -85,8 +95,9 @@ class CudaOps:
         xp, ldx, n, h, w, cin = _act(x, "x")
         dyp, lddy, n2, h2, w2, cout = _act(dy, "dy")
         assert (n, h, w) == (n2, h2, w2)
-        check(self.lib.plume_conv3x3_wgrad(xp, ldx, dyp, lddy, _f32(dw, "dw", cout * 9 * cin),
-                                           int(bool(accumulate)), ptr(None), 0, n, h, w, cin, cout,
+        kcin = _weight_cin(dw.numel(), cout, cin, ldx)
+        check(self.lib.plume_conv3x3_wgrad(xp, ldx, dyp, lddy, _f32(dw, "dw", cout * 9 * kcin),
+                                           int(bool(accumulate)), ptr(None), 0, n, h, w, kcin, cout,
                                            current_stream()), "plume_conv3x3_wgrad")
         self.launches += 1
 

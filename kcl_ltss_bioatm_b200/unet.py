@@ -296,7 +296,6 @@ class UNetB200:
             return torch.empty(n, hh, ww, c, dtype=self.act_dtype, device=dev)
 
         b = _Buffers(n, h, w)
-        b.x0 = act(h, w, spec.cin_padded) if spec.cin_padded != spec.in_channels else None
         b.y1, b.a1, b.y2, b.cat, b.pool, b.am = [], [], [], [], [], []
         b.dy1, b.da1, b.dy2, b.da2 = [], [], [], []          # decoder activations (raw / activated)
         b.g_a, b.g_y, b.g_cat, b.g_pool = [], [], [], []       # gradient scratch per level
@@ -370,13 +369,14 @@ class UNetB200:
         if x.dtype != self.act_dtype or x.dim() != 4:
             raise ValueError(f"input must be a 4-D NHWC {self.act_dtype} tensor, got {x.dtype} {tuple(x.shape)}")
         if x.shape[-1] == spec.cin_padded and x.is_contiguous():
-            return x  # already zero padded to the kernel's channel count (tiled inference cuts tiles so)
+            return x  # already zero padded to the first layer's K
         if x.shape[-1] != spec.in_channels:
             raise ValueError(f"input must have {spec.in_channels} channels, got {x.shape[-1]}")
         if spec.in_channels % 8:
             raise ValueError("in_channels must be a multiple of 8 (16-byte NHWC vectors); pad on the host")
-        self.ops.pad_channels(x.contiguous(), b.x0)
-        return b.x0
+        # No padded copy: the first layer's weights carry zero input channels up to a multiple of 64 and the
+        # TMA loads zero-fill the activation's missing channels (plume_conv3x3_fwd: ldx < Cin).
+        return x.contiguous()
 
     def _conv_block_train(self, name: str, x, y, a, pool=None):
         """conv3x3 (+bias) -> [batch statistics -> BatchNorm] -> ReLU, optionally fused with the 2x2 pool.

@@ -38,7 +38,8 @@ class RefOps:
     # ---- 3x3 convolution (weights KRSC = [Cout][3][3][Cin]) ------------------------------------
     def conv3x3_fwd(self, x, w_fwd, scale, shift, relu, y, stat_sum=None, stat_sq=None):
         cout, cin = y.shape[-1], x.shape[-1]
-        w = w_fwd.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        kcin = w_fwd.numel() // (9 * cout)  # the weights may carry zero-padded input channels beyond x's
+        w = w_fwd.float().view(cout, 3, 3, kcin)[..., :cin].permute(0, 3, 1, 2)
         o = F.conv2d(_nchw(x), w, padding=1)
         if scale is not None:
             o = o * scale.view(1, -1, 1, 1)
@@ -61,7 +62,11 @@ class RefOps:
     def conv3x3_wgrad(self, x, dy, dw, accumulate=False):
         cout, cin = dy.shape[-1], x.shape[-1]
         g = torch.nn.grad.conv2d_weight(_nchw(x), (cout, cin, 3, 3), _nchw(dy), padding=1)
-        g = g.permute(0, 2, 3, 1).reshape(dw.shape)
+        g = g.permute(0, 2, 3, 1)
+        kcin = dw.numel() // (9 * cout)
+        if kcin != cin:  # dW of the weights' zero-padded input channels is zero
+            g = F.pad(g, (0, kcin - cin))
+        g = g.reshape(dw.shape)
         if accumulate:
             dw += g
         else:

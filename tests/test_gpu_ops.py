@@ -362,3 +362,36 @@ def test_pack_batch_matches_per_layer_packing(ops):
         assert torch.equal(wf.cpu(), wf_r)
         if wd_r is not None:
             assert torch.equal(wd.cpu(), wd_r)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 32, 32), (1, 8, 8), (1, 20, 12)])
+def test_conv3x3_fewer_input_channels_than_weights(ops, n, h, w):
+    """The 8-band input against first-layer weights zero-padded to 64 input channels (ldx < Cin): TMA
+    zero-fills the missing channels in the forward and the weight-gradient kernels (halo and generic paths)."""
+    cu, rf = ops
+    cx, kcin, cout = 8, 64, 64
+    x = rnd(n, h, w, cx, seed=3).to(BF)
+    wm = torch.zeros(cout, 3, 3, kcin)
+    wm[..., :cx] = rnd(cout, 3, 3, cx, seed=4) / (9 * cx) ** 0.5
+    wf_r = wm.to(BF)
+    y_ref = torch.empty(n, h, w, cout, dtype=BF)
+    rf.conv3x3_fwd(x, wf_r, None, None, 1, y_ref)
+    y = torch.empty(n, h, w, cout, dtype=BF, device=DEV)
+    cu.conv3x3_fwd(x.to(DEV), wf_r.to(DEV), None, None, 1, y)
+    torch.cuda.synchronize()
+    assert relmax(y, y_ref) < 1.6e-2
+    # padded copy gives the bit-identical result
+    xp = torch.zeros(n, h, w, kcin, dtype=BF, device=DEV)
+    xp[..., :cx] = x.to(DEV)
+    y2 = torch.empty_like(y)
+    cu.conv3x3_fwd(xp, wf_r.to(DEV), None, None, 1, y2)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+    dy = rnd(n, h, w, cout, seed=6).to(BF)
+    dw_ref = torch.empty(cout, 3, 3, kcin)
+    rf.conv3x3_wgrad(x, dy, dw_ref)
+    dw = torch.full((cout, 3, 3, kcin), 7.0, device=DEV)
+    cu.conv3x3_wgrad(x.to(DEV), dy.to(DEV), dw)
+    torch.cuda.synchronize()
+    assert relmax(dw, dw_ref) < 1e-3
+    assert dw[..., cx:].abs().max().item() == 0
