@@ -1252,12 +1252,38 @@ struct WgradConfig {
 };
 
 static int split_for(int ctas, int ktiles, int min_ktiles, int* per_out) {
-  // aim for ~2 waves of CTAs, but keep at least `min_ktiles` K tiles per split
-  int want = std::max(1, (2 * 148 + ctas - 1) / ctas);
-  want = std::min(want, std::max(1, ktiles / min_ktiles));
-  const int per = (ktiles + want - 1) / want;
-  *per_out = per;
-  return (ktiles + per - 1) / per;
+  // Split K so that the CTAs fill whole waves of the 148 SMs: one CTA past a wave boundary costs a whole
+  // extra wave (measured: 99 splits x 3 CTAs = 297 CTAs ran 401 us, 148 x 3 = 444 CTAs 299 us).  Cost of a
+  // candidate in K-tile units = waves * (K tiles per CTA + kEpilogue), kEpilogue ~ pipeline fill + the
+  // fp32 reductions of one CTA (about 6 us per extra wave measured on the 64 -> 64 layer).
+  constexpr int kSms = 148, kEpilogue = 10, kMaxWaves = 4;
+  static const int force_waves = [] {  // diagnostics: PLUME_WGRAD_WAVES=n -> the most splits that fit n waves
+    const char* e = getenv("PLUME_WGRAD_WAVES");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 8) ? v : 0;
+  }();
+  const int s_cap = std::max(1, ktiles / min_ktiles);
+  int best_s = 1, best_per = ktiles;
+  long long best_cost = -1;
+  if (force_waves) {
+    best_s = std::min(s_cap, std::max(1, (force_waves * kSms) / ctas));
+    best_per = (ktiles + best_s - 1) / best_s;
+  } else {
+    const int s_max = std::min(s_cap, std::max(1, (kMaxWaves * kSms) / ctas));
+    for (int s = 1; s <= s_max; ++s) {
+      const int per = (ktiles + s - 1) / s;
+      const int s_real = (ktiles + per - 1) / per;
+      const long long waves = (1ll * ctas * s_real + kSms - 1) / kSms;
+      const long long cost = waves * (per + kEpilogue);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_s = s_real;
+        best_per = per;
+      }
+    }
+  }
+  *per_out = best_per;
+  return (ktiles + best_per - 1) / best_per;
 }
 
 static WgradConfig wgrad_config(int N, int H, int W, int num_taps, int Cin, int Cout, int dy_views) {
