@@ -1069,9 +1069,19 @@ int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStr
 __global__ void __launch_bounds__(256)
     pack_batch_kernel(const plume_pack_desc* __restrict__ descs, int n) {
   __shared__ float tile[32][33];
-  int e = 0;
-  while (e + 1 < n && static_cast<int>(blockIdx.x) >= descs[e + 1].first_block) ++e;
-  const plume_pack_desc d = descs[e];
+  __shared__ int s_entry;
+  // which layer owns this block: one coalesced read of the first_block column, then a ballot
+  if (threadIdx.x < 32) {
+    int e = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + threadIdx.x;
+      const bool le = i < n && descs[i].first_block <= static_cast<int>(blockIdx.x);
+      e += __popc(__ballot_sync(0xffffffffu, le));
+    }
+    if (threadIdx.x == 0) s_entry = e - 1;
+  }
+  __syncthreads();
+  const plume_pack_desc d = descs[s_entry];
   const int local = blockIdx.x - d.first_block;
   const int tiles_ci = (d.Cin + 31) / 32, tiles_co = (d.Cout + 31) / 32;
   const int ci0 = (local % tiles_ci) * 32;

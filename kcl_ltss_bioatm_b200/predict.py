@@ -63,7 +63,7 @@ class ScenePredictor:
         mask = torch.empty(hs, ws, dtype=torch.uint8, device=dev)
         prob = torch.empty(hs, ws, dtype=torch.float32, device=dev) if want_prob else None
         bt = min(self.batch_tiles, len(ys_l))
-        cd = m.spec.in_channels  # the first layer zero-fills up to its K on load, no padded copy
+        cd = m.spec.cin_padded  # tiles are cut already zero padded to the first layer's K
         if self._tiles is None or self._tiles.shape[0] != bt or self._tiles.shape[1] != T:
             self._tiles = torch.empty(bt, T, T, cd, dtype=m.act_dtype, device=dev)
         was = m.training

@@ -112,7 +112,7 @@ class Trainer:
                 for _ in range(2):
                     m.train(True)
                     m.forward(xs, ts)
-                    m.backward()
+                    m.backward(defer_tail=True)
                     m.step_count += 1
                     coef.copy_(m.adam_coefficients(m.step_count).to(x.device))
                     m.optimizer_step_dev(coef)
@@ -123,7 +123,7 @@ class Trainer:
             launches0 = m.ops.launches
             with torch.cuda.graph(graph):
                 m.forward(xs, ts)
-                m.backward()
+                m.backward(defer_tail=True)
                 m.optimizer_step_dev(coef)
             m.num_batches_tracked = nbt  # capture runs the Python bookkeeping once without executing kernels
             self.graph_launches = m.ops.launches - launches0  # kernels of ours inside one replay

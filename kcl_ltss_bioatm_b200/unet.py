@@ -121,6 +121,10 @@ class UNetB200:
         self._side: Optional["torch.cuda.Stream"] = None   # weight gradients (lowest priority)
         self._chain: Optional["torch.cuda.Stream"] = None  # the backward pass's critical chain (high priority)
         self._gy_busy: Dict[int, "torch.cuda.Event"] = {}
+        self._tail_event: Optional["torch.cuda.Event"] = None  # side stream: all wgrads before enc0's are done
+        self._tail_open = False                                # backward returned without joining the side stream
+        self._defer_ok = not os.environ.get("PLUME_NO_DEFER_TAIL")
+        self._tail_offset = min(s.offset for k, s in self.layout.slots.items() if k.startswith("enc0."))
 
         if seed is not None:
             self.init_parameters(seed)
@@ -264,6 +268,7 @@ class UNetB200:
 
     def grad_dict(self) -> "OrderedDict[str, torch.Tensor]":
         """Current gradients under the oracle's parameter names (for parity checks)."""
+        self._close_tail()
         return self._export(self.grads, with_buffers=False)
 
     def optimizer_state(self) -> dict:
@@ -296,6 +301,7 @@ class UNetB200:
             return torch.empty(n, hh, ww, c, dtype=self.act_dtype, device=dev)
 
         b = _Buffers(n, h, w)
+        b.x0 = act(h, w, spec.cin_padded) if spec.cin_padded != spec.in_channels else None
         b.y1, b.a1, b.y2, b.cat, b.pool, b.am = [], [], [], [], [], []
         b.dy1, b.da1, b.dy2, b.da2 = [], [], [], []          # decoder activations (raw / activated)
         b.g_a, b.g_y, b.g_cat, b.g_pool = [], [], [], []       # gradient scratch per level
@@ -374,9 +380,12 @@ class UNetB200:
             raise ValueError(f"input must have {spec.in_channels} channels, got {x.shape[-1]}")
         if spec.in_channels % 8:
             raise ValueError("in_channels must be a multiple of 8 (16-byte NHWC vectors); pad on the host")
-        # No padded copy: the first layer's weights carry zero input channels up to a multiple of 64 and the
-        # TMA loads zero-fill the activation's missing channels (plume_conv3x3_fwd: ldx < Cin).
-        return x.contiguous()
+        # The C ABI could read the 8-band tensor directly (plume_conv3x3_fwd with ldx < Cin: TMA zero-fills
+        # the missing channels), but boxes with 16 valid bytes per pixel load slowly: measured 205 us vs
+        # 166 us for the first convolution and 226 us vs 155 us for its weight gradient, more than the
+        # 58 us this padded copy costs.
+        self.ops.pad_channels(x.contiguous(), b.x0)
+        return b.x0
 
     def _conv_block_train(self, name: str, x, y, a, pool=None):
         """conv3x3 (+bias) -> [batch statistics -> BatchNorm] -> ReLU, optionally fused with the 2x2 pool.
@@ -411,6 +420,7 @@ class UNetB200:
         """x: [N,H,W,C_in] bf16 (device).  Training mode: batch statistics, activations kept for backward;
         if `target` (uint8 [N,H,W]) is given the loss sums are accumulated.  Returns fp32 logits [N,H,W]."""
         spec, d, ops = self.spec, self.spec.depth, self.ops
+        self._close_tail()
         n, h, w, _ = x.shape
         b = self._ensure_buffers(n, h, w)
         self.pack_weights()
@@ -460,7 +470,7 @@ class UNetB200:
         return b.logits
 
     # ------------------------------------------------------------------ backward
-    def _on_side(self, after: Optional["torch.cuda.Event"], fn) -> Optional["torch.cuda.Event"]:
+    def _on_side(self, after: Optional["torch.cuda.Event"], fn, tail: bool = False) -> Optional["torch.cuda.Event"]:
         """Run `fn` (weight-gradient launches) on the side stream once `after` has happened; returns an event
         that fires when they are done.  Without overlap: runs inline, returns None."""
         if not self.overlap_wgrad:
@@ -468,6 +478,9 @@ class UNetB200:
             return None
         self._side.wait_event(after)
         with torch.cuda.stream(self._side):
+            if tail and self._tail_event is None:
+                self._tail_event = torch.cuda.Event()
+                self._tail_event.record(self._side)
             fn()
             done = torch.cuda.Event()
             done.record(self._side)
@@ -501,20 +514,26 @@ class UNetB200:
         if g_in is not None:
             ops.conv3x3_dgrad(g_y, self.wd(name), g_in)
         # the flat gradient buffer was zeroed (or holds the previous micro-batches), so always accumulate
-        done = self._on_side(ready, lambda: ops.conv3x3_wgrad(x_in, g_y, self.g(f"{name}.weight"), True))
+        done = self._on_side(ready, lambda: ops.conv3x3_wgrad(x_in, g_y, self.g(f"{name}.weight"), True),
+                             tail=name.startswith("enc0."))
         if done is not None:
             self._gy_busy[g_y.data_ptr()] = done
 
-    def backward(self, accumulate: bool = False, sync: bool = True, loss_scale: float = 1.0) -> None:
+    def backward(self, accumulate: bool = False, sync: bool = True, loss_scale: float = 1.0,
+                 defer_tail: bool = False) -> None:
         """Gradient of the loss computed by the last training forward (with target) into ``self.grads``.
         Under data parallelism the loss is pre-scaled by 1/world and finished gradient buckets are
         all-reduced (sum) asynchronously while the rest of the backward pass runs.
         accumulate=True adds to the existing gradients (micro-batching); sync=False skips the all-reduce
-        (all but the last micro-batch); loss_scale multiplies the loss (1/num_micro_batches)."""
+        (all but the last micro-batch); loss_scale multiplies the loss (1/num_micro_batches).
+        defer_tail=True (internal, train_step): return with the first encoder block's weight gradients
+        possibly still running on the side stream; only ``optimizer_step*`` may follow, which updates
+        every other parameter meanwhile (see _adam_launch)."""
         spec, d, ops = self.spec, self.spec.depth, self.ops
         b = self._buf
         if b is None or b.target is None:
             raise RuntimeError("backward() needs a preceding training forward(x, target)")
+        self._close_tail()
         if not self.overlap_wgrad:
             self._backward_body(b, bool(accumulate), bool(sync), loss_scale)
             return
@@ -529,8 +548,12 @@ class UNetB200:
         with torch.cuda.stream(self._chain):
             self._backward_body(b, bool(accumulate), bool(sync), loss_scale)
         caller.wait_stream(self._chain)   # join: the optimizer / next forward see every gradient
-        caller.wait_stream(self._side)
         self._gy_busy = {}
+        if defer_tail and self.world == 1 and self._tail_event is not None and self._defer_ok:
+            caller.wait_event(self._tail_event)   # every weight gradient except the tail block's
+            self._tail_open = True
+        else:
+            caller.wait_stream(self._side)
 
     def _backward_body(self, b: _Buffers, acc: bool, sync: bool, loss_scale: float) -> None:
         spec, d, ops = self.spec, self.spec.depth, self.ops
@@ -540,6 +563,7 @@ class UNetB200:
         self._next_bucket = 0
         self._sync = sync
         self._gy_busy = {}
+        self._tail_event = None
         feat = b.da2[0]
         ops.head_bwd(feat, self.p("head.weight"), b.logits, b.target, self.head_sums, spec.bce_weight,
                      spec.dice_weight, spec.dice_eps, loss_scale / self.world, b.g_a[0], self.g("head.weight"),
@@ -627,12 +651,33 @@ class UNetB200:
         self._pending = []
 
     # ------------------------------------------------------------------ optimizer / step
+    def _close_tail(self) -> None:
+        """Join the side stream if backward(defer_tail=True) left it running (anything but the optimizer
+        follows): the tail weight gradients read activations and write ``grads``."""
+        if self._tail_open:
+            self._tail_open = False
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+
+    def _adam_launch(self, launch) -> None:
+        """launch(lo, hi) enqueues Adam on the flat range [lo, hi).  After backward(defer_tail=True) the first
+        encoder block's weight gradients (the last ones the backward pass produces, at the end of the flat
+        buffer) may still be running: everything before them is updated now, overlapping those kernels."""
+        total = self.layout.total
+        if self._tail_open:
+            self._tail_open = False
+            launch(0, self._tail_offset)
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            launch(self._tail_offset, total)
+        else:
+            launch(0, total)
+
     def optimizer_step(self) -> None:
         spec = self.spec
         self.wait_grads()
         self.step_count += 1
-        self.ops.adam(self.params, self.grads, self.adam_m, self.adam_v, spec.lr, spec.betas[0], spec.betas[1],
-                      spec.adam_eps, self.step_count)
+        self._adam_launch(lambda lo, hi: self.ops.adam(
+            self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], spec.lr,
+            spec.betas[0], spec.betas[1], spec.adam_eps, self.step_count))
         self._param_version += 1
 
     def adam_coefficients(self, step: int) -> torch.Tensor:
@@ -647,14 +692,15 @@ class UNetB200:
         """Adam with coefficients already in device memory (CUDA-graph capturable); the caller advances
         ``step_count`` and refreshes `coef` before every replay."""
         self.wait_grads()
-        self.ops.adam_dev(self.params, self.grads, self.adam_m, self.adam_v, coef)
+        self._adam_launch(lambda lo, hi: self.ops.adam_dev(
+            self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], coef))
         self._param_version += 1
 
     def train_step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One optimisation step; returns the device tensor [loss, bce, dice] (no host sync)."""
         self.train(True)
         self.forward(x, target)
-        self.backward()
+        self.backward(defer_tail=True)
         self.optimizer_step()
         return self.loss_out
 

@@ -3,12 +3,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from kcl_ltss_bioatm_b200.data import synthetic_batch
 from kcl_ltss_bioatm_b200.spec import UNetSpec
 from kcl_ltss_bioatm_b200.trainer import Trainer
-for (b, hw) in [(32, 256), (1, 256)]:
+only = len(sys.argv) > 1 and sys.argv[1] == 'graph-only'
+for (b, hw) in ([(32, 256)] if only else [(32, 256), (1, 256)]):
     spec = UNetSpec()
     tr = Trainer(spec, device="cuda:0")
     x, t = synthetic_batch(b, hw, hw, spec.in_channels, seed=1)
     x, t = x.cuda(), t.cuda()
-    for mode in ("eager", "graph"):
+    for mode in (("graph",) if only else ("eager", "graph")):
         fn = tr.step if mode == "eager" else tr.step_graphed
         for _ in range(5):
             fn(x, t)
