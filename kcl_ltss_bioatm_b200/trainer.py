@@ -55,6 +55,9 @@ class Trainer:
                               bucket_mb=bucket_mb)
         self.micro_batches = micro_batches
         self.pg = process_group
+        # Data-parallel steps stay eager.  Capturing the bucketed NCCL all-reduces inside the step's CUDA graph
+        # (PLUME_GRAPH_DP=1) hung on 2 x B200 with torch 2.11 / NCCL 2.28.9 and is off by default.
+        self.graph_dp = os.environ.get("PLUME_GRAPH_DP", "0") == "1"
         self.log = logging.getLogger("train_model")
         if process_group is not None:
             import torch.distributed as dist
@@ -90,7 +93,7 @@ class Trainer:
         bias-correction coefficients into an 8-float device buffer, then the graph is replayed.  Captured
         on first use per (N, H, W); single process only (the data-parallel all-reduce stays eager)."""
         m = self.model
-        if self.pg is not None or self.micro_batches != 1:
+        if self.micro_batches != 1 or m.device.type != "cuda" or (self.pg is not None and not self.graph_dp):
             return self.step(x, target)
         key = tuple(x.shape)
         g = getattr(self, "_graphs", None)
