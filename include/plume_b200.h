@@ -192,6 +192,17 @@ int plume_stitch_threshold(const float* logits, const int* ys, const int* xs, in
                            int margin, float logit_threshold, uint8_t* mask, float* prob, int Hs,
                            int Ws, plume_stream_t stream);
 
+/* ---- label geometry: plume hulls -> masks (replaces plume_selector.py:88-116 in_hull / find_plume_aod) ---- */
+/* masks[k][r][c] (uint8, `count` windows of Hm x Wm) = 1 where pixel (x, y) = (xs[k] + c, ys[k] + r) lies inside
+ * or on the boundary of any of the n convex polygons, else 0.  ys / xs are int32 device arrays (NULL = one window
+ * at the origin, i.e. a whole-scene mask).  Polygon i has vertices verts_xy[2*j], verts_xy[2*j+1] for
+ * j in [poly_offsets[i], poly_offsets[i+1]), int32 pixel coordinates in counter-clockwise order, and the bounding
+ * box bbox[4*i .. 4*i+3] = (xmin, ymin, xmax, ymax).  The test is exact (int64 cross products), the same decision
+ * as the reference's Delaunay find_simplex(p) >= 0 for integer coordinates.  All pointers are device memory. */
+int plume_rasterize_hulls(const int* verts_xy, const int* poly_offsets, const int* bbox, int n_polys,
+                          const int* ys, const int* xs, int count, int Hm, int Wm, uint8_t* masks,
+                          plume_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,4 +331,14 @@ int plume_stitch_threshold(const float* logits, const int* ys, const int* xs, in
                           S(stream));
 }
 
+int plume_rasterize_hulls(const int* verts_xy, const int* poly_offsets, const int* bbox, int n_polys,
+                          const int* ys, const int* xs, int count, int Hm, int Wm, uint8_t* masks,
+                          plume_stream_t stream) {
+  PLUME_CHECK(masks, "rasterize_hulls: null mask pointer");
+  PLUME_CHECK(n_polys >= 0 && (n_polys == 0 || (verts_xy && poly_offsets && bbox)),
+              "rasterize_hulls: null polygon arrays");
+  PLUME_CHECK((reinterpret_cast<uintptr_t>(bbox) & 15) == 0, "rasterize_hulls: bbox must be 16-byte aligned");
+  return rasterize_hulls(verts_xy, poly_offsets, bbox, n_polys, ys, xs, count, Hm, Wm, masks, S(stream));
+}
+
 }  // extern "C"

@@ -57,4 +57,7 @@ int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, cons
 int stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T, int margin,
                      float thr, uint8_t* mask, float* prob, int Hs, int Ws, cudaStream_t s);
 
+int rasterize_hulls(const int* verts, const int* offs, const int* bbox, int n_polys, const int* ys,
+                    const int* xs, int count, int Hm, int Wm, uint8_t* masks, cudaStream_t s);
+
 }  // namespace plume

@@ -53,6 +53,7 @@ SIGNATURES = {
     "plume_adam_dev": (_I, [_P, _P, _P, _P, _LL, _P, _P]),
     "plume_extract_tiles": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
+    "plume_rasterize_hulls": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
 }
 
 

@@ -318,3 +318,27 @@ class CudaOps:
                                               margin, float(logit_threshold), ptr(mask), _f32(prob, "prob"),
                                               hs, ws, current_stream()), "plume_stitch_threshold")
         self.launches += 1
+
+    # ------------------------------------------------------------------ label geometry
+    def rasterize_hulls(self, verts, offsets, bbox, masks, ys=None, xs=None):
+        """verts int32 [nv, 2] (x, y) counter-clockwise per polygon, offsets int32 [n+1], bbox int32 [n, 4]
+        (xmin, ymin, xmax, ymax); masks uint8 [count, Hm, Wm] (or [Hm, Wm] without ys / xs), written 0 / 1."""
+        for t, name in ((verts, "verts"), (offsets, "offsets"), (bbox, "bbox")):
+            if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+                raise TypeError(f"{name}: expected a contiguous int32 CUDA tensor")
+        if masks.dtype != torch.uint8 or not masks.is_cuda or not masks.is_contiguous():
+            raise TypeError("masks: expected a contiguous uint8 CUDA tensor")
+        n = offsets.numel() - 1
+        if bbox.numel() != 4 * n or verts.dim() != 2 or verts.shape[1] != 2:
+            raise ValueError("rasterize_hulls: polygon arrays do not agree")
+        if ys is None:
+            if masks.dim() != 2:
+                raise ValueError("masks must be [Hm, Wm] when no window origins are given")
+            count, (hm, wm) = 1, masks.shape
+        else:
+            count, hm, wm = masks.shape
+            if ys.numel() != count or xs.numel() != count or ys.dtype != torch.int32 or xs.dtype != torch.int32:
+                raise ValueError("ys / xs: one int32 origin per window")
+        check(self.lib.plume_rasterize_hulls(ptr(verts), ptr(offsets), ptr(bbox), n, ptr(ys), ptr(xs), count, hm, wm,
+                                             ptr(masks), current_stream()), "plume_rasterize_hulls")
+        self.launches += 1

@@ -299,3 +299,17 @@ class RefOps:
             mask[sy0:sy1, sx0:sx1] = (z >= logit_threshold).to(torch.uint8)
             if prob is not None:
                 prob[sy0:sy1, sx0:sx1] = torch.sigmoid(z)
+
+    # ---- label geometry ----------------------------------------------------------------------------
+    def rasterize_hulls(self, verts, offsets, bbox, masks, ys=None, xs=None):
+        from oracle.hull_ref import rasterize_ref
+
+        v, o = verts.cpu().numpy(), offsets.cpu().numpy()
+        hulls = [(v[o[i]:o[i + 1], 0], v[o[i]:o[i + 1], 1]) for i in range(len(o) - 1)]
+        if ys is None:
+            h, w = masks.shape
+            masks.copy_(torch.from_numpy(rasterize_ref(hulls, h, w)))
+        else:
+            _, h, w = masks.shape
+            for k in range(masks.shape[0]):
+                masks[k].copy_(torch.from_numpy(rasterize_ref(hulls, h, w, origin=(int(ys[k]), int(xs[k])))))
