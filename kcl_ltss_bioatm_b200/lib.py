@@ -13,6 +13,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_v
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplume_b200.so")
+# experiments: an alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("PLUME_B200_LIB", LIB_PATH)
 
 _P, _I, _F, _LL, _D = c_void_p, c_int, c_float, c_longlong, c_double
 
