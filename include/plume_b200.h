@@ -203,6 +203,17 @@ int plume_rasterize_hulls(const int* verts_xy, const int* poly_offsets, const in
                           const int* ys, const int* xs, int count, int Hm, int Wm, uint8_t* masks,
                           plume_stream_t stream);
 
+/* ---- fire -> pixel geolocation (replaces plume_identifier_gaussian_profile.py:85-106, the per-fire search) ---- */
+/* out_row_col[2*f], [2*f+1] = row, column of the pixel nearest to fire f among the pixels whose latitude and
+ * longitude lie strictly inside the +-half_box_deg box around the fire (haversine distance in float64, first
+ * pixel in row-major order on ties), or -1, -1 when the box holds no pixel.  lats / lons are float64 [H][W];
+ * workspace is device memory of plume_locate_fires_workspace_bytes(n_fires) bytes.  The reference's edge filter
+ * (:108-114) is applied by the host wrapper.  All pointers are device memory. */
+size_t plume_locate_fires_workspace_bytes(int n_fires);
+int plume_locate_fires(const double* lats, const double* lons, int H, int W, const double* fire_lat,
+                       const double* fire_lon, int n_fires, double half_box_deg, void* workspace,
+                       size_t workspace_bytes, int* out_row_col, plume_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -341,4 +341,14 @@ int plume_rasterize_hulls(const int* verts_xy, const int* poly_offsets, const in
   return rasterize_hulls(verts_xy, poly_offsets, bbox, n_polys, ys, xs, count, Hm, Wm, masks, S(stream));
 }
 
+size_t plume_locate_fires_workspace_bytes(int n_fires) { return locate_fires_workspace_bytes(n_fires); }
+int plume_locate_fires(const double* lats, const double* lons, int H, int W, const double* fire_lat,
+                       const double* fire_lon, int n_fires, double half_box_deg, void* workspace,
+                       size_t workspace_bytes, int* out_row_col, plume_stream_t stream) {
+  PLUME_CHECK(n_fires <= 0 || (lats && lons && fire_lat && fire_lon && workspace && out_row_col),
+              "locate_fires: null pointer");
+  return locate_fires(lats, lons, H, W, fire_lat, fire_lon, n_fires, half_box_deg, workspace, workspace_bytes,
+                      out_row_col, S(stream));
+}
+
 }  // extern "C"

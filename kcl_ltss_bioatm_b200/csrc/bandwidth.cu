@@ -1199,114 +1199,4 @@ int stitch_threshold(const float* logits, const int* ys, const int* xs, int coun
   return check_launch("stitch_threshold");
 }
 
-// ------------------------------------------------------------------------------------------------
-// plume hulls -> masks.  A block owns a 32 (rows) x 128 (cols) pixel region of one window; polygons are
-// taken 256 at a time: every thread bounding-box-tests one of them against the region, the survivors are
-// compacted into a list and all threads walk that list.  A thread owns 16 consecutive pixels of one row (one 16-byte store); per polygon it
-// first clips its span against the box, then evaluates the edge functions (int64, exact) per pixel.
-// ------------------------------------------------------------------------------------------------
-constexpr int kRasterRows = 32, kRasterCols = 128;
-
-__global__ void __launch_bounds__(256)
-    rasterize_hulls_kernel(const int* __restrict__ verts, const int* __restrict__ offs,
-                           const int* __restrict__ bbox, int n_polys, const int* __restrict__ ys,
-                           const int* __restrict__ xs, int Hm, int Wm, uint8_t* __restrict__ masks) {
-  __shared__ int s_list[256];   // polygons (of the current 256) whose box overlaps this block's region
-  __shared__ int s_warp[8];
-  const int win = blockIdx.z;
-  const int oy = ys ? ys[win] : 0, ox = xs ? xs[win] : 0;
-  const int r0 = blockIdx.y * kRasterRows, c0 = blockIdx.x * kRasterCols;
-  const int row = r0 + (threadIdx.x >> 3), col = c0 + (threadIdx.x & 7) * 16;
-  // region in scene coordinates
-  const int rx0 = ox + c0, rx1 = ox + min(c0 + kRasterCols, Wm) - 1;
-  const int ry0 = oy + r0, ry1 = oy + min(r0 + kRasterRows, Hm) - 1;
-  const int py = oy + row, px0 = ox + col;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t bits = 0;  // bit i: pixel col + i is inside some polygon
-  for (int base = 0; base < n_polys; base += 256) {
-    const int i = base + threadIdx.x;
-    bool hit = false;
-    if (i < n_polys) {
-      const int4 b = *reinterpret_cast<const int4*>(bbox + 4 * i);
-      hit = !(b.x > rx1 || b.z < rx0 || b.y > ry1 || b.w < ry0);
-    }
-    // compact the survivors (ballot + per-warp counts): the walk below costs one iteration per survivor
-    const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_warp[warp] = __popc(ballot);
-    __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int c = s_warp[q];
-      if (q < warp) before += c;
-      total += c;
-    }
-    if (hit) s_list[before + __popc(ballot & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    for (int j = 0; j < total; ++j) {
-      const int p = s_list[j];
-      const int4 b = *reinterpret_cast<const int4*>(bbox + 4 * p);
-      if (py < b.y || py > b.w || px0 > b.z || px0 + 15 < b.x || bits == 0xFFFFu) continue;
-      const int v0 = offs[p], v1 = offs[p + 1];
-      uint32_t in = 0xFFFFu;
-      int ax = verts[2 * (v1 - 1)], ay = verts[2 * (v1 - 1) + 1];
-      for (int v = v0; v < v1 && in; ++v) {
-        const int bx = verts[2 * v], by = verts[2 * v + 1];
-        // edge function at pixel (px0 + k, py): e0 - k * dy, inside (or on the edge) when >= 0.  It is linear
-        // along the span, so its signs at the two ends decide whole spans; only straddling edges go per pixel.
-        const long long dx = bx - ax, dy = by - ay;
-        const long long e0 = dx * (py - ay) - dy * (px0 - ax);
-        const long long e15 = e0 - 15 * dy;
-        if (e0 < 0 && e15 < 0) {
-          in = 0;
-        } else if (e0 < 0 || e15 < 0) {
-          long long e = e0;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            if (e < 0) in &= ~(1u << k);
-            e -= dy;
-          }
-        }
-        ax = bx;
-        ay = by;
-      }
-      bits |= in;
-    }
-    __syncthreads();
-  }
-  if (row >= Hm || col >= Wm) return;
-  uint8_t* dst = masks + (static_cast<long long>(win) * Hm + row) * Wm + col;
-  if (col + 16 <= Wm && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t n = (bits >> (4 * q)) & 0xFu;
-      w[q] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
-    }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-  } else {
-    for (int k = 0; k < 16 && col + k < Wm; ++k) dst[k] = (bits >> k) & 1u;
-  }
-}
-
-int rasterize_hulls(const int* verts, const int* offs, const int* bbox, int n_polys, const int* ys,
-                    const int* xs, int count, int Hm, int Wm, uint8_t* masks, cudaStream_t s) {
-  if (count <= 0 || Hm <= 0 || Wm <= 0) return 0;
-  if ((ys == nullptr) != (xs == nullptr)) {
-    set_error("rasterize_hulls: ys and xs must both be given or both be null");
-    return -1;
-  }
-  if (ys == nullptr && count != 1) {
-    set_error("rasterize_hulls: without window origins there is exactly one window");
-    return -1;
-  }
-  if (count > 65535) {
-    set_error("rasterize_hulls: at most 65535 windows per call");
-    return -1;
-  }
-  dim3 grid((Wm + kRasterCols - 1) / kRasterCols, (Hm + kRasterRows - 1) / kRasterRows, count);
-  rasterize_hulls_kernel<<<grid, 256, 0, s>>>(verts, offs, bbox, n_polys, ys, xs, Hm, Wm, masks);
-  return check_launch("rasterize_hulls");
-}
-
 }  // namespace plume

@@ -60,4 +60,9 @@ int stitch_threshold(const float* logits, const int* ys, const int* xs, int coun
 int rasterize_hulls(const int* verts, const int* offs, const int* bbox, int n_polys, const int* ys,
                     const int* xs, int count, int Hm, int Wm, uint8_t* masks, cudaStream_t s);
 
+size_t locate_fires_workspace_bytes(int n_fires);
+int locate_fires(const double* lats, const double* lons, int H, int W, const double* fire_lat,
+                 const double* fire_lon, int n_fires, double half_box, void* workspace, size_t workspace_bytes,
+                 int* out_rc, cudaStream_t s);
+
 }  // namespace plume

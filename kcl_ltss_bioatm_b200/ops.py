@@ -342,3 +342,23 @@ class CudaOps:
         check(self.lib.plume_rasterize_hulls(ptr(verts), ptr(offsets), ptr(bbox), n, ptr(ys), ptr(xs), count, hm, wm,
                                              ptr(masks), current_stream()), "plume_rasterize_hulls")
         self.launches += 1
+
+    def locate_fires(self, lats, lons, fire_lat, fire_lon, half_box_deg, out_rc):
+        """lats / lons float64 [H, W], fire_lat / fire_lon float64 [n] -> out_rc int32 [n, 2] (row, col; -1, -1 when
+        no pixel lies inside the fire's +-half_box_deg box)."""
+        for t, name in ((lats, "lats"), (lons, "lons"), (fire_lat, "fire_lat"), (fire_lon, "fire_lon")):
+            if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+                raise TypeError(f"{name}: expected a contiguous float64 CUDA tensor")
+        if lats.dim() != 2 or lats.shape != lons.shape:
+            raise ValueError("lats / lons must be [H, W] grids of the same shape")
+        n = fire_lat.numel()
+        if fire_lon.numel() != n or out_rc.dtype != torch.int32 or tuple(out_rc.shape) != (n, 2) or not out_rc.is_cuda \
+                or not out_rc.is_contiguous():
+            raise ValueError("fire arrays / out_rc do not agree")
+        nbytes = int(self.lib.plume_locate_fires_workspace_bytes(n))
+        ws = torch.empty(max(nbytes, 32), dtype=torch.uint8, device=lats.device)  # caching allocator: 512 B aligned
+        h, w = lats.shape
+        check(self.lib.plume_locate_fires(ptr(lats), ptr(lons), h, w, ptr(fire_lat), ptr(fire_lon), n,
+                                          float(half_box_deg), ptr(ws), nbytes, ptr(out_rc), current_stream()),
+              "plume_locate_fires")
+        self.launches += 4 if n else 0

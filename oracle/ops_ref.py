@@ -313,3 +313,11 @@ class RefOps:
             _, h, w = masks.shape
             for k in range(masks.shape[0]):
                 masks[k].copy_(torch.from_numpy(rasterize_ref(hulls, h, w, origin=(int(ys[k]), int(xs[k])))))
+
+    def locate_fires(self, lats, lons, fire_lat, fire_lon, half_box_deg, out_rc):
+        from oracle import fire_ref
+
+        assert half_box_deg == fire_ref.HALF_BOX_DEG
+        rc = fire_ref.nearest_pixel_ref(fire_lat.cpu().numpy(), fire_lon.cpu().numpy(), lats.cpu().numpy(),
+                                        lons.cpu().numpy())
+        out_rc.copy_(torch.from_numpy(rc).to(torch.int32))
