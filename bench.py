@@ -382,9 +382,17 @@ def _run_gpu(args):
     e2e_value = tiles / e2e_s
     fk = gemm["fwd_kernel"]
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    roof = {"bound": "tensor", "kernel": "igemm_fwd_kernel (conv3x3 fwd + dgrad, convT fwd + dgrad)",
+    # DRAM traffic of the same kernel family from the committed ncu launch list (per launch, like `achieved`)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f).get("fwd_kernel", {})
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    roof = {"bound": "tensor", "kernel": "igemm_conv3_kernel + igemm_fwd_kernel (conv3x3 fwd + dgrad, convT fwd + dgrad)",
             "achieved": fk["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": fk["tflops"] / peak_tf if peak_tf else None, "traffic": None,
+            "frac": fk["tflops"] / peak_tf if peak_tf else None, "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu)",
+            "traffic_source": traffic_src,
             "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
             "launches_timed": fk["launches"], "ms_per_step": fk["ms"] / max(roof_steps, 1),
             "measured_in": f"{roof_steps} eagerly launched single-stream steps of the same workload "
