@@ -1,0 +1,24 @@
+"""Deterministic synthetic AOD fields shared by scripts/make_sweep_golden.py and the sweep tests (the golden
+file stores results only)."""
+import numpy as np
+
+
+def synthetic_aod(h, w, seed):
+    """Smooth background + elongated plumes + salt noise (singletons the erosion must remove); float32."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    aod = 0.05 + 0.03 * np.sin(yy / 17.0) * np.cos(xx / 23.0)
+    fires = []
+    for _ in range(6):
+        cy, cx = rng.uniform(20, h - 20), rng.uniform(20, w - 20)
+        th = rng.uniform(0, np.pi)
+        ln, wd = rng.uniform(15, 45), rng.uniform(3, 8)
+        u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)
+        v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+        aod += rng.uniform(0.3, 1.1) * np.exp(-0.5 * ((u / ln) ** 2 + (v / wd) ** 2))
+        fires.append((int(np.clip(cy, 16, h - 17)), int(np.clip(cx, 16, w - 17))))
+    salt = rng.random((h, w)) < 0.01
+    aod[salt] += rng.uniform(0.2, 1.0, int(salt.sum()))
+    # extra fires: far from any plume (no label in the window), and on a plume edge
+    fires += [(16, 16), (h - 17, w - 17), (h // 2, w // 2)]
+    return aod.astype(np.float32), np.array(fires, dtype=np.int64)

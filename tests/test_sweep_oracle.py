@@ -1,0 +1,53 @@
+"""CPU: pins oracle/sweep_ref.py against outputs of the REFERENCE's functions
+(plume_identifier_gaussian_profile.py:142-240, scikit-image primitives replaced by scipy.ndimage stand-ins --
+see scripts/make_sweep_golden.py) recorded in tests/golden/sweep_cases.npz."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sweep_ref
+from tests.sweep_data import synthetic_aod
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sweep_cases.npz"))
+N = int(G["n_cases"])
+
+
+def case(i):
+    k = f"c{i}"
+    h, w, seed = (int(v) for v in G[k + "_hws"])
+    aod, fires = synthetic_aod(h, w, seed)
+    assert np.array_equal(fires, G[k + "_fires"])
+    thr = G[k + "_thr"]
+    masks = np.unpackbits(G[k + "_masks"])[: len(thr) * h * w].reshape(len(thr), h, w).astype(bool)
+    return aod, fires, thr, masks, G[k + "_extents"], G[k + "_index"]
+
+
+def test_constants():
+    assert int(G["p_id_win_size"]) == sweep_ref.P_ID_WIN_SIZE
+    w = sweep_ref.P_ID_WIN_SIZE
+    dy, dx = np.meshgrid(np.arange(-w, w + 1), np.arange(-w, w + 1), indexing="ij")
+    assert np.array_equal(np.sqrt(dx ** 2 + dy ** 2), G["distance_matrix"])
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_masks_extents_and_threshold_index_match_reference(i):
+    aod, fires, thr, masks, extents, index = case(i)
+    got = sweep_ref.threshold_masks_ref(aod, thr)
+    assert np.array_equal(got, masks)
+    ext = sweep_ref.find_plume_extents_ref(got, fires[:, 0], fires[:, 1])
+    assert np.array_equal(ext, extents)
+    idx = [-1 if v is None else v for v in sweep_ref.find_threshold_index_ref(ext)]
+    assert idx == index.tolist()
+    assert (extents > 0).any() and (extents == 0).any()
+
+
+def test_find_threshold_index_tables():
+    idx = [-1 if v is None else v for v in sweep_ref.find_threshold_index_ref(G["tables"])]
+    assert idx == G["tables_index"].tolist()
+
+
+def test_label_canonical_form():
+    m = np.array([[1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 0, 0], [1, 1, 0, 1]], dtype=bool)
+    lab = sweep_ref.label_ref(m)
+    assert lab.tolist() == [[1, 0, 0, 4], [0, 1, 0, 4], [0, 0, 0, 0], [13, 13, 0, 16]]   # diagonal joins (8-conn.)
