@@ -214,6 +214,23 @@ int plume_locate_fires(const double* lats, const double* lons, int H, int W, con
                        const double* fire_lon, int n_fires, double half_box_deg, void* workspace,
                        size_t workspace_bytes, int* out_row_col, plume_stream_t stream);
 
+/* ---- threshold sweep (replaces plume_identifier_gaussian_profile.py:142-202) ------------------------------ */
+/* masks[t][y][x] (uint8 0/1) = binary_dilation(binary_erosion(aod > thresholds[t])) with the cross-shaped
+ * footprint (erosion treats pixels beyond the border as set, dilation as unset); aod float32 [H][W], compared
+ * in float64 against the float64 thresholds (T <= 64), every threshold from one read of the image. */
+int plume_threshold_masks(const float* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
+                          plume_stream_t stream);
+/* 8-connected components of every mask plane.  labels[t][i] = -1 for background, else the smallest row-major
+ * pixel index of the pixel's component (a canonical label); sizes[t][i] = pixel count of the component whose
+ * canonical label is i (0 elsewhere).  labels / sizes are int32 [T][H][W]. */
+int plume_label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes,
+                           plume_stream_t stream);
+/* extents[t][f] = size of the component nearest to fire f = (fire_row_col[2f], fire_row_col[2f+1]) inside the
+ * (2 win + 1)^2 window around it (Euclidean pixel distance, first pixel in row-major window order on ties), 0 if
+ * the window holds no component: find_plume_extents / extract_label of the reference. */
+int plume_fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_row_col,
+                       int n_fires, int win, int* extents, plume_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -351,4 +351,20 @@ int plume_locate_fires(const double* lats, const double* lons, int H, int W, con
                       out_row_col, S(stream));
 }
 
+int plume_threshold_masks(const float* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
+                          plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || (aod && thresholds && masks), "threshold_masks: null pointer");
+  return threshold_masks(aod, H, W, thresholds, T, masks, S(stream));
+}
+int plume_label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes,
+                           plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || (masks && labels && sizes), "label_components: null pointer");
+  return label_components(masks, T, H, W, labels, sizes, S(stream));
+}
+int plume_fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_row_col,
+                       int n_fires, int win, int* extents, plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || n_fires <= 0 || (labels && sizes && fire_row_col && extents), "fire_extents: null pointer");
+  return fire_extents(labels, sizes, T, H, W, fire_row_col, n_fires, win, extents, S(stream));
+}
+
 }  // extern "C"

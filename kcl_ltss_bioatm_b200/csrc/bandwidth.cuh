@@ -65,4 +65,9 @@ int locate_fires(const double* lats, const double* lons, int H, int W, const dou
                  const double* fire_lon, int n_fires, double half_box, void* workspace, size_t workspace_bytes,
                  int* out_rc, cudaStream_t s);
 
+int threshold_masks(const float* aod, int H, int W, const double* thr, int T, uint8_t* masks, cudaStream_t s);
+int label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes, cudaStream_t s);
+int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_rc, int n_fires, int win,
+                 int* extents, cudaStream_t s);
+
 }  // namespace plume

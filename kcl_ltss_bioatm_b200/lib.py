@@ -56,6 +56,9 @@ SIGNATURES = {
     "plume_extract_tiles": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
     "plume_rasterize_hulls": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "plume_threshold_masks": (_I, [_P, _I, _I, _P, _I, _P, _P]),
+    "plume_label_components": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "plume_fire_extents": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "plume_locate_fires_workspace_bytes": (ctypes.c_size_t, [_I]),
     "plume_locate_fires": (_I, [_P, _P, _I, _I, _P, _P, _I, ctypes.c_double, _P, ctypes.c_size_t, _P, _P]),
 }

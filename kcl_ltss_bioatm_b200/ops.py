@@ -362,3 +362,46 @@ class CudaOps:
                                           float(half_box_deg), ptr(ws), nbytes, ptr(out_rc), current_stream()),
               "plume_locate_fires")
         self.launches += 4 if n else 0
+
+    # ------------------------------------------------------------------ threshold sweep
+    @staticmethod
+    def _dev(t, dtype, name):
+        if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+            raise TypeError(f"{name}: expected a contiguous {dtype} CUDA tensor")
+        return ptr(t)
+
+    def threshold_masks(self, aod, thresholds, masks):
+        """aod float32 [H, W], thresholds float64 [T] -> masks uint8 [T, H, W] = dilate(erode(aod > t))."""
+        h, w = aod.shape
+        t = thresholds.numel()
+        if tuple(masks.shape) != (t, h, w):
+            raise ValueError("masks must be [T, H, W]")
+        check(self.lib.plume_threshold_masks(self._dev(aod, torch.float32, "aod"), h, w,
+                                             self._dev(thresholds, torch.float64, "thresholds"), t,
+                                             self._dev(masks, torch.uint8, "masks"), current_stream()),
+              "plume_threshold_masks")
+        self.launches += 1
+
+    def label_components(self, masks, labels, sizes):
+        """masks uint8 [T, H, W] -> labels int32 [T, H, W] (-1 background, else the component's smallest pixel
+        index), sizes int32 [T, H, W] (component size at its canonical index)."""
+        t, h, w = masks.shape
+        if labels.shape != masks.shape or sizes.shape != masks.shape:
+            raise ValueError("labels / sizes must have the masks' shape")
+        check(self.lib.plume_label_components(self._dev(masks, torch.uint8, "masks"), t, h, w,
+                                              self._dev(labels, torch.int32, "labels"),
+                                              self._dev(sizes, torch.int32, "sizes"), current_stream()),
+              "plume_label_components")
+        self.launches += 3
+
+    def fire_extents(self, labels, sizes, fire_rc, win, extents):
+        """fire_rc int32 [n, 2] -> extents int32 [T, n]: size of the component nearest to each fire in its window."""
+        t, h, w = labels.shape
+        n = fire_rc.shape[0]
+        if tuple(extents.shape) != (t, n) or fire_rc.dim() != 2 or fire_rc.shape[1] != 2:
+            raise ValueError("extents must be [T, n_fires], fire_rc [n_fires, 2]")
+        check(self.lib.plume_fire_extents(self._dev(labels, torch.int32, "labels"), self._dev(sizes, torch.int32, "sizes"),
+                                          t, h, w, self._dev(fire_rc, torch.int32, "fire_rc"), n, int(win),
+                                          self._dev(extents, torch.int32, "extents"), current_stream()),
+              "plume_fire_extents")
+        self.launches += 1

@@ -321,3 +321,31 @@ class RefOps:
         rc = fire_ref.nearest_pixel_ref(fire_lat.cpu().numpy(), fire_lon.cpu().numpy(), lats.cpu().numpy(),
                                         lons.cpu().numpy())
         out_rc.copy_(torch.from_numpy(rc).to(torch.int32))
+
+    # ---- threshold sweep ---------------------------------------------------------------------------
+    def threshold_masks(self, aod, thresholds, masks):
+        from oracle.sweep_ref import threshold_masks_ref
+
+        masks.copy_(torch.from_numpy(threshold_masks_ref(aod.cpu().numpy(), thresholds.cpu().numpy()).astype("uint8")))
+
+    def label_components(self, masks, labels, sizes):
+        import numpy as np
+
+        from oracle.sweep_ref import label_ref
+
+        for t in range(masks.shape[0]):
+            lab = label_ref(masks[t].cpu().numpy().astype(bool))          # 0 background, else 1 + smallest index
+            labels[t].copy_(torch.from_numpy((lab - 1).astype("int32")))
+            cnt = np.bincount(lab.ravel(), minlength=lab.size + 1)[1:]
+            cnt[lab.ravel() == 0] = cnt[lab.ravel() == 0] * 0
+            sizes[t].copy_(torch.from_numpy(cnt.reshape(lab.shape).astype("int32")))
+
+    def fire_extents(self, labels, sizes, fire_rc, win, extents):
+        from oracle.sweep_ref import extract_label_ref
+
+        for t in range(labels.shape[0]):
+            lab = labels[t].cpu().numpy().astype("int64") + 1
+            sz = sizes[t].cpu().numpy().ravel()
+            for f, (r, c) in enumerate(fire_rc.cpu().numpy()):
+                l = extract_label_ref(lab, int(r), int(c), win)
+                extents[t, f] = 0 if l is None else int(sz[l - 1])

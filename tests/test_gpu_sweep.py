@@ -1,0 +1,92 @@
+"""GPU: threshold masks, connected components and plume extents through the C ABI against the oracle and the
+golden vectors recorded from the reference's functions (boolean / integer work: exact)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from kcl_ltss_bioatm_b200 import sweep
+from oracle import sweep_ref
+from tests.sweep_data import synthetic_aod
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sweep_cases.npz"))
+N = int(G["n_cases"])
+
+
+@pytest.fixture(scope="module")
+def sw():
+    return sweep.ThresholdSweep("cuda:0")
+
+
+def case(i):
+    k = f"c{i}"
+    h, w, seed = (int(v) for v in G[k + "_hws"])
+    aod, fires = synthetic_aod(h, w, seed)
+    thr = G[k + "_thr"]
+    masks = np.unpackbits(G[k + "_masks"])[: len(thr) * h * w].reshape(len(thr), h, w).astype(bool)
+    return aod, fires, thr, masks, G[k + "_extents"], G[k + "_index"]
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_sweep_equals_reference_golden(sw, i):
+    aod, fires, thr, masks, extents, index = case(i)
+    m = sw.masks(aod, thr)
+    assert np.array_equal(m.cpu().numpy().astype(bool), masks)
+    ext = sw.extents(aod, thr, fires[:, 0], fires[:, 1])
+    assert ext.dtype == np.float64 and np.array_equal(ext, extents)
+    idx = [-1 if v is None else v for v in sweep.find_threshold_index(ext)]
+    assert idx == index.tolist()
+
+
+def test_reference_named_functions(sw):
+    aod, fires, thr, masks, extents, _ = case(0)
+    d = sweep.generate_mask_dict(aod, thr)
+    assert list(d.keys()) == list(thr) and all(np.array_equal(d[t], masks[k]) for k, t in enumerate(thr))
+    assert np.array_equal(sweep.find_plume_extents(d, fires[:, 0], fires[:, 1]), extents)
+
+
+@pytest.mark.parametrize("h,w,density", [(1, 1, 1.0), (7, 300, 0.5), (64, 64, 0.62), (257, 129, 0.4), (600, 800, 0.55)])
+def test_components_equal_oracle_on_random_masks(sw, h, w, density):
+    """Percolation-like random masks: long winding components, many merges across block boundaries."""
+    rng = np.random.default_rng(h * 1000 + w)
+    masks = (rng.random((3, h, w)) < density)
+    masks[1] = ~masks[1] if h > 1 else masks[1]
+    if h >= 8 and w >= 8:                       # a spiral: the worst case for label propagation
+        sp = np.zeros((h, w), dtype=bool)
+        y0, x0, y1, x1 = 0, 0, h - 1, w - 1
+        while y1 - y0 > 3 and x1 - x0 > 3:
+            sp[y0, x0:x1 + 1] = True
+            sp[y0:y1 + 1, x1] = True
+            sp[y1, x0 + 2:x1 + 1] = True
+            sp[y0 + 2:y1 + 1, x0 + 2] = True
+            y0, x0, y1, x1 = y0 + 2, x0 + 2, y1 - 2, x1 - 2
+        masks[2] = sp
+    labels, sizes = sw.label(torch.from_numpy(masks.astype(np.uint8)).cuda())
+    labels, sizes = labels.cpu().numpy(), sizes.cpu().numpy()
+    for t in range(3):
+        ref = sweep_ref.label_ref(masks[t])               # 0 background, else 1 + smallest index of the component
+        assert np.array_equal(labels[t].astype(np.int64) + 1, ref)
+        cnt = np.bincount(ref.ravel(), minlength=h * w + 1)[1:].reshape(h, w)
+        roots = (ref.ravel() == np.arange(1, h * w + 1)).reshape(h, w)
+        assert np.array_equal(sizes[t], np.where(roots, cnt, 0))
+
+
+def test_masks_border_rules_and_float64_compare(sw):
+    aod = np.full((6, 7), 1.0, dtype=np.float32)          # everything set: erosion must not eat the border
+    assert sw.masks(aod, [0.5]).cpu().numpy().all()
+    aod[:] = 0.0
+    aod[2, 3] = 1.0                                       # a singleton disappears
+    assert not sw.masks(aod, [0.5]).cpu().numpy().any()
+    x = np.float32(0.48)                                  # float32(0.48) > 0.48 in float64, as numpy compares
+    aod[:] = x
+    assert sw.masks(aod, [0.48]).cpu().numpy().all() == bool(np.float64(x) > 0.48)
+    ref = sweep_ref.threshold_masks_ref(aod, [0.48])
+    assert np.array_equal(sw.masks(aod, [0.48]).cpu().numpy().astype(bool), ref)
+
+
+def test_fire_too_close_to_edge_is_rejected(sw):
+    aod, _, thr, _, _, _ = case(0)
+    with pytest.raises(ValueError):
+        sw.extents(aod, thr, [3], [40])
