@@ -81,9 +81,15 @@ int threshold_masks(const float* aod, int H, int W, const double* thr, int T, ui
 // ------------------------------------------------------------------------------------------------
 // Connected components, 8-connectivity.  parent[] holds, per plane, a union-find forest over pixel indices;
 // links always point to the smaller index, so a component's root is its smallest row-major index (the
-// canonical label).  Merge: a pixel joins its west neighbour and, in the row above, its north neighbour -- or,
-// when north is background, north-west and north-east (if north is set they are already joined through
-// north's own west link / north-east's west link).
+// canonical label).  Run based: a warp owns 32 consecutive pixels of a row.
+//   init  : every set pixel points straight at the first pixel of its horizontal run inside the warp's
+//           segment (ballot + count-leading-zeros, no atomics).
+//   merge : unions only where a connection is new -- a segment's first pixel with the pixel to its left, and
+//           with the row above only at the leftmost pixel of a run that touches an upper run: at a run start
+//           north (or, if north is unset, north-west and north-east); inside a run only north-east when north
+//           is unset (everything else was already joined by the pixel to the left).
+//   flatten: every pixel looks up its root; the size counters are bumped once per (warp, root) with
+//           __match_any_sync instead of once per pixel (large components would serialise on one address).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(const int* parent, int x) {
   int p = parent[x];
@@ -111,64 +117,104 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
+struct RowSeg {
+  int t, y, x;       // plane, row, column of this lane's pixel
+  bool valid;        // inside the image
+};
+__device__ __forceinline__ RowSeg row_segment(int H, int W, int T) {
+  const int segs = (W + 31) / 32;
+  const long long warp = (1ll * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  RowSeg r;
+  r.t = static_cast<int>(warp / (1ll * H * segs));
+  const int rem = static_cast<int>(warp % (1ll * H * segs));
+  r.y = rem / segs;
+  r.x = (rem % segs) * 32 + (threadIdx.x & 31);
+  r.valid = r.t < T && r.x < W;
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
-    ccl_init_kernel(const uint8_t* __restrict__ masks, long long total, int plane, int* __restrict__ parent,
+    ccl_init_kernel(const uint8_t* __restrict__ masks, int T, int H, int W, int* __restrict__ parent,
                     int* __restrict__ sizes) {
-  const long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  parent[i] = masks[i] ? static_cast<int>(i % plane) : -1;
+  const RowSeg r = row_segment(H, W, T);
+  const int lane = threadIdx.x & 31;
+  const long long i = (1ll * r.t * H + r.y) * W + r.x;
+  const bool m = r.valid && masks[i];
+  const uint32_t bits = __ballot_sync(0xffffffffu, m);
+  if (!r.valid) return;
+  int p = -1;
+  if (m) {
+    const uint32_t lower = (1u << lane) - 1u;
+    const uint32_t zeros = ~bits & lower;                    // unset pixels to the left, inside the segment
+    const int start = zeros ? 32 - __clz(zeros) : 0;         // first lane of this lane's run
+    p = r.y * W + (r.x - lane) + start;
+  }
+  parent[i] = p;
   sizes[i] = 0;
 }
 
 __global__ void __launch_bounds__(256)
-    ccl_merge_kernel(const uint8_t* __restrict__ masks, int H, int W, int* __restrict__ parent_all) {
-  const int plane = H * W;
-  const long long g = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
-  if (g >= plane) return;
-  const uint8_t* m = masks + 1ll * t * plane;
-  int* parent = parent_all + 1ll * t * plane;
-  const int i = static_cast<int>(g);
+    ccl_merge_kernel(const uint8_t* __restrict__ masks, int T, int H, int W, int* __restrict__ parent_all) {
+  const RowSeg r = row_segment(H, W, T);
+  if (!r.valid) return;
+  const int lane = threadIdx.x & 31;
+  const long long plane = 1ll * H * W;
+  const uint8_t* m = masks + r.t * plane;
+  int* parent = parent_all + r.t * plane;
+  const int i = r.y * W + r.x;
   if (!m[i]) return;
-  const int y = i / W, x = i % W;
-  if (x > 0 && m[i - 1]) uf_union(parent, i, i - 1);
-  if (y > 0) {
-    if (m[i - W]) {
-      uf_union(parent, i, i - W);
-    } else {
-      if (x > 0 && m[i - W - 1]) uf_union(parent, i, i - W - 1);
-      if (x + 1 < W && m[i - W + 1]) uf_union(parent, i, i - W + 1);
-    }
+  const bool w = r.x > 0 && m[i - 1];
+  if (lane == 0 && w) uf_union(parent, i, i - 1);            // the run continues from the segment to the left
+  if (r.y == 0) return;
+  const bool n = m[i - W];
+  const bool ne = r.x + 1 < W && m[i - W + 1];
+  if (w) {
+    if (!n && ne) uf_union(parent, i, i - W + 1);
+  } else if (n) {
+    uf_union(parent, i, i - W);
+  } else {
+    if (r.x > 0 && m[i - W - 1]) uf_union(parent, i, i - W - 1);
+    if (ne) uf_union(parent, i, i - W + 1);
   }
 }
 
 __global__ void __launch_bounds__(256)
-    ccl_flatten_kernel(int H, int W, int* __restrict__ parent_all, int* __restrict__ sizes_all) {
-  const int plane = H * W;
-  const long long g = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
-  if (g >= plane) return;
-  int* parent = parent_all + 1ll * t * plane;
-  const int i = static_cast<int>(g);
-  if (parent[i] < 0) return;
-  const int root = uf_find(parent, i);
-  parent[i] = root;   // readers that race with this see the old parent or the root: both are ancestors
-  atomicAdd(&sizes_all[1ll * t * plane + root], 1);
+    ccl_flatten_kernel(int T, int H, int W, int* __restrict__ parent_all, int* __restrict__ sizes_all) {
+  const RowSeg r = row_segment(H, W, T);
+  const int lane = threadIdx.x & 31;
+  const long long plane = 1ll * H * W;
+  int root = -1;
+  if (r.valid) {
+    int* parent = parent_all + r.t * plane;
+    const int i = r.y * W + r.x;
+    if (parent[i] >= 0) {
+      root = uf_find(parent, i);
+      parent[i] = root;   // readers that race with this see the old parent or the root: both are ancestors
+    }
+  }
+  const uint32_t active = __ballot_sync(0xffffffffu, root >= 0);
+  if (root < 0) return;
+  const uint32_t same = __match_any_sync(active, root);
+  if (lane == __ffs(same) - 1) atomicAdd(&sizes_all[r.t * plane + root], __popc(same));
 }
 
 int label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes, cudaStream_t s) {
   if (T <= 0 || H <= 0 || W <= 0) return 0;
   const long long plane = 1ll * H * W;
-  if (plane >= 0x7FFFFFFFll || T > 65535) {
-    set_error("label_components: plane too large or too many planes");
+  if (plane >= 0x7FFFFFFFll) {
+    set_error("label_components: plane too large");
     return -1;
   }
-  const long long total = plane * T;
-  ccl_init_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(masks, total, static_cast<int>(plane),
-                                                                             labels, sizes);
-  dim3 grid(static_cast<unsigned>((plane + 255) / 256), T);
-  ccl_merge_kernel<<<grid, 256, 0, s>>>(masks, H, W, labels);
-  ccl_flatten_kernel<<<grid, 256, 0, s>>>(H, W, labels, sizes);
+  const long long warps = 1ll * T * H * ((W + 31) / 32);
+  const long long blocks = (warps + 7) / 8;
+  if (blocks >= 0x7FFFFFFFll) {
+    set_error("label_components: too many pixels for one call");
+    return -1;
+  }
+  const unsigned grid = static_cast<unsigned>(blocks);
+  ccl_init_kernel<<<grid, 256, 0, s>>>(masks, T, H, W, labels, sizes);
+  ccl_merge_kernel<<<grid, 256, 0, s>>>(masks, T, H, W, labels);
+  ccl_flatten_kernel<<<grid, 256, 0, s>>>(T, H, W, labels, sizes);
   return check_launch_sweep("label_components");
 }
 
