@@ -1,5 +1,5 @@
 // HBM-bandwidth kernels of the UNet hot path: BatchNorm apply / backward, 2x2 max pool (+argmax),
-// 1x1 head + sigmoid + BCE/Dice, fused Adam, weight packing, split-K reduction, tile cut / stitch.
+// 1x1 head + sigmoid + BCE/Dice, fused Adam, weight packing, tile cut / stitch.
 // All activation traffic is 128-bit vectorised (8 bf16), coalesced along the NHWC channel dimension;
 // grids are sized in multiples of the SM count and walk the data with a grid-stride loop in which a
 // thread keeps the same 8 channels, so per-channel parameters live in registers.

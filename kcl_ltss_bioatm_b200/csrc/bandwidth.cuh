@@ -1,5 +1,6 @@
-// Internal C++ interface of the bandwidth kernels (bandwidth.cu).  Input and output buffers of one
-// call must not alias: inputs are read through the non-coherent path.
+// Internal C++ interface of the bandwidth kernels (bandwidth.cu), the label-geometry kernels (geometry.cu)
+// and the threshold-sweep kernels (sweep.cu).  Input and output buffers of one call must not alias: inputs
+// are read through the non-coherent path.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>

@@ -411,7 +411,6 @@ struct Conv3Params {
   float* stat_sum;
   float* stat_sq;
   long long* prof;                // optional [grid][8] cycle counters (plume_debug_set_prof)
-  int dbg_mode;                   // diagnostics (PLUME_CONV3_DBG): 1 = skip epilogue work, 2 = no TMA loads
 };
 
 constexpr int kHaloBytes = 18 * 1024;  // 8 w x 18 h pixels x 64 channels bf16
@@ -936,7 +935,6 @@ static int try_launch_conv3(const FwdDesc& d) {
   p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
   p.stat_sum = d.stat_sum; p.stat_sq = d.stat_sq;
   p.prof = g_prof_buf;
-  p.dbg_mode = 0;
 
   // mode 0: weights resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (a slot is
   //         12 MMAs of work; fewer cannot cover the TMA latency)
@@ -1241,8 +1239,8 @@ static void wgrad_geometry(int N, int H, int W, int* bw, int* bh, int* bn, int* 
 
 static int wgrad_block_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
 
-// One place decides which weight-gradient kernel runs and how K is split, so that the workspace size
-// reported through the C ABI always matches what the launcher does.
+// One place decides which weight-gradient kernel runs and how K is split, so that what the C ABI reports
+// (plume_wgrad_splits) always matches what the launcher does.
 struct WgradConfig {
   bool halo;        // igemm_wgrad3_kernel (3x3, halo reuse) vs the generic igemm_wgrad_kernel
   int block_n;
