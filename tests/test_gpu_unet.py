@@ -285,3 +285,53 @@ def test_no_cpu_fallback_in_product_path():
     with pytest.raises(TypeError):
         cu.scale_shift_act(torch.zeros(1, 2, 2, 8, dtype=torch.bfloat16), None, None, 1,
                            torch.zeros(1, 2, 2, 8, dtype=torch.bfloat16))
+
+
+def test_non_square_ragged_tiles_three_steps():
+    """n = 3 tiles of 40 x 72 (partial GEMM tiles along both axes at every level), depth 2: three optimisation
+    steps track the oracle's losses."""
+    spec = UNetSpec(base_filters=64, depth=2)
+    torch.manual_seed(0)
+    ref = UNetRef(spec).train()
+    opt = make_optimizer(ref, spec)
+    net = make_net(spec, seed=0)
+    for i in range(3):
+        x, t = synthetic_batch(3, 40, 72, spec.in_channels, seed=50 + i)
+        opt.zero_grad()
+        loss_ref = plume_loss(ref(nchw(x))[:, 0], t, spec)
+        loss_ref.backward()
+        opt.step()
+        out = net.train_step(x.to(DEV), t.to(DEV))
+        torch.cuda.synchronize()
+        assert abs(out[0].item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item()), (i, out[0].item(), loss_ref.item())
+    with pytest.raises(ValueError):
+        net.forward(torch.zeros(1, 42, 72, spec.in_channels, dtype=torch.bfloat16, device=DEV))   # 42 % 4 != 0
+
+
+def test_micro_batches_accumulate_like_one_backward_without_batchnorm():
+    """Gradient accumulation over 2 micro-batches == one backward over the whole batch when nothing couples the
+    samples (no BatchNorm, no Dice): checks accumulate / loss_scale / the deferred side-stream join."""
+    from kcl_ltss_bioatm_b200.trainer import Trainer
+
+    spec = UNetSpec(base_filters=64, depth=2, norm="none", dice_weight=0.0)
+    x, t = synthetic_batch(4, 32, 32, spec.in_channels, seed=9)
+    a = Trainer(spec, device=DEV, seed=3, micro_batches=1)
+    b = Trainer(spec, device=DEV, seed=3, micro_batches=2)
+    a.model.train(True)
+    a.model.forward(x.to(DEV), t.to(DEV))
+    a.model.backward()
+    b.model.train(True)
+    for i in range(2):
+        b.model.forward(x[2 * i:2 * i + 2].to(DEV), t[2 * i:2 * i + 2].to(DEV))
+        b.model.backward(accumulate=i > 0, loss_scale=0.5)
+    torch.cuda.synchronize()
+    ga, gb = a.model.grads.cpu(), b.model.grads.cpu()
+    assert ((ga - gb).abs().max() / ga.abs().max()).item() < 2e-3
+    # and through Trainer.step: parameters after one step agree
+    a2 = Trainer(spec, device=DEV, seed=3, micro_batches=1)
+    b2 = Trainer(spec, device=DEV, seed=3, micro_batches=2)
+    a2.step(x.to(DEV), t.to(DEV))
+    b2.step(x.to(DEV), t.to(DEV))
+    torch.cuda.synchronize()
+    pa, pb = a2.model.params.cpu(), b2.model.params.cpu()
+    assert (pa - pb).abs().max().item() <= 2.5e-3      # Adam's first step moves every weight by ~lr regardless of scale
