@@ -258,13 +258,15 @@ __global__ void __launch_bounds__(256, 1)
       const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
+      // A tile may span several output views (transposed conv: the four (i,j) phases are the four 64-column
+      // chunks of one 256-wide tile, so the input tile is read once for all of them); a 64-column chunk never
+      // straddles views (cout_per_view % 64 == 0).  Per-channel vectors are indexed by n % cout_per_view.
       const int col0 = n_tile * BLOCK_N;
-      const int ov = col0 / p.cout_per_view;
-      const int ch0 = col0 % p.cout_per_view;
 
       for (int c = et; c < BLOCK_N; c += 128) {
-        s_scale[c] = p.scale ? p.scale[ch0 + c] : 1.0f;
-        s_shift[c] = p.shift ? p.shift[ch0 + c] : 0.0f;
+        const int ch = (col0 + c) % p.cout_per_view;
+        s_scale[c] = p.scale ? p.scale[ch] : 1.0f;
+        s_shift[c] = p.shift ? p.shift[ch] : 0.0f;
         s_sum[c] = 0.0f;
         s_sq[c] = 0.0f;
       }
@@ -301,8 +303,9 @@ __global__ void __launch_bounds__(256, 1)
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (et == 0) {
-          tma_store_4d(&omaps.m[ov], sbase + L::OFF_STG + sb * L::STG_BYTES, ch0 + chunk * 64, w0, h0,
-                       n0);
+          const int col = col0 + chunk * 64;
+          tma_store_4d(&omaps.m[col / p.cout_per_view], sbase + L::OFF_STG + sb * L::STG_BYTES,
+                       col % p.cout_per_view, w0, h0, n0);
           tma_store_commit();
         }
         if (do_stats) {
@@ -329,8 +332,9 @@ __global__ void __launch_bounds__(256, 1)
       if (do_stats) {
         named_bar_sync(1, 128);
         for (int c = et; c < BLOCK_N; c += 128) {
-          atomicAdd(p.stat_sum + ch0 + c, s_sum[c]);
-          atomicAdd(p.stat_sq + ch0 + c, s_sq[c]);
+          const int ch = (col0 + c) % p.cout_per_view;
+          atomicAdd(p.stat_sum + ch, s_sum[c]);
+          atomicAdd(p.stat_sq + ch, s_sq[c]);
         }
       }
     }
@@ -1011,7 +1015,12 @@ int launch_igemm_fwd(const FwdDesc& d) {
   }
   int bw, bh, bn;
   pick_box(W, H, 128, 16, &bw, &bh, &bn);
-  const int block_n = (d.cout_per_view % 256 == 0) ? 256 : (d.cout_per_view % 128 == 0 ? 128 : 64);
+  // 64-channel views (the first decoder level's transposed conv): one 256-wide tile covers all four views, so
+  // the input tile is read once instead of four times (153 -> 137 us); wider views keep one view per tile
+  // (spanning measured slower there: 72 -> 76 us)
+  const int block_n = (d.cout_per_view == 64 && d.num_out_views == 4)
+                          ? 256
+                          : ((d.cout_per_view % 256 == 0) ? 256 : (d.cout_per_view % 128 == 0 ? 128 : 64));
 
   TmapPack4 amaps, omaps;
   CUtensorMap bmap;
