@@ -180,6 +180,8 @@ class GemmTimer:
 
     FWD_KERNEL = ("conv3x3_fwd", "conv3x3_dgrad", "convT_fwd", "convT_dgrad")
     WGRAD = ("conv3x3_wgrad", "convT_wgrad")
+    # HBM-bound BatchNorm kernels: algorithmic bytes per bf16 element (reads + writes), DESIGN.md section 3.4
+    STREAM = {"scale_shift_act": 4.0, "bn_bwd_reduce": 4.0, "bn_bwd_apply": 6.0}
 
     def __init__(self, ops, logical_cin0: int, padded_cin0: int):
         import torch
@@ -188,7 +190,7 @@ class GemmTimer:
         self.records = []  # (family, flops, ev0, ev1)
         self.enabled = False
         self.cin0, self.cin0_pad = logical_cin0, padded_cin0
-        for name in self.FWD_KERNEL + self.WGRAD:
+        for name in self.FWD_KERNEL + self.WGRAD + tuple(self.STREAM):
             setattr(ops, name, self._wrap(name, getattr(ops, name)))
 
     def _flops(self, name, a):
@@ -213,7 +215,7 @@ class GemmTimer:
         raise KeyError(name)
 
     def _wrap(self, name, fn):
-        fam = "fwd_kernel" if name in self.FWD_KERNEL else "wgrad_kernel"
+        fam = "fwd_kernel" if name in self.FWD_KERNEL else ("wgrad_kernel" if name in self.WGRAD else "stream_kernel")
 
         def timed(*a, **kw):
             if not self.enabled:
@@ -223,14 +225,15 @@ class GemmTimer:
             e0.record()
             r = fn(*a, **kw)
             e1.record()
-            self.records.append((fam, self._flops(name, a), e0, e1))
+            work = self.STREAM[name] * a[0].numel() if name in self.STREAM else self._flops(name, a)
+            self.records.append((fam, work, e0, e1))
             return r
 
         return timed
 
     def summary(self):
         out = {}
-        for fam in ("fwd_kernel", "wgrad_kernel"):
+        for fam in ("fwd_kernel", "wgrad_kernel", "stream_kernel"):
             rec = [r for r in self.records if r[0] == fam]
             ms = sum(r[2].elapsed_time(r[3]) for r in rec)
             fl = sum(r[1] for r in rec)
@@ -401,6 +404,12 @@ def _run_gpu(args):
     roof_w = {"bound": "tensor", "kernel": "igemm_wgrad3_kernel / igemm_wgrad_kernel (split-K, fp32 atomics into dW)", "achieved": wk["tflops"],
               "peak": peak_tf, "unit": "TFLOP/s", "frac": wk["tflops"] / peak_tf if peak_tf else None,
               "launches_timed": wk["launches"], "ms_per_step": wk["ms"] / max(roof_steps, 1)}
+    sk = gemm["stream_kernel"]   # for this family "flops" holds algorithmic bytes
+    peak_bw = float(peaks.get("hbm_gbs", 0) or 0)
+    gbs = sk["flops"] / (sk["ms"] * 1e-3) / 1e9 if sk["ms"] > 0 else 0.0
+    roof_s = {"bound": "hbm", "kernel": "scale_shift_act + bn_bwd_reduce + bn_bwd_apply (BatchNorm apply / backward)",
+              "achieved": gbs, "peak": peak_bw or None, "unit": "GB/s", "frac": gbs / peak_bw if peak_bw else None,
+              "launches_timed": sk["launches"], "ms_per_step": sk["ms"] / max(roof_steps, 1)}
     step_tf = train_flops_per_tile(spec, TILE, TILE) * BATCH / (ms_total / args.steps * 1e-3) / 1e12
 
     # ---------------- CPU baseline: config 1 on the host cores (bounded to ~20 s)
@@ -425,7 +434,7 @@ def _run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches,
-        "roofline": roof, "roofline_wgrad": roof_w,
+        "roofline": roof, "roofline_wgrad": roof_w, "roofline_hbm": roof_s,
         "step_tflops": step_tf, "step_frac_of_peak": step_tf / peak_tf if peak_tf else None,
         "clocks": clocks, "cpu_baseline": cpu, "final_loss": loss_now,
     }
