@@ -335,3 +335,25 @@ def test_micro_batches_accumulate_like_one_backward_without_batchnorm():
     torch.cuda.synchronize()
     pa, pb = a2.model.params.cpu(), b2.model.params.cpu()
     assert (pa - pb).abs().max().item() <= 2.5e-3      # Adam's first step moves every weight by ~lr regardless of scale
+
+
+def test_device_prefetcher_delivers_every_batch_in_order():
+    """Seven pinned host batches through two device slots: each yielded pair equals its host batch, even when the
+    consumer's kernels on a slot are still queued while the next copies are issued (the slot's `free` event)."""
+    from kcl_ltss_bioatm_b200.data import DevicePrefetcher
+
+    host = []
+    for i in range(7):
+        x = torch.full((4, 64, 64, 8), float(i + 1), dtype=torch.bfloat16).pin_memory()
+        t = torch.full((4, 64, 64), i % 2, dtype=torch.uint8).pin_memory()
+        host.append((x, t))
+    sums, big = [], torch.randn(4096, 4096, device=DEV)
+    for x, t in DevicePrefetcher(host, DEV, depth=2):
+        for _ in range(3):                        # keep the stream busy so the consumer lags behind the copies
+            big = big @ big * 1e-4
+        sums.append((x.float().sum(), t.sum(dtype=torch.int64)))
+    torch.cuda.synchronize()
+    n = 4 * 64 * 64
+    assert [int(s.item()) for s, _ in sums] == [n * 8 * (i + 1) for i in range(7)]
+    assert [int(c.item()) for _, c in sums] == [n * (i % 2) for i in range(7)]
+    assert list(DevicePrefetcher(host[:2], "cpu")) == host[:2]      # CPU device: passes the host batches through
