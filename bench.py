@@ -375,6 +375,7 @@ def _run_gpu(args):
     if pg is not None:
         import torch.distributed as dist
         dist.barrier(group=pg)
+        trainer.release_graphs()   # captured NCCL kernels must be gone before the communicator is
         dist.destroy_process_group()
     if rank != 0:
         return 0, None

@@ -55,8 +55,11 @@ class Trainer:
                               bucket_mb=bucket_mb)
         self.micro_batches = micro_batches
         self.pg = process_group
-        # Data-parallel steps stay eager.  Capturing the bucketed NCCL all-reduces inside the step's CUDA graph
-        # (PLUME_GRAPH_DP=1) hung on 2 x B200 with torch 2.11 / NCCL 2.28.9 and is off by default.
+        # Data-parallel steps run eagerly by default.  PLUME_GRAPH_DP=1 captures them too (bucketed NCCL all-reduces
+        # inside the step's CUDA graph): verified on 2 x B200 (+0.7 % device-resident, +2 % end to end), not yet on
+        # 8.  Two requirements found the hard way: capture in "thread_local" error mode (the NCCL watchdog thread
+        # touches the CUDA API) and release_graphs() before destroy_process_group() -- tearing the communicator
+        # down while a graph still holds its kernels hangs.
         self.graph_dp = os.environ.get("PLUME_GRAPH_DP", "0") == "1"
         self.log = logging.getLogger("train_model")
         if process_group is not None:
@@ -124,7 +127,8 @@ class Trainer:
             m.train(True)
             nbt = m.num_batches_tracked
             launches0 = m.ops.launches
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.pg is not None else "global"):
                 m.forward(xs, ts)
                 m.backward(defer_tail=True)
                 m.optimizer_step_dev(coef)
@@ -146,6 +150,14 @@ class Trainer:
         graph.replay()
         m.ops.launches += self.graph_launches
         return m.loss_out
+
+    def release_graphs(self) -> None:
+        """Drop the captured CUDA graphs.  Must be called before ``destroy_process_group()`` when data-parallel
+        steps were captured: destroying the NCCL communicator while a graph still holds its kernels hangs."""
+        g = getattr(self, "_graphs", None)
+        if g:
+            torch.cuda.synchronize()
+            g.clear()
 
     def fit(self, steps: int, batch_fn: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
             log_every: int = 10, on_step: Optional[Callable[[int, float], None]] = None):
