@@ -303,8 +303,8 @@ def _run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
         return float(t.item())
 
-    # Single GPU: the step is replayed from a captured CUDA graph (Trainer.step_graphed, one graph launch per
-    # step); data parallel: eager steps (the bucketed all-reduce is issued from inside backward).
+    # The step is replayed from a captured CUDA graph (Trainer.step_graphed, one graph launch per step); under
+    # data parallelism the bucketed NCCL all-reduces are captured with it (PLUME_GRAPH_DP=0: eager steps).
     graphed = pg is None or trainer.graph_dp
     step_fn = trainer.step_graphed if graphed else trainer.step
 

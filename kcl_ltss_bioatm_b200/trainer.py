@@ -55,12 +55,12 @@ class Trainer:
                               bucket_mb=bucket_mb)
         self.micro_batches = micro_batches
         self.pg = process_group
-        # Data-parallel steps run eagerly by default.  PLUME_GRAPH_DP=1 captures them too (bucketed NCCL all-reduces
-        # inside the step's CUDA graph): verified on 2 x B200 (+0.7 % device-resident, +2 % end to end), not yet on
-        # 8.  Two requirements found the hard way: capture in "thread_local" error mode (the NCCL watchdog thread
+        # Data-parallel steps are captured too (the bucketed NCCL all-reduces live inside the step's CUDA graph):
+        # verified on 2 and 8 x B200 (8 GPUs: 12.04 vs 12.53 ms/step eager).  PLUME_GRAPH_DP=0 keeps them eager.
+        # Two requirements found the hard way: capture in "thread_local" error mode (the NCCL watchdog thread
         # touches the CUDA API) and release_graphs() before destroy_process_group() -- tearing the communicator
         # down while a graph still holds its kernels hangs.
-        self.graph_dp = os.environ.get("PLUME_GRAPH_DP", "0") == "1"
+        self.graph_dp = os.environ.get("PLUME_GRAPH_DP", "1") != "0"
         self.log = logging.getLogger("train_model")
         if process_group is not None:
             import torch.distributed as dist
