@@ -1,7 +1,7 @@
 """Measurement of the fire -> pixel geolocation, one JSON line: a 1200 x 1200 MAIAC-like
 lat/lon grid (float64) and 2048 fires, all located in one call.  Device time by CUDA events (20 calls after 3
 warm-ups).  Algorithmic bytes: the two float64 grids are read once per pass (2 x 23 MB) plus the fire arrays;
-the roofline entry reports that against the HBM copy peak.  cpu_baseline: the numpy
+the roofline entry reports that against the HBM copy peak.  cpu_baseline: the plain-C
 oracle (the reference's algorithm) on a bounded sample of the same fires, one core."""
 import json
 import os
@@ -44,12 +44,14 @@ for _ in range(5):
     rows, cols = loc.locate(flat, flon)
 e2e_s = (time.perf_counter() - t0) / 5
 
-from oracle import fire_ref  # noqa: E402
-S = 64
+from oracle import c_ref, fire_ref  # noqa: E402
+c_ref.nearest_pixels(flat[:1], flon[:1], lat[:8, :8], lon[:8, :8])      # build / load outside the timed region
+S = 256
 t0 = time.perf_counter()
-ref = fire_ref.nearest_pixel_ref(flat[:S], flon[:S], lat, lon)
+ref = c_ref.nearest_pixels(flat[:S], flon[:S], lat, lon)               # plain-C oracle, one core
 cpu_s = time.perf_counter() - t0
-ok = bool(np.array_equal(ref, out.cpu().numpy()[:S]))
+ok = bool(np.array_equal(ref, out.cpu().numpy()[:S].astype(np.int64)))
+ok = ok and bool(np.array_equal(fire_ref.nearest_pixel_ref(flat[:16], flon[:16], lat, lon), ref[:16]))
 
 peaks = {}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -67,7 +69,7 @@ line = {
                  "frac": streamed / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                  "note": "bound by the per-chunk fire culling and the float64 haversine of the candidates, not by HBM"},
     "cpu_baseline": {"value": S / cpu_s, "unit": "fires/s", "cores": 1, "kind": "port",
-                     "sample": f"numpy oracle (the reference's per-fire full-image masks), first {S} fires ({cpu_s:.2f} s)"},
+                     "sample": f"plain-C oracle (per fire one pass over the image, as the reference's per-fire masks), first {S} fires ({cpu_s:.2f} s)"},
     "parity_on_sample": ok,
 }
 print(json.dumps(line))

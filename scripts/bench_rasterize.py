@@ -2,8 +2,8 @@
 a 4096 x 4096 scene with 512 plume hulls (hull sizes like the reference's plume acceptance window, 100-2000 px
 area grown by the 5 x 5 dilation), whole-scene mask.  Kernel time by CUDA events on the launching stream
 (20 launches after 3 warm-ups; the 16.8 MB mask is re-written every launch), roofline = HBM: algorithmic bytes =
-H*W mask bytes written + the polygon arrays read once.  cpu_baseline: the numpy oracle on a bounded sample
-(the same hulls over a 1024 x 1024 corner), one core."""
+H*W mask bytes written + the polygon arrays read once.  cpu_baseline: the plain-C oracle on the whole scene,
+one core."""
 import json
 import os
 import sys
@@ -55,13 +55,16 @@ for _ in range(5):
     m_host = r.scene_mask(hulls, H, W).cpu()
 e2e_s = (time.perf_counter() - t0) / 5
 
-# CPU baseline (oracle, bounded sample) + parity on that sample
-from oracle import hull_ref  # noqa: E402
-S = 1024
+# CPU baseline: the plain-C oracle (oracle/geo_ref.c, one core) on the whole scene + parity on the whole scene;
+# the numpy oracle on a corner as a second check
+from oracle import c_ref, hull_ref  # noqa: E402
+c_ref.rasterize(hulls[:2], 64, 64)          # build / load outside the timed region
 t0 = time.perf_counter()
-ref = hull_ref.rasterize_ref(hulls, S, S)
+ref = c_ref.rasterize(hulls, H, W)
 cpu_s = time.perf_counter() - t0
-ok = bool(np.array_equal(ref, m_host[:S, :S].numpy()))
+ok = bool(np.array_equal(ref, m_host.numpy()))
+S = 512
+ok = ok and bool(np.array_equal(hull_ref.rasterize_ref(hulls, S, S), m_host[:S, :S].numpy()))
 
 peaks = {}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -77,8 +80,8 @@ line = {
     "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                  "note": "1 byte written per pixel is the whole algorithmic traffic; the kernel is bound by the per-pixel edge tests of the hulls that overlap a 32x128 block, not by HBM"},
-    "cpu_baseline": {"value": S * S / cpu_s / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": "port",
-                     "sample": f"numpy oracle, the same {N} hulls over the {S}x{S} corner ({cpu_s:.2f} s)"},
+    "cpu_baseline": {"value": H * W / cpu_s / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+                     "sample": f"plain-C oracle (bounding-box culled edge functions), the whole {H}x{W} scene with the same {N} hulls ({cpu_s:.3f} s)"},
     "parity_on_sample": ok,
 }
 print(json.dumps(line))

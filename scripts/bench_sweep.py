@@ -3,7 +3,7 @@ tile size), 64 fire clusters and the reference's three sweeps (25 thresholds eac
 0.5 / 0.75 / 1.0, plume_identifier_gaussian_profile.py:34-35, 489-495) = what the reference does per timestamp.
 Device time by CUDA events around masks + labelling + extents of all three sweeps (10 repetitions after 2 warm-ups).
 Algorithmic bytes per sweep: the image read once, per threshold the mask written and read (1 B) and the label
-and size planes written (4 B each).  cpu_baseline: the scipy / numpy oracle on ONE of the three sweeps, one core."""
+and size planes written (4 B each).  cpu_baseline: the plain-C oracle on all three sweeps, one core."""
 import json
 import os
 import sys
@@ -60,11 +60,16 @@ for _ in range(3):
     res = [sw.extents(aod, t, rows, cols) for t in sweeps]
 e2e_s = (time.perf_counter() - t0) / 3
 
-from oracle import sweep_ref  # noqa: E402
+from oracle import c_ref, sweep_ref  # noqa: E402
+c_ref.label8(np.zeros((4, 4), dtype=np.uint8))                         # build / load outside the timed region
 t0 = time.perf_counter()
-ref = sweep_ref.find_plume_extents_ref(sweep_ref.threshold_masks_ref(aod, sweeps[0]), rows, cols)
+ref = [c_ref.plume_extents(c_ref.threshold_masks(aod, t), rows, cols) for t in sweeps]   # plain-C oracle, one core
 cpu_s = time.perf_counter() - t0
-ok = bool(np.array_equal(ref, res[0]))
+ok = all(bool(np.array_equal(a, b)) for a, b in zip(ref, res))
+small = sweep_ref.find_plume_extents_ref(sweep_ref.threshold_masks_ref(aod[:300, :300], sweeps[0][:5]),
+                                         np.clip(rows[:8], 16, 283), np.clip(cols[:8], 16, 283))
+ok = ok and bool(np.array_equal(small, c_ref.plume_extents(c_ref.threshold_masks(aod[:300, :300], sweeps[0][:5]),
+                                                             np.clip(rows[:8], 16, 283), np.clip(cols[:8], 16, 283))))
 
 peaks = {}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -80,8 +85,8 @@ line = {
     "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                  "note": "union-find merge and flatten are latency / atomic bound, not streaming"},
-    "cpu_baseline": {"value": 1.0 / (3 * cpu_s), "unit": "timestamps/s", "cores": 1, "kind": "port",
-                     "sample": f"scipy/numpy oracle, one of the three sweeps ({cpu_s:.2f} s; x3 per timestamp)"},
+    "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "timestamps/s", "cores": 1, "kind": "port",
+                     "sample": f"plain-C oracle (two-pass union-find labelling), all three sweeps of the timestamp ({cpu_s:.2f} s)"},
     "parity_on_sample": ok,
 }
 print(json.dumps(line))
