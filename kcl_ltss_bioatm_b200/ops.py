@@ -2,8 +2,8 @@
 
 Tensors are torch CUDA tensors in NHWC; bf16 activations may be channel slices of a wider buffer
 (``concat[..., :C]``) -- the pixel stride is read from ``stride(2)``.  Outputs are preallocated by the
-caller (nothing is allocated per call except the growable weight-gradient workspace), so a whole
-step is a fixed sequence of launches on the current stream.
+caller (nothing is allocated per call; ``locate_fires`` reuses one growable scratch buffer), so a whole step is
+a fixed sequence of launches on the current stream.
 
 The same method names and argument meaning are implemented on CPU in ``oracle/ops_ref.py``; that class
 is test infrastructure (the checker), never imported from here.
@@ -356,7 +356,7 @@ class CudaOps:
                 or not out_rc.is_contiguous():
             raise ValueError("fire arrays / out_rc do not agree")
         nbytes = int(self.lib.plume_locate_fires_workspace_bytes(n))
-        ws = torch.empty(max(nbytes, 32), dtype=torch.uint8, device=lats.device)  # caching allocator: 512 B aligned
+        ws = self._workspace(nbytes, lats.device)  # grown on demand, reused across calls (512-byte aligned)
         h, w = lats.shape
         check(self.lib.plume_locate_fires(ptr(lats), ptr(lons), h, w, ptr(fire_lat), ptr(fire_lon), n,
                                           float(half_box_deg), ptr(ws), nbytes, ptr(out_rc), current_stream()),
