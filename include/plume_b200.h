@@ -136,16 +136,19 @@ int plume_maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const 
                          plume_stream_t stream);
 
 /* BatchNorm+ReLU backward.  Pass 1 reduces, per channel, sum(g) and sum(g*xhat) with
- * g = da * [scale*y+shift > 0] (or g = da when relu == 0), xhat = (y-mean)*invstd.
- * Pass 2 writes dy = scale * (g - sum_g/count - xhat*sum_gx/count) and accumulates sum(dy) (the conv
- * bias gradient); dgamma = sum_gx, dbeta = sum_g. */
+ * g = da * [scale*y+shift > 0] (or g = da when relu == 0), xhat = (y-mean)*invstd, into sum_g / sum_gx
+ * (fp32[C] scratch the caller zeroes before every backward pass: they must hold THIS batch's sums only).
+ * Pass 2 writes dy = scale * (g - sum_g/count - xhat*sum_gx/count), accumulates sum(dy) (the conv bias
+ * gradient) and, when dgamma / dbeta are given, hands the parameter gradients over:
+ * dgamma = sum_gx, dbeta = sum_g (added to the existing values when accumulate != 0: micro-batching). */
 int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
                         const float* shift, const float* mean, const float* invstd, int relu,
                         float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream);
 int plume_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu,
                        const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
-                       long long pixels, int C, plume_stream_t stream);
+                       float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
+                       plume_stream_t stream);
 /* ReLU(+bias) backward for norm == "none": dy = da * [a > 0]; accumulates sum(dy) per channel. */
 int plume_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy,
                    float* sum_dy, long long pixels, int C, plume_stream_t stream);

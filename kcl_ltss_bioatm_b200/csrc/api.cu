@@ -263,11 +263,12 @@ int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const 
 int plume_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu,
                        const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
-                       long long pixels, int C, plume_stream_t stream) {
+                       float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
+                       plume_stream_t stream) {
   PLUME_CHECK(da && y && scale && shift && mean && invstd && sum_g && sum_gx && dy,
               "bn_bwd_apply: null pointer");
   return bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy,
-                      sum_dy, pixels, C, S(stream));
+                      sum_dy, dgamma, dbeta, accumulate, pixels, C, S(stream));
 }
 int plume_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
                    long long pixels, int C, plume_stream_t stream) {

@@ -526,8 +526,16 @@ __global__ void __launch_bounds__(kThreads)
                         const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                         const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
                         float inv_count, __nv_bfloat16* __restrict__ dy, long long lddy, float* sum_dy,
-                        long long pixels, int CV) {
+                        float* dgamma, float* dbeta, int accumulate, long long pixels, int CV) {
   extern __shared__ float s_acc[];
+  // the finished per-channel sums are the BatchNorm parameter gradients; one block hands them over (sum_g /
+  // sum_gx are a per-backward scratch, so that micro-batch accumulation never feeds stale sums into this pass)
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    for (int c = threadIdx.x; c < CV * 8; c += kThreads) {
+      dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sum_gx[c];
+      dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sum_g[c];
+    }
+  }
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
   const long long pstep = (1ll * gridDim.x * kThreads) / CV;
@@ -588,7 +596,11 @@ __global__ void __launch_bounds__(kThreads)
 int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                  const float* shift, const float* mean, const float* invstd, int relu,
                  const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
-                 long long pixels, int C, cudaStream_t s) {
+                 float* dgamma, float* dbeta, int accumulate, long long pixels, int C, cudaStream_t s) {
+  if ((dgamma == nullptr) != (dbeta == nullptr)) {
+    set_error("bn_bwd_apply: dgamma and dbeta go together");
+    return -1;
+  }
   if (C % 8 || ldda % 8 || ldy % 8 || lddy % 8 || C <= 0) {
     set_error("bn_bwd_apply: channels/strides must be multiples of 8");
     return -1;
@@ -600,7 +612,7 @@ int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* 
   bn_bwd_apply_kernel<<<grid, kThreads, smem, s>>>(
       static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
       shift, mean, invstd, relu, sum_g, sum_gx, 1.f / static_cast<float>(pixels),
-      static_cast<__nv_bfloat16*>(dy), lddy, sum_dy, pixels, CV);
+      static_cast<__nv_bfloat16*>(dy), lddy, sum_dy, dgamma, dbeta, accumulate, pixels, CV);
   return check_launch("bn_bwd_apply");
 }
 

@@ -34,7 +34,7 @@ int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float*
 int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                  const float* shift, const float* mean, const float* invstd, int relu,
                  const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
-                 long long pixels, int C, cudaStream_t s);
+                 float* dgamma, float* dbeta, int accumulate, long long pixels, int C, cudaStream_t s);
 int relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
              long long pixels, int C, cudaStream_t s);
 int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cudaStream_t s);

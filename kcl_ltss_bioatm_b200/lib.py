@@ -45,7 +45,7 @@ SIGNATURES = {
     "plume_maxpool2x2_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "plume_maxpool2x2_bwd": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "plume_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _LL, _I, _P]),
-    "plume_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _LL, _I, _P]),
+    "plume_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _LL, _I, _P]),
     "plume_relu_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _LL, _I, _P]),
     "plume_channel_sum": (_I, [_P, _I, _P, _LL, _I, _P]),
     "plume_head_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P]),

@@ -242,15 +242,19 @@ class CudaOps:
                                            current_stream()), "plume_bn_bwd_reduce")
         self.launches += 1
 
-    def bn_bwd_apply(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, sum_dy):
+    def bn_bwd_apply(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, sum_dy,
+                     dgamma=None, dbeta=None, accumulate=False):
+        """sum_g / sum_gx: this batch's sums from bn_bwd_reduce (a scratch zeroed per backward pass); dgamma /
+        dbeta: where the parameter gradients go (added to when accumulate)."""
         dap, ldda, n, h, w, c = _act(da, "da")
         yp, ldy, *_ = _act(y, "y")
         dyp, lddy, *_ = _act(dy, "dy")
         check(self.lib.plume_bn_bwd_apply(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
                                           _f32(mean, "mean"), _f32(invstd, "invstd"), int(bool(relu)),
-                                          _f32(sum_g, "sum_g"), _f32(sum_gx, "sum_gx"), dyp, lddy,
-                                          _f32(sum_dy, "sum_dy"), n * h * w, c, current_stream()),
-              "plume_bn_bwd_apply")
+                                          _f32(sum_g, "sum_g", c), _f32(sum_gx, "sum_gx", c), dyp, lddy,
+                                          _f32(sum_dy, "sum_dy"), _f32(dgamma, "dgamma", c),
+                                          _f32(dbeta, "dbeta", c), int(bool(accumulate)), n * h * w, c,
+                                          current_stream()), "plume_bn_bwd_apply")
         self.launches += 1
 
     def relu_bwd(self, da, a, dy, sum_dy):

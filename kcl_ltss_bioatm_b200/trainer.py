@@ -89,12 +89,31 @@ class Trainer:
         m.optimizer_step()
         return m.loss_out
 
-    # ------------------------------------------------------------------ CUDA-graph step (single GPU)
+    # ------------------------------------------------------------------ CUDA-graph step
+    def _snapshot(self):
+        """Everything an optimisation step mutates, so that the un-captured warm-up step can be undone."""
+        m = self.model
+        return (m.params.clone(), m.adam_m.clone(), m.adam_v.clone(), m._stat_region.clone(), m.step_count,
+                m.num_batches_tracked)
+
+    def _restore(self, snap) -> None:
+        m = self.model
+        m.params.copy_(snap[0])
+        m.adam_m.copy_(snap[1])
+        m.adam_v.copy_(snap[2])
+        m._stat_region.copy_(snap[3])
+        m.step_count, m.num_batches_tracked = snap[4], snap[5]
+        m._param_version += 1
+
     def step_graphed(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        """Same optimisation step replayed from a captured CUDA graph (forward, backward, Adam: ~170 kernel
-        launches become one graph launch).  The batch is copied into static device buffers, the Adam
-        bias-correction coefficients into an 8-float device buffer, then the graph is replayed.  Captured
-        on first use per (N, H, W); single process only (the data-parallel all-reduce stays eager)."""
+        """Same optimisation step replayed from a captured CUDA graph (forward, backward, the bucketed gradient
+        all-reduces under data parallelism, Adam: ~170 kernel launches become one graph launch).  The batch is
+        copied into static device buffers, the Adam bias-correction coefficients into an 8-float device buffer,
+        then the graph is replayed.  Captured on first use per (N, H, W); every call, the capturing one
+        included, performs exactly ONE optimisation step: capture is preceded by one un-captured warm-up step
+        (one-time work such as kernel attributes and buffer allocation must not be captured) whose effect on
+        parameters, Adam moments, running statistics and counters is rolled back from a snapshot.  Each captured
+        shape keeps its own activation buffers alive (the graph holds raw pointers into them)."""
         m = self.model
         if self.micro_batches != 1 or m.device.type != "cuda" or (self.pg is not None and not self.graph_dp):
             return self.step(x, target)
@@ -110,33 +129,32 @@ class Trainer:
             coef_host = [(torch.zeros(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
             xs.copy_(x)
             ts.copy_(target)
-            # two eager steps on a side stream: lazy one-time work (kernel attributes, buffers) must not be
-            # captured, and they are real optimisation steps on this batch
+            m._buf = None  # a fresh activation set for this shape: other shapes' graphs keep theirs
+            snap = self._snapshot()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):
-                    m.train(True)
-                    m.forward(xs, ts)
-                    m.backward(defer_tail=True)
-                    m.step_count += 1
-                    coef.copy_(m.adam_coefficients(m.step_count).to(x.device))
-                    m.optimizer_step_dev(coef)
+                m.train(True)
+                m.forward(xs, ts)
+                m.backward(defer_tail=True)
+                coef.copy_(m.adam_coefficients(m.step_count + 1).to(x.device))
+                m.optimizer_step_dev(coef)
+                self._restore(snap)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             m.train(True)
-            nbt = m.num_batches_tracked
             launches0 = m.ops.launches
             # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.pg is not None else "global"):
                 m.forward(xs, ts)
                 m.backward(defer_tail=True)
                 m.optimizer_step_dev(coef)
-            m.num_batches_tracked = nbt  # capture runs the Python bookkeeping once without executing kernels
+            m.num_batches_tracked = snap[5]  # capture runs the Python bookkeeping once without executing kernels
             self.graph_launches = m.ops.launches - launches0  # kernels of ours inside one replay
-            g[key] = (graph, xs, ts, coef, coef_host, 2)
-            return m.loss_out  # the two warm-up steps already consumed this batch
-        graph, xs, ts, coef, coef_host, _ = g[key]
+            m.ops.launches = launches0
+            g[key] = (graph, xs, ts, coef, coef_host, m._buf)
+        graph, xs, ts, coef, coef_host, bufs = g[key]
+        m._buf = bufs  # the activations this graph writes (grad_dict / a following eager backward read them)
         xs.copy_(x, non_blocking=True)
         ts.copy_(target, non_blocking=True)
         m.step_count += 1
@@ -149,6 +167,10 @@ class Trainer:
         ev.record()
         graph.replay()
         m.ops.launches += self.graph_launches
+        # the replay updated the parameters and the running statistics on the device: the packed bf16 weights
+        # and the folded eval coefficients cached on the host side are stale
+        m._param_version += 1
+        m._stats_version += 1
         return m.loss_out
 
     def release_graphs(self) -> None:

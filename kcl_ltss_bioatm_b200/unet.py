@@ -85,6 +85,10 @@ class UNetB200:
         zoff += 8
         self._zero_region = torch.zeros(zoff, dtype=torch.float32, device=dev)
         self._stat_region = torch.zeros(soff, dtype=torch.float32, device=dev)
+        # BatchNorm-backward sums of THIS backward pass ([sum_g | sum_gx] per layer, same offsets as the forward
+        # statistics): zeroed at the start of every backward, never the gradient slots themselves -- with
+        # micro-batch accumulation those hold the previous slices' sums, which must not enter bn_bwd_apply
+        self._bwd_region = torch.zeros(max(self._head_sums_off, 1), dtype=torch.float32, device=dev)
         for name, L in self.convs.items():
             c, z, s = L.cout, zmap[name], smap[name]
             st = self._stat_region
@@ -94,6 +98,7 @@ class UNetB200:
                 "invstd": st[s + 3 * c:s + 4 * c], "running_mean": st[s + 4 * c:s + 5 * c],
                 "running_var": st[s + 5 * c:s + 6 * c], "fold_scale": st[s + 6 * c:s + 7 * c],
                 "fold_shift": st[s + 7 * c:s + 8 * c],
+                "sum_g": self._bwd_region[z:z + c], "sum_gx": self._bwd_region[z + c:z + 2 * c],
             }
             self._bn[name]["running_var"].fill_(1.0)
         self.head_sums = self._zero_region[self._head_sums_off:self._head_sums_off + 4]
@@ -102,7 +107,8 @@ class UNetB200:
         self._buf: Optional[_Buffers] = None
         self._packed_version = -1
         self._param_version = 0
-        self._folded_version = -1
+        self._stats_version = 0     # advances with every training forward (the running statistics change)
+        self._folded_version = (-1, -1)
 
         # data parallel
         self.pg = process_group
@@ -360,14 +366,15 @@ class UNetB200:
         self._packed_version = self._param_version
 
     def _fold_bn(self) -> None:
-        if not self.use_bn or self._folded_version == self._param_version:
+        version = (self._param_version, self._stats_version)
+        if not self.use_bn or self._folded_version == version:
             return
         for name, L in self.convs.items():
             st = self._bn[name]
             self.ops.bn_fold_eval(self.p(f"{L.bn}.weight"), self.p(f"{L.bn}.bias"), st["running_mean"],
                                   st["running_var"], self.p(f"{name}.bias"), self.spec.bn_eps,
                                   st["fold_scale"], st["fold_shift"])
-        self._folded_version = self._param_version
+        self._folded_version = version
 
     # ------------------------------------------------------------------ forward
     def _prep_input(self, x: torch.Tensor, b: _Buffers) -> torch.Tensor:
@@ -429,6 +436,7 @@ class UNetB200:
             self._zero_region.zero_()
             if self.use_bn:
                 self.num_batches_tracked += 1
+                self._stats_version += 1
         else:
             self._fold_bn()
         cur = self._prep_input(x, b)
@@ -503,10 +511,11 @@ class UNetB200:
             torch.cuda.current_stream(self.device).wait_event(busy)
         if self.use_bn:
             st = self._bn[name]
-            dbeta, dgamma = self.g(f"{L.bn}.bias"), self.g(f"{L.bn}.weight")
-            ops.bn_bwd_reduce(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, dbeta, dgamma)
-            ops.bn_bwd_apply(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, dbeta, dgamma,
-                             g_y, self.g(f"{name}.bias"))
+            ops.bn_bwd_reduce(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, st["sum_g"],
+                              st["sum_gx"])
+            ops.bn_bwd_apply(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, st["sum_g"],
+                             st["sum_gx"], g_y, self.g(f"{name}.bias"), self.g(f"{L.bn}.weight"),
+                             self.g(f"{L.bn}.bias"), acc)
         else:
             ops.relu_bwd(g_a, a, g_y, self.g(f"{name}.bias"))
         ready = self._mark()
@@ -559,6 +568,8 @@ class UNetB200:
         spec, d, ops = self.spec, self.spec.depth, self.ops
         if not acc:
             self.grads.zero_()
+        if self.use_bn:
+            self._bwd_region.zero_()
         self._pending = []
         self._next_bucket = 0
         self._sync = sync

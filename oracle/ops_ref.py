@@ -203,7 +203,15 @@ class RefOps:
         sum_g += g.sum(dim=(0, 1, 2))
         sum_gx += (g * xhat).sum(dim=(0, 1, 2))
 
-    def bn_bwd_apply(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, sum_dy):
+    def bn_bwd_apply(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, sum_dy,
+                     dgamma=None, dbeta=None, accumulate=False):
+        if dgamma is not None:
+            if accumulate:
+                dgamma += sum_gx
+                dbeta += sum_g
+            else:
+                dgamma.copy_(sum_gx)
+                dbeta.copy_(sum_g)
         yf = y.float()
         g = da.float()
         if relu:

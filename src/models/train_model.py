@@ -29,18 +29,70 @@ logging.basicConfig(level=logging.INFO, format=LOG_FMT)
 logger = logging.getLogger(__name__)
 
 
+class TileFiles:
+    """Index of every tile in ``<folder>/*.pt`` ({"x": [n,h,w,c], "mask": [n,h,w]} as written by
+    ``labels.write_training_tiles``).  Tiles are numbered globally across files; batch `it` of rank `r` is the
+    `per_rank` consecutive tiles starting at ``(it * world + r) * per_rank`` (wrapping around), so every tile of
+    every file is visited and every rank gets the same count.  Shapes are validated once, up front."""
+
+    def __init__(self, files, spec):
+        self.files, self.counts = files, []
+        self.hw = None
+        div = spec.divisor()
+        for f in files:
+            blob = torch.load(f, map_location="cpu")
+            x, m = blob["x"], blob["mask"]
+            if x.dim() != 4 or m.dim() != 3 or x.shape[0] != m.shape[0] or tuple(x.shape[1:3]) != tuple(m.shape[1:]):
+                raise ValueError(f"{f}: expected x [n,h,w,c] and mask [n,h,w], got {tuple(x.shape)} / {tuple(m.shape)}")
+            if x.shape[-1] != spec.in_channels:
+                raise ValueError(f"{f}: expected {spec.in_channels} bands, got {x.shape[-1]}")
+            if x.shape[1] % div or x.shape[2] % div:
+                raise ValueError(f"{f}: tile size {x.shape[1]}x{x.shape[2]} is not a multiple of {div}")
+            if self.hw is None:
+                self.hw = tuple(x.shape[1:3])
+            elif tuple(x.shape[1:3]) != self.hw:
+                raise ValueError(f"{f}: tile size {tuple(x.shape[1:3])} differs from {self.hw} in {files[0]}")
+            self.counts.append(int(x.shape[0]))
+        self.total = sum(self.counts)
+        if self.total == 0:
+            raise ValueError(f"no tiles in {len(files)} files")
+        self._cache = (None, None)
+
+    def locate(self, g):
+        """Global tile index -> (file index, index inside the file)."""
+        g %= self.total
+        for fi, c in enumerate(self.counts):
+            if g < c:
+                return fi, g
+            g -= c
+        raise AssertionError
+
+    def _blob(self, fi):
+        if self._cache[0] != fi:
+            self._cache = (fi, torch.load(self.files[fi], map_location="cpu"))
+        return self._cache[1]
+
+    def batch(self, it, per_rank, rank, world):
+        start = (it * world + rank) * per_rank
+        xs, ms = [], []
+        for g in range(start, start + per_rank):
+            fi, k = self.locate(g)
+            blob = self._blob(fi)
+            xs.append(blob["x"][k])
+            ms.append(blob["mask"][k])
+        return torch.stack(xs).to(torch.bfloat16), torch.stack(ms).to(torch.uint8)
+
+
 def _file_batches(folder, per_rank, rank, world, device, spec):
     files = sorted(glob.glob(os.path.join(folder, "*.pt")))
     if not files:
         return None
-    logger.info("training on %d tile files under %s", len(files), folder)
+    index = TileFiles(files, spec)
+    logger.info("training on %d tiles in %d files under %s", index.total, len(files), folder)
 
     def batch_fn(it):
-        blob = torch.load(files[(it * world + rank) % len(files)], map_location="cpu")
-        x, m = blob["x"][:per_rank], blob["mask"][:per_rank]
-        if x.shape[-1] != spec.in_channels:
-            raise ValueError(f"{files[0]}: expected {spec.in_channels} bands, got {x.shape[-1]}")
-        return x.to(torch.bfloat16).to(device, non_blocking=True), m.to(torch.uint8).to(device, non_blocking=True)
+        x, m = index.batch(it, per_rank, rank, world)
+        return x.to(device, non_blocking=True), m.to(device, non_blocking=True)
 
     return batch_fn
 

@@ -214,18 +214,12 @@ def test_cuda_graph_step_matches_eager_step():
         x, t = batches[i % 3]
         la.append(a.step(x, t)[0].item())
         c.step(x, t)
-        if i == 0:
-            # the first graphed call performs two eager steps on its batch while capturing: mirror that
-            a.step(x, t)
-            c.step(x, t)
-            b.step_graphed(x, t)
-            lb.append(la[-1])
-        else:
-            lb.append(b.step_graphed(x, t)[0].item())
+        lb.append(b.step_graphed(x, t)[0].item())   # the capturing call is one optimisation step like any other
     torch.cuda.synchronize()
-    assert a.model.step_count == b.model.step_count == 9
-    assert a.model.num_batches_tracked == b.model.num_batches_tracked
-    for u, v in zip(la[2:], lb[2:]):
+    assert a.model.step_count == b.model.step_count == 8
+    assert a.model.num_batches_tracked == b.model.num_batches_tracked == 8
+    assert abs(la[0] - lb[0]) <= 1e-4 * abs(la[0])    # first step: identical weights, only summation order differs
+    for u, v in zip(la, lb):
         assert abs(u - v) <= 5e-3 * abs(u), (la, lb)
     sa, sb, sc = a.model.state_dict(), b.model.state_dict(), c.model.state_dict()
     for k in sa:

@@ -235,3 +235,67 @@ def test_bad_geometry_is_rejected(small):
         net.forward(x)
     with pytest.raises(ValueError):
         net.forward(torch.zeros(1, 16, 16, spec.in_channels + 8, dtype=BF))
+
+
+def test_batchnorm_micro_batches_second_slice_equals_standalone_backward():
+    """With BatchNorm, backward(accumulate=True) of slice 2 must add exactly the gradient a standalone backward of
+    slice 2 produces: the BatchNorm-backward sums of a slice are per-backward scratch, never the (accumulating)
+    dgamma / dbeta slots.  fp32 operator oracle, so the identity is exact to rounding."""
+    spec = UNetSpec(base_filters=64, depth=2)
+    x, t = make_batch(4, 16, 16, spec.in_channels, seed=11)
+    x = x.float()
+
+    def grads_of(slices):
+        net = UNetB200(spec, ops=RefOps(torch.float32), device="cpu", seed=0)
+        for i, sl in enumerate(slices):
+            net.forward(x[sl], t[sl])
+            net.backward(accumulate=i > 0, loss_scale=0.5)
+        return net.grads.clone()
+
+    g1, g2 = grads_of([slice(0, 2)]), grads_of([slice(2, 4)])
+    both = grads_of([slice(0, 2), slice(2, 4)])
+    assert rel(both, g1 + g2) < 1e-5
+    # and against autograd of the oracle doing the same two half-batch passes
+    torch.manual_seed(0)
+    ref = UNetRef(spec).train()
+    for sl in (slice(0, 2), slice(2, 4)):
+        (0.5 * plume_loss(ref(x[sl].permute(0, 3, 1, 2))[:, 0], t[sl], spec)).backward()
+    net = UNetB200(spec, ops=RefOps(torch.float32), device="cpu", seed=0)
+    net.grads.copy_(both)
+    gd = net.grad_dict()
+    for k, p in ref.named_parameters():
+        if k.endswith("conv1.bias") or k.endswith("conv2.bias"):
+            continue
+        assert rel(gd[k], p.grad) < 1e-4, k
+
+
+def test_tile_file_loader_visits_every_tile_and_validates(tmp_path):
+    """src/models/train_model.py's file-backed loader: tiles are indexed globally across files (none skipped), every
+    rank gets `per_rank` tiles, shapes are validated with the offending path in the message."""
+    from src.models.train_model import TileFiles
+
+    spec = UNetSpec(base_filters=64, depth=2)
+    counts, base = [5, 2, 3], 0
+    for i, n in enumerate(counts):
+        xs = torch.zeros(n, 8, 8, spec.in_channels)
+        for k in range(n):
+            xs[k] = base + k          # the tile's global index
+        torch.save({"x": xs, "mask": torch.zeros(n, 8, 8, dtype=torch.uint8)}, tmp_path / f"tiles_{i}.pt")
+        base += n
+    files = sorted(str(p) for p in tmp_path.glob("*.pt"))
+    idx = TileFiles(files, spec)
+    assert idx.total == 10
+    seen = []
+    for it in range(3):
+        for rank in range(2):
+            xb, mb = idx.batch(it, 2, rank, 2)
+            assert xb.shape == (2, 8, 8, spec.in_channels) and xb.dtype == BF and mb.dtype == torch.uint8
+            seen += [int(v) for v in xb[:, 0, 0, 0].float().tolist()]
+    assert seen == [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 0, 1]          # consecutive, wrapping, nothing skipped
+    torch.save({"x": torch.zeros(1, 8, 8, 3), "mask": torch.zeros(1, 8, 8, dtype=torch.uint8)}, tmp_path / "zz_bad.pt")
+    with pytest.raises(ValueError, match="zz_bad.pt"):
+        TileFiles(files + [str(tmp_path / "zz_bad.pt")], spec)
+    torch.save({"x": torch.zeros(1, 6, 8, spec.in_channels), "mask": torch.zeros(1, 6, 8, dtype=torch.uint8)},
+               tmp_path / "zz_odd.pt")
+    with pytest.raises(ValueError, match="zz_odd.pt"):
+        TileFiles([str(tmp_path / "zz_odd.pt")], spec)
