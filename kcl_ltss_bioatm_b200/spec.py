@@ -201,3 +201,13 @@ def train_flops_per_tile(spec: UNetSpec, h: int, w: int) -> float:
     f = fwd_flops_per_tile(spec, h, w)
     first = 2.0 * 9 * spec.in_channels * spec.base_filters * h * w
     return 3.0 * f["total"] - first
+
+
+def num_parameters(spec: UNetSpec) -> int:
+    """Logical (oracle) parameter count: conv / transposed-conv / head weights and biases, BatchNorm affine."""
+    n = 0
+    for L in conv_layers(spec).values():
+        n += L.cout * 9 * L.cin + L.cout + (2 * L.cout if spec.norm == "batch" else 0)
+    for U in up_layers(spec).values():
+        n += 4 * U.cin * U.cout + U.cout
+    return n + spec.base_filters * spec.n_classes + spec.n_classes
