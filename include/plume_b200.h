@@ -40,15 +40,16 @@ void plume_debug_set_prof(long long* buf);
 /* ---- tensor-core implicit GEMM (tcgen05 / TMEM / TMA) -------------------------------------- */
 
 /* y = act(conv3x3(x, w) * scale + shift); optional per-channel sum / sum-of-squares of the bf16
- * outputs accumulated (atomically) into stat_sum / stat_sq (fp32[Cout], caller zeroes them).
+ * outputs accumulated (atomically) into stat_sum / stat_sq (fp64[Cout], caller zeroes them; per-tile partial
+ * sums are fp32, the cross-tile accumulation is fp64 so that E[y^2] - E[y]^2 survives |mean| >> std).
  * Cin and Cout must be multiples of 64.  scale/shift may be NULL (1 / 0).
  * Fewer real input channels than Cin: pass ldx < Cin (a multiple of 8).  x is then taken as dense with
  * ldx channels per pixel and the weights' remaining input channels read as zero (TMA out-of-bounds fill)
  * -- how the 8-band input feeds the first layer without a padded copy.  Same rule in plume_conv3x3_wgrad,
  * where the gradient of those weight columns comes out zero. */
 int plume_conv3x3_fwd(const void* x, int ldx, const void* w_krsc_bf16, const float* scale,
-                      const float* shift, int relu, void* y, int ldy, float* stat_sum,
-                      float* stat_sq, int N, int H, int W, int Cin, int Cout, plume_stream_t stream);
+                      const float* shift, int relu, void* y, int ldy, double* stat_sum,
+                      double* stat_sq, int N, int H, int W, int Cin, int Cout, plume_stream_t stream);
 
 /* dx = conv3x3(dy, w_dgrad) with w_dgrad[ci][r][s][co] = w[co][2-r][2-s][ci] (plume_pack_conv3x3). */
 int plume_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad_bf16, void* dx, int lddx, int N,
@@ -106,10 +107,10 @@ int plume_pack_batch(const plume_pack_desc* descs, int n, int total_blocks, plum
 int plume_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels,
                        plume_stream_t stream);
 
-/* BatchNorm (training) from accumulated sums: mean/var over `count` values per channel, updates the
+/* BatchNorm (training) from accumulated sums (fp64): mean/var over `count` values per channel, updates the
  * running statistics (unbiased variance, PyTorch convention) and emits the fused scale = gamma*invstd,
  * shift = beta - mean*scale used by the apply kernels, plus mean / invstd for the backward pass. */
-int plume_bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+int plume_bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
                       const float* beta, float eps, float momentum, float* running_mean,
                       float* running_var, float* scale, float* shift, float* mean, float* invstd,
                       int C, plume_stream_t stream);

@@ -61,7 +61,7 @@ int plume_num_sms(void) {
 }
 
 int plume_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale, const float* shift,
-                      int relu, void* y, int ldy, float* stat_sum, float* stat_sq, int N, int H, int W,
+                      int relu, void* y, int ldy, double* stat_sum, double* stat_sq, int N, int H, int W,
                       int Cin, int Cout, plume_stream_t stream) {
   PLUME_CHECK(x && w && y, "conv3x3_fwd: null pointer");
   // ldx < Cin: x is dense with ldx channels per pixel; the weights' remaining input channels read as zero
@@ -211,7 +211,7 @@ int plume_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixe
   return pad_channels(in, Cs, out, Cd, pixels, S(stream));
 }
 
-int plume_bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+int plume_bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
                       const float* beta, float eps, float momentum, float* running_mean,
                       float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
                       plume_stream_t stream) {

@@ -158,16 +158,17 @@ int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, cu
 // ------------------------------------------------------------------------------------------------
 // BatchNorm finalize / fold
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* sum, const float* sq, float inv_count,
+__global__ void bn_finalize_kernel(const double* sum, const double* sq, double inv_count,
                                    float unbias, const float* gamma, const float* beta, float eps,
                                    float momentum, float* running_mean, float* running_var,
                                    float* scale, float* shift, float* mean_out, float* invstd_out,
                                    int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mean = sum[c] * inv_count;
-  float var = sq[c] * inv_count - mean * mean;
-  var = fmaxf(var, 0.f);
+  // mean and variance in double: E[y^2] - E[y]^2 cancels catastrophically in fp32 once |mean| >> std
+  const double mean_d = sum[c] * inv_count;
+  const float mean = static_cast<float>(mean_d);
+  const float var = static_cast<float>(fmax(sq[c] * inv_count - mean_d * mean_d, 0.0));
   const float invstd = rsqrtf(var + eps);
   const float g = gamma ? gamma[c] : 1.f;
   const float b = beta ? beta[c] : 0.f;
@@ -180,7 +181,7 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sq, float inv_
   if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
 }
 
-int bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+int bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean,
                 float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
                 cudaStream_t s) {
@@ -189,7 +190,7 @@ int bn_finalize(const float* sum, const float* sq, long long count, const float*
     return -1;
   }
   const float unbias = count > 1 ? static_cast<float>(count) / static_cast<float>(count - 1) : 1.f;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sq, 1.f / static_cast<float>(count), unbias,
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sq, 1.0 / static_cast<double>(count), unbias,
                                                      gamma, beta, eps, momentum, running_mean,
                                                      running_var, scale, shift, mean, invstd, C);
   return check_launch("bn_finalize");

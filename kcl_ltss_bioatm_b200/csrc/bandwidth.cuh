@@ -13,7 +13,7 @@ namespace plume {
 void set_error(const std::string& msg);
 
 int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, cudaStream_t s);
-int bn_finalize(const float* sum, const float* sq, long long count, const float* gamma,
+int bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean,
                 float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
                 cudaStream_t s);

@@ -80,8 +80,8 @@ struct FwdParams {
   const float* scale;
   const float* shift;
   int relu;
-  float* stat_sum;
-  float* stat_sq;
+  double* stat_sum;
+  double* stat_sq;
 };
 
 template <int BLOCK_N, int STAGES, int STAGING>
@@ -333,8 +333,9 @@ __global__ void __launch_bounds__(256, 1)
         named_bar_sync(1, 128);
         for (int c = et; c < BLOCK_N; c += 128) {
           const int ch = (col0 + c) % p.cout_per_view;
-          atomicAdd(p.stat_sum + ch, s_sum[c]);
-          atomicAdd(p.stat_sq + ch, s_sq[c]);
+          // fp64 accumulators: a channel with |mean| >> std loses its variance to cancellation in fp32
+          atomicAdd(p.stat_sum + ch, static_cast<double>(s_sum[c]));
+          atomicAdd(p.stat_sq + ch, static_cast<double>(s_sq[c]));
         }
       }
     }
@@ -412,8 +413,8 @@ struct Conv3Params {
   const float* scale;
   const float* shift;
   int relu;
-  float* stat_sum;
-  float* stat_sq;
+  double* stat_sum;
+  double* stat_sq;
   long long* prof;                // optional [grid][8] cycle counters (plume_debug_set_prof)
 };
 
@@ -867,8 +868,8 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       if (do_stats) {
         named_bar_sync(bar_a, 128);
         for (int c = et; c < BLOCK_N; c += 128) {
-          atomicAdd(p.stat_sum + ch0 + c, s_sum[c]);
-          atomicAdd(p.stat_sq + ch0 + c, s_sq[c]);
+          atomicAdd(p.stat_sum + ch0 + c, static_cast<double>(s_sum[c]));
+          atomicAdd(p.stat_sq + ch0 + c, static_cast<double>(s_sq[c]));
         }
       }
     }

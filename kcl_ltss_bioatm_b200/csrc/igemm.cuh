@@ -21,8 +21,8 @@ struct FwdDesc {
   const float* scale; // per output channel (index = n % cout_per_view), may be null (=1)
   const float* shift; // per output channel, may be null (=0)
   int relu;
-  float* stat_sum;    // optional per-channel sum / sum of squares of the bf16 outputs
-  float* stat_sq;
+  double* stat_sum;   // optional per-channel sum / sum of squares of the bf16 outputs (fp64 accumulators)
+  double* stat_sq;
   cudaStream_t stream;
 };
 int launch_igemm_fwd(const FwdDesc& d);

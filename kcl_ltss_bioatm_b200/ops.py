@@ -51,6 +51,16 @@ def _f32(t, name: str, numel: int | None = None):
     return ptr(t)
 
 
+def _f64(t, name: str, numel: int | None = None):
+    if t is None:
+        return ptr(None)
+    if t.dtype != torch.float64 or not t.is_contiguous() or not t.is_cuda:
+        raise TypeError(f"{name}: expected a contiguous fp64 CUDA tensor")
+    if numel is not None and t.numel() < numel:
+        raise ValueError(f"{name}: needs {numel} elements, has {t.numel()}")
+    return ptr(t)
+
+
 class CudaOps:
     """Launches the sm_100a kernels.  Fails loudly when the library or a GPU is missing."""
 
@@ -78,7 +88,7 @@ class CudaOps:
         assert w_fwd.dtype == torch.bfloat16 and w_fwd.is_contiguous()
         check(self.lib.plume_conv3x3_fwd(xp, ldx, ptr(w_fwd), _f32(scale, "scale", cout),
                                          _f32(shift, "shift", cout), int(bool(relu)), yp, ldy,
-                                         _f32(stat_sum, "stat_sum", cout), _f32(stat_sq, "stat_sq", cout),
+                                         _f64(stat_sum, "stat_sum", cout), _f64(stat_sq, "stat_sq", cout),
                                          n, h, w, kcin, cout, current_stream()), "plume_conv3x3_fwd")
         self.launches += 1
 
@@ -181,7 +191,7 @@ class CudaOps:
     def bn_finalize(self, ssum, ssq, count, gamma, beta, eps, momentum, running_mean, running_var,
                     scale, shift, mean, invstd):
         c = ssum.numel()
-        check(self.lib.plume_bn_finalize(_f32(ssum, "sum"), _f32(ssq, "sq"), int(count), _f32(gamma, "gamma"),
+        check(self.lib.plume_bn_finalize(_f64(ssum, "sum"), _f64(ssq, "sq"), int(count), _f32(gamma, "gamma"),
                                          _f32(beta, "beta"), float(eps), float(momentum),
                                          _f32(running_mean, "rm"), _f32(running_var, "rv"),
                                          _f32(scale, "scale"), _f32(shift, "shift"), _f32(mean, "mean"),

@@ -73,7 +73,7 @@ class UNetB200:
 
         # per-BatchNorm state: running statistics + per-step statistics / fused coefficients
         self._bn: Dict[str, Dict[str, torch.Tensor]] = {}
-        zoff = 0          # region zeroed every step: [sum | sq] per BN layer, then head sums
+        zoff = 0          # fp64 region zeroed every step: [sum | sq] per BN layer, then the head's loss sums (as fp32)
         soff = 0          # persistent per-layer vectors
         zmap, smap = {}, {}
         for name, L in self.convs.items():
@@ -82,8 +82,10 @@ class UNetB200:
             smap[name] = soff
             soff += 8 * L.cout
         self._head_sums_off = zoff
-        zoff += 8
-        self._zero_region = torch.zeros(zoff, dtype=torch.float32, device=dev)
+        zoff += 4         # 4 doubles = room for 8 floats
+        # the BatchNorm statistics accumulate in fp64 (E[y^2] - E[y]^2 cancels in fp32 when |mean| >> std); the head's
+        # four loss sums are fp32 views into the tail of the same buffer so that one memset zeroes everything
+        self._zero_region = torch.zeros(zoff, dtype=torch.float64, device=dev)
         self._stat_region = torch.zeros(soff, dtype=torch.float32, device=dev)
         # BatchNorm-backward sums of THIS backward pass ([sum_g | sum_gx] per layer, same offsets as the forward
         # statistics): zeroed at the start of every backward, never the gradient slots themselves -- with
@@ -101,7 +103,7 @@ class UNetB200:
                 "sum_g": self._bwd_region[z:z + c], "sum_gx": self._bwd_region[z + c:z + 2 * c],
             }
             self._bn[name]["running_var"].fill_(1.0)
-        self.head_sums = self._zero_region[self._head_sums_off:self._head_sums_off + 4]
+        self.head_sums = self._zero_region[self._head_sums_off:self._head_sums_off + 4].view(torch.float32)[:4]
         self.loss_out = torch.zeros(3, dtype=torch.float32, device=dev)
 
         self._buf: Optional[_Buffers] = None

@@ -49,7 +49,7 @@ class RefOps:
             o = o.relu()
         y.copy_(_nhwc(o).to(self.act_dtype))
         if stat_sum is not None:
-            yr = y.float()
+            yr = y.to(stat_sum.dtype)      # the accumulators are fp64 on the device
             stat_sum += yr.sum(dim=(0, 1, 2))
             stat_sq += (yr * yr).sum(dim=(0, 1, 2))
 
@@ -123,8 +123,9 @@ class RefOps:
 
     def bn_finalize(self, ssum, ssq, count, gamma, beta, eps, momentum, running_mean, running_var,
                     scale, shift, mean, invstd):
-        m = ssum / count
-        var = (ssq / count - m * m).clamp_min(0)
+        m = ssum.double() / count
+        var = (ssq.double() / count - m * m).clamp_min(0).float()
+        m = m.float()
         istd = torch.rsqrt(var + eps)
         g = gamma if gamma is not None else torch.ones_like(m)
         b = beta if beta is not None else torch.zeros_like(m)

@@ -79,10 +79,10 @@ def group_conv(cu, rf):
         shift = (0.1 * rnd(cout, seed=4)).float()
         for relu, stats in ((0, False), (1, True)):
             y_ref = torch.empty(n, h, w, cout, dtype=torch.bfloat16)
-            ss_r, sq_r = torch.zeros(cout), torch.zeros(cout)
+            ss_r, sq_r = torch.zeros(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64)
             rf.conv3x3_fwd(x, wt, scale, shift, relu, y_ref, ss_r if stats else None, sq_r if stats else None)
             y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
-            ss, sq = torch.zeros(cout, device=DEV), torch.zeros(cout, device=DEV)
+            ss, sq = (torch.zeros(cout, dtype=torch.float64, device=DEV) for _ in range(2))
             cu.conv3x3_fwd(x.to(DEV), wt.to(DEV), scale.to(DEV), shift.to(DEV), relu, y,
                            ss if stats else None, sq if stats else None)
             sync(cu, "conv3x3_fwd")
@@ -253,8 +253,8 @@ def group_bw(cu, rf):
         report("   maxpool_bwd", dx, dx_r, tol=0)
         # BN finalize + backward
         cnt = n * h * w
-        ss = y.float().sum(dim=(0, 1, 2))
-        sq = (y.float() ** 2).sum(dim=(0, 1, 2))
+        ss = y.double().sum(dim=(0, 1, 2))
+        sq = (y.double() ** 2).sum(dim=(0, 1, 2))
         gamma = (1 + 0.1 * rnd(c, seed=7)).float()
         beta = (0.1 * rnd(c, seed=8)).float()
         outs_r = [torch.zeros(c) for _ in range(4)]

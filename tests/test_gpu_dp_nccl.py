@@ -73,3 +73,51 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path):
     g = single.grads.cpu()
     err = (r0["grads"] - g).abs().max() / g.abs().max()
     assert err < 1e-4, float(err)
+
+
+def _worker_graphed(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from kcl_ltss_bioatm_b200.data import synthetic_batch
+    from kcl_ltss_bioatm_b200.spec import UNetSpec
+    from kcl_ltss_bioatm_b200.trainer import Trainer
+
+    spec = UNetSpec(base_filters=64, depth=2)          # with BatchNorm (per-GPU statistics) and Dice
+    batches = [synthetic_batch(4, 64, 64, spec.in_channels, seed=40 + 7 * rank + i, device=f"cuda:{rank}")
+               for i in range(3)]
+    eager = Trainer(spec, device=f"cuda:{rank}", process_group=dist.group.WORLD, seed=1, bucket_mb=0.5)
+    graphed = Trainer(spec, device=f"cuda:{rank}", process_group=dist.group.WORLD, seed=1, bucket_mb=0.5)
+    assert graphed.graph_dp and len(graphed.model._buckets) >= 3
+    le, lg = [], []
+    for i in range(6):
+        x, t = batches[i % 3]
+        le.append(float(eager.step(x, t)[0].item()))
+        lg.append(float(graphed.step_graphed(x, t)[0].item()))
+    torch.cuda.synchronize()
+    torch.save({"le": le, "lg": lg, "pe": eager.model.params.cpu(), "pg": graphed.model.params.cpu(),
+                "steps": (eager.model.step_count, graphed.model.step_count)}, os.path.join(out_dir, f"g{rank}.pt"))
+    dist.barrier()
+    graphed.release_graphs()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_graphed_steps_match_eager_steps(tmp_path):
+    """Data-parallel steps replayed from a CUDA graph (bucketed NCCL all-reduces captured inside) against the same
+    steps launched eagerly: same losses step by step, same parameters on both ranks, parameters of the two modes
+    equal up to what the unordered fp32 reductions allow."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29800 + os.getpid() % 90
+    mp.spawn(_worker_graphed, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    assert r0["steps"] == r1["steps"] == (6, 6)
+    assert torch.equal(r0["pg"], r1["pg"]) and torch.equal(r0["pe"], r1["pe"])     # replicas stay identical
+    for r in (r0, r1):
+        assert abs(r["le"][0] - r["lg"][0]) <= 1e-4 * abs(r["le"][0])              # step 1: identical weights
+        for a, b in zip(r["le"], r["lg"]):
+            assert abs(a - b) <= 1e-2 * abs(a), (r["le"], r["lg"])
+    d = (r0["pe"] - r0["pg"]).abs()
+    assert d.median().item() <= 1e-4 and (d.norm() / r0["pe"].norm()).item() <= 2e-2

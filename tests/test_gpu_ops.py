@@ -49,10 +49,10 @@ def test_conv3x3_fwd_epilogue_stats(ops, n, h, w, cin, cout):
     scale, shift = 1 + 0.1 * rnd(cout, seed=3), 0.1 * rnd(cout, seed=4)
     for relu, stats in ((0, False), (1, True)):
         y_ref = torch.empty(n, h, w, cout, dtype=BF)
-        ss_r, sq_r = torch.zeros(cout), torch.zeros(cout)
+        ss_r, sq_r = torch.zeros(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64)
         rf.conv3x3_fwd(x, wt, scale, shift, relu, y_ref, ss_r if stats else None, sq_r if stats else None)
         y = torch.full((n, h, w, cout), float("nan"), dtype=BF, device=DEV)
-        ss, sq = torch.zeros(cout, device=DEV), torch.zeros(cout, device=DEV)
+        ss, sq = (torch.zeros(cout, dtype=torch.float64, device=DEV) for _ in range(2))
         cu.conv3x3_fwd(x.to(DEV), wt.to(DEV), scale.to(DEV), shift.to(DEV), relu, y,
                        ss if stats else None, sq if stats else None)
         torch.cuda.synchronize()
@@ -209,7 +209,7 @@ def test_bn_pool_relu_kernels(ops, n, h, w, c, ld):
     assert relmax(dx, dx_r) < 4e-3
     # BatchNorm finalize / fold / backward
     cnt = n * h * w
-    ss, sq = y.float().sum((0, 1, 2)), (y.float() ** 2).sum((0, 1, 2))
+    ss, sq = y.double().sum((0, 1, 2)), (y.double() ** 2).sum((0, 1, 2))
     gamma, beta = 1 + 0.1 * rnd(c, seed=7), 0.1 * rnd(c, seed=8)
     outs_r = [torch.zeros(c) for _ in range(4)]
     rm_r, rv_r = torch.zeros(c), torch.ones(c)
@@ -238,8 +238,14 @@ def test_bn_pool_relu_kernels(ops, n, h, w, c, ld):
     dy_r, sdy_r = torch.empty(n, h, w, c, dtype=BF), torch.zeros(c)
     rf.bn_bwd_apply(da, y, *outs_r, 1, sg_r, sgx_r, dy_r, sdy_r)
     dyo, sdy = torch.empty(n, h, w, c, dtype=BF, device=DEV), torch.zeros(c, device=DEV)
-    cu.bn_bwd_apply(dad, yd, *coef_d, 1, sg_r.to(DEV), sgx_r.to(DEV), dyo, sdy)
+    # parameter-gradient hand-over: overwrite, then accumulate on top of what is there
+    dgam, dbet = torch.full((c,), 3.0, device=DEV), torch.full((c,), -2.0, device=DEV)
+    cu.bn_bwd_apply(dad, yd, *coef_d, 1, sg_r.to(DEV), sgx_r.to(DEV), dyo, sdy, dgam, dbet, False)
     torch.cuda.synchronize()
+    assert torch.equal(dgam.cpu(), sgx_r) and torch.equal(dbet.cpu(), sg_r)
+    cu.bn_bwd_apply(dad, yd, *coef_d, 1, sg_r.to(DEV), sgx_r.to(DEV), dyo, None, dgam, dbet, True)
+    torch.cuda.synchronize()
+    assert torch.equal(dgam.cpu(), 2 * sgx_r) and torch.equal(dbet.cpu(), 2 * sg_r)
     assert relmax(dyo, dy_r) < 4e-3
     assert (sdy.cpu() - sdy_r).abs().max().item() < 2e-2 * dy_r.float().abs().max().item() * cnt ** 0.5
     rdy_r, rs_r = torch.empty(n, h, w, c, dtype=BF), torch.zeros(c)
@@ -395,3 +401,79 @@ def test_conv3x3_fewer_input_channels_than_weights(ops, n, h, w):
     torch.cuda.synchronize()
     assert relmax(dw, dw_ref) < 1e-3
     assert dw[..., cx:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("cin,cout,mode", [(64, 64, "<64,0> resident weights"), (128, 64, "<64,1> weight triples"),
+                                           (128, 128, "<128,1> triples, half-tile staging"),
+                                           (256, 256, "<256,2> single weight tiles")])
+def test_conv3_repeated_launches_are_bit_identical(ops, cin, cout, mode):
+    """200 launches of igemm_conv3_kernel on the same inputs give bit-identical outputs in every mode.  The kernel's
+    relay-thread protocol (mbarrier observed by a relay, counter published through shared memory, MMAs issued behind
+    a weak load of that counter) has no summation-order freedom (each issuer owns a TMEM tile, the epilogue adds
+    them in a fixed order), so any run-to-run difference would be a race on operand visibility."""
+    cu, rf = ops
+    n, h, w = 3, 48, 40      # more tiles than SMs -> several tiles per CTA, ragged edges along both axes
+    x = rnd(n, h, w, cin, seed=11).to(BF).to(DEV)
+    wt = (rnd(cout, 3, 3, cin, seed=12) / (9 * cin) ** 0.5).to(BF).to(DEV)
+    scale, shift = (1 + 0.1 * rnd(cout, seed=13)).to(DEV), (0.1 * rnd(cout, seed=14)).to(DEV)
+    first = torch.empty(n, h, w, cout, dtype=BF, device=DEV)
+    cu.conv3x3_fwd(x, wt, scale, shift, 1, first)
+    y_ref = torch.empty(n, h, w, cout, dtype=BF)
+    rf.conv3x3_fwd(x.cpu(), wt.cpu(), scale.cpu(), shift.cpu(), 1, y_ref)
+    torch.cuda.synchronize()
+    assert relmax(first, y_ref) < 1.6e-2
+    y = torch.empty_like(first)
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    for i in range(200):
+        y.fill_(float("nan"))
+        cu.conv3x3_fwd(x, wt, scale, shift, 1, y)
+        bad += (y.view(torch.int16) != first.view(torch.int16)).sum()
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0, f"{mode}: {int(bad.item())} differing elements over 200 launches"
+
+
+def test_wgrad3_repeated_launches_agree_to_rounding(ops):
+    """The split-K weight gradient adds its partial sums with fp32 atomics (order not fixed): repeated launches must
+    agree to fp32 rounding of the sum, nothing more."""
+    cu, _ = ops
+    n, h, w, cin, cout = 4, 32, 32, 128, 128
+    x, dy = rnd(n, h, w, cin, seed=1).to(BF).to(DEV), rnd(n, h, w, cout, seed=2).to(BF).to(DEV)
+    first = torch.empty(cout, 3, 3, cin, device=DEV)
+    cu.conv3x3_wgrad(x, dy, first)
+    worst = torch.zeros((), device=DEV)
+    dw = torch.empty_like(first)
+    for _ in range(50):
+        cu.conv3x3_wgrad(x, dy, dw)
+        worst = torch.maximum(worst, (dw - first).abs().max())
+    torch.cuda.synchronize()
+    assert worst.item() <= 2e-5 * first.abs().max().item()
+
+
+@pytest.mark.parametrize("ratio", [10.0, 100.0])
+def test_batchnorm_statistics_survive_large_mean_over_std(ops, ratio):
+    """A conv output population with |mean| / std = 10 and 100 (a bias-dominated channel): the batch statistics
+    come from per-tile fp32 partial sums accumulated in fp64, and bn_finalize forms E[y^2] - E[y]^2 in fp64, so
+    the variance keeps its digits (in fp32 the cross-tile sums alone lose ~4 % of it at ratio 100)."""
+    cu, rf = ops
+    n, h, w, cin, cout = 8, 64, 64, 64, 64
+    x = rnd(n, h, w, cin, seed=21).to(BF)
+    wt = (rnd(cout, 3, 3, cin, seed=22) / (9 * cin) ** 0.5).to(BF)
+    y0 = torch.empty(n, h, w, cout, dtype=BF)
+    rf.conv3x3_fwd(x, wt, None, None, 0, y0)
+    std0 = y0.float().std().item()
+    shift = torch.full((cout,), ratio * std0)                # conv bias: mean = ratio x std
+    y_ref = torch.empty(n, h, w, cout, dtype=BF)
+    rf.conv3x3_fwd(x, wt, None, shift, 0, y_ref)
+    y = torch.empty(n, h, w, cout, dtype=BF, device=DEV)
+    ss, sq = (torch.zeros(cout, dtype=torch.float64, device=DEV) for _ in range(2))
+    cu.conv3x3_fwd(x.to(DEV), wt.to(DEV), None, shift.to(DEV), 0, y, ss, sq)
+    outs = [torch.zeros(cout, device=DEV) for _ in range(4)]
+    rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+    cu.bn_finalize(ss, sq, n * h * w, None, None, 1e-5, 0.1, rm, rv, *outs)
+    torch.cuda.synchronize()
+    yd = y.double().cpu().reshape(-1, cout)                 # exact statistics of what the kernel stored
+    mean_true, var_true = yd.mean(0), yd.var(0, unbiased=False)
+    mean, invstd = outs[2].double().cpu(), outs[3].double().cpu()
+    assert ((mean - mean_true).abs() / mean_true.abs()).max().item() < 1e-6
+    assert ((1 / invstd ** 2 - 1e-5 - var_true).abs() / var_true).max().item() < 2e-3
+    assert relmax(y, y_ref) < 1.6e-2

@@ -86,33 +86,111 @@ def test_training_forward_logits_and_loss(spec, n, hw):
     assert abs(net.loss_out[0].item() - loss_ref) <= 1e-2 * abs(loss_ref)
 
 
-def test_gradients_match_autograd_direction():
-    """bf16 gradients vs fp32 autograd: cosine >= 0.95 per tensor (see tests/test_host_logic.py for why a
-    direction test, and for the exact fp32 check of the schedule); the GPU kernels must also agree with
-    the CPU operator oracle run with the same bf16 rounding points."""
+def _grad_parity(spec, n, hw, seed, l2_bar, cos_bar):
+    """GPU gradients of one training forward/backward against (i) the CPU operator oracle driven by the same host
+    schedule with the same bf16 rounding points: relative L2 error per tensor <= l2_bar; (ii) fp32 autograd of the
+    whole-network oracle: cosine >= cos_bar per tensor (bf16 storage noise is amplified by BatchNorm's backward, so
+    against fp32 only the direction is pinned)."""
     from kcl_ltss_bioatm_b200.unet import UNetB200
 
-    spec = UNetSpec(base_filters=64, depth=2)
     torch.manual_seed(0)
     ref = UNetRef(spec).train()
     net = make_net(spec, seed=0)
     cpu = UNetB200(spec, ops=RefOps(), device="cpu", seed=0)
-    x, t = synthetic_batch(4, 32, 32, spec.in_channels, seed=3)
+    x, t = synthetic_batch(n, hw, hw, spec.in_channels, seed=seed)
     plume_loss(ref(nchw(x))[:, 0], t, spec).backward()
-    net.forward(x.to(DEV), t.to(DEV))
+    z = net.forward(x.to(DEV), t.to(DEV))
     net.backward()
-    cpu.forward(x, t)
+    zc = cpu.forward(x, t)
     cpu.backward()
     torch.cuda.synchronize()
+    assert l2rel(z, zc) <= 5e-3, l2rel(z, zc)
     gd, gc = net.grad_dict(), cpu.grad_dict()
+    worst = {}
     for k, p in ref.named_parameters():
         if k.endswith("conv1.bias") or k.endswith("conv2.bias"):
             continue  # cancelled by BatchNorm: pure rounding noise on every implementation
         a, b, c = gd[k].flatten().float(), p.grad.flatten().float(), gc[k].flatten().float()
-        cos_ref = torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)
-        cos_cpu = torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)
-        assert cos_ref > 0.95, (k, float(cos_ref))
-        assert cos_cpu > 0.97, (k, float(cos_cpu))
+        worst[k] = (((a - c).norm() / (c.norm() + 1e-30)).item(),
+                    (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item())
+    k_l2 = max(worst, key=lambda k: worst[k][0])
+    k_cos = min(worst, key=lambda k: worst[k][1])
+    print(f"gradients, {len(worst)} tensors: worst rel-L2 vs same-rounding CPU oracle {worst[k_l2][0]:.3e} ({k_l2}); "
+          f"worst cosine vs fp32 autograd {worst[k_cos][1]:.4f} ({k_cos})")
+    for k, (e, c) in worst.items():
+        assert e <= l2_bar, (k, e)
+        assert c >= cos_bar, (k, c)
+
+
+def test_gradients_match_same_rounding_oracle_and_autograd_direction():
+    _grad_parity(UNetSpec(base_filters=64, depth=2), 4, 32, seed=3, l2_bar=2e-2, cos_bar=0.95)
+
+
+def test_default_spec_256px_batch4_forward_and_gradients():
+    """The BASELINE configs[1] network at its real tile size (4 tiles of 256 x 256): logits against the fp32 oracle
+    and the bf16-storage floor, every parameter gradient against the same-rounding CPU oracle and autograd."""
+    spec = UNetSpec()
+    _grad_parity(spec, 4, 256, seed=21, l2_bar=3e-2, cos_bar=0.90)
+
+
+def test_wide_spec_forward_and_gradients():
+    """BASELINE configs[4]'s network (base 128, depth 5, channels up to 4096, 497 M parameters) on 2 tiles of 64 x 64
+    (the bottleneck runs at 2 x 2 pixels: generic small-image kernels, K up to 9 x 4096)."""
+    spec = UNetSpec.wide()
+    torch.manual_seed(0)
+    ref = UNetRef(spec).train()
+    net = make_net(spec, seed=0)
+    x, t = synthetic_batch(2, 64, 64, spec.in_channels, seed=31)
+    z_ref = ref(nchw(x))[:, 0]
+    loss_ref = plume_loss(z_ref, t, spec)
+    loss_ref.backward()
+    with torch.no_grad():
+        z_b16 = with_bf16_storage(ref)(nchw(x))[:, 0]
+    z = net.forward(x.to(DEV), t.to(DEV))
+    net.backward()
+    torch.cuda.synchronize()
+    e2, floor = l2rel(z, z_ref), l2rel(z_b16, z_ref)
+    print(f"wide spec train-mode logits: rel L2 {e2:.3e} vs fp32 oracle (bf16-storage floor {floor:.3e}), "
+          f"loss {net.loss_out[0].item():.5f} vs {loss_ref.item():.5f}")
+    assert e2 <= 1.25 * floor + 1e-3 and e2 <= 2e-2
+    assert abs(net.loss_out[0].item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    gd = net.grad_dict()
+    worst = 1.0
+    for k, p in ref.named_parameters():
+        if k.endswith("conv1.bias") or k.endswith("conv2.bias"):
+            continue
+        a, b = gd[k].flatten().float(), p.grad.flatten().float()
+        c = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+        worst = min(worst, c)
+        assert c >= 0.90, (k, c)
+    print(f"wide spec gradients: worst cosine vs fp32 autograd {worst:.4f}")
+    assert net.num_parameters() == sum(p.numel() for p in ref.parameters()) == 497_470_977
+
+
+def test_batchnorm_micro_batches_on_gpu_match_cpu_oracle():
+    """Gradient accumulation over two micro-batches WITH BatchNorm: the second slice's BatchNorm-backward
+    sums must not see the first slice's.  GPU vs the CPU operator oracle running the same two-slice schedule, and the
+    accumulated gradient equals the sum of the two standalone backwards."""
+    from kcl_ltss_bioatm_b200.unet import UNetB200
+
+    spec = UNetSpec(base_filters=64, depth=2)
+    x, t = synthetic_batch(4, 32, 32, spec.in_channels, seed=13)
+
+    def run(make, to):
+        outs = []
+        for slices in ([slice(0, 2)], [slice(2, 4)], [slice(0, 2), slice(2, 4)]):
+            net = make()
+            for i, sl in enumerate(slices):
+                net.forward(to(x[sl]), to(t[sl]))
+                net.backward(accumulate=i > 0, loss_scale=0.5)
+            outs.append(net.grads.detach().float().cpu().clone())
+        return outs
+
+    g1, g2, both = run(lambda: make_net(spec, seed=0), lambda v: v.to(DEV))
+    c1, c2, cboth = run(lambda: UNetB200(spec, ops=RefOps(), device="cpu", seed=0), lambda v: v)
+    torch.cuda.synchronize()
+    assert ((both - (g1 + g2)).norm() / both.norm()).item() < 1e-5
+    assert ((both - cboth).norm() / cboth.norm()).item() < 2e-2
 
 
 def test_eval_logits_and_mask_agreement():
@@ -165,6 +243,34 @@ def test_loss_curve_200_steps_within_2_percent():
     print(f"loss curve: start {lr[0]:.4f}/{lg[0]:.4f}, end {lr[-1]:.4f}/{lg[-1]:.4f}, "
           f"max per-step deviation {dev.max() * 100:.2f} % (mean {dev.mean() * 100:.3f} %)")
     assert lr[-20:].mean() < 0.5 * lr[:5].mean()   # the oracle actually learns on this data
+    assert dev.max().item() <= 0.02
+
+
+def test_loss_curve_200_steps_default_spec_within_2_percent():
+    """The same 200-step comparison on the DEFAULT spec (depth 4, 23 layers), 8 tiles of 64 x 64 per step, 40 distinct
+    batches, lr 2e-4 (the non-chaotic regime, see above).  Every step within 2 % of the fp32 oracle's loss."""
+    spec = UNetSpec(lr=2e-4)
+    steps, n, hw, nb = 200, 8, 64, 40
+    torch.manual_seed(0)
+    ref = UNetRef(spec).train()
+    opt = make_optimizer(ref, spec)
+    net = make_net(spec, seed=0)
+    batches = [synthetic_batch(n, hw, hw, spec.in_channels, seed=2000 + i) for i in range(nb)]
+    dev_batches = [(x.to(DEV), t.to(DEV)) for x, t in batches]
+    lr, lg = [], []
+    for i in range(steps):
+        x, t = batches[i % nb]
+        opt.zero_grad()
+        loss = plume_loss(ref(nchw(x))[:, 0], t, spec)
+        loss.backward()
+        opt.step()
+        lr.append(float(loss.detach()))
+        lg.append(float(net.train_step(*dev_batches[i % nb])[0].item()))
+    lr, lg = torch.tensor(lr), torch.tensor(lg)
+    dev = ((lg - lr).abs() / lr)
+    print(f"default-spec loss curve: start {lr[0]:.4f}/{lg[0]:.4f}, end {lr[-1]:.4f}/{lg[-1]:.4f}, "
+          f"max per-step deviation {dev.max() * 100:.2f} % (mean {dev.mean() * 100:.3f} %)")
+    assert lr[-20:].mean() < 0.7 * lr[:5].mean()
     assert dev.max().item() <= 0.02
 
 
@@ -230,6 +336,32 @@ def test_cuda_graph_step_matches_eager_step():
     xe, _ = synthetic_batch(2, 32, 32, spec.in_channels, seed=99)
     za, zb = a.model.predict_logits(xe.to(DEV)).clone(), b.model.predict_logits(xe.to(DEV)).clone()
     assert l2rel(zb, za) <= 5e-2
+
+
+def test_eval_between_graphed_steps_sees_fresh_weights_and_statistics():
+    """a graph replay updates parameters and running statistics on the device; an eval forward after it
+    must repack the bf16 weights and refold BatchNorm.  Two trainers fed the same batches, one graphed with eval
+    calls interleaved, one eager with a single eval at the end, must predict the same logits; and replaying a graph
+    captured for one shape after another shape was used must still train (per-shape activation buffers)."""
+    from kcl_ltss_bioatm_b200.trainer import Trainer
+
+    spec = UNetSpec(base_filters=64, depth=2)
+    a, b = Trainer(spec, device=DEV, seed=5), Trainer(spec, device=DEV, seed=5)
+    small = [synthetic_batch(4, 32, 32, spec.in_channels, seed=70 + i) for i in range(2)]
+    big = synthetic_batch(2, 64, 64, spec.in_channels, seed=80)
+    xe, _ = synthetic_batch(2, 32, 32, spec.in_channels, seed=99)
+    seq = [small[0], small[1], big, small[0], big, small[1]]
+    for x, t in seq:
+        a.step(x.to(DEV), t.to(DEV))
+        b.step_graphed(x.to(DEV), t.to(DEV))
+        b.model.predict_logits(xe.to(DEV))            # interleaved eval: must not freeze stale coefficients
+    za, zb = a.model.predict_logits(xe.to(DEV)).clone(), b.model.predict_logits(xe.to(DEV)).clone()
+    torch.cuda.synchronize()
+    assert a.model.step_count == b.model.step_count == len(seq)
+    assert l2rel(zb, za) <= 2e-2, l2rel(zb, za)
+    # a stale fold would leave the initial running statistics (mean 0 / var 1) in the eval coefficients
+    fresh = make_net(spec, seed=5)
+    assert l2rel(fresh.predict_logits(xe.to(DEV)), za) > 0.1
 
 
 def test_tiled_scene_inference_matches_oracle_tiling():
