@@ -184,6 +184,43 @@ int plume_adam(float* param, const float* grad, float* m, float* v, long long n,
 int plume_adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
                    plume_stream_t stream);
 
+/* ---- fp32-activation variants of the bandwidth kernels (the "tf32" precision mode) ----------------------
+ * Same arguments and semantics as the functions above with every activation tensor NHWC **fp32** (pixel strides in
+ * elements, multiples of 8; nothing is rounded on store).  BASELINE.json's north_star asks for a tf32 mode whose
+ * logits agree with the fp32 oracle to 1e-3; see plume_conv3x3_fwd_tf32 below for the GEMM side. */
+int plume_pad_channels_f32(const void* in, int Cs, void* out, int Cd, long long pixels,
+                       plume_stream_t stream);
+int plume_scale_shift_act_f32(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                          void* a, int lda, long long pixels, int C, plume_stream_t stream);
+int plume_scale_shift_act_pool_f32(const void* y, int ldy, const float* scale, const float* shift,
+                               int relu, void* skip, int ldskip, void* pooled, int ldpooled,
+                               uint8_t* argmax, int N, int H, int W, int C, plume_stream_t stream);
+int plume_maxpool2x2_fwd_f32(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H,
+                         int W, int C, plume_stream_t stream);
+int plume_maxpool2x2_bwd_f32(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
+                         int lddskip, void* dx, int lddx, int N, int H, int W, int C,
+                         plume_stream_t stream);
+int plume_bn_bwd_reduce_f32(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, int relu,
+                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream);
+int plume_bn_bwd_apply_f32(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
+                       float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
+                       plume_stream_t stream);
+int plume_relu_bwd_f32(const void* da, int ldda, const void* a, int lda, void* dy, int lddy,
+                   float* sum_dy, long long pixels, int C, plume_stream_t stream);
+int plume_channel_sum_f32(const void* x, int ldx, float* out, long long pixels, int C,
+                      plume_stream_t stream);
+int plume_head_fwd_f32(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream);
+int plume_head_bwd_f32(const void* feat, int ldf, const float* w, const float* logits,
+                   const uint8_t* target, const float* sums, float bce_weight, float dice_weight,
+                   float dice_eps, float grad_scale, void* dfeat, int lddf, float* dw, float* db,
+                   long long pixels, int C, plume_stream_t stream);
+int plume_extract_tiles_f32(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
+                        int count, int T, void* tiles, int Cd, plume_stream_t stream);
+
 /* ---- tiled large-scene inference -------------------------------------------------------------- */
 /* Cut `count` tiles of T x T (NHWC bf16, Cd channels, zero padded past Cs and past the scene edge)
  * out of a scene [Hs][Ws][Cs] bf16; tile k covers origin (ys[k], xs[k]) given as int32 device arrays. */

@@ -205,10 +205,18 @@ int plume_pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, p
   return pack_convT2x2(w, wf, wd, Cout, Cin, S(stream));
 }
 
+static int impl_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels,
+                       plume_stream_t stream, int dt) {
+  PLUME_CHECK(in && out, "pad_channels: null pointer");
+  return pad_channels(in, Cs, out, Cd, pixels, dt, S(stream));
+}
 int plume_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels,
                        plume_stream_t stream) {
-  PLUME_CHECK(in && out, "pad_channels: null pointer");
-  return pad_channels(in, Cs, out, Cd, pixels, S(stream));
+  return impl_pad_channels(in, Cs, out, Cd, pixels, stream, 0);
+}
+int plume_pad_channels_f32(const void* in, int Cs, void* out, int Cd, long long pixels,
+                       plume_stream_t stream) {
+  return impl_pad_channels(in, Cs, out, Cd, pixels, stream, 1);
 }
 
 int plume_bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
@@ -227,78 +235,174 @@ int plume_bn_fold_eval(const float* gamma, const float* beta, const float* runni
                       S(stream));
 }
 
-int plume_scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu,
-                          void* a, int lda, long long pixels, int C, plume_stream_t stream) {
+static int impl_scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                          void* a, int lda, long long pixels, int C, plume_stream_t stream, int dt) {
   PLUME_CHECK(y && a && scale && shift, "scale_shift_act: null pointer");
   PLUME_CHECK(y != a, "scale_shift_act: in-place operation is not supported");
-  return scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, S(stream));
+  return scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, dt, S(stream));
+}
+int plume_scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                          void* a, int lda, long long pixels, int C, plume_stream_t stream) {
+  return impl_scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, stream, 0);
+}
+int plume_scale_shift_act_f32(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                          void* a, int lda, long long pixels, int C, plume_stream_t stream) {
+  return impl_scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, stream, 1);
+}
+static int impl_scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                               void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax,
+                               int N, int H, int W, int C, plume_stream_t stream, int dt) {
+  PLUME_CHECK(y && pooled && argmax && scale && shift, "scale_shift_act_pool: null pointer");
+  return scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H,
+                              W, C, dt, S(stream));
 }
 int plume_scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift, int relu,
                                void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax,
                                int N, int H, int W, int C, plume_stream_t stream) {
-  PLUME_CHECK(y && pooled && argmax && scale && shift, "scale_shift_act_pool: null pointer");
-  return scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H,
-                              W, C, S(stream));
+  return impl_scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H, W, C, stream, 0);
+}
+int plume_scale_shift_act_pool_f32(const void* y, int ldy, const float* scale, const float* shift, int relu,
+                               void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax,
+                               int N, int H, int W, int C, plume_stream_t stream) {
+  return impl_scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H, W, C, stream, 1);
+}
+static int impl_maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
+                         int C, plume_stream_t stream, int dt) {
+  PLUME_CHECK(x && y && argmax, "maxpool2x2_fwd: null pointer");
+  return maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, dt, S(stream));
 }
 int plume_maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
                          int C, plume_stream_t stream) {
-  PLUME_CHECK(x && y && argmax, "maxpool2x2_fwd: null pointer");
-  return maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, S(stream));
+  return impl_maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, stream, 0);
+}
+int plume_maxpool2x2_fwd_f32(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
+                         int C, plume_stream_t stream) {
+  return impl_maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, stream, 1);
+}
+static int impl_maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
+                         int lddskip, void* dx, int lddx, int N, int H, int W, int C,
+                         plume_stream_t stream, int dt) {
+  PLUME_CHECK(dy && argmax && dx, "maxpool2x2_bwd: null pointer");
+  return maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, dt, S(stream));
 }
 int plume_maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
                          int lddskip, void* dx, int lddx, int N, int H, int W, int C,
                          plume_stream_t stream) {
-  PLUME_CHECK(dy && argmax && dx, "maxpool2x2_bwd: null pointer");
-  return maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, S(stream));
+  return impl_maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, stream, 0);
+}
+int plume_maxpool2x2_bwd_f32(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
+                         int lddskip, void* dx, int lddx, int N, int H, int W, int C,
+                         plume_stream_t stream) {
+  return impl_maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, stream, 1);
 }
 
-int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
+static int impl_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
                         const float* shift, const float* mean, const float* invstd, int relu,
-                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream) {
+                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream, int dt) {
   PLUME_CHECK(da && y && scale && shift && mean && invstd && sum_g && sum_gx,
               "bn_bwd_reduce: null pointer");
   return bn_bwd_reduce(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C,
-                       S(stream));
+                       dt, S(stream));
+}
+int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, int relu,
+                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream) {
+  return impl_bn_bwd_reduce(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C, stream, 0);
+}
+int plume_bn_bwd_reduce_f32(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, int relu,
+                        float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream) {
+  return impl_bn_bwd_reduce(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C, stream, 1);
+}
+static int impl_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
+                       float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
+                       plume_stream_t stream, int dt) {
+  PLUME_CHECK(da && y && scale && shift && mean && invstd && sum_g && sum_gx && dy,
+              "bn_bwd_apply: null pointer");
+  return bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy,
+                      sum_dy, dgamma, dbeta, accumulate, pixels, C, dt, S(stream));
 }
 int plume_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu,
                        const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
                        float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
                        plume_stream_t stream) {
-  PLUME_CHECK(da && y && scale && shift && mean && invstd && sum_g && sum_gx && dy,
-              "bn_bwd_apply: null pointer");
-  return bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy,
-                      sum_dy, dgamma, dbeta, accumulate, pixels, C, S(stream));
+  return impl_bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy, sum_dy, dgamma, dbeta, accumulate, pixels, C, stream, 0);
+}
+int plume_bn_bwd_apply_f32(const void* da, int ldda, const void* y, int ldy, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
+                       float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
+                       plume_stream_t stream) {
+  return impl_bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy, sum_dy, dgamma, dbeta, accumulate, pixels, C, stream, 1);
+}
+static int impl_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
+                   long long pixels, int C, plume_stream_t stream, int dt) {
+  PLUME_CHECK(da && a && dy, "relu_bwd: null pointer");
+  return relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, dt, S(stream));
 }
 int plume_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
                    long long pixels, int C, plume_stream_t stream) {
-  PLUME_CHECK(da && a && dy, "relu_bwd: null pointer");
-  return relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, S(stream));
+  return impl_relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, stream, 0);
+}
+int plume_relu_bwd_f32(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
+                   long long pixels, int C, plume_stream_t stream) {
+  return impl_relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, stream, 1);
+}
+static int impl_channel_sum(const void* x, int ldx, float* out, long long pixels, int C,
+                      plume_stream_t stream, int dt) {
+  PLUME_CHECK(x && out, "channel_sum: null pointer");
+  return channel_sum(x, ldx, out, pixels, C, dt, S(stream));
 }
 int plume_channel_sum(const void* x, int ldx, float* out, long long pixels, int C,
                       plume_stream_t stream) {
-  PLUME_CHECK(x && out, "channel_sum: null pointer");
-  return channel_sum(x, ldx, out, pixels, C, S(stream));
+  return impl_channel_sum(x, ldx, out, pixels, C, stream, 0);
+}
+int plume_channel_sum_f32(const void* x, int ldx, float* out, long long pixels, int C,
+                      plume_stream_t stream) {
+  return impl_channel_sum(x, ldx, out, pixels, C, stream, 1);
 }
 
-int plume_head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
-                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream) {
+static int impl_head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream, int dt) {
   PLUME_CHECK(feat && w && logits, "head_fwd: null pointer");
   PLUME_CHECK(!target || sums, "head_fwd: target given without sums");
-  return head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, S(stream));
+  return head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, dt, S(stream));
+}
+int plume_head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream) {
+  return impl_head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, stream, 0);
+}
+int plume_head_fwd_f32(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+                   float* logits, float* sums, long long pixels, int C, plume_stream_t stream) {
+  return impl_head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, stream, 1);
 }
 int plume_head_loss(const float* sums, long long pixels, float bce_weight, float dice_weight,
                     float dice_eps, float* loss_out, plume_stream_t stream) {
   PLUME_CHECK(sums && loss_out, "head_loss: null pointer");
   return head_loss(sums, pixels, bce_weight, dice_weight, dice_eps, loss_out, S(stream));
 }
+static int impl_head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                   const float* sums, float bce_weight, float dice_weight, float dice_eps,
+                   float grad_scale, void* dfeat, int lddf, float* dw, float* db, long long pixels,
+                   int C, plume_stream_t stream, int dt) {
+  PLUME_CHECK(feat && w && logits && target && sums && dfeat && dw && db, "head_bwd: null pointer");
+  return head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale,
+                  dfeat, lddf, dw, db, pixels, C, dt, S(stream));
+}
 int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
                    const float* sums, float bce_weight, float dice_weight, float dice_eps,
                    float grad_scale, void* dfeat, int lddf, float* dw, float* db, long long pixels,
                    int C, plume_stream_t stream) {
-  PLUME_CHECK(feat && w && logits && target && sums && dfeat && dw && db, "head_bwd: null pointer");
-  return head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale,
-                  dfeat, lddf, dw, db, pixels, C, S(stream));
+  return impl_head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat, lddf, dw, db, pixels, C, stream, 0);
+}
+int plume_head_bwd_f32(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                   const float* sums, float bce_weight, float dice_weight, float dice_eps,
+                   float grad_scale, void* dfeat, int lddf, float* dw, float* db, long long pixels,
+                   int C, plume_stream_t stream) {
+  return impl_head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat, lddf, dw, db, pixels, C, stream, 1);
 }
 
 int plume_adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
@@ -319,10 +423,18 @@ int plume_adam_dev(float* param, const float* grad, float* m, float* v, long lon
   return adam_dev(param, grad, m, v, n, coef, S(stream));
 }
 
+static int impl_extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
+                        int count, int T, void* tiles, int Cd, plume_stream_t stream, int dt) {
+  PLUME_CHECK(scene && ys && xs && tiles, "extract_tiles: null pointer");
+  return extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, dt, S(stream));
+}
 int plume_extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
                         int count, int T, void* tiles, int Cd, plume_stream_t stream) {
-  PLUME_CHECK(scene && ys && xs && tiles, "extract_tiles: null pointer");
-  return extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, S(stream));
+  return impl_extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, stream, 0);
+}
+int plume_extract_tiles_f32(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
+                        int count, int T, void* tiles, int Cd, plume_stream_t stream) {
+  return impl_extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, stream, 1);
 }
 int plume_stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T,
                            int margin, float logit_threshold, uint8_t* mask, float* prob, int Hs, int Ws,

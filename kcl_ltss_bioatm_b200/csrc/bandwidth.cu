@@ -90,6 +90,81 @@ __device__ __forceinline__ BF8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
   return v;
 }
+// Activation storage traits: a thread moves 8 channels of one pixel per access; bf16 = one 16-byte vector,
+// fp32 (the tf32-precision mode) = two.  `pack` is where the storage rounding happens (none for fp32).
+struct alignas(16) F8 {
+  float f[8];
+};
+template <typename T>
+struct Act;
+template <>
+struct Act<__nv_bfloat16> {
+  using V8 = BF8;
+  static __device__ __forceinline__ V8 ld(const __nv_bfloat16* p) { return ld_bf8(p); }
+  static __device__ __forceinline__ V8 ld_stream(const __nv_bfloat16* p) { return ld_bf8_stream(p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const V8& v) { st_bf8(p, v); }
+  static __device__ __forceinline__ void unpack(const V8& v, float (&f)[8]) { unpack8(v, f); }
+  static __device__ __forceinline__ V8 pack(const float (&f)[8]) { return pack8(f); }
+  static __device__ __forceinline__ V8 zero() {
+    V8 v;
+    v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
+    return v;
+  }
+};
+template <>
+struct Act<float> {
+  using V8 = F8;
+  static __device__ __forceinline__ V8 ld(const float* p) {
+    V8 v;
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+    v.f[0] = a.x; v.f[1] = a.y; v.f[2] = a.z; v.f[3] = a.w;
+    v.f[4] = b.x; v.f[5] = b.y; v.f[6] = b.z; v.f[7] = b.w;
+    return v;
+  }
+  static __device__ __forceinline__ V8 ld_stream(const float* p) {
+    V8 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.f[0]), "=f"(v.f[1]), "=f"(v.f[2]), "=f"(v.f[3])
+                 : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.f[4]), "=f"(v.f[5]), "=f"(v.f[6]), "=f"(v.f[7])
+                 : "l"(p + 4));
+    return v;
+  }
+  static __device__ __forceinline__ void st(float* p, const V8& v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v.f[0], v.f[1], v.f[2], v.f[3]);
+    *(reinterpret_cast<float4*>(p) + 1) = make_float4(v.f[4], v.f[5], v.f[6], v.f[7]);
+  }
+  static __device__ __forceinline__ void unpack(const V8& v, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = v.f[i];
+  }
+  static __device__ __forceinline__ V8 pack(const float (&f)[8]) {
+    V8 v;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.f[i] = f[i];
+    return v;
+  }
+  static __device__ __forceinline__ V8 zero() {
+    V8 v;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.f[i] = 0.f;
+    return v;
+  }
+};
+// Launches `call` with T bound to the activation storage type (dt: 0 = bf16, 1 = fp32).
+#define PLUME_ACT_DISPATCH(dt, ...)       \
+  do {                                    \
+    if ((dt) == 1) {                      \
+      using T = float;                    \
+      __VA_ARGS__;                        \
+    } else {                              \
+      using T = __nv_bfloat16;            \
+      __VA_ARGS__;                        \
+    }                                     \
+  } while (0)
+
 __device__ __forceinline__ void ld_f8(const float* p, float (&f)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -129,20 +204,21 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[K][8], int cv_
 // ------------------------------------------------------------------------------------------------
 // pad_channels
 // ------------------------------------------------------------------------------------------------
-__global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ in, int cvs,
-                                    __nv_bfloat16* __restrict__ out, int cvd, long long total) {
+template <typename T>
+__global__ void pad_channels_kernel(const T* __restrict__ in, int cvs,
+                                    T* __restrict__ out, int cvd, long long total) {
   const long long step = 1ll * gridDim.x * blockDim.x;
   for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
     const long long p = i / cvd;
     const int cv = static_cast<int>(i % cvd);
-    BF8 v;
-    v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
-    if (cv < cvs) v = ld_bf8_stream(in + (p * cvs + cv) * 8);
-    st_bf8(out + i * 8, v);
+    typename Act<T>::V8 v;
+    v = Act<T>::zero();
+    if (cv < cvs) v = Act<T>::ld_stream(in + (p * cvs + cv) * 8);
+    Act<T>::st(out + i * 8, v);
   }
 }
 
-int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, cudaStream_t s) {
+int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, int dt, cudaStream_t s) {
   if (Cs % 8 || Cd % 8 || Cs > Cd || Cs <= 0) {
     set_error("pad_channels: channel counts must be multiples of 8 with Cs <= Cd");
     return -1;
@@ -150,8 +226,8 @@ int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, cu
   if (pixels <= 0) return 0;
   const long long total = pixels * (Cd / 8);
   const int grid = grid_for(total, 1);
-  pad_channels_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(in), Cs / 8,
-                                                static_cast<__nv_bfloat16*>(out), Cd / 8, total);
+  PLUME_ACT_DISPATCH(dt, (pad_channels_kernel<T><<<grid, kThreads, 0, s>>>(static_cast<const T*>(in), Cs / 8,
+                                                                          static_cast<T*>(out), Cd / 8, total)));
   return check_launch("pad_channels");
 }
 
@@ -215,10 +291,11 @@ int bn_fold_eval(const float* gamma, const float* beta, const float* rm, const f
 // ------------------------------------------------------------------------------------------------
 // scale/shift/act (BN apply + ReLU)
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    scale_shift_act_kernel(const __nv_bfloat16* __restrict__ y, long long ldy,
+    scale_shift_act_kernel(const T* __restrict__ y, long long ldy,
                            const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                           __nv_bfloat16* __restrict__ a, long long lda, long long pixels, int CV) {
+                           T* __restrict__ a, long long lda, long long pixels, int CV) {
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
   const long long pstep = (1ll * gridDim.x * kThreads) / CV;
@@ -228,11 +305,11 @@ __global__ void __launch_bounds__(kThreads)
   long long p = i0 / CV;
   // two pixels in flight per iteration
   for (; p + pstep < pixels; p += 2 * pstep) {
-    const BF8 v0 = ld_bf8_stream(y + p * ldy + cv * 8);
-    const BF8 v1 = ld_bf8_stream(y + (p + pstep) * ldy + cv * 8);
+    const typename Act<T>::V8 v0 = Act<T>::ld_stream(y + p * ldy + cv * 8);
+    const typename Act<T>::V8 v1 = Act<T>::ld_stream(y + (p + pstep) * ldy + cv * 8);
     float f0[8], f1[8];
-    unpack8(v0, f0);
-    unpack8(v1, f1);
+    Act<T>::unpack(v0, f0);
+    Act<T>::unpack(v1, f1);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       f0[e] = fmaf(f0[e], sc[e], sh[e]);
@@ -242,24 +319,24 @@ __global__ void __launch_bounds__(kThreads)
         f1[e] = fmaxf(f1[e], 0.f);
       }
     }
-    st_bf8(a + p * lda + cv * 8, pack8(f0));
-    st_bf8(a + (p + pstep) * lda + cv * 8, pack8(f1));
+    Act<T>::st(a + p * lda + cv * 8, Act<T>::pack(f0));
+    Act<T>::st(a + (p + pstep) * lda + cv * 8, Act<T>::pack(f1));
   }
   if (p < pixels) {
-    const BF8 v0 = ld_bf8_stream(y + p * ldy + cv * 8);
+    const typename Act<T>::V8 v0 = Act<T>::ld_stream(y + p * ldy + cv * 8);
     float f0[8];
-    unpack8(v0, f0);
+    Act<T>::unpack(v0, f0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       f0[e] = fmaf(f0[e], sc[e], sh[e]);
       if (relu) f0[e] = fmaxf(f0[e], 0.f);
     }
-    st_bf8(a + p * lda + cv * 8, pack8(f0));
+    Act<T>::st(a + p * lda + cv * 8, Act<T>::pack(f0));
   }
 }
 
 int scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu, void* a,
-                    int lda, long long pixels, int C, cudaStream_t s) {
+                    int lda, long long pixels, int C, int dt, cudaStream_t s) {
   if (C % 8 || ldy % 8 || lda % 8 || C <= 0) {
     set_error("scale_shift_act: channels/strides must be multiples of 8");
     return -1;
@@ -267,21 +344,20 @@ int scale_shift_act(const void* y, int ldy, const float* scale, const float* shi
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV);
-  scale_shift_act_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(y), ldy, scale,
-                                                   shift, relu, static_cast<__nv_bfloat16*>(a), lda,
-                                                   pixels, CV);
+  PLUME_ACT_DISPATCH(dt, (scale_shift_act_kernel<T><<<grid, kThreads, 0, s>>>(
+                             static_cast<const T*>(y), ldy, scale, shift, relu, static_cast<T*>(a), lda, pixels, CV)));
   return check_launch("scale_shift_act");
 }
 
 // ------------------------------------------------------------------------------------------------
 // scale/shift/act fused with 2x2 max pool (+argmax), and the plain pool
 // ------------------------------------------------------------------------------------------------
-template <bool kAct, bool kSkip>
+template <typename T, bool kAct, bool kSkip>
 __global__ void __launch_bounds__(kThreads)
-    act_pool_kernel(const __nv_bfloat16* __restrict__ y, long long ldy,
+    act_pool_kernel(const T* __restrict__ y, long long ldy,
                     const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                    __nv_bfloat16* __restrict__ skip, long long ldskip,
-                    __nv_bfloat16* __restrict__ pooled, long long ldpooled,
+                    T* __restrict__ skip, long long ldskip,
+                    T* __restrict__ pooled, long long ldpooled,
                     uint8_t* __restrict__ argmax, int N, int Ho, int Wo, int CV) {
   // one thread per (pooled pixel, channel group)
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
@@ -300,30 +376,30 @@ __global__ void __launch_bounds__(kThreads)
     const int ho = static_cast<int>(t % Ho);
     const long long n = t / Ho;
     const long long ip = (n * (2 * Ho) + 2 * ho) * W + 2 * wo;  // top-left input pixel
-    BF8 v[4];
-    v[0] = ld_bf8_stream(y + ip * ldy + cv * 8);
-    v[1] = ld_bf8_stream(y + (ip + 1) * ldy + cv * 8);
-    v[2] = ld_bf8_stream(y + (ip + W) * ldy + cv * 8);
-    v[3] = ld_bf8_stream(y + (ip + W + 1) * ldy + cv * 8);
+    typename Act<T>::V8 v[4];
+    v[0] = Act<T>::ld_stream(y + ip * ldy + cv * 8);
+    v[1] = Act<T>::ld_stream(y + (ip + 1) * ldy + cv * 8);
+    v[2] = Act<T>::ld_stream(y + (ip + W) * ldy + cv * 8);
+    v[3] = Act<T>::ld_stream(y + (ip + W + 1) * ldy + cv * 8);
     float f[4][8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      unpack8(v[k], f[k]);
+      Act<T>::unpack(v[k], f[k]);
       if (kAct) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           f[k][e] = fmaf(f[k][e], sc[e], sh[e]);
           if (relu) f[k][e] = fmaxf(f[k][e], 0.f);
         }
-        v[k] = pack8(f[k]);
-        unpack8(v[k], f[k]);  // pool the rounded values (what the next layer reads)
+        v[k] = Act<T>::pack(f[k]);
+        Act<T>::unpack(v[k], f[k]);  // pool the rounded values (what the next layer reads)
       }
     }
     if (kSkip) {
-      st_bf8(skip + ip * ldskip + cv * 8, v[0]);
-      st_bf8(skip + (ip + 1) * ldskip + cv * 8, v[1]);
-      st_bf8(skip + (ip + W) * ldskip + cv * 8, v[2]);
-      st_bf8(skip + (ip + W + 1) * ldskip + cv * 8, v[3]);
+      Act<T>::st(skip + ip * ldskip + cv * 8, v[0]);
+      Act<T>::st(skip + (ip + 1) * ldskip + cv * 8, v[1]);
+      Act<T>::st(skip + (ip + W) * ldskip + cv * 8, v[2]);
+      Act<T>::st(skip + (ip + W + 1) * ldskip + cv * 8, v[3]);
     }
     float best[8];
     uint32_t idx_lo = 0, idx_hi = 0;
@@ -338,14 +414,14 @@ __global__ void __launch_bounds__(kThreads)
       if (e < 4) idx_lo |= bi << (8 * e);
       else idx_hi |= bi << (8 * (e - 4));
     }
-    st_bf8(pooled + op * ldpooled + cv * 8, pack8(best));
+    Act<T>::st(pooled + op * ldpooled + cv * 8, Act<T>::pack(best));
     *reinterpret_cast<uint2*>(argmax + (op * CV + cv) * 8) = make_uint2(idx_lo, idx_hi);
   }
 }
 
 static int pool_common(bool act, bool with_skip, const void* y, int ldy, const float* scale,
                        const float* shift, int relu, void* skip, int ldskip, void* pooled,
-                       int ldpooled, uint8_t* argmax, int N, int H, int W, int C, cudaStream_t s) {
+                       int ldpooled, uint8_t* argmax, int N, int H, int W, int C, int dt, cudaStream_t s) {
   if (C % 8 || ldy % 8 || ldpooled % 8 || (with_skip && ldskip % 8) || C <= 0) {
     set_error("maxpool: channels/strides must be multiples of 8");
     return -1;
@@ -358,37 +434,40 @@ static int pool_common(bool act, bool with_skip, const void* y, int ldy, const f
   const int CV = C / 8;
   const long long work = 1ll * N * (H / 2) * (W / 2) * CV;
   const int grid = grid_for(work, CV);
-  auto yy = static_cast<const __nv_bfloat16*>(y);
-  auto sk = static_cast<__nv_bfloat16*>(skip);
-  auto po = static_cast<__nv_bfloat16*>(pooled);
-  if (act && with_skip)
-    act_pool_kernel<true, true><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip, po,
-                                                          ldpooled, argmax, N, H / 2, W / 2, CV);
-  else if (act)
-    act_pool_kernel<true, false><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip,
-                                                           po, ldpooled, argmax, N, H / 2, W / 2, CV);
-  else
-    act_pool_kernel<false, false><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip,
-                                                            po, ldpooled, argmax, N, H / 2, W / 2, CV);
+  PLUME_ACT_DISPATCH(dt, {
+    auto yy = static_cast<const T*>(y);
+    auto sk = static_cast<T*>(skip);
+    auto po = static_cast<T*>(pooled);
+    if (act && with_skip)
+      act_pool_kernel<T, true, true><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip, po,
+                                                               ldpooled, argmax, N, H / 2, W / 2, CV);
+    else if (act)
+      act_pool_kernel<T, true, false><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip, po,
+                                                                ldpooled, argmax, N, H / 2, W / 2, CV);
+    else
+      act_pool_kernel<T, false, false><<<grid, kThreads, 0, s>>>(yy, ldy, scale, shift, relu, sk, ldskip, po,
+                                                                 ldpooled, argmax, N, H / 2, W / 2, CV);
+  });
   return check_launch("maxpool2x2");
 }
 
 int scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift, int relu,
                          void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax, int N,
-                         int H, int W, int C, cudaStream_t s) {
+                         int H, int W, int C, int dt, cudaStream_t s) {
   return pool_common(true, skip != nullptr, y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled,
-                     argmax, N, H, W, C, s);
+                     argmax, N, H, W, C, dt, s);
 }
 int maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
-                   int C, cudaStream_t s) {
+                   int C, int dt, cudaStream_t s) {
   return pool_common(false, false, x, ldx, nullptr, nullptr, 0, nullptr, 0, y, ldy, argmax, N, H, W, C,
-                     s);
+                     dt, s);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
-                       const uint8_t* __restrict__ argmax, const __nv_bfloat16* __restrict__ dskip,
-                       long long lddskip, __nv_bfloat16* __restrict__ dx, long long lddx, int N, int Ho,
+    maxpool_bwd_kernel(const T* __restrict__ dy, long long lddy,
+                       const uint8_t* __restrict__ argmax, const T* __restrict__ dskip,
+                       long long lddskip, T* __restrict__ dx, long long lddx, int N, int Ho,
                        int Wo, int CV) {
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
@@ -402,14 +481,14 @@ __global__ void __launch_bounds__(kThreads)
     const long long n = t / Ho;
     const long long ip = (n * (2 * Ho) + 2 * ho) * W + 2 * wo;
     float g[8];
-    unpack8(ld_bf8_stream(dy + op * lddy + cv * 8), g);
+    Act<T>::unpack(Act<T>::ld_stream(dy + op * lddy + cv * 8), g);
     const uint2 am = *reinterpret_cast<const uint2*>(argmax + (op * CV + cv) * 8);
     const long long off[4] = {ip, ip + 1, ip + W, ip + W + 1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float o[8];
       if (dskip) {
-        unpack8(ld_bf8_stream(dskip + off[k] * lddskip + cv * 8), o);
+        Act<T>::unpack(Act<T>::ld_stream(dskip + off[k] * lddskip + cv * 8), o);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.f;
@@ -419,13 +498,13 @@ __global__ void __launch_bounds__(kThreads)
         const uint32_t bi = ((e < 4 ? am.x : am.y) >> (8 * (e & 3))) & 0xffu;
         if (bi == static_cast<uint32_t>(k)) o[e] += g[e];
       }
-      st_bf8(dx + off[k] * lddx + cv * 8, pack8(o));
+      Act<T>::st(dx + off[k] * lddx + cv * 8, Act<T>::pack(o));
     }
   }
 }
 
 int maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
-                   void* dx, int lddx, int N, int H, int W, int C, cudaStream_t s) {
+                   void* dx, int lddx, int N, int H, int W, int C, int dt, cudaStream_t s) {
   if (C % 8 || lddy % 8 || lddx % 8 || (dskip && lddskip % 8) || C <= 0) {
     set_error("maxpool_bwd: channels/strides must be multiples of 8");
     return -1;
@@ -438,18 +517,19 @@ int maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* 
   const int CV = C / 8;
   const long long work = 1ll * N * (H / 2) * (W / 2) * CV;
   const int grid = grid_for(work, CV);
-  maxpool_bwd_kernel<<<grid, kThreads, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(dy), lddy, argmax, static_cast<const __nv_bfloat16*>(dskip),
-      lddskip, static_cast<__nv_bfloat16*>(dx), lddx, N, H / 2, W / 2, CV);
+  PLUME_ACT_DISPATCH(dt, (maxpool_bwd_kernel<T><<<grid, kThreads, 0, s>>>(
+                             static_cast<const T*>(dy), lddy, argmax, static_cast<const T*>(dskip), lddskip,
+                             static_cast<T*>(dx), lddx, N, H / 2, W / 2, CV)));
   return check_launch("maxpool2x2_bwd");
 }
 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm + ReLU backward
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, long long ldda,
-                         const __nv_bfloat16* __restrict__ y, long long ldy,
+    bn_bwd_reduce_kernel(const T* __restrict__ da, long long ldda,
+                         const T* __restrict__ y, long long ldy,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                          float* sum_g, float* sum_gx, long long pixels, int CV) {
@@ -468,17 +548,17 @@ __global__ void __launch_bounds__(kThreads)
   constexpr int U = 4;  // pixels in flight per thread: 8 independent 16-byte loads cover the HBM latency
   long long p = i0 / CV;
   for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
-    BF8 gv[U], yv[U];
+    typename Act<T>::V8 gv[U], yv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      gv[u] = ld_bf8_stream(da + (p + u * pstep) * ldda + cv * 8);
-      yv[u] = ld_bf8_stream(y + (p + u * pstep) * ldy + cv * 8);
+      gv[u] = Act<T>::ld_stream(da + (p + u * pstep) * ldda + cv * 8);
+      yv[u] = Act<T>::ld_stream(y + (p + u * pstep) * ldy + cv * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float g[8], yy[8];
-      unpack8(gv[u], g);
-      unpack8(yv[u], yy);
+      Act<T>::unpack(gv[u], g);
+      Act<T>::unpack(yv[u], yy);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
@@ -489,8 +569,8 @@ __global__ void __launch_bounds__(kThreads)
   }
   for (; p < pixels; p += pstep) {
     float g[8], yy[8];
-    unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
-    unpack8(ld_bf8_stream(y + p * ldy + cv * 8), yy);
+    Act<T>::unpack(Act<T>::ld_stream(da + p * ldda + cv * 8), g);
+    Act<T>::unpack(Act<T>::ld_stream(y + p * ldy + cv * 8), yy);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
@@ -504,7 +584,7 @@ __global__ void __launch_bounds__(kThreads)
 
 int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
                   const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
-                  float* sum_gx, long long pixels, int C, cudaStream_t s) {
+                  float* sum_gx, long long pixels, int C, int dt, cudaStream_t s) {
   if (C % 8 || ldda % 8 || ldy % 8 || C <= 0) {
     set_error("bn_bwd_reduce: channels/strides must be multiples of 8");
     return -1;
@@ -514,19 +594,20 @@ int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float*
   // two blocks per SM = what the 108 registers allow: one wave, no tail (244 -> 215 us over the five layer shapes)
   const int grid = grid_for(pixels * CV, CV, 2, 16);
   const size_t smem = 2ull * std::min(CV, kThreads) * 8 * sizeof(float);
-  bn_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(
-      static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
-      shift, mean, invstd, relu, sum_g, sum_gx, pixels, CV);
+  PLUME_ACT_DISPATCH(dt, (bn_bwd_reduce_kernel<T><<<grid, kThreads, smem, s>>>(
+                             static_cast<const T*>(da), ldda, static_cast<const T*>(y), ldy, scale, shift, mean,
+                             invstd, relu, sum_g, sum_gx, pixels, CV)));
   return check_launch("bn_bwd_reduce");
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, long long ldda,
-                        const __nv_bfloat16* __restrict__ y, long long ldy,
+    bn_bwd_apply_kernel(const T* __restrict__ da, long long ldda,
+                        const T* __restrict__ y, long long ldy,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                         const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
-                        float inv_count, __nv_bfloat16* __restrict__ dy, long long lddy, float* sum_dy,
+                        float inv_count, T* __restrict__ dy, long long lddy, float* sum_dy,
                         float* dgamma, float* dbeta, int accumulate, long long pixels, int CV) {
   extern __shared__ float s_acc[];
   // the finished per-channel sums are the BatchNorm parameter gradients; one block hands them over (sum_g /
@@ -555,21 +636,21 @@ __global__ void __launch_bounds__(kThreads)
   float acc[1][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
-  auto one = [&](const BF8& gvv, const BF8& yvv, long long pp) {
+  auto one = [&](const typename Act<T>::V8& gvv, const typename Act<T>::V8& yvv, long long pp) {
     float g[8], yy[8], o[8];
-    unpack8(gvv, g);
-    unpack8(yvv, yy);
+    Act<T>::unpack(gvv, g);
+    Act<T>::unpack(yvv, yy);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
       const float xhat = (yy[e] - mu[e]) * is[e];
       o[e] = sc[e] * (gg - mg[e] - xhat * mgx[e]);
     }
-    const BF8 ov = pack8(o);
-    st_bf8(dy + pp * lddy + cv * 8, ov);
+    const typename Act<T>::V8 ov = Act<T>::pack(o);
+    Act<T>::st(dy + pp * lddy + cv * 8, ov);
     if (sum_dy) {
       float r[8];
-      unpack8(ov, r);
+      Act<T>::unpack(ov, r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[0][e] += r[e];
     }
@@ -577,17 +658,17 @@ __global__ void __launch_bounds__(kThreads)
   constexpr int U = 4;
   long long p = i0 / CV;
   for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
-    BF8 gv[U], yv[U];
+    typename Act<T>::V8 gv[U], yv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      gv[u] = ld_bf8_stream(da + (p + u * pstep) * ldda + cv * 8);
-      yv[u] = ld_bf8_stream(y + (p + u * pstep) * ldy + cv * 8);
+      gv[u] = Act<T>::ld_stream(da + (p + u * pstep) * ldda + cv * 8);
+      yv[u] = Act<T>::ld_stream(y + (p + u * pstep) * ldy + cv * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) one(gv[u], yv[u], p + u * pstep);
   }
   for (; p < pixels; p += pstep)
-    one(ld_bf8_stream(da + p * ldda + cv * 8), ld_bf8_stream(y + p * ldy + cv * 8), p);
+    one(Act<T>::ld_stream(da + p * ldda + cv * 8), Act<T>::ld_stream(y + p * ldy + cv * 8), p);
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
     block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
@@ -597,7 +678,7 @@ __global__ void __launch_bounds__(kThreads)
 int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                  const float* shift, const float* mean, const float* invstd, int relu,
                  const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
-                 float* dgamma, float* dbeta, int accumulate, long long pixels, int C, cudaStream_t s) {
+                 float* dgamma, float* dbeta, int accumulate, long long pixels, int C, int dt, cudaStream_t s) {
   if ((dgamma == nullptr) != (dbeta == nullptr)) {
     set_error("bn_bwd_apply: dgamma and dbeta go together");
     return -1;
@@ -610,17 +691,18 @@ int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* 
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 2, 16);  // one wave at the kernel's occupancy (see bn_bwd_reduce)
   const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
-  bn_bwd_apply_kernel<<<grid, kThreads, smem, s>>>(
-      static_cast<const __nv_bfloat16*>(da), ldda, static_cast<const __nv_bfloat16*>(y), ldy, scale,
-      shift, mean, invstd, relu, sum_g, sum_gx, 1.f / static_cast<float>(pixels),
-      static_cast<__nv_bfloat16*>(dy), lddy, sum_dy, dgamma, dbeta, accumulate, pixels, CV);
+  PLUME_ACT_DISPATCH(dt, (bn_bwd_apply_kernel<T><<<grid, kThreads, smem, s>>>(
+                             static_cast<const T*>(da), ldda, static_cast<const T*>(y), ldy, scale, shift, mean,
+                             invstd, relu, sum_g, sum_gx, 1.f / static_cast<float>(pixels), static_cast<T*>(dy),
+                             lddy, sum_dy, dgamma, dbeta, accumulate, pixels, CV)));
   return check_launch("bn_bwd_apply");
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, long long ldda,
-                    const __nv_bfloat16* __restrict__ a, long long lda,
-                    __nv_bfloat16* __restrict__ dy, long long lddy, float* sum_dy, long long pixels,
+    relu_bwd_kernel(const T* __restrict__ da, long long ldda,
+                    const T* __restrict__ a, long long lda,
+                    T* __restrict__ dy, long long lddy, float* sum_dy, long long pixels,
                     int CV) {
   extern __shared__ float s_acc[];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
@@ -631,14 +713,14 @@ __global__ void __launch_bounds__(kThreads)
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   for (long long p = i0 / CV; p < pixels; p += pstep) {
     float g[8], aa[8];
-    unpack8(ld_bf8_stream(da + p * ldda + cv * 8), g);
-    unpack8(ld_bf8_stream(a + p * lda + cv * 8), aa);
+    Act<T>::unpack(Act<T>::ld_stream(da + p * ldda + cv * 8), g);
+    Act<T>::unpack(Act<T>::ld_stream(a + p * lda + cv * 8), aa);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       g[e] = aa[e] > 0.f ? g[e] : 0.f;
       acc[0][e] += g[e];
     }
-    st_bf8(dy + p * lddy + cv * 8, pack8(g));
+    Act<T>::st(dy + p * lddy + cv * 8, Act<T>::pack(g));
   }
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
@@ -647,7 +729,7 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 int relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
-             long long pixels, int C, cudaStream_t s) {
+             long long pixels, int C, int dt, cudaStream_t s) {
   if (C % 8 || ldda % 8 || lda % 8 || lddy % 8 || C <= 0) {
     set_error("relu_bwd: channels/strides must be multiples of 8");
     return -1;
@@ -656,15 +738,15 @@ int relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int ldd
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4);
   const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
-  relu_bwd_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(da), ldda,
-                                               static_cast<const __nv_bfloat16*>(a), lda,
-                                               static_cast<__nv_bfloat16*>(dy), lddy, sum_dy, pixels,
-                                               CV);
+  PLUME_ACT_DISPATCH(dt, (relu_bwd_kernel<T><<<grid, kThreads, smem, s>>>(
+                             static_cast<const T*>(da), ldda, static_cast<const T*>(a), lda, static_cast<T*>(dy),
+                             lddy, sum_dy, pixels, CV)));
   return check_launch("relu_bwd");
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* out,
+    channel_sum_kernel(const T* __restrict__ x, long long ldx, float* out,
                        long long pixels, int CV) {
   extern __shared__ float s_acc[];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
@@ -675,7 +757,7 @@ __global__ void __launch_bounds__(kThreads)
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   for (long long p = i0 / CV; p < pixels; p += pstep) {
     float f[8];
-    unpack8(ld_bf8_stream(x + p * ldx + cv * 8), f);
+    Act<T>::unpack(Act<T>::ld_stream(x + p * ldx + cv * 8), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] += f[e];
   }
@@ -683,7 +765,7 @@ __global__ void __launch_bounds__(kThreads)
   block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
 }
 
-int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cudaStream_t s) {
+int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, int dt, cudaStream_t s) {
   if (C % 8 || ldx % 8 || C <= 0) {
     set_error("channel_sum: channels/strides must be multiples of 8");
     return -1;
@@ -692,8 +774,8 @@ int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cud
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4, 16);
   const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
-  channel_sum_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, out,
-                                                  pixels, CV);
+  PLUME_ACT_DISPATCH(dt, (channel_sum_kernel<T><<<grid, kThreads, smem, s>>>(static_cast<const T*>(x), ldx, out,
+                                                                            pixels, CV)));
   return check_launch("channel_sum");
 }
 
@@ -703,8 +785,9 @@ int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cud
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
 
 // CV (= C/8, a power of two <= 32) consecutive lanes share one pixel.
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, long long ldf,
+    head_fwd_kernel(const T* __restrict__ feat, long long ldf,
                     const float* __restrict__ w, const float* __restrict__ b,
                     const uint8_t* __restrict__ target, float* __restrict__ logits, float* sums,
                     long long pixels, int CV) {
@@ -722,18 +805,18 @@ __global__ void __launch_bounds__(kThreads)
   const long long p0 = i0 / CV;
   const long long iters = (pixels + pstep - 1) / pstep;
   for (long long it = 0; it < iters; it += U) {
-    BF8 v[U];
+    typename Act<T>::V8 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + (it + u) * pstep;
-      if (it + u < iters && p < pixels) v[u] = ld_bf8_stream(feat + p * ldf + cv * 8);
-      else v[u].u[0] = v[u].u[1] = v[u].u[2] = v[u].u[3] = 0u;
+      if (it + u < iters && p < pixels) v[u] = Act<T>::ld_stream(feat + p * ldf + cv * 8);
+      else v[u] = Act<T>::zero();
     }
     float dots[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float f[8];
-      unpack8(v[u], f);
+      Act<T>::unpack(v[u], f);
       float dot = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) dot = fmaf(f[e], wv[e], dot);
@@ -791,7 +874,7 @@ static bool head_cv_ok(int C) {
 }
 
 int head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
-             float* logits, float* sums, long long pixels, int C, cudaStream_t s) {
+             float* logits, float* sums, long long pixels, int C, int dt, cudaStream_t s) {
   if (!head_cv_ok(C) || ldf % 8) {
     set_error("head_fwd: C must be 8*2^k <= 256 and ld a multiple of 8");
     return -1;
@@ -799,8 +882,8 @@ int head_fwd(const void* feat, int ldf, const float* w, const float* b, const ui
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4);
-  head_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), ldf, w, b, target,
-                                            logits, sums, pixels, CV);
+  PLUME_ACT_DISPATCH(dt, (head_fwd_kernel<T><<<grid, kThreads, 0, s>>>(static_cast<const T*>(feat), ldf, w, b,
+                                                                      target, logits, sums, pixels, CV)));
   return check_launch("head_fwd");
 }
 
@@ -823,12 +906,13 @@ int head_loss(const float* sums, long long pixels, float bce_w, float dice_w, fl
   return check_launch("head_loss");
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, long long ldf,
+    head_bwd_kernel(const T* __restrict__ feat, long long ldf,
                     const float* __restrict__ w, const float* __restrict__ logits,
                     const uint8_t* __restrict__ target, const float* __restrict__ sums, float inv_pixels,
                     float bce_w, float dice_w, float eps, float grad_scale,
-                    __nv_bfloat16* __restrict__ dfeat, long long lddf, float* dw, float* db,
+                    T* __restrict__ dfeat, long long lddf, float* dw, float* db,
                     long long pixels, int CV) {
   extern __shared__ float s_acc[];
   __shared__ float s_db[kThreads / 32];
@@ -845,28 +929,28 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   float a_db = 0.f;
-  auto one = [&](long long p, const BF8& fv, float z, float t) {
+  auto one = [&](long long p, const typename Act<T>::V8& fv, float z, float t) {
     const float pr = sigmoidf_(z);
     const float ddice = -(2.f * t * S - I2) * invS2;
     const float dz = grad_scale * (bce_w * (pr - t) * inv_pixels + dice_w * ddice * pr * (1.f - pr));
     float f[8], o[8];
-    unpack8(fv, f);
+    Act<T>::unpack(fv, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       o[e] = dz * wv[e];
       acc[0][e] = fmaf(dz, f[e], acc[0][e]);
     }
-    st_bf8(dfeat + p * lddf + cv * 8, pack8(o));
+    Act<T>::st(dfeat + p * lddf + cv * 8, Act<T>::pack(o));
     if (cv == 0) a_db += dz;
   };
   constexpr int U = 4;
   long long p = i0 / CV;
   for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
-    BF8 fv[U];
+    typename Act<T>::V8 fv[U];
     float zz[U], tt[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      fv[u] = ld_bf8_stream(feat + (p + u * pstep) * ldf + cv * 8);
+      fv[u] = Act<T>::ld_stream(feat + (p + u * pstep) * ldf + cv * 8);
       zz[u] = __ldg(logits + p + u * pstep);
       tt[u] = target[p + u * pstep] ? 1.f : 0.f;
     }
@@ -874,7 +958,7 @@ __global__ void __launch_bounds__(kThreads)
     for (int u = 0; u < U; ++u) one(p + u * pstep, fv[u], zz[u], tt[u]);
   }
   for (; p < pixels; p += pstep)
-    one(p, ld_bf8_stream(feat + p * ldf + cv * 8), __ldg(logits + p), target[p] ? 1.f : 0.f);
+    one(p, Act<T>::ld_stream(feat + p * ldf + cv * 8), __ldg(logits + p), target[p] ? 1.f : 0.f);
   float* const outs[1] = {dw};
   block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
   a_db = warp_sum(a_db);
@@ -889,7 +973,7 @@ __global__ void __launch_bounds__(kThreads)
 
 int head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
              const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
-             int lddf, float* dw, float* db, long long pixels, int C, cudaStream_t s) {
+             int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s) {
   if (!head_cv_ok(C) || ldf % 8 || lddf % 8) {
     set_error("head_bwd: C must be 8*2^k <= 256 and strides multiples of 8");
     return -1;
@@ -898,10 +982,10 @@ int head_bwd(const void* feat, int ldf, const float* w, const float* logits, con
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4);
   const size_t smem = 1ull * CV * 8 * sizeof(float);
-  head_bwd_kernel<<<grid, kThreads, smem, s>>>(
-      static_cast<const __nv_bfloat16*>(feat), ldf, w, logits, target, sums,
-      1.f / static_cast<float>(pixels), bce_w, dice_w, eps, grad_scale,
-      static_cast<__nv_bfloat16*>(dfeat), lddf, dw, db, pixels, CV);
+  PLUME_ACT_DISPATCH(dt, (head_bwd_kernel<T><<<grid, kThreads, smem, s>>>(
+                             static_cast<const T*>(feat), ldf, w, logits, target, sums,
+                             1.f / static_cast<float>(pixels), bce_w, dice_w, eps, grad_scale, static_cast<T*>(dfeat),
+                             lddf, dw, db, pixels, CV)));
   return check_launch("head_bwd");
 }
 
@@ -1147,38 +1231,39 @@ int pack_batch(const plume_pack_desc* descs, int n, int total_blocks, cudaStream
 // ------------------------------------------------------------------------------------------------
 // tiled inference: cut tiles out of a scene, stitch logits back by centre crop + threshold
 // ------------------------------------------------------------------------------------------------
-__global__ void extract_tiles_kernel(const __nv_bfloat16* __restrict__ scene, int Hs, int Ws, int cvs,
-                                     const int* __restrict__ ys, const int* __restrict__ xs, int T,
-                                     __nv_bfloat16* __restrict__ tiles, int cvd, long long total) {
+template <typename T>
+__global__ void extract_tiles_kernel(const T* __restrict__ scene, int Hs, int Ws, int cvs,
+                                     const int* __restrict__ ys, const int* __restrict__ xs, int tile,
+                                     T* __restrict__ tiles, int cvd, long long total) {
   const long long step = 1ll * gridDim.x * blockDim.x;
   for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
     const int cv = static_cast<int>(i % cvd);
     long long t = i / cvd;
-    const int x = static_cast<int>(t % T);
-    t /= T;
-    const int y = static_cast<int>(t % T);
-    const int k = static_cast<int>(t / T);
+    const int x = static_cast<int>(t % tile);
+    t /= tile;
+    const int y = static_cast<int>(t % tile);
+    const int k = static_cast<int>(t / tile);
     const int sy = ys[k] + y, sx = xs[k] + x;
-    BF8 v;
-    v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
+    typename Act<T>::V8 v;
+    v = Act<T>::zero();
     if (cv < cvs && sy >= 0 && sy < Hs && sx >= 0 && sx < Ws)
-      v = ld_bf8(scene + ((1ll * sy * Ws + sx) * cvs + cv) * 8);
-    st_bf8(tiles + i * 8, v);
+      v = Act<T>::ld(scene + ((1ll * sy * Ws + sx) * cvs + cv) * 8);
+    Act<T>::st(tiles + i * 8, v);
   }
 }
 
 int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs, int count,
-                  int T, void* tiles, int Cd, cudaStream_t s) {
+                  int tile, void* tiles, int Cd, int dt, cudaStream_t s) {
   if (Cs % 8 || Cd % 8 || Cs > Cd || Cs <= 0) {
     set_error("extract_tiles: channel counts must be multiples of 8 with Cs <= Cd");
     return -1;
   }
   if (count <= 0) return 0;
-  const long long total = 1ll * count * T * T * (Cd / 8);
+  const long long total = 1ll * count * tile * tile * (Cd / 8);
   const int grid = grid_for(total, 1);
-  extract_tiles_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(scene), Hs, Ws,
-                                                 Cs / 8, ys, xs, T, static_cast<__nv_bfloat16*>(tiles),
-                                                 Cd / 8, total);
+  PLUME_ACT_DISPATCH(dt, (extract_tiles_kernel<T><<<grid, kThreads, 0, s>>>(
+                             static_cast<const T*>(scene), Hs, Ws, Cs / 8, ys, xs, tile, static_cast<T*>(tiles), Cd / 8,
+                             total)));
   return check_launch("extract_tiles");
 }
 

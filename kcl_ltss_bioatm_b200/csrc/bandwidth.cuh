@@ -1,4 +1,4 @@
-// Internal C++ interface of the bandwidth kernels (bandwidth.cu), the label-geometry kernels (geometry.cu)
+// Internal C++ interface of the bandwidth kernels (bandwidth.cu; `dt` = activation storage: 0 bf16, 1 fp32), the label-geometry kernels (geometry.cu)
 // and the threshold-sweep kernels (sweep.cu).  Input and output buffers of one call must not alias: inputs
 // are read through the non-coherent path.
 #pragma once
@@ -12,7 +12,7 @@ namespace plume {
 
 void set_error(const std::string& msg);
 
-int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, cudaStream_t s);
+int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, int dt, cudaStream_t s);
 int bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean,
                 float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
@@ -20,31 +20,31 @@ int bn_finalize(const double* sum, const double* sq, long long count, const floa
 int bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                  const float* bias, float eps, float* scale, float* shift, int C, cudaStream_t s);
 int scale_shift_act(const void* y, int ldy, const float* scale, const float* shift, int relu, void* a,
-                    int lda, long long pixels, int C, cudaStream_t s);
+                    int lda, long long pixels, int C, int dt, cudaStream_t s);
 int scale_shift_act_pool(const void* y, int ldy, const float* scale, const float* shift, int relu,
                          void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax, int N,
-                         int H, int W, int C, cudaStream_t s);
+                         int H, int W, int C, int dt, cudaStream_t s);
 int maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
-                   int C, cudaStream_t s);
+                   int C, int dt, cudaStream_t s);
 int maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
-                   void* dx, int lddx, int N, int H, int W, int C, cudaStream_t s);
+                   void* dx, int lddx, int N, int H, int W, int C, int dt, cudaStream_t s);
 int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
                   const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
-                  float* sum_gx, long long pixels, int C, cudaStream_t s);
+                  float* sum_gx, long long pixels, int C, int dt, cudaStream_t s);
 int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* scale,
                  const float* shift, const float* mean, const float* invstd, int relu,
                  const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
-                 float* dgamma, float* dbeta, int accumulate, long long pixels, int C, cudaStream_t s);
+                 float* dgamma, float* dbeta, int accumulate, long long pixels, int C, int dt, cudaStream_t s);
 int relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
-             long long pixels, int C, cudaStream_t s);
-int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, cudaStream_t s);
+             long long pixels, int C, int dt, cudaStream_t s);
+int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, int dt, cudaStream_t s);
 int head_fwd(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
-             float* logits, float* sums, long long pixels, int C, cudaStream_t s);
+             float* logits, float* sums, long long pixels, int C, int dt, cudaStream_t s);
 int head_loss(const float* sums, long long pixels, float bce_w, float dice_w, float eps, float* out,
               cudaStream_t s);
 int head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
              const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
-             int lddf, float* dw, float* db, long long pixels, int C, cudaStream_t s);
+             int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s);
 int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
          double beta2, double eps, int step, float grad_scale, cudaStream_t s);
 int adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
@@ -54,7 +54,7 @@ int pack_convT2x2(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStr
 int pack_blocks(int kind, int Cout, int Cin);
 int pack_batch(const plume_pack_desc* descs, int n, int total_blocks, cudaStream_t s);
 int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs, int count,
-                  int T, void* tiles, int Cd, cudaStream_t s);
+                  int T, void* tiles, int Cd, int dt, cudaStream_t s);
 int stitch_threshold(const float* logits, const int* ys, const int* xs, int count, int T, int margin,
                      float thr, uint8_t* mask, float* prob, int Hs, int Ws, cudaStream_t s);
 

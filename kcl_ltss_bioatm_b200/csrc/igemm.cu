@@ -757,11 +757,37 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     int it = g;
     long long t_epi_wait = 0;
     const long long t_epi_begin = clock64();
+    // BatchNorm statistics: a tile's column sums are formed in fp32 (shared memory), then carried across this
+    // warpgroup's tiles in fp64 REGISTERS (thread et owns channels et, et + 128) and added to the global fp64
+    // accumulators once per run of tiles with the same channel slice -- normally once per CTA.  One global
+    // atomic per channel per TILE (16 K tiles x 128 addresses on the 64-wide layers) doubled those layers'
+    // time when the accumulators became fp64 (340 vs 170 us).
+    constexpr int ACC_PER_THREAD = (BLOCK_N + 127) / 128;
+    double acc_s[ACC_PER_THREAD], acc_q[ACC_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < ACC_PER_THREAD; ++i) acc_s[i] = acc_q[i] = 0.0;
+    int acc_ch0 = -1;
+    auto flush_stats = [&]() {
+      if (acc_ch0 < 0) return;
+#pragma unroll
+      for (int i = 0; i < ACC_PER_THREAD; ++i) {
+        const int c = et + 128 * i;
+        if (c < BLOCK_N) {
+          atomicAdd(p.stat_sum + acc_ch0 + c, acc_s[i]);
+          atomicAdd(p.stat_sq + acc_ch0 + c, acc_q[i]);
+        }
+        acc_s[i] = acc_q[i] = 0.0;
+      }
+    };
     for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
       int n_tile, img, w0, h0;
       decode(tile, n_tile, img, w0, h0);
       const int acc_phase = (it >> 1) & 1;
       const int ch0 = n_tile * BLOCK_N;
+      if (do_stats && ch0 != acc_ch0) {
+        flush_stats();
+        acc_ch0 = ch0;
+      }
       if (n_tile != last_n_tile) {  // per-channel parameters change only with the N tile
         for (int c = et; c < BLOCK_N; c += 128) {
           s_scale[c] = p.scale ? p.scale[ch0 + c] : 1.0f;
@@ -867,12 +893,17 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       }
       if (do_stats) {
         named_bar_sync(bar_a, 128);
-        for (int c = et; c < BLOCK_N; c += 128) {
-          atomicAdd(p.stat_sum + ch0 + c, static_cast<double>(s_sum[c]));
-          atomicAdd(p.stat_sq + ch0 + c, static_cast<double>(s_sq[c]));
+#pragma unroll
+        for (int i = 0; i < ACC_PER_THREAD; ++i) {
+          const int c = et + 128 * i;
+          if (c < BLOCK_N) {   // the same thread zeroes s_sum[c] at the top of the next tile
+            acc_s[i] += static_cast<double>(s_sum[c]);
+            acc_q[i] += static_cast<double>(s_sq[c]);
+          }
         }
       }
     }
+    if (do_stats) flush_stats();
     if (et == 0) tma_store_wait_all<0>();
     if (p.prof && et == 0 && g == 0) {
       p.prof[blockIdx.x * 8 + 6] = clock64() - t_epi_begin;  // epilogue warpgroup 0: total

@@ -53,6 +53,18 @@ SIGNATURES = {
     "plume_head_bwd": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
     "plume_adam": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P]),
     "plume_adam_dev": (_I, [_P, _P, _P, _P, _LL, _P, _P]),
+    "plume_pad_channels_f32": (_I, [_P, _I, _P, _I, _LL, _P]),
+    "plume_scale_shift_act_f32": (_I, [_P, _I, _P, _P, _I, _P, _I, _LL, _I, _P]),
+    "plume_scale_shift_act_pool_f32": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "plume_maxpool2x2_fwd_f32": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "plume_maxpool2x2_bwd_f32": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "plume_bn_bwd_reduce_f32": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _LL, _I, _P]),
+    "plume_bn_bwd_apply_f32": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _LL, _I, _P]),
+    "plume_relu_bwd_f32": (_I, [_P, _I, _P, _I, _P, _I, _P, _LL, _I, _P]),
+    "plume_channel_sum_f32": (_I, [_P, _I, _P, _LL, _I, _P]),
+    "plume_head_fwd_f32": (_I, [_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P]),
+    "plume_head_bwd_f32": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
+    "plume_extract_tiles_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_extract_tiles": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
     "plume_rasterize_hulls": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),

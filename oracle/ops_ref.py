@@ -358,3 +358,34 @@ class RefOps:
             for f, (r, c) in enumerate(fire_rc.cpu().numpy()):
                 l = extract_label_ref(lab, int(r), int(c), win)
                 extents[t, f] = 0 if l is None else int(sz[l - 1])
+
+
+class RefOpsF64Accum(RefOps):
+    """RefOps with the same bf16 rounding points but the 3x3 convolutions accumulated in float64, i.e. a different
+    summation order.  Two implementations that differ only in accumulation order flip isolated bf16 roundings, and
+    BatchNorm's backward amplifies those flips; the distance between RefOps and this class is therefore the NOISE
+    FLOOR of any "same rounding points" comparison (tests/test_gpu_unet.py::_grad_parity measures it per tensor)."""
+
+    name = "ref-f64-accum"
+
+    def conv3x3_fwd(self, x, w_fwd, scale, shift, relu, y, stat_sum=None, stat_sq=None):
+        cout, cin = y.shape[-1], x.shape[-1]
+        kcin = w_fwd.numel() // (9 * cout)
+        w = w_fwd.double().view(cout, 3, 3, kcin)[..., :cin].permute(0, 3, 1, 2)
+        o = F.conv2d(_nchw(x).double(), w, padding=1).float()
+        if scale is not None:
+            o = o * scale.view(1, -1, 1, 1)
+        if shift is not None:
+            o = o + shift.view(1, -1, 1, 1)
+        if relu:
+            o = o.relu()
+        y.copy_(_nhwc(o).to(self.act_dtype))
+        if stat_sum is not None:
+            yr = y.to(stat_sum.dtype)
+            stat_sum += yr.sum(dim=(0, 1, 2))
+            stat_sq += (yr * yr).sum(dim=(0, 1, 2))
+
+    def conv3x3_dgrad(self, dy, w_dgrad, dx):
+        cin, cout = dx.shape[-1], dy.shape[-1]
+        w = w_dgrad.double().view(cin, 3, 3, cout).permute(0, 3, 1, 2)
+        dx.copy_(_nhwc(F.conv2d(_nchw(dy).double(), w, padding=1).float()).to(self.act_dtype))
