@@ -38,6 +38,12 @@ ActView phase_view(const void* ptr, int ld, int N, int H, int W, int C, int i, i
   return v;
 }
 bool bad_ld(int ld, int C) { return ld < C || (ld % 8) != 0; }
+// bf16x3 views: the pixel stride covers the hi and the lo plane (ld / 2 elements each)
+bool bad_ld(int ld, int C, int split) { return split ? (ld % 16 != 0 || ld / 2 < C) : bad_ld(ld, C); }
+ActView with_plane(ActView v, int ld, int split) {
+  v.plane = split ? ld / 2 : 0;
+  return v;
+}
 #define PLUME_CHECK(cond, msg) \
   do {                         \
     if (!(cond)) {             \
@@ -60,21 +66,23 @@ int plume_num_sms(void) {
   return n;
 }
 
-int plume_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale, const float* shift,
+static int impl_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale, const float* shift,
                       int relu, void* y, int ldy, double* stat_sum, double* stat_sq, int N, int H, int W,
-                      int Cin, int Cout, plume_stream_t stream) {
+                      int Cin, int Cout, plume_stream_t stream, int split) {
   PLUME_CHECK(x && w && y, "conv3x3_fwd: null pointer");
   // ldx < Cin: x is dense with ldx channels per pixel; the weights' remaining input channels read as zero
-  const int Cx = ldx < Cin ? ldx : Cin;
-  PLUME_CHECK(Cx > 0 && !bad_ld(ldx, Cx) && !bad_ld(ldy, Cout), "conv3x3_fwd: bad pixel stride");
+  const int ldx1 = split ? ldx / 2 : ldx;   // channels per pixel of one plane
+  const int Cx = ldx1 < Cin ? ldx1 : Cin;
+  PLUME_CHECK(Cx > 0 && !bad_ld(ldx, Cx, split) && !bad_ld(ldy, Cout, split), "conv3x3_fwd: bad pixel stride");
   PLUME_CHECK((stat_sum == nullptr) == (stat_sq == nullptr), "conv3x3_fwd: stat_sum/stat_sq mismatch");
   FwdDesc d{};
-  d.in[0] = view(x, ldx, N, H, W, Cx);
+  d.split = split;
+  d.in[0] = with_plane(view(x, ldx, N, H, W, Cx), ldx, split);
   d.num_in_views = 1;
   d.num_taps = 9;
   d.Cin = Cin;
   d.wmat = w;
-  d.out[0] = view(y, ldy, N, H, W, Cout);
+  d.out[0] = with_plane(view(y, ldy, N, H, W, Cout), ldy, split);
   d.num_out_views = 1;
   d.cout_per_view = Cout;
   d.scale = scale; d.shift = shift; d.relu = relu;
@@ -82,22 +90,41 @@ int plume_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale,
   d.stream = S(stream);
   return launch_igemm_fwd(d);
 }
+int plume_conv3x3_fwd(const void* x, int ldx, const void* w, const float* scale, const float* shift,
+                      int relu, void* y, int ldy, double* stat_sum, double* stat_sq, int N, int H, int W,
+                      int Cin, int Cout, plume_stream_t stream) {
+  return impl_conv3x3_fwd(x, ldx, w, scale, shift, relu, y, ldy, stat_sum, stat_sq, N, H, W, Cin, Cout, stream, 0);
+}
+int plume_conv3x3_fwd_x3(const void* x, int ldx, const void* w, const float* scale, const float* shift,
+                      int relu, void* y, int ldy, double* stat_sum, double* stat_sq, int N, int H, int W,
+                      int Cin, int Cout, plume_stream_t stream) {
+  return impl_conv3x3_fwd(x, ldx, w, scale, shift, relu, y, ldy, stat_sum, stat_sq, N, H, W, Cin, Cout, stream, 1);
+}
 
-int plume_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad, void* dx, int lddx, int N, int H,
-                        int W, int Cin, int Cout, plume_stream_t stream) {
+static int impl_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                        int W, int Cin, int Cout, plume_stream_t stream, int split) {
   PLUME_CHECK(dy && w_dgrad && dx, "conv3x3_dgrad: null pointer");
-  PLUME_CHECK(!bad_ld(lddy, Cout) && !bad_ld(lddx, Cin), "conv3x3_dgrad: bad pixel stride");
+  PLUME_CHECK(!bad_ld(lddy, Cout, split) && !bad_ld(lddx, Cin, split), "conv3x3_dgrad: bad pixel stride");
   FwdDesc d{};
-  d.in[0] = view(dy, lddy, N, H, W, Cout);
+  d.split = split;
+  d.in[0] = with_plane(view(dy, lddy, N, H, W, Cout), lddy, split);
   d.num_in_views = 1;
   d.num_taps = 9;
   d.Cin = Cout;
   d.wmat = w_dgrad;
-  d.out[0] = view(dx, lddx, N, H, W, Cin);
+  d.out[0] = with_plane(view(dx, lddx, N, H, W, Cin), lddx, split);
   d.num_out_views = 1;
   d.cout_per_view = Cin;
   d.stream = S(stream);
   return launch_igemm_fwd(d);
+}
+int plume_conv3x3_dgrad(const void* dy, int lddy, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                        int W, int Cin, int Cout, plume_stream_t stream) {
+  return impl_conv3x3_dgrad(dy, lddy, w_dgrad, dx, lddx, N, H, W, Cin, Cout, stream, 0);
+}
+int plume_conv3x3_dgrad_x3(const void* dy, int lddy, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                        int W, int Cin, int Cout, plume_stream_t stream) {
+  return impl_conv3x3_dgrad(dy, lddy, w_dgrad, dx, lddx, N, H, W, Cin, Cout, stream, 1);
 }
 
 int plume_wgrad_splits(int N, int H, int W, int taps, int Cin, int Cout) {
@@ -109,20 +136,22 @@ size_t plume_wgrad_workspace_bytes(int N, int H, int W, int taps, int Cin, int C
   return 0;  // split-K partial sums are reduced with fp32 atomics; no workspace is needed any more
 }
 
-int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw, int accumulate,
+static int impl_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw, int accumulate,
                         void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
-                        plume_stream_t stream) {
+                        plume_stream_t stream, int split) {
   (void)workspace; (void)workspace_bytes;
   PLUME_CHECK(x && dy && dw, "conv3x3_wgrad: null pointer");
-  const int Cx = ldx < Cin ? ldx : Cin;  // see plume_conv3x3_fwd
-  PLUME_CHECK(Cx > 0 && !bad_ld(ldx, Cx) && !bad_ld(lddy, Cout), "conv3x3_wgrad: bad pixel stride");
+  const int ldx1 = split ? ldx / 2 : ldx;
+  const int Cx = ldx1 < Cin ? ldx1 : Cin;  // see plume_conv3x3_fwd
+  PLUME_CHECK(Cx > 0 && !bad_ld(ldx, Cx, split) && !bad_ld(lddy, Cout, split), "conv3x3_wgrad: bad pixel stride");
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 9ull * Cin * Cout, S(stream));
     PLUME_CHECK(e == cudaSuccess, "conv3x3_wgrad: cudaMemsetAsync failed");
   }
   WgradDesc d{};
-  d.x = view(x, ldx, N, H, W, Cx);
-  d.dy[0] = view(dy, lddy, N, H, W, Cout);
+  d.split = split;
+  d.x = with_plane(view(x, ldx, N, H, W, Cx), ldx, split);
+  d.dy[0] = with_plane(view(dy, lddy, N, H, W, Cout), lddy, split);
   d.num_dy_views = 1;
   d.num_taps = 9;
   d.Cin = Cin; d.Cout = Cout;
@@ -132,55 +161,87 @@ int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float*
   d.stream = S(stream);
   return launch_igemm_wgrad(d);
 }
+int plume_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw, int accumulate,
+                        void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
+                        plume_stream_t stream) {
+  return impl_conv3x3_wgrad(x, ldx, dy, lddy, dw, accumulate, workspace, workspace_bytes, N, H, W, Cin, Cout, stream, 0);
+}
+int plume_conv3x3_wgrad_x3(const void* x, int ldx, const void* dy, int lddy, float* dw, int accumulate,
+                        void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
+                        plume_stream_t stream) {
+  return impl_conv3x3_wgrad(x, ldx, dy, lddy, dw, accumulate, workspace, workspace_bytes, N, H, W, Cin, Cout, stream, 1);
+}
 
-int plume_convT2x2_concat_fwd(const void* x, int ldx, const void* w, const float* bias, void* u, int ldu,
-                              int N, int H, int W, int Cin, int Cout, plume_stream_t stream) {
+static int impl_convT2x2_concat_fwd(const void* x, int ldx, const void* w, const float* bias, void* u, int ldu,
+                              int N, int H, int W, int Cin, int Cout, plume_stream_t stream, int split) {
   PLUME_CHECK(x && w && u, "convT2x2_fwd: null pointer");
-  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(ldu, Cout), "convT2x2_fwd: bad pixel stride");
+  PLUME_CHECK(!bad_ld(ldx, Cin, split) && !bad_ld(ldu, Cout, split), "convT2x2_fwd: bad pixel stride");
   FwdDesc d{};
-  d.in[0] = view(x, ldx, N, H, W, Cin);
+  d.split = split;
+  d.in[0] = with_plane(view(x, ldx, N, H, W, Cin), ldx, split);
   d.num_in_views = 1;
   d.num_taps = 1;
   d.Cin = Cin;
   d.wmat = w;
-  for (int ij = 0; ij < 4; ++ij) d.out[ij] = phase_view(u, ldu, N, H, W, Cout, ij >> 1, ij & 1);
+  for (int ij = 0; ij < 4; ++ij)
+    d.out[ij] = with_plane(phase_view(u, ldu, N, H, W, Cout, ij >> 1, ij & 1), ldu, split);
   d.num_out_views = 4;
   d.cout_per_view = Cout;
   d.shift = bias;
   d.stream = S(stream);
   return launch_igemm_fwd(d);
 }
+int plume_convT2x2_concat_fwd(const void* x, int ldx, const void* w, const float* bias, void* u, int ldu,
+                              int N, int H, int W, int Cin, int Cout, plume_stream_t stream) {
+  return impl_convT2x2_concat_fwd(x, ldx, w, bias, u, ldu, N, H, W, Cin, Cout, stream, 0);
+}
+int plume_convT2x2_concat_fwd_x3(const void* x, int ldx, const void* w, const float* bias, void* u, int ldu,
+                              int N, int H, int W, int Cin, int Cout, plume_stream_t stream) {
+  return impl_convT2x2_concat_fwd(x, ldx, w, bias, u, ldu, N, H, W, Cin, Cout, stream, 1);
+}
 
-int plume_convT2x2_dgrad(const void* du, int lddu, const void* w_dgrad, void* dx, int lddx, int N, int H,
-                         int W, int Cin, int Cout, plume_stream_t stream) {
+static int impl_convT2x2_dgrad(const void* du, int lddu, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                         int W, int Cin, int Cout, plume_stream_t stream, int split) {
   PLUME_CHECK(du && w_dgrad && dx, "convT2x2_dgrad: null pointer");
-  PLUME_CHECK(!bad_ld(lddu, Cout) && !bad_ld(lddx, Cin), "convT2x2_dgrad: bad pixel stride");
+  PLUME_CHECK(!bad_ld(lddu, Cout, split) && !bad_ld(lddx, Cin, split), "convT2x2_dgrad: bad pixel stride");
   FwdDesc d{};
-  for (int ij = 0; ij < 4; ++ij) d.in[ij] = phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1);
+  d.split = split;
+  for (int ij = 0; ij < 4; ++ij)
+    d.in[ij] = with_plane(phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1), lddu, split);
   d.num_in_views = 4;
   d.num_taps = 4;
   d.Cin = Cout;
   d.wmat = w_dgrad;
-  d.out[0] = view(dx, lddx, N, H, W, Cin);
+  d.out[0] = with_plane(view(dx, lddx, N, H, W, Cin), lddx, split);
   d.num_out_views = 1;
   d.cout_per_view = Cin;
   d.stream = S(stream);
   return launch_igemm_fwd(d);
 }
+int plume_convT2x2_dgrad(const void* du, int lddu, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                         int W, int Cin, int Cout, plume_stream_t stream) {
+  return impl_convT2x2_dgrad(du, lddu, w_dgrad, dx, lddx, N, H, W, Cin, Cout, stream, 0);
+}
+int plume_convT2x2_dgrad_x3(const void* du, int lddu, const void* w_dgrad, void* dx, int lddx, int N, int H,
+                         int W, int Cin, int Cout, plume_stream_t stream) {
+  return impl_convT2x2_dgrad(du, lddu, w_dgrad, dx, lddx, N, H, W, Cin, Cout, stream, 1);
+}
 
-int plume_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float* dw, int accumulate,
+static int impl_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float* dw, int accumulate,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
-                         plume_stream_t stream) {
+                         plume_stream_t stream, int split) {
   (void)workspace; (void)workspace_bytes;
   PLUME_CHECK(x && du && dw, "convT2x2_wgrad: null pointer");
-  PLUME_CHECK(!bad_ld(ldx, Cin) && !bad_ld(lddu, Cout), "convT2x2_wgrad: bad pixel stride");
+  PLUME_CHECK(!bad_ld(ldx, Cin, split) && !bad_ld(lddu, Cout, split), "convT2x2_wgrad: bad pixel stride");
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 4ull * Cin * Cout, S(stream));
     PLUME_CHECK(e == cudaSuccess, "convT2x2_wgrad: cudaMemsetAsync failed");
   }
   WgradDesc d{};
-  d.x = view(x, ldx, N, H, W, Cin);
-  for (int ij = 0; ij < 4; ++ij) d.dy[ij] = phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1);
+  d.split = split;
+  d.x = with_plane(view(x, ldx, N, H, W, Cin), ldx, split);
+  for (int ij = 0; ij < 4; ++ij)
+    d.dy[ij] = with_plane(phase_view(du, lddu, N, H, W, Cout, ij >> 1, ij & 1), lddu, split);
   d.num_dy_views = 4;
   d.num_taps = 4;
   d.Cin = Cin; d.Cout = Cout;
@@ -189,6 +250,16 @@ int plume_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float
   d.s_t = 1ll * Cout * Cin;
   d.stream = S(stream);
   return launch_igemm_wgrad(d);
+}
+int plume_convT2x2_wgrad(const void* x, int ldx, const void* du, int lddu, float* dw, int accumulate,
+                         void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
+                         plume_stream_t stream) {
+  return impl_convT2x2_wgrad(x, ldx, du, lddu, dw, accumulate, workspace, workspace_bytes, N, H, W, Cin, Cout, stream, 0);
+}
+int plume_convT2x2_wgrad_x3(const void* x, int ldx, const void* du, int lddu, float* dw, int accumulate,
+                         void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
+                         plume_stream_t stream) {
+  return impl_convT2x2_wgrad(x, ldx, du, lddu, dw, accumulate, workspace, workspace_bytes, N, H, W, Cin, Cout, stream, 1);
 }
 
 int plume_pack_conv3x3(const float* w, void* wf, void* wd, int Cout, int Cin, plume_stream_t stream) {
@@ -214,7 +285,7 @@ int plume_pad_channels(const void* in, int Cs, void* out, int Cd, long long pixe
                        plume_stream_t stream) {
   return impl_pad_channels(in, Cs, out, Cd, pixels, stream, 0);
 }
-int plume_pad_channels_f32(const void* in, int Cs, void* out, int Cd, long long pixels,
+int plume_pad_channels_x3(const void* in, int Cs, void* out, int Cd, long long pixels,
                        plume_stream_t stream) {
   return impl_pad_channels(in, Cs, out, Cd, pixels, stream, 1);
 }
@@ -245,7 +316,7 @@ int plume_scale_shift_act(const void* y, int ldy, const float* scale, const floa
                           void* a, int lda, long long pixels, int C, plume_stream_t stream) {
   return impl_scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, stream, 0);
 }
-int plume_scale_shift_act_f32(const void* y, int ldy, const float* scale, const float* shift, int relu,
+int plume_scale_shift_act_x3(const void* y, int ldy, const float* scale, const float* shift, int relu,
                           void* a, int lda, long long pixels, int C, plume_stream_t stream) {
   return impl_scale_shift_act(y, ldy, scale, shift, relu, a, lda, pixels, C, stream, 1);
 }
@@ -261,7 +332,7 @@ int plume_scale_shift_act_pool(const void* y, int ldy, const float* scale, const
                                int N, int H, int W, int C, plume_stream_t stream) {
   return impl_scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H, W, C, stream, 0);
 }
-int plume_scale_shift_act_pool_f32(const void* y, int ldy, const float* scale, const float* shift, int relu,
+int plume_scale_shift_act_pool_x3(const void* y, int ldy, const float* scale, const float* shift, int relu,
                                void* skip, int ldskip, void* pooled, int ldpooled, uint8_t* argmax,
                                int N, int H, int W, int C, plume_stream_t stream) {
   return impl_scale_shift_act_pool(y, ldy, scale, shift, relu, skip, ldskip, pooled, ldpooled, argmax, N, H, W, C, stream, 1);
@@ -275,7 +346,7 @@ int plume_maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argm
                          int C, plume_stream_t stream) {
   return impl_maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, stream, 0);
 }
-int plume_maxpool2x2_fwd_f32(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
+int plume_maxpool2x2_fwd_x3(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
                          int C, plume_stream_t stream) {
   return impl_maxpool2x2_fwd(x, ldx, y, ldy, argmax, N, H, W, C, stream, 1);
 }
@@ -290,7 +361,7 @@ int plume_maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const 
                          plume_stream_t stream) {
   return impl_maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, stream, 0);
 }
-int plume_maxpool2x2_bwd_f32(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
+int plume_maxpool2x2_bwd_x3(const void* dy, int lddy, const uint8_t* argmax, const void* dskip,
                          int lddskip, void* dx, int lddx, int N, int H, int W, int C,
                          plume_stream_t stream) {
   return impl_maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, stream, 1);
@@ -309,7 +380,7 @@ int plume_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const 
                         float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream) {
   return impl_bn_bwd_reduce(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C, stream, 0);
 }
-int plume_bn_bwd_reduce_f32(const void* da, int ldda, const void* y, int ldy, const float* scale,
+int plume_bn_bwd_reduce_x3(const void* da, int ldda, const void* y, int ldy, const float* scale,
                         const float* shift, const float* mean, const float* invstd, int relu,
                         float* sum_g, float* sum_gx, long long pixels, int C, plume_stream_t stream) {
   return impl_bn_bwd_reduce(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C, stream, 1);
@@ -331,7 +402,7 @@ int plume_bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const f
                        plume_stream_t stream) {
   return impl_bn_bwd_apply(da, ldda, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, dy, lddy, sum_dy, dgamma, dbeta, accumulate, pixels, C, stream, 0);
 }
-int plume_bn_bwd_apply_f32(const void* da, int ldda, const void* y, int ldy, const float* scale,
+int plume_bn_bwd_apply_x3(const void* da, int ldda, const void* y, int ldy, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu,
                        const float* sum_g, const float* sum_gx, void* dy, int lddy, float* sum_dy,
                        float* dgamma, float* dbeta, int accumulate, long long pixels, int C,
@@ -347,7 +418,7 @@ int plume_relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, i
                    long long pixels, int C, plume_stream_t stream) {
   return impl_relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, stream, 0);
 }
-int plume_relu_bwd_f32(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
+int plume_relu_bwd_x3(const void* da, int ldda, const void* a, int lda, void* dy, int lddy, float* sum_dy,
                    long long pixels, int C, plume_stream_t stream) {
   return impl_relu_bwd(da, ldda, a, lda, dy, lddy, sum_dy, pixels, C, stream, 1);
 }
@@ -360,7 +431,7 @@ int plume_channel_sum(const void* x, int ldx, float* out, long long pixels, int 
                       plume_stream_t stream) {
   return impl_channel_sum(x, ldx, out, pixels, C, stream, 0);
 }
-int plume_channel_sum_f32(const void* x, int ldx, float* out, long long pixels, int C,
+int plume_channel_sum_x3(const void* x, int ldx, float* out, long long pixels, int C,
                       plume_stream_t stream) {
   return impl_channel_sum(x, ldx, out, pixels, C, stream, 1);
 }
@@ -375,7 +446,7 @@ int plume_head_fwd(const void* feat, int ldf, const float* w, const float* b, co
                    float* logits, float* sums, long long pixels, int C, plume_stream_t stream) {
   return impl_head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, stream, 0);
 }
-int plume_head_fwd_f32(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
+int plume_head_fwd_x3(const void* feat, int ldf, const float* w, const float* b, const uint8_t* target,
                    float* logits, float* sums, long long pixels, int C, plume_stream_t stream) {
   return impl_head_fwd(feat, ldf, w, b, target, logits, sums, pixels, C, stream, 1);
 }
@@ -398,7 +469,7 @@ int plume_head_bwd(const void* feat, int ldf, const float* w, const float* logit
                    int C, plume_stream_t stream) {
   return impl_head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat, lddf, dw, db, pixels, C, stream, 0);
 }
-int plume_head_bwd_f32(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+int plume_head_bwd_x3(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
                    const float* sums, float bce_weight, float dice_weight, float dice_eps,
                    float grad_scale, void* dfeat, int lddf, float* dw, float* db, long long pixels,
                    int C, plume_stream_t stream) {
@@ -432,7 +503,7 @@ int plume_extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys
                         int count, int T, void* tiles, int Cd, plume_stream_t stream) {
   return impl_extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, stream, 0);
 }
-int plume_extract_tiles_f32(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
+int plume_extract_tiles_x3(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
                         int count, int T, void* tiles, int Cd, plume_stream_t stream) {
   return impl_extract_tiles(scene, Hs, Ws, Cs, ys, xs, count, T, tiles, Cd, stream, 1);
 }
@@ -478,6 +549,37 @@ int plume_fire_extents(const int* labels, const int* sizes, int T, int H, int W,
                        int n_fires, int win, int* extents, plume_stream_t stream) {
   PLUME_CHECK(T <= 0 || n_fires <= 0 || (labels && sizes && fire_row_col && extents), "fire_extents: null pointer");
   return fire_extents(labels, sizes, T, H, W, fire_row_col, n_fires, win, extents, S(stream));
+}
+
+int plume_utm_zone_histogram(const double* lon, long long n, int* hist64, plume_stream_t stream) {
+  PLUME_CHECK(hist64 && (n <= 0 || lon), "utm_zone_histogram: null pointer");
+  return utm_zone_histogram(lon, n, hist64, S(stream));
+}
+int plume_utm_forward(const double* lat, const double* lon, long long n, int zone, double* x, double* y,
+                      plume_stream_t stream) {
+  PLUME_CHECK(n <= 0 || (lat && lon && x && y), "utm_forward: null pointer");
+  return utm_forward(lat, lon, n, zone, x, y, S(stream));
+}
+int plume_utm_inverse(const double* x, const double* y, long long n, int zone, double* lat, double* lon,
+                      plume_stream_t stream) {
+  PLUME_CHECK(n <= 0 || (lat && lon && x && y), "utm_inverse: null pointer");
+  return utm_inverse(x, y, n, zone, lat, lon, S(stream));
+}
+size_t plume_resample_workspace_bytes(int n_src, double min_x, double min_y, double max_x, double max_y,
+                                      double radius) {
+  return resample_workspace_bytes(n_src, min_x, min_y, max_x, max_y, radius);
+}
+int plume_resample_nearest_index(const double* src_lat, const double* src_lon, int n_src, int zone, double min_x,
+                                 double min_y, double max_x, double max_y, int x_size, int y_size, double radius,
+                                 void* workspace, size_t workspace_bytes, int* out_idx, plume_stream_t stream) {
+  PLUME_CHECK(out_idx && (n_src <= 0 || (src_lat && src_lon)), "resample_nearest_index: null pointer");
+  return resample_nearest_index(src_lat, src_lon, n_src, zone, min_x, min_y, max_x, max_y, x_size, y_size, radius,
+                                workspace, workspace_bytes, out_idx, S(stream));
+}
+int plume_gather_fill(const void* src, int elem_bytes, const int* idx, long long n, double fill_value, void* out,
+                      plume_stream_t stream) {
+  PLUME_CHECK(n <= 0 || (src && idx && out), "gather_fill: null pointer");
+  return gather_fill(src, elem_bytes, idx, n, fill_value, out, S(stream));
 }
 
 }  // extern "C"

@@ -90,19 +90,29 @@ __device__ __forceinline__ BF8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
   return v;
 }
-// Activation storage traits: a thread moves 8 channels of one pixel per access; bf16 = one 16-byte vector,
-// fp32 (the tf32-precision mode) = two.  `pack` is where the storage rounding happens (none for fp32).
-struct alignas(16) F8 {
-  float f[8];
+// Activation storage traits: a thread moves 8 channels of one pixel per access.
+//   __nv_bfloat16 : one 16-byte vector (the default storage);
+//   Split2        : the "bf16x3" high-precision mode.  A value is stored as hi + lo, two bf16 numbers
+//                   (hi = bf16(v), lo = bf16(v - hi): 16 significant bits), in two channel PLANES per pixel:
+//                   pixel stride ld (in bf16 elements) covers both planes, hi of channel c at [p*ld + c], lo at
+//                   [p*ld + ld/2 + c].  Each plane is an ordinary NHWC bf16 tensor as far as TMA is concerned, so
+//                   the GEMMs form x*w = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with three passes of the bf16 MMAs.
+// `plane` (= ld / 2) is ignored by the bf16 traits.  `pack` is where the storage rounding happens.
+struct Split2 {
+  __nv_bfloat16 v;
+};
+struct SP8 {
+  BF8 hi, lo;
 };
 template <typename T>
 struct Act;
 template <>
 struct Act<__nv_bfloat16> {
   using V8 = BF8;
-  static __device__ __forceinline__ V8 ld(const __nv_bfloat16* p) { return ld_bf8(p); }
-  static __device__ __forceinline__ V8 ld_stream(const __nv_bfloat16* p) { return ld_bf8_stream(p); }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, const V8& v) { st_bf8(p, v); }
+  static constexpr int kPlanes = 1;
+  static __device__ __forceinline__ V8 ld(const __nv_bfloat16* p, long long) { return ld_bf8(p); }
+  static __device__ __forceinline__ V8 ld_stream(const __nv_bfloat16* p, long long) { return ld_bf8_stream(p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, long long, const V8& v) { st_bf8(p, v); }
   static __device__ __forceinline__ void unpack(const V8& v, float (&f)[8]) { unpack8(v, f); }
   static __device__ __forceinline__ V8 pack(const float (&f)[8]) { return pack8(f); }
   static __device__ __forceinline__ V8 zero() {
@@ -112,52 +122,57 @@ struct Act<__nv_bfloat16> {
   }
 };
 template <>
-struct Act<float> {
-  using V8 = F8;
-  static __device__ __forceinline__ V8 ld(const float* p) {
+struct Act<Split2> {
+  using V8 = SP8;
+  static constexpr int kPlanes = 2;
+  static __device__ __forceinline__ const __nv_bfloat16* b(const Split2* p) {
+    return reinterpret_cast<const __nv_bfloat16*>(p);
+  }
+  static __device__ __forceinline__ V8 ld(const Split2* p, long long plane) {
     V8 v;
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
-    v.f[0] = a.x; v.f[1] = a.y; v.f[2] = a.z; v.f[3] = a.w;
-    v.f[4] = b.x; v.f[5] = b.y; v.f[6] = b.z; v.f[7] = b.w;
+    v.hi = ld_bf8(b(p));
+    v.lo = ld_bf8(b(p) + plane);
     return v;
   }
-  static __device__ __forceinline__ V8 ld_stream(const float* p) {
+  static __device__ __forceinline__ V8 ld_stream(const Split2* p, long long plane) {
     V8 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.f[0]), "=f"(v.f[1]), "=f"(v.f[2]), "=f"(v.f[3])
-                 : "l"(p));
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.f[4]), "=f"(v.f[5]), "=f"(v.f[6]), "=f"(v.f[7])
-                 : "l"(p + 4));
+    v.hi = ld_bf8_stream(b(p));
+    v.lo = ld_bf8_stream(b(p) + plane);
     return v;
   }
-  static __device__ __forceinline__ void st(float* p, const V8& v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v.f[0], v.f[1], v.f[2], v.f[3]);
-    *(reinterpret_cast<float4*>(p) + 1) = make_float4(v.f[4], v.f[5], v.f[6], v.f[7]);
+  static __device__ __forceinline__ void st(Split2* p, long long plane, const V8& v) {
+    st_bf8(reinterpret_cast<__nv_bfloat16*>(p), v.hi);
+    st_bf8(reinterpret_cast<__nv_bfloat16*>(p) + plane, v.lo);
   }
   static __device__ __forceinline__ void unpack(const V8& v, float (&f)[8]) {
+    float l[8];
+    unpack8(v.hi, f);
+    unpack8(v.lo, l);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = v.f[i];
+    for (int i = 0; i < 8; ++i) f[i] += l[i];
   }
   static __device__ __forceinline__ V8 pack(const float (&f)[8]) {
     V8 v;
+    v.hi = pack8(f);
+    float h[8], r[8];
+    unpack8(v.hi, h);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v.f[i] = f[i];
+    for (int i = 0; i < 8; ++i) r[i] = f[i] - h[i];  // exact in fp32
+    v.lo = pack8(r);
     return v;
   }
   static __device__ __forceinline__ V8 zero() {
     V8 v;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v.f[i] = 0.f;
+    v.hi.u[0] = v.hi.u[1] = v.hi.u[2] = v.hi.u[3] = 0u;
+    v.lo = v.hi;
     return v;
   }
 };
-// Launches `call` with T bound to the activation storage type (dt: 0 = bf16, 1 = fp32).
+// Launches `call` with T bound to the activation storage type (dt: 0 = bf16, 1 = bf16x3 split planes).
 #define PLUME_ACT_DISPATCH(dt, ...)       \
   do {                                    \
     if ((dt) == 1) {                      \
-      using T = float;                    \
+      using T = Split2;                   \
       __VA_ARGS__;                        \
     } else {                              \
       using T = __nv_bfloat16;            \
@@ -205,16 +220,19 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[K][8], int cv_
 // pad_channels
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void pad_channels_kernel(const T* __restrict__ in, int cvs,
+__global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ in, int cvs,
                                     T* __restrict__ out, int cvd, long long total) {
+  // the source is always plain bf16 (the input bands); the destination is in the activation storage format
   const long long step = 1ll * gridDim.x * blockDim.x;
+  const long long ldo = 1ll * Act<T>::kPlanes * cvd * 8;
   for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
     const long long p = i / cvd;
     const int cv = static_cast<int>(i % cvd);
-    typename Act<T>::V8 v;
-    v = Act<T>::zero();
-    if (cv < cvs) v = Act<T>::ld_stream(in + (p * cvs + cv) * 8);
-    Act<T>::st(out + i * 8, v);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    if (cv < cvs) unpack8(ld_bf8_stream(in + (p * cvs + cv) * 8), f);
+    Act<T>::st(out + p * ldo + cv * 8, ldo >> 1, Act<T>::pack(f));
   }
 }
 
@@ -226,8 +244,8 @@ int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, in
   if (pixels <= 0) return 0;
   const long long total = pixels * (Cd / 8);
   const int grid = grid_for(total, 1);
-  PLUME_ACT_DISPATCH(dt, (pad_channels_kernel<T><<<grid, kThreads, 0, s>>>(static_cast<const T*>(in), Cs / 8,
-                                                                          static_cast<T*>(out), Cd / 8, total)));
+  PLUME_ACT_DISPATCH(dt, (pad_channels_kernel<T><<<grid, kThreads, 0, s>>>(
+                             static_cast<const __nv_bfloat16*>(in), Cs / 8, static_cast<T*>(out), Cd / 8, total)));
   return check_launch("pad_channels");
 }
 
@@ -305,8 +323,8 @@ __global__ void __launch_bounds__(kThreads)
   long long p = i0 / CV;
   // two pixels in flight per iteration
   for (; p + pstep < pixels; p += 2 * pstep) {
-    const typename Act<T>::V8 v0 = Act<T>::ld_stream(y + p * ldy + cv * 8);
-    const typename Act<T>::V8 v1 = Act<T>::ld_stream(y + (p + pstep) * ldy + cv * 8);
+    const typename Act<T>::V8 v0 = Act<T>::ld_stream(y + p * ldy + cv * 8, ldy >> 1);
+    const typename Act<T>::V8 v1 = Act<T>::ld_stream(y + (p + pstep) * ldy + cv * 8, ldy >> 1);
     float f0[8], f1[8];
     Act<T>::unpack(v0, f0);
     Act<T>::unpack(v1, f1);
@@ -319,11 +337,11 @@ __global__ void __launch_bounds__(kThreads)
         f1[e] = fmaxf(f1[e], 0.f);
       }
     }
-    Act<T>::st(a + p * lda + cv * 8, Act<T>::pack(f0));
-    Act<T>::st(a + (p + pstep) * lda + cv * 8, Act<T>::pack(f1));
+    Act<T>::st(a + p * lda + cv * 8, lda >> 1, Act<T>::pack(f0));
+    Act<T>::st(a + (p + pstep) * lda + cv * 8, lda >> 1, Act<T>::pack(f1));
   }
   if (p < pixels) {
-    const typename Act<T>::V8 v0 = Act<T>::ld_stream(y + p * ldy + cv * 8);
+    const typename Act<T>::V8 v0 = Act<T>::ld_stream(y + p * ldy + cv * 8, ldy >> 1);
     float f0[8];
     Act<T>::unpack(v0, f0);
 #pragma unroll
@@ -331,7 +349,7 @@ __global__ void __launch_bounds__(kThreads)
       f0[e] = fmaf(f0[e], sc[e], sh[e]);
       if (relu) f0[e] = fmaxf(f0[e], 0.f);
     }
-    Act<T>::st(a + p * lda + cv * 8, Act<T>::pack(f0));
+    Act<T>::st(a + p * lda + cv * 8, lda >> 1, Act<T>::pack(f0));
   }
 }
 
@@ -377,10 +395,10 @@ __global__ void __launch_bounds__(kThreads)
     const long long n = t / Ho;
     const long long ip = (n * (2 * Ho) + 2 * ho) * W + 2 * wo;  // top-left input pixel
     typename Act<T>::V8 v[4];
-    v[0] = Act<T>::ld_stream(y + ip * ldy + cv * 8);
-    v[1] = Act<T>::ld_stream(y + (ip + 1) * ldy + cv * 8);
-    v[2] = Act<T>::ld_stream(y + (ip + W) * ldy + cv * 8);
-    v[3] = Act<T>::ld_stream(y + (ip + W + 1) * ldy + cv * 8);
+    v[0] = Act<T>::ld_stream(y + ip * ldy + cv * 8, ldy >> 1);
+    v[1] = Act<T>::ld_stream(y + (ip + 1) * ldy + cv * 8, ldy >> 1);
+    v[2] = Act<T>::ld_stream(y + (ip + W) * ldy + cv * 8, ldy >> 1);
+    v[3] = Act<T>::ld_stream(y + (ip + W + 1) * ldy + cv * 8, ldy >> 1);
     float f[4][8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -396,10 +414,10 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
     if (kSkip) {
-      Act<T>::st(skip + ip * ldskip + cv * 8, v[0]);
-      Act<T>::st(skip + (ip + 1) * ldskip + cv * 8, v[1]);
-      Act<T>::st(skip + (ip + W) * ldskip + cv * 8, v[2]);
-      Act<T>::st(skip + (ip + W + 1) * ldskip + cv * 8, v[3]);
+      Act<T>::st(skip + ip * ldskip + cv * 8, ldskip >> 1, v[0]);
+      Act<T>::st(skip + (ip + 1) * ldskip + cv * 8, ldskip >> 1, v[1]);
+      Act<T>::st(skip + (ip + W) * ldskip + cv * 8, ldskip >> 1, v[2]);
+      Act<T>::st(skip + (ip + W + 1) * ldskip + cv * 8, ldskip >> 1, v[3]);
     }
     float best[8];
     uint32_t idx_lo = 0, idx_hi = 0;
@@ -414,7 +432,7 @@ __global__ void __launch_bounds__(kThreads)
       if (e < 4) idx_lo |= bi << (8 * e);
       else idx_hi |= bi << (8 * (e - 4));
     }
-    Act<T>::st(pooled + op * ldpooled + cv * 8, Act<T>::pack(best));
+    Act<T>::st(pooled + op * ldpooled + cv * 8, ldpooled >> 1, Act<T>::pack(best));
     *reinterpret_cast<uint2*>(argmax + (op * CV + cv) * 8) = make_uint2(idx_lo, idx_hi);
   }
 }
@@ -481,14 +499,14 @@ __global__ void __launch_bounds__(kThreads)
     const long long n = t / Ho;
     const long long ip = (n * (2 * Ho) + 2 * ho) * W + 2 * wo;
     float g[8];
-    Act<T>::unpack(Act<T>::ld_stream(dy + op * lddy + cv * 8), g);
+    Act<T>::unpack(Act<T>::ld_stream(dy + op * lddy + cv * 8, lddy >> 1), g);
     const uint2 am = *reinterpret_cast<const uint2*>(argmax + (op * CV + cv) * 8);
     const long long off[4] = {ip, ip + 1, ip + W, ip + W + 1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float o[8];
       if (dskip) {
-        Act<T>::unpack(Act<T>::ld_stream(dskip + off[k] * lddskip + cv * 8), o);
+        Act<T>::unpack(Act<T>::ld_stream(dskip + off[k] * lddskip + cv * 8, lddskip >> 1), o);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.f;
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(kThreads)
         const uint32_t bi = ((e < 4 ? am.x : am.y) >> (8 * (e & 3))) & 0xffu;
         if (bi == static_cast<uint32_t>(k)) o[e] += g[e];
       }
-      Act<T>::st(dx + off[k] * lddx + cv * 8, Act<T>::pack(o));
+      Act<T>::st(dx + off[k] * lddx + cv * 8, lddx >> 1, Act<T>::pack(o));
     }
   }
 }
@@ -551,8 +569,8 @@ __global__ void __launch_bounds__(kThreads)
     typename Act<T>::V8 gv[U], yv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      gv[u] = Act<T>::ld_stream(da + (p + u * pstep) * ldda + cv * 8);
-      yv[u] = Act<T>::ld_stream(y + (p + u * pstep) * ldy + cv * 8);
+      gv[u] = Act<T>::ld_stream(da + (p + u * pstep) * ldda + cv * 8, ldda >> 1);
+      yv[u] = Act<T>::ld_stream(y + (p + u * pstep) * ldy + cv * 8, ldy >> 1);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -569,8 +587,8 @@ __global__ void __launch_bounds__(kThreads)
   }
   for (; p < pixels; p += pstep) {
     float g[8], yy[8];
-    Act<T>::unpack(Act<T>::ld_stream(da + p * ldda + cv * 8), g);
-    Act<T>::unpack(Act<T>::ld_stream(y + p * ldy + cv * 8), yy);
+    Act<T>::unpack(Act<T>::ld_stream(da + p * ldda + cv * 8, ldda >> 1), g);
+    Act<T>::unpack(Act<T>::ld_stream(y + p * ldy + cv * 8, ldy >> 1), yy);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float gg = (!relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
@@ -647,7 +665,7 @@ __global__ void __launch_bounds__(kThreads)
       o[e] = sc[e] * (gg - mg[e] - xhat * mgx[e]);
     }
     const typename Act<T>::V8 ov = Act<T>::pack(o);
-    Act<T>::st(dy + pp * lddy + cv * 8, ov);
+    Act<T>::st(dy + pp * lddy + cv * 8, lddy >> 1, ov);
     if (sum_dy) {
       float r[8];
       Act<T>::unpack(ov, r);
@@ -661,14 +679,14 @@ __global__ void __launch_bounds__(kThreads)
     typename Act<T>::V8 gv[U], yv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      gv[u] = Act<T>::ld_stream(da + (p + u * pstep) * ldda + cv * 8);
-      yv[u] = Act<T>::ld_stream(y + (p + u * pstep) * ldy + cv * 8);
+      gv[u] = Act<T>::ld_stream(da + (p + u * pstep) * ldda + cv * 8, ldda >> 1);
+      yv[u] = Act<T>::ld_stream(y + (p + u * pstep) * ldy + cv * 8, ldy >> 1);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) one(gv[u], yv[u], p + u * pstep);
   }
   for (; p < pixels; p += pstep)
-    one(Act<T>::ld_stream(da + p * ldda + cv * 8), Act<T>::ld_stream(y + p * ldy + cv * 8), p);
+    one(Act<T>::ld_stream(da + p * ldda + cv * 8, ldda >> 1), Act<T>::ld_stream(y + p * ldy + cv * 8, ldy >> 1), p);
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
     block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
@@ -713,14 +731,14 @@ __global__ void __launch_bounds__(kThreads)
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   for (long long p = i0 / CV; p < pixels; p += pstep) {
     float g[8], aa[8];
-    Act<T>::unpack(Act<T>::ld_stream(da + p * ldda + cv * 8), g);
-    Act<T>::unpack(Act<T>::ld_stream(a + p * lda + cv * 8), aa);
+    Act<T>::unpack(Act<T>::ld_stream(da + p * ldda + cv * 8, ldda >> 1), g);
+    Act<T>::unpack(Act<T>::ld_stream(a + p * lda + cv * 8, lda >> 1), aa);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       g[e] = aa[e] > 0.f ? g[e] : 0.f;
       acc[0][e] += g[e];
     }
-    Act<T>::st(dy + p * lddy + cv * 8, Act<T>::pack(g));
+    Act<T>::st(dy + p * lddy + cv * 8, lddy >> 1, Act<T>::pack(g));
   }
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
@@ -757,7 +775,7 @@ __global__ void __launch_bounds__(kThreads)
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   for (long long p = i0 / CV; p < pixels; p += pstep) {
     float f[8];
-    Act<T>::unpack(Act<T>::ld_stream(x + p * ldx + cv * 8), f);
+    Act<T>::unpack(Act<T>::ld_stream(x + p * ldx + cv * 8, ldx >> 1), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] += f[e];
   }
@@ -809,7 +827,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + (it + u) * pstep;
-      if (it + u < iters && p < pixels) v[u] = Act<T>::ld_stream(feat + p * ldf + cv * 8);
+      if (it + u < iters && p < pixels) v[u] = Act<T>::ld_stream(feat + p * ldf + cv * 8, ldf >> 1);
       else v[u] = Act<T>::zero();
     }
     float dots[U];
@@ -940,7 +958,7 @@ __global__ void __launch_bounds__(kThreads)
       o[e] = dz * wv[e];
       acc[0][e] = fmaf(dz, f[e], acc[0][e]);
     }
-    Act<T>::st(dfeat + p * lddf + cv * 8, Act<T>::pack(o));
+    Act<T>::st(dfeat + p * lddf + cv * 8, lddf >> 1, Act<T>::pack(o));
     if (cv == 0) a_db += dz;
   };
   constexpr int U = 4;
@@ -950,7 +968,7 @@ __global__ void __launch_bounds__(kThreads)
     float zz[U], tt[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      fv[u] = Act<T>::ld_stream(feat + (p + u * pstep) * ldf + cv * 8);
+      fv[u] = Act<T>::ld_stream(feat + (p + u * pstep) * ldf + cv * 8, ldf >> 1);
       zz[u] = __ldg(logits + p + u * pstep);
       tt[u] = target[p + u * pstep] ? 1.f : 0.f;
     }
@@ -958,7 +976,7 @@ __global__ void __launch_bounds__(kThreads)
     for (int u = 0; u < U; ++u) one(p + u * pstep, fv[u], zz[u], tt[u]);
   }
   for (; p < pixels; p += pstep)
-    one(p, Act<T>::ld_stream(feat + p * ldf + cv * 8), __ldg(logits + p), target[p] ? 1.f : 0.f);
+    one(p, Act<T>::ld_stream(feat + p * ldf + cv * 8, ldf >> 1), __ldg(logits + p), target[p] ? 1.f : 0.f);
   float* const outs[1] = {dw};
   block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
   a_db = warp_sum(a_db);
@@ -1190,7 +1208,10 @@ __global__ void __launch_bounds__(256)
   const int ci0 = (local % tiles_ci) * 32;
   const int co0 = ((local / tiles_ci) % tiles_co) * 32;
   const int t = local / (tiles_ci * tiles_co);
-  const int taps = d.kind == 0 ? 9 : 4;
+  const int conv3 = (d.kind & 1) == 0;
+  const bool split = (d.kind & 2) != 0;   // bf16x3 mode: the hi matrix is followed by the lo matrix (same layout)
+  const int taps = conv3 ? 9 : 4;
+  const long long numel = 1ll * taps * d.Cout * d.Cin;
   const float* __restrict__ w = d.w;
   __nv_bfloat16* __restrict__ wf = static_cast<__nv_bfloat16*>(d.w_fwd_bf16);
   __nv_bfloat16* __restrict__ wd = static_cast<__nv_bfloat16*>(d.w_dgrad_bf16);
@@ -1200,26 +1221,35 @@ __global__ void __launch_bounds__(256)
     const int co = co0 + ty + 8 * k, ci = ci0 + tx;
     float v = 0.f;
     if (co < d.Cout && ci < d.Cin) {
-      const long long i = d.kind == 0 ? (1ll * co * 9 + t) * d.Cin + ci : (1ll * t * d.Cout + co) * d.Cin + ci;
+      const long long i = conv3 ? (1ll * co * 9 + t) * d.Cin + ci : (1ll * t * d.Cout + co) * d.Cin + ci;
       v = w[i];
-      if (wf) wf[i] = __float2bfloat16_rn(v);
+      if (wf) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        wf[i] = h;
+        if (split) wf[numel + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
     tile[ty + 8 * k][tx] = v;
   }
   if (!wd) return;
   __syncthreads();
-  const int td = d.kind == 0 ? 8 - t : t;
+  const int td = conv3 ? 8 - t : t;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int ci = ci0 + ty + 8 * k, co = co0 + tx;
-    if (co < d.Cout && ci < d.Cin)
-      wd[(1ll * ci * taps + td) * d.Cout + co] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+    if (co < d.Cout && ci < d.Cin) {
+      const float v = tile[tx][ty + 8 * k];
+      const long long j = (1ll * ci * taps + td) * d.Cout + co;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      wd[j] = h;
+      if (split) wd[numel + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
   }
 }
 
 int pack_blocks(int kind, int Cout, int Cin) {
   if (Cout <= 0 || Cin <= 0) return 0;
-  return ((Cin + 31) / 32) * ((Cout + 31) / 32) * (kind == 0 ? 9 : 4);
+  return ((Cin + 31) / 32) * ((Cout + 31) / 32) * ((kind & 1) == 0 ? 9 : 4);
 }
 
 int pack_batch(const plume_pack_desc* descs, int n, int total_blocks, cudaStream_t s) {
@@ -1232,23 +1262,27 @@ int pack_batch(const plume_pack_desc* descs, int n, int total_blocks, cudaStream
 // tiled inference: cut tiles out of a scene, stitch logits back by centre crop + threshold
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void extract_tiles_kernel(const T* __restrict__ scene, int Hs, int Ws, int cvs,
+__global__ void extract_tiles_kernel(const __nv_bfloat16* __restrict__ scene, int Hs, int Ws, int cvs,
                                      const int* __restrict__ ys, const int* __restrict__ xs, int tile,
                                      T* __restrict__ tiles, int cvd, long long total) {
+  // the scene is always plain bf16; the tiles are in the activation storage format
   const long long step = 1ll * gridDim.x * blockDim.x;
+  const long long ldo = 1ll * Act<T>::kPlanes * cvd * 8;
   for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
     const int cv = static_cast<int>(i % cvd);
     long long t = i / cvd;
+    const long long pix = t;
     const int x = static_cast<int>(t % tile);
     t /= tile;
     const int y = static_cast<int>(t % tile);
     const int k = static_cast<int>(t / tile);
     const int sy = ys[k] + y, sx = xs[k] + x;
-    typename Act<T>::V8 v;
-    v = Act<T>::zero();
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = 0.f;
     if (cv < cvs && sy >= 0 && sy < Hs && sx >= 0 && sx < Ws)
-      v = Act<T>::ld(scene + ((1ll * sy * Ws + sx) * cvs + cv) * 8);
-    Act<T>::st(tiles + i * 8, v);
+      unpack8(ld_bf8(scene + ((1ll * sy * Ws + sx) * cvs + cv) * 8), f);
+    Act<T>::st(tiles + pix * ldo + cv * 8, ldo >> 1, Act<T>::pack(f));
   }
 }
 
@@ -1262,7 +1296,8 @@ int extract_tiles(const void* scene, int Hs, int Ws, int Cs, const int* ys, cons
   const long long total = 1ll * count * tile * tile * (Cd / 8);
   const int grid = grid_for(total, 1);
   PLUME_ACT_DISPATCH(dt, (extract_tiles_kernel<T><<<grid, kThreads, 0, s>>>(
-                             static_cast<const T*>(scene), Hs, Ws, Cs / 8, ys, xs, tile, static_cast<T*>(tiles), Cd / 8,
+                             static_cast<const __nv_bfloat16*>(scene), Hs, Ws, Cs / 8, ys, xs, tile, static_cast<T*>(tiles),
+                             Cd / 8,
                              total)));
   return check_launch("extract_tiles");
 }

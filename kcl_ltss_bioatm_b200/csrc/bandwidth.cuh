@@ -71,4 +71,15 @@ int label_components(const uint8_t* masks, int T, int H, int W, int* labels, int
 int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_rc, int n_fires, int win,
                  int* extents, cudaStream_t s);
 
+// UTM projection + nearest-neighbour swath -> grid resampling (resample.cu)
+int utm_zone_histogram(const double* lon, long long n, int* hist64, cudaStream_t s);
+int utm_forward(const double* lat, const double* lon, long long n, int zone, double* x, double* y, cudaStream_t s);
+int utm_inverse(const double* x, const double* y, long long n, int zone, double* lat, double* lon, cudaStream_t s);
+size_t resample_workspace_bytes(int n_src, double min_x, double min_y, double max_x, double max_y, double radius);
+int resample_nearest_index(const double* src_lat, const double* src_lon, int n_src, int zone, double min_x,
+                           double min_y, double max_x, double max_y, int x_size, int y_size, double radius,
+                           void* workspace, size_t workspace_bytes, int* out_idx, cudaStream_t s);
+int gather_fill(const void* src, int elem_bytes, const int* idx, long long n, double fill, void* out,
+                cudaStream_t s);
+
 }  // namespace plume

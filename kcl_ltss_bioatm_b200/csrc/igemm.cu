@@ -37,6 +37,13 @@ int read_debug_word() {
 struct TmapPack4 {
   CUtensorMap m[4];
 };
+// views 0-3, and in the bf16x3 mode their lo planes at 4-7
+struct TmapPack8 {
+  CUtensorMap m[8];
+};
+struct TmapPack2 {
+  CUtensorMap m[2];
+};
 
 static int num_sms() {
   static int n = 0;
@@ -77,6 +84,7 @@ struct FwdParams {
   int kb_per_tap;                 // Cin / 64
   int k_per_tap;                  // Cin
   int cout_per_view;
+  int n_total;                    // rows of the weight matrix (bf16x3: the lo matrix follows at row n_total)
   const float* scale;
   const float* shift;
   int relu;
@@ -122,11 +130,52 @@ __device__ __forceinline__ void epi_store_half(const uint32_t (&v)[32], int jbas
   }
 }
 
-template <int BLOCK_N, int STAGES, int STAGING>
+// bf16x3 mode: the same, with the value split into hi = bf16(t) and lo = bf16(t - hi), staged as two tiles.
+__device__ __forceinline__ void epi_store_half_split(const uint32_t (&v)[32], int jbase, const float* sc,
+                                                     const float* sh, int relu, bool valid, uint8_t* stg_hi,
+                                                     uint8_t* stg_lo, int row) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float y[8], r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = fmaf(__uint_as_float(v[j * 8 + e]), sc[j * 8 + e], sh[j * 8 + e]);
+      if (relu) t = fmaxf(t, 0.0f);
+      y[e] = valid ? t : 0.0f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(y[0], y[1]);
+    o.y = pack_bf16x2(y[2], y[3]);
+    o.z = pack_bf16x2(y[4], y[5]);
+    o.w = pack_bf16x2(y[6], y[7]);
+    const uint32_t hw[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 h = unpack_bf16x2(hw[e]);
+      r[2 * e] = y[2 * e] - h.x;          // exact in fp32
+      r[2 * e + 1] = y[2 * e + 1] - h.y;
+    }
+    uint4 l;
+    l.x = pack_bf16x2(r[0], r[1]);
+    l.y = pack_bf16x2(r[2], r[3]);
+    l.z = pack_bf16x2(r[4], r[5]);
+    l.w = pack_bf16x2(r[6], r[7]);
+    const int off = row * 128 + (((jbase + j) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(stg_hi + off) = o;
+    *reinterpret_cast<uint4*>(stg_lo + off) = l;
+  }
+}
+
+// SPLIT = the bf16x3 high-precision mode: every activation is two bf16 planes (hi, lo; maps 0-3 / 4-7), the
+// weight matrix is followed by its lo matrix at row n_total, and the K loop runs three passes into the same
+// accumulator: x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (the dropped lo*lo term is 2^-18 relative).  The epilogue
+// splits the fp32 result again (STAGING == 2: one staging tile per plane).
+template <int BLOCK_N, int STAGES, int STAGING, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
-    igemm_fwd_kernel(const __grid_constant__ TmapPack4 amaps,
+    igemm_fwd_kernel(const __grid_constant__ TmapPack8 amaps,
                      const __grid_constant__ CUtensorMap bmap,
-                     const __grid_constant__ TmapPack4 omaps, const FwdParams p) {
+                     const __grid_constant__ TmapPack8 omaps, const FwdParams p) {
+  static_assert(!SPLIT || STAGING == 2, "bf16x3 mode stages a hi and a lo tile");
   using L = FwdSmem<BLOCK_N, STAGES, STAGING>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -170,7 +219,8 @@ __global__ void __launch_bounds__(256, 1)
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
-  const int kiters = p.num_taps * p.kb_per_tap;
+  constexpr int PASSES = SPLIT ? 3 : 1;
+  const int kiters = PASSES * p.num_taps * p.kb_per_tap;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
@@ -182,7 +232,11 @@ __global__ void __launch_bounds__(256, 1)
         const int w0 = (m_tile % p.tiles_w) * p.TW;
         const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
+        for (int pt = 0; pt < PASSES * p.num_taps; ++pt) {
+          const int pass = SPLIT ? pt / p.num_taps : 0;
+          const int tap = SPLIT ? pt - pass * p.num_taps : pt;
+          const int a_plane = pass == 2 ? 4 : 0;                 // x_lo in the third pass
+          const int b_row0 = pass == 1 ? p.n_total : 0;          // w_lo in the second pass
           int dw = 0, dh = 0, av = 0;
           if (p.per_tap_view) {
             av = tap;
@@ -195,9 +249,9 @@ __global__ void __launch_bounds__(256, 1)
             const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
             const uint32_t b_addr = a_addr + L::A_BYTES;
             mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
-            tma_load_4d(a_addr, &amaps.m[av], full_bar(stage), kb * 64, w0 + dw, h0 + dh, n0);
+            tma_load_4d(a_addr, &amaps.m[av + a_plane], full_bar(stage), kb * 64, w0 + dw, h0 + dh, n0);
             tma_load_2d(b_addr, &bmap, full_bar(stage), tap * p.k_per_tap + kb * 64,
-                        n_tile * BLOCK_N);
+                        b_row0 + n_tile * BLOCK_N);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -292,20 +346,31 @@ __global__ void __launch_bounds__(256, 1)
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));  // accumulator drained: MMA may overwrite it
         }
-        const int sb = (STAGING == 2) ? (chunk_ctr & 1) : 0;
-        if (et == 0) tma_store_wait_read<STAGING - 1>();  // staging buffer `sb` no longer being read
+        const int sb = (STAGING == 2 && !SPLIT) ? (chunk_ctr & 1) : 0;
+        // staging buffer `sb` (bf16x3: both buffers) no longer being read by an earlier store
+        if (et == 0) tma_store_wait_read<SPLIT ? 0 : STAGING - 1>();
         named_bar_sync(1, 128);
 
         uint8_t* stg = gbase + L::OFF_STG + sb * L::STG_BYTES;
-        epi_store_half(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg, row);
-        epi_store_half(v1, 4, s_scale + chunk * 64 + 32, s_shift + chunk * 64 + 32, p.relu, valid,
-                       stg, row);
+        if (SPLIT) {
+          epi_store_half_split(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg,
+                               stg + L::STG_BYTES, row);
+          epi_store_half_split(v1, 4, s_scale + chunk * 64 + 32, s_shift + chunk * 64 + 32, p.relu, valid, stg,
+                               stg + L::STG_BYTES, row);
+        } else {
+          epi_store_half(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg, row);
+          epi_store_half(v1, 4, s_scale + chunk * 64 + 32, s_shift + chunk * 64 + 32, p.relu, valid,
+                         stg, row);
+        }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (et == 0) {
           const int col = col0 + chunk * 64;
           tma_store_4d(&omaps.m[col / p.cout_per_view], sbase + L::OFF_STG + sb * L::STG_BYTES,
                        col % p.cout_per_view, w0, h0, n0);
+          if (SPLIT)
+            tma_store_4d(&omaps.m[4 + col / p.cout_per_view], sbase + L::OFF_STG + L::STG_BYTES,
+                         col % p.cout_per_view, w0, h0, n0);
           tma_store_commit();
         }
         if (do_stats) {
@@ -315,9 +380,13 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
             const int r = q * 32 + rr;
-            const uint32_t u =
-                *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((j ^ (r & 7)) << 4) + wsub * 4);
-            const float2 f = unpack_bf16x2(u);
+            const int off = r * 128 + ((j ^ (r & 7)) << 4) + wsub * 4;
+            float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(stg + off));
+            if (SPLIT) {  // the stored value is hi + lo
+              const float2 l = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(stg + L::STG_BYTES + off));
+              f.x += l.x;
+              f.y += l.y;
+            }
             s0 += f.x;
             s1 += f.y;
             q0 = fmaf(f.x, f.x, q0);
@@ -347,11 +416,11 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
-template <int BLOCK_N, int STAGES, int STAGING>
-static int launch_fwd_inst(const TmapPack4& amaps, const CUtensorMap& bmap, const TmapPack4& omaps,
+template <int BLOCK_N, int STAGES, int STAGING, bool SPLIT = false>
+static int launch_fwd_inst(const TmapPack8& amaps, const CUtensorMap& bmap, const TmapPack8& omaps,
                            const FwdParams& p, int total_tiles, cudaStream_t stream) {
   using L = FwdSmem<BLOCK_N, STAGES, STAGING>;
-  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES, STAGING>;
+  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES, STAGING, SPLIT>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -1041,7 +1110,7 @@ int launch_igemm_fwd(const FwdDesc& d) {
       set_error("igemm_fwd: output view extents differ from the input extents");
       return -1;
     }
-  {
+  if (!d.split) {
     const int r = try_launch_conv3(d);
     if (r <= 0) return r;
   }
@@ -1054,7 +1123,7 @@ int launch_igemm_fwd(const FwdDesc& d) {
                           ? 256
                           : ((d.cout_per_view % 256 == 0) ? 256 : (d.cout_per_view % 128 == 0 ? 128 : 64));
 
-  TmapPack4 amaps, omaps;
+  TmapPack8 amaps, omaps;
   CUtensorMap bmap;
   for (int i = 0; i < 4; ++i) {
     const ActView& v = d.in[i < d.num_in_views ? i : 0];
@@ -1069,10 +1138,21 @@ int launch_igemm_fwd(const FwdDesc& d) {
       return -1;
     }
     if (make_act_map(&omaps.m[i], o, 64, bw, bh, bn)) return -1;
+    if (d.split) {
+      if (v.plane <= 0 || o.plane <= 0) {
+        set_error("igemm_fwd: bf16x3 views need their lo-plane offset");
+        return -1;
+      }
+      if (make_act_map(&amaps.m[4 + i], lo_plane(v), 64, bw, bh, bn)) return -1;
+      if (make_act_map(&omaps.m[4 + i], lo_plane(o), 64, bw, bh, bn)) return -1;
+    } else {
+      amaps.m[4 + i] = amaps.m[i];
+      omaps.m[4 + i] = omaps.m[i];
+    }
   }
   const long long n_total = static_cast<long long>(d.num_out_views) * d.cout_per_view;
   const long long k_total = static_cast<long long>(d.num_taps) * d.Cin;
-  if (make_mat_map(&bmap, d.wmat, n_total, k_total, 64, block_n)) return -1;
+  if (make_mat_map(&bmap, d.wmat, d.split ? 2 * n_total : n_total, k_total, 64, block_n)) return -1;
 
   FwdParams p;
   p.TW = bw; p.TH = bh; p.TN = bn;
@@ -1086,6 +1166,7 @@ int launch_igemm_fwd(const FwdDesc& d) {
   p.kb_per_tap = d.Cin / 64;
   p.k_per_tap = d.Cin;
   p.cout_per_view = d.cout_per_view;
+  p.n_total = static_cast<int>(n_total);
   p.scale = d.scale;
   p.shift = d.shift;
   p.relu = d.relu;
@@ -1095,6 +1176,13 @@ int launch_igemm_fwd(const FwdDesc& d) {
   if (total > 0x7fffffffll) {
     set_error("igemm_fwd: too many tiles");
     return -1;
+  }
+  if (d.split) {
+    switch (block_n) {
+      case 256: return launch_fwd_inst<256, 3, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
+      case 128: return launch_fwd_inst<128, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
+      default:  return launch_fwd_inst<64, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
+    }
   }
   switch (block_n) {
     case 256: return launch_fwd_inst<256, 4, 1>(amaps, bmap, omaps, p, (int)total, d.stream);
@@ -1131,11 +1219,14 @@ struct WgSmem {
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
-template <int BLOCK_N, int STAGES>
+// SPLIT (bf16x3 mode): X and dY are hi/lo plane pairs (xmaps.m[0/1], dymaps.m[0-3 / 4-7]); the K loop runs over
+// the CTA's pixel tiles three times: x_hi*dy_hi + x_hi*dy_lo + x_lo*dy_hi, all into the same accumulator.
+template <int BLOCK_N, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
-    igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap,
-                       const __grid_constant__ TmapPack4 dymaps, const WgradParams p) {
+    igemm_wgrad_kernel(const __grid_constant__ TmapPack2 xmaps,
+                       const __grid_constant__ TmapPack8 dymaps, const WgradParams p) {
   using L = WgSmem<BLOCK_N, STAGES>;
+  constexpr int PASSES = SPLIT ? 3 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
@@ -1150,7 +1241,7 @@ __global__ void __launch_bounds__(256, 1)
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_TMEMPTR);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&xmaps.m[0]);
     tma_prefetch_desc(&dymaps.m[0]);
   }
   if (warp == 1 && lane == 0) {
@@ -1199,9 +1290,13 @@ __global__ void __launch_bounds__(256, 1)
         dhA = tapA / 3 - 1; dwA = tapA % 3 - 1;
         dhB = tapB / 3 - 1; dwB = tapB % 3 - 1;
       }
-      const int dyv = p.per_tap_dy ? tapA : 0;
+      const int dyv0 = p.per_tap_dy ? tapA : 0;
       int stage = 0, phase = 0;
-      for (int kt = kt_begin; kt < kt_end; ++kt) {
+      for (int pk = 0; pk < PASSES * nk; ++pk) {
+        const int pass = SPLIT ? pk / nk : 0;
+        const int kt = kt_begin + (SPLIT ? pk - pass * nk : pk);
+        const CUtensorMap& xmap = xmaps.m[pass == 2 ? 1 : 0];   // x_lo in the third pass
+        const int dyv = dyv0 + (pass == 1 ? 4 : 0);             // dy_lo in the second pass
         const int w0 = (kt % p.tiles_w) * p.PW;
         const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.PH;
         const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.PN;
@@ -1225,7 +1320,7 @@ __global__ void __launch_bounds__(256, 1)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
       int stage = 0, phase = 0;
-      for (int i = 0; i < nk; ++i) {
+      for (int i = 0; i < PASSES * nk; ++i) {
         mbar_wait(full_bar(stage), phase, 6, &g_dbg_word);
         tc_fence_after();
         const uint32_t a_addr = sbase + stage * L::STAGE_BYTES;
@@ -1621,11 +1716,11 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   return launch_wgrad3_inst<64>(xmap, dymap, p, smem, c.ctas_mn, d.stream);
 }
 
-template <int BLOCK_N, int STAGES>
-static int launch_wgrad_inst(const CUtensorMap& xmap, const TmapPack4& dymaps, const WgradParams& p,
+template <int BLOCK_N, int STAGES, bool SPLIT = false>
+static int launch_wgrad_inst(const TmapPack2& xmap, const TmapPack8& dymaps, const WgradParams& p,
                              cudaStream_t stream) {
   using L = WgSmem<BLOCK_N, STAGES>;
-  auto kern = igemm_wgrad_kernel<BLOCK_N, STAGES>;
+  auto kern = igemm_wgrad_kernel<BLOCK_N, STAGES, SPLIT>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -1674,18 +1769,37 @@ int launch_igemm_wgrad(const WgradDesc& d) {
       return -1;
     }
   }
-  const WgradConfig c = wgrad_config(N, H, W, d.num_taps, d.Cin, d.Cout, d.num_dy_views);
+  // bf16x3 mode always takes the generic kernel (dy_views = 4 rules the halo kernel out)
+  const WgradConfig c = wgrad_config(N, H, W, d.num_taps, d.Cin, d.Cout, d.split ? 4 : d.num_dy_views);
   if (c.halo) return launch_wgrad3(d, c);
 
   int bw, bh, bn, ktiles;
   wgrad_geometry(N, H, W, &bw, &bh, &bn, &ktiles);
   const int block_n = c.block_n;
-  CUtensorMap xmap;
-  TmapPack4 dymaps;
-  if (make_act_map(&xmap, d.x, 64, bw, bh, bn)) return -1;
+  TmapPack2 xmap;
+  TmapPack8 dymaps;
+  if (make_act_map(&xmap.m[0], d.x, 64, bw, bh, bn)) return -1;
+  if (d.split) {
+    if (d.x.plane <= 0) {
+      set_error("igemm_wgrad: bf16x3 views need their lo-plane offset");
+      return -1;
+    }
+    if (make_act_map(&xmap.m[1], lo_plane(d.x), 64, bw, bh, bn)) return -1;
+  } else {
+    xmap.m[1] = xmap.m[0];
+  }
   for (int i = 0; i < 4; ++i) {
     const ActView& v = d.dy[i < d.num_dy_views ? i : 0];
     if (make_act_map(&dymaps.m[i], v, 64, bw, bh, bn)) return -1;
+    if (d.split) {
+      if (v.plane <= 0) {
+        set_error("igemm_wgrad: bf16x3 views need their lo-plane offset");
+        return -1;
+      }
+      if (make_act_map(&dymaps.m[4 + i], lo_plane(v), 64, bw, bh, bn)) return -1;
+    } else {
+      dymaps.m[4 + i] = dymaps.m[i];
+    }
   }
   WgradParams p;
   p.PW = bw; p.PH = bh; p.PN = bn;
@@ -1705,6 +1819,13 @@ int launch_igemm_wgrad(const WgradDesc& d) {
   p.dw = d.dw;
   p.s_co = d.s_co;
   p.s_t = d.s_t;
+  if (d.split) {
+    switch (block_n) {
+      case 256: return launch_wgrad_inst<256, 4, true>(xmap, dymaps, p, d.stream);
+      case 128: return launch_wgrad_inst<128, 6, true>(xmap, dymaps, p, d.stream);
+      default:  return launch_wgrad_inst<64, 8, true>(xmap, dymaps, p, d.stream);
+    }
+  }
   switch (block_n) {
     case 256: return launch_wgrad_inst<256, 4>(xmap, dymaps, p, d.stream);
     case 128: return launch_wgrad_inst<128, 6>(xmap, dymaps, p, d.stream);

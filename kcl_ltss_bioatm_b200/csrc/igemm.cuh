@@ -24,6 +24,9 @@ struct FwdDesc {
   double* stat_sum;   // optional per-channel sum / sum of squares of the bf16 outputs (fp64 accumulators)
   double* stat_sq;
   cudaStream_t stream;
+  // bf16x3 high-precision mode: every view is a hi plane with its lo plane `view.plane` elements further, wmat is
+  // the hi matrix followed by the lo matrix (same shape); three MMA passes (hi*hi + hi*lo + lo*hi)
+  int split;
 };
 int launch_igemm_fwd(const FwdDesc& d);
 
@@ -41,6 +44,7 @@ struct WgradDesc {
   float* dw;          // fp32 gradient, accumulated into (caller zeroes it for a plain assignment)
   long long s_co, s_t;
   cudaStream_t stream;
+  int split;          // bf16x3 mode (see FwdDesc): x and dy are hi/lo plane pairs
 };
 // Chooses the K split for a problem; returns the number of splits (>=1).
 int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout);

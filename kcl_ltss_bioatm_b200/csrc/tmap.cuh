@@ -36,8 +36,15 @@ struct ActView {
   const void* ptr;
   int C, W, H, N;
   long long pix_stride, row_stride, img_stride;
-  int esize = 2;  // bytes per element: 2 = bf16, 4 = fp32 (tf32 operands)
+  int esize = 2;  // bytes per element (bf16)
+  long long plane = 0;  // bf16x3 mode: element offset from `ptr` (the hi plane) to the lo plane of the same view
 };
+// The lo plane of a bf16x3 view as a view of its own.
+inline ActView lo_plane(const ActView& v) {
+  ActView l = v;
+  l.ptr = static_cast<const char*>(v.ptr) + v.plane * 2;
+  return l;
+}
 
 inline ActView dense_view(const void* ptr, int N, int H, int W, int C_total, int c_off, int C) {
   ActView v;

@@ -33,6 +33,12 @@ SIGNATURES = {
     "plume_convT2x2_concat_fwd": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "plume_convT2x2_dgrad": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "plume_convT2x2_wgrad": (_I, [_P, _I, _P, _I, _P, _I, _P, c_size_t, _I, _I, _I, _I, _I, _P]),
+    "plume_conv3x3_fwd_x3": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "plume_conv3x3_dgrad_x3": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "plume_conv3x3_wgrad_x3": (_I, [_P, _I, _P, _I, _P, _I, _P, c_size_t, _I, _I, _I, _I, _I, _P]),
+    "plume_convT2x2_concat_fwd_x3": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "plume_convT2x2_dgrad_x3": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "plume_convT2x2_wgrad_x3": (_I, [_P, _I, _P, _I, _P, _I, _P, c_size_t, _I, _I, _I, _I, _I, _P]),
     "plume_pack_conv3x3": (_I, [_P, _P, _P, _I, _I, _P]),
     "plume_pack_convT2x2": (_I, [_P, _P, _P, _I, _I, _P]),
     "plume_pack_blocks": (_I, [_I, _I, _I]),
@@ -53,24 +59,30 @@ SIGNATURES = {
     "plume_head_bwd": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
     "plume_adam": (_I, [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P]),
     "plume_adam_dev": (_I, [_P, _P, _P, _P, _LL, _P, _P]),
-    "plume_pad_channels_f32": (_I, [_P, _I, _P, _I, _LL, _P]),
-    "plume_scale_shift_act_f32": (_I, [_P, _I, _P, _P, _I, _P, _I, _LL, _I, _P]),
-    "plume_scale_shift_act_pool_f32": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
-    "plume_maxpool2x2_fwd_f32": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
-    "plume_maxpool2x2_bwd_f32": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
-    "plume_bn_bwd_reduce_f32": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _LL, _I, _P]),
-    "plume_bn_bwd_apply_f32": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _LL, _I, _P]),
-    "plume_relu_bwd_f32": (_I, [_P, _I, _P, _I, _P, _I, _P, _LL, _I, _P]),
-    "plume_channel_sum_f32": (_I, [_P, _I, _P, _LL, _I, _P]),
-    "plume_head_fwd_f32": (_I, [_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P]),
-    "plume_head_bwd_f32": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
-    "plume_extract_tiles_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
+    "plume_pad_channels_x3": (_I, [_P, _I, _P, _I, _LL, _P]),
+    "plume_scale_shift_act_x3": (_I, [_P, _I, _P, _P, _I, _P, _I, _LL, _I, _P]),
+    "plume_scale_shift_act_pool_x3": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "plume_maxpool2x2_fwd_x3": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "plume_maxpool2x2_bwd_x3": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "plume_bn_bwd_reduce_x3": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _LL, _I, _P]),
+    "plume_bn_bwd_apply_x3": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _LL, _I, _P]),
+    "plume_relu_bwd_x3": (_I, [_P, _I, _P, _I, _P, _I, _P, _LL, _I, _P]),
+    "plume_channel_sum_x3": (_I, [_P, _I, _P, _LL, _I, _P]),
+    "plume_head_fwd_x3": (_I, [_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P]),
+    "plume_head_bwd_x3": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _LL, _I, _P]),
+    "plume_extract_tiles_x3": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_extract_tiles": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
     "plume_rasterize_hulls": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "plume_threshold_masks": (_I, [_P, _I, _I, _P, _I, _P, _P]),
     "plume_label_components": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "plume_fire_extents": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
+    "plume_utm_zone_histogram": (_I, [_P, _LL, _P, _P]),
+    "plume_utm_forward": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
+    "plume_utm_inverse": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
+    "plume_resample_workspace_bytes": (c_size_t, [_I, _D, _D, _D, _D, _D]),
+    "plume_resample_nearest_index": (_I, [_P, _P, _I, _I, _D, _D, _D, _D, _I, _I, _D, _P, c_size_t, _P, _P]),
+    "plume_gather_fill": (_I, [_P, _I, _P, _LL, _D, _P, _P]),
     "plume_locate_fires_workspace_bytes": (ctypes.c_size_t, [_I]),
     "plume_locate_fires": (_I, [_P, _P, _I, _I, _P, _P, _I, ctypes.c_double, _P, ctypes.c_size_t, _P, _P]),
 }

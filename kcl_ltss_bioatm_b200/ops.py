@@ -16,16 +16,24 @@ from . import lib as _lib
 from .lib import check, current_stream, ptr
 
 
-def _act(t: torch.Tensor, name: str):
-    """(pointer, pixel stride, N, H, W, C) of an NHWC bf16 activation view."""
-    if t.dtype != torch.bfloat16 or t.dim() != 4:
-        raise TypeError(f"{name}: expected a 4-D bf16 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
+def _act(t: torch.Tensor, name: str, planes: int = 1):
+    """(pointer, pixel stride, N, H, W, C) of an NHWC bf16 activation view.  planes == 2 (bf16x3 mode): the tensor
+    is [N, H, W, 2, C] -- a hi and a lo plane per pixel -- and the pixel stride covers both planes."""
+    if t.dtype != torch.bfloat16 or t.dim() != (4 if planes == 1 else 5):
+        raise TypeError(f"{name}: expected a {4 if planes == 1 else 5}-D bf16 NHWC tensor, got {t.dtype} "
+                        f"{tuple(t.shape)}")
     if not t.is_cuda:
         raise TypeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
-    n, h, w, c = t.shape
-    sn, sh, sw, sc = t.stride()
-    ld = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
-    ok = (sc == 1 or c == 1) and ld >= c and ld % 8 == 0
+    if planes == 1:
+        n, h, w, c = t.shape
+        sn, sh, sw, sc = t.stride()
+        ld = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
+        ok = (sc == 1 or c == 1) and ld >= c and ld % 8 == 0
+    else:
+        n, h, w, pl, c = t.shape
+        sn, sh, sw, sp, sc = t.stride()
+        ld = 2 * sp
+        ok = pl == 2 and (sc == 1 or c == 1) and sp >= c and sp % 8 == 0
     ok = ok and (w == 1 or sw == ld) and (h == 1 or sh == w * ld) and (n == 1 or sn == h * w * ld)
     if not ok:
         raise ValueError(f"{name}: not a dense-pixel NHWC view: shape {tuple(t.shape)} strides {t.stride()}")
@@ -36,7 +44,7 @@ def _weight_cin(w_numel: int, cout: int, cin: int, ldx: int) -> int:
     """Input channels per tap of a 3x3 weight tensor.  It may exceed the activation's channel count when
     the activation is dense (ldx == cin): the C ABI then reads the missing channels as zero (ldx < Cin)."""
     kcin = w_numel // (9 * cout)
-    if kcin * 9 * cout != w_numel or kcin < cin or (kcin > cin and ldx != cin):
+    if kcin * 9 * cout != w_numel or kcin < cin or (kcin > cin and ldx != cin):  # ldx: channels of one plane
         raise ValueError(f"3x3 weights with {w_numel} elements do not fit Cout={cout}, Cin={cin} (ld {ldx})")
     return kcin
 
@@ -66,12 +74,25 @@ class CudaOps:
 
     name = "b200"
 
-    def __init__(self) -> None:
+    def __init__(self, precision: str = "bf16") -> None:
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.PlumeError("CUDA device required: the B200 path has no CPU fallback")
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        self.precision = precision
+        # bf16x3: activations are [N, H, W, 2, C] (hi / lo planes), the bf16 weight copies hold a hi and a lo
+        # matrix, and every activation-typed entry point is its *_x3 variant (include/plume_b200.h)
+        self.planes = 2 if precision == "bf16x3" else 1
+        self._sfx = "_x3" if self.planes == 2 else ""
         self._ws: torch.Tensor | None = None
         self.launches = 0  # kernels of ours enqueued so far (bench.py reports the per-step count)
+
+    def _fn(self, name: str):
+        return getattr(self.lib, name + self._sfx)
+
+    def _a(self, t: torch.Tensor, name: str):
+        return _act(t, name, self.planes)
 
     # ------------------------------------------------------------------ helpers
     def _workspace(self, nbytes: int, device) -> torch.Tensor:
@@ -81,59 +102,59 @@ class CudaOps:
 
     # ------------------------------------------------------------------ tensor-core GEMMs
     def conv3x3_fwd(self, x, w_fwd, scale, shift, relu, y, stat_sum=None, stat_sq=None):
-        xp, ldx, n, h, w, cin = _act(x, "x")
-        yp, ldy, n2, h2, w2, cout = _act(y, "y")
+        xp, ldx, n, h, w, cin = self._a(x, "x")
+        yp, ldy, n2, h2, w2, cout = self._a(y, "y")
         assert (n, h, w) == (n2, h2, w2)
-        kcin = _weight_cin(w_fwd.numel(), cout, cin, ldx)
+        kcin = _weight_cin(w_fwd.numel() // self.planes, cout, cin, ldx // self.planes)
         assert w_fwd.dtype == torch.bfloat16 and w_fwd.is_contiguous()
-        check(self.lib.plume_conv3x3_fwd(xp, ldx, ptr(w_fwd), _f32(scale, "scale", cout),
+        check(self._fn("plume_conv3x3_fwd")(xp, ldx, ptr(w_fwd), _f32(scale, "scale", cout),
                                          _f32(shift, "shift", cout), int(bool(relu)), yp, ldy,
                                          _f64(stat_sum, "stat_sum", cout), _f64(stat_sq, "stat_sq", cout),
                                          n, h, w, kcin, cout, current_stream()), "plume_conv3x3_fwd")
         self.launches += 1
 
     def conv3x3_dgrad(self, dy, w_dgrad, dx):
-        dyp, lddy, n, h, w, cout = _act(dy, "dy")
-        dxp, lddx, n2, h2, w2, cin = _act(dx, "dx")
+        dyp, lddy, n, h, w, cout = self._a(dy, "dy")
+        dxp, lddx, n2, h2, w2, cin = self._a(dx, "dx")
         assert (n, h, w) == (n2, h2, w2)
-        assert w_dgrad.dtype == torch.bfloat16 and w_dgrad.numel() == cout * 9 * cin
-        check(self.lib.plume_conv3x3_dgrad(dyp, lddy, ptr(w_dgrad), dxp, lddx, n, h, w, cin, cout,
+        assert w_dgrad.dtype == torch.bfloat16 and w_dgrad.numel() == self.planes * cout * 9 * cin
+        check(self._fn("plume_conv3x3_dgrad")(dyp, lddy, ptr(w_dgrad), dxp, lddx, n, h, w, cin, cout,
                                            current_stream()), "plume_conv3x3_dgrad")
         self.launches += 1
 
     def conv3x3_wgrad(self, x, dy, dw, accumulate=False):
-        xp, ldx, n, h, w, cin = _act(x, "x")
-        dyp, lddy, n2, h2, w2, cout = _act(dy, "dy")
+        xp, ldx, n, h, w, cin = self._a(x, "x")
+        dyp, lddy, n2, h2, w2, cout = self._a(dy, "dy")
         assert (n, h, w) == (n2, h2, w2)
-        kcin = _weight_cin(dw.numel(), cout, cin, ldx)
-        check(self.lib.plume_conv3x3_wgrad(xp, ldx, dyp, lddy, _f32(dw, "dw", cout * 9 * kcin),
+        kcin = _weight_cin(dw.numel(), cout, cin, ldx // self.planes)
+        check(self._fn("plume_conv3x3_wgrad")(xp, ldx, dyp, lddy, _f32(dw, "dw", cout * 9 * kcin),
                                            int(bool(accumulate)), ptr(None), 0, n, h, w, kcin, cout,
                                            current_stream()), "plume_conv3x3_wgrad")
         self.launches += 1
 
     def convT_fwd(self, x, w_fwd, bias, u):
-        xp, ldx, n, h, w, cin = _act(x, "x")
-        up, ldu, n2, h2, w2, cout = _act(u, "u")
+        xp, ldx, n, h, w, cin = self._a(x, "x")
+        up, ldu, n2, h2, w2, cout = self._a(u, "u")
         assert (n2, h2, w2) == (n, 2 * h, 2 * w)
-        assert w_fwd.dtype == torch.bfloat16 and w_fwd.numel() == 4 * cout * cin
-        check(self.lib.plume_convT2x2_concat_fwd(xp, ldx, ptr(w_fwd), _f32(bias, "bias", cout), up, ldu,
+        assert w_fwd.dtype == torch.bfloat16 and w_fwd.numel() == self.planes * 4 * cout * cin
+        check(self._fn("plume_convT2x2_concat_fwd")(xp, ldx, ptr(w_fwd), _f32(bias, "bias", cout), up, ldu,
                                                  n, h, w, cin, cout, current_stream()),
               "plume_convT2x2_concat_fwd")
         self.launches += 1
 
     def convT_dgrad(self, du, w_dgrad, dx):
-        dup, lddu, n2, h2, w2, cout = _act(du, "du")
-        dxp, lddx, n, h, w, cin = _act(dx, "dx")
+        dup, lddu, n2, h2, w2, cout = self._a(du, "du")
+        dxp, lddx, n, h, w, cin = self._a(dx, "dx")
         assert (n2, h2, w2) == (n, 2 * h, 2 * w)
-        check(self.lib.plume_convT2x2_dgrad(dup, lddu, ptr(w_dgrad), dxp, lddx, n, h, w, cin, cout,
+        check(self._fn("plume_convT2x2_dgrad")(dup, lddu, ptr(w_dgrad), dxp, lddx, n, h, w, cin, cout,
                                             current_stream()), "plume_convT2x2_dgrad")
         self.launches += 1
 
     def convT_wgrad(self, x, du, dw, accumulate=False):
-        xp, ldx, n, h, w, cin = _act(x, "x")
-        dup, lddu, n2, h2, w2, cout = _act(du, "du")
+        xp, ldx, n, h, w, cin = self._a(x, "x")
+        dup, lddu, n2, h2, w2, cout = self._a(du, "du")
         assert (n2, h2, w2) == (n, 2 * h, 2 * w)
-        check(self.lib.plume_convT2x2_wgrad(xp, ldx, dup, lddu, _f32(dw, "dw", 4 * cout * cin),
+        check(self._fn("plume_convT2x2_wgrad")(xp, ldx, dup, lddu, _f32(dw, "dw", 4 * cout * cin),
                                             int(bool(accumulate)), ptr(None), 0, n, h, w, cin, cout,
                                             current_stream()), "plume_convT2x2_wgrad")
         self.launches += 1
@@ -155,7 +176,8 @@ class CudaOps:
         """jobs: sequence of (kind, w, wf, wd) with kind "conv3x3" (w [Cout,3,3,Cin]) or "convT" (w [4,Cout,Cin]);
         wf / wd may be None.  One launch for all of them; the descriptor table (plume_pack_desc, device
         memory) is built once per distinct set of buffers."""
-        key = tuple((k, w.data_ptr(), ptr(wf).value, ptr(wd).value) for k, w, wf, wd in jobs)
+        # the shapes belong to the key: a freed buffer's address can come back for a layer of another shape
+        key = tuple((k, tuple(w.shape), w.data_ptr(), ptr(wf).value, ptr(wd).value) for k, w, wf, wd in jobs)
         cached = getattr(self, "_pack_tables", None)
         if cached is None:
             cached = self._pack_tables = {}
@@ -167,6 +189,10 @@ class CudaOps:
             for kind, w, wf, wd in jobs:
                 k = 0 if kind == "conv3x3" else 1
                 cout, cin = (w.shape[0], w.shape[3]) if k == 0 else (w.shape[1], w.shape[2])
+                for t in (wf, wd):
+                    if t is not None and t.numel() != self.planes * w.numel():
+                        raise ValueError("pack_batch: operand copy has the wrong size for this precision")
+                k |= 2 if self.planes == 2 else 0   # bf16x3: hi matrix followed by the lo matrix
                 _f32(w, "w")
                 blob += struct.pack("<QQQiiii", w.data_ptr(), ptr(wf).value or 0, ptr(wd).value or 0, k, cout, cin,
                                     first)
@@ -183,8 +209,9 @@ class CudaOps:
         if not (x.is_cuda and out.is_cuda):
             raise TypeError("pad_channels: expected CUDA tensors (there is no CPU path)")
         assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype == torch.bfloat16
+        assert x.dim() == 4 and out.dim() == 3 + self.planes     # the source is plain bf16 in either mode
         pixels = x.numel() // x.shape[-1]
-        check(self.lib.plume_pad_channels(ptr(x), x.shape[-1], ptr(out), out.shape[-1], pixels,
+        check(self._fn("plume_pad_channels")(ptr(x), x.shape[-1], ptr(out), out.shape[-1], pixels,
                                           current_stream()), "plume_pad_channels")
         self.launches += 1
 
@@ -207,46 +234,46 @@ class CudaOps:
         self.launches += 1
 
     def scale_shift_act(self, y, scale, shift, relu, a):
-        yp, ldy, n, h, w, c = _act(y, "y")
-        ap, lda, *_ = _act(a, "a")
-        check(self.lib.plume_scale_shift_act(yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c),
+        yp, ldy, n, h, w, c = self._a(y, "y")
+        ap, lda, *_ = self._a(a, "a")
+        check(self._fn("plume_scale_shift_act")(yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c),
                                              int(bool(relu)), ap, lda, n * h * w, c, current_stream()),
               "plume_scale_shift_act")
         self.launches += 1
 
     def scale_shift_act_pool(self, y, scale, shift, relu, skip, pooled, argmax):
-        yp, ldy, n, h, w, c = _act(y, "y")
+        yp, ldy, n, h, w, c = self._a(y, "y")
         sp, lds = (ptr(None), 0)
         if skip is not None:
-            sp, lds, *_ = _act(skip, "skip")
-        pp, ldp, n2, h2, w2, _ = _act(pooled, "pooled")
+            sp, lds, *_ = self._a(skip, "skip")
+        pp, ldp, n2, h2, w2, _ = self._a(pooled, "pooled")
         assert (n2, h2, w2) == (n, h // 2, w // 2) and argmax.dtype == torch.uint8 and argmax.is_contiguous()
-        check(self.lib.plume_scale_shift_act_pool(yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c),
+        check(self._fn("plume_scale_shift_act_pool")(yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c),
                                                   int(bool(relu)), sp, lds, pp, ldp, ptr(argmax), n, h, w, c,
                                                   current_stream()), "plume_scale_shift_act_pool")
         self.launches += 1
 
     def maxpool_fwd(self, x, y, argmax):
-        xp, ldx, n, h, w, c = _act(x, "x")
-        yp, ldy, *_ = _act(y, "y")
-        check(self.lib.plume_maxpool2x2_fwd(xp, ldx, yp, ldy, ptr(argmax), n, h, w, c, current_stream()),
+        xp, ldx, n, h, w, c = self._a(x, "x")
+        yp, ldy, *_ = self._a(y, "y")
+        check(self._fn("plume_maxpool2x2_fwd")(xp, ldx, yp, ldy, ptr(argmax), n, h, w, c, current_stream()),
               "plume_maxpool2x2_fwd")
         self.launches += 1
 
     def maxpool_bwd(self, dy, argmax, dskip, dx):
-        dyp, lddy, *_ = _act(dy, "dy")
-        dxp, lddx, n, h, w, c = _act(dx, "dx")
+        dyp, lddy, *_ = self._a(dy, "dy")
+        dxp, lddx, n, h, w, c = self._a(dx, "dx")
         sp, lds = (ptr(None), 0)
         if dskip is not None:
-            sp, lds, *_ = _act(dskip, "dskip")
-        check(self.lib.plume_maxpool2x2_bwd(dyp, lddy, ptr(argmax), sp, lds, dxp, lddx, n, h, w, c,
+            sp, lds, *_ = self._a(dskip, "dskip")
+        check(self._fn("plume_maxpool2x2_bwd")(dyp, lddy, ptr(argmax), sp, lds, dxp, lddx, n, h, w, c,
                                             current_stream()), "plume_maxpool2x2_bwd")
         self.launches += 1
 
     def bn_bwd_reduce(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx):
-        dap, ldda, n, h, w, c = _act(da, "da")
-        yp, ldy, *_ = _act(y, "y")
-        check(self.lib.plume_bn_bwd_reduce(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
+        dap, ldda, n, h, w, c = self._a(da, "da")
+        yp, ldy, *_ = self._a(y, "y")
+        check(self._fn("plume_bn_bwd_reduce")(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
                                            _f32(mean, "mean"), _f32(invstd, "invstd"), int(bool(relu)),
                                            _f32(sum_g, "sum_g", c), _f32(sum_gx, "sum_gx", c), n * h * w, c,
                                            current_stream()), "plume_bn_bwd_reduce")
@@ -256,10 +283,10 @@ class CudaOps:
                      dgamma=None, dbeta=None, accumulate=False):
         """sum_g / sum_gx: this batch's sums from bn_bwd_reduce (a scratch zeroed per backward pass); dgamma /
         dbeta: where the parameter gradients go (added to when accumulate)."""
-        dap, ldda, n, h, w, c = _act(da, "da")
-        yp, ldy, *_ = _act(y, "y")
-        dyp, lddy, *_ = _act(dy, "dy")
-        check(self.lib.plume_bn_bwd_apply(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
+        dap, ldda, n, h, w, c = self._a(da, "da")
+        yp, ldy, *_ = self._a(y, "y")
+        dyp, lddy, *_ = self._a(dy, "dy")
+        check(self._fn("plume_bn_bwd_apply")(dap, ldda, yp, ldy, _f32(scale, "scale"), _f32(shift, "shift"),
                                           _f32(mean, "mean"), _f32(invstd, "invstd"), int(bool(relu)),
                                           _f32(sum_g, "sum_g", c), _f32(sum_gx, "sum_gx", c), dyp, lddy,
                                           _f32(sum_dy, "sum_dy"), _f32(dgamma, "dgamma", c),
@@ -268,22 +295,22 @@ class CudaOps:
         self.launches += 1
 
     def relu_bwd(self, da, a, dy, sum_dy):
-        dap, ldda, n, h, w, c = _act(da, "da")
-        ap, lda, *_ = _act(a, "a")
-        dyp, lddy, *_ = _act(dy, "dy")
-        check(self.lib.plume_relu_bwd(dap, ldda, ap, lda, dyp, lddy, _f32(sum_dy, "sum_dy"), n * h * w, c,
+        dap, ldda, n, h, w, c = self._a(da, "da")
+        ap, lda, *_ = self._a(a, "a")
+        dyp, lddy, *_ = self._a(dy, "dy")
+        check(self._fn("plume_relu_bwd")(dap, ldda, ap, lda, dyp, lddy, _f32(sum_dy, "sum_dy"), n * h * w, c,
                                       current_stream()), "plume_relu_bwd")
         self.launches += 1
 
     def channel_sum(self, x, out):
-        xp, ldx, n, h, w, c = _act(x, "x")
-        check(self.lib.plume_channel_sum(xp, ldx, _f32(out, "out", c), n * h * w, c, current_stream()),
+        xp, ldx, n, h, w, c = self._a(x, "x")
+        check(self._fn("plume_channel_sum")(xp, ldx, _f32(out, "out", c), n * h * w, c, current_stream()),
               "plume_channel_sum")
         self.launches += 1
 
     def head_fwd(self, feat, w, b, target, logits, sums):
-        fp, ldf, n, h, wd, c = _act(feat, "feat")
-        check(self.lib.plume_head_fwd(fp, ldf, _f32(w, "w", c), _f32(b, "b", 1), ptr(target),
+        fp, ldf, n, h, wd, c = self._a(feat, "feat")
+        check(self._fn("plume_head_fwd")(fp, ldf, _f32(w, "w", c), _f32(b, "b", 1), ptr(target),
                                       _f32(logits, "logits", n * h * wd), _f32(sums, "sums"), n * h * wd, c,
                                       current_stream()), "plume_head_fwd")
         self.launches += 1
@@ -295,9 +322,9 @@ class CudaOps:
         self.launches += 1
 
     def head_bwd(self, feat, w, logits, target, sums, bce_w, dice_w, eps, grad_scale, dfeat, dw, db):
-        fp, ldf, n, h, wd, c = _act(feat, "feat")
-        dfp, lddf, *_ = _act(dfeat, "dfeat")
-        check(self.lib.plume_head_bwd(fp, ldf, _f32(w, "w", c), _f32(logits, "logits"), ptr(target),
+        fp, ldf, n, h, wd, c = self._a(feat, "feat")
+        dfp, lddf, *_ = self._a(dfeat, "dfeat")
+        check(self._fn("plume_head_bwd")(fp, ldf, _f32(w, "w", c), _f32(logits, "logits"), ptr(target),
                                       _f32(sums, "sums", 4), float(bce_w), float(dice_w), float(eps),
                                       float(grad_scale), dfp, lddf, _f32(dw, "dw", c), _f32(db, "db", 1),
                                       n * h * wd, c, current_stream()), "plume_head_bwd")
@@ -322,7 +349,8 @@ class CudaOps:
         hs, ws, cs = scene.shape
         count = ys.numel()
         assert tiles.shape[0] >= count and tiles.is_contiguous() and scene.is_contiguous()
-        check(self.lib.plume_extract_tiles(ptr(scene), hs, ws, cs, ptr(ys), ptr(xs), count, tile, ptr(tiles),
+        assert scene.dtype == torch.bfloat16 and tiles.dim() == 3 + self.planes   # the scene is plain bf16
+        check(self._fn("plume_extract_tiles")(ptr(scene), hs, ws, cs, ptr(ys), ptr(xs), count, tile, ptr(tiles),
                                            tiles.shape[-1], current_stream()), "plume_extract_tiles")
         self.launches += 1
 
@@ -418,4 +446,48 @@ class CudaOps:
                                           t, h, w, self._dev(fire_rc, torch.int32, "fire_rc"), n, int(win),
                                           self._dev(extents, torch.int32, "extents"), current_stream()),
               "plume_fire_extents")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ UTM projection / nearest-neighbour resampling
+    def utm_zone_histogram(self, lons, hist):
+        """lons float64 (any shape) -> hist int32 [64]: hist[z] = pixels whose UTM zone is z (tools.py:27-28)."""
+        check(self.lib.plume_utm_zone_histogram(self._dev(lons, torch.float64, "lons"), lons.numel(),
+                                                self._dev(hist, torch.int32, "hist"), current_stream()),
+              "plume_utm_zone_histogram")
+        self.launches += 1
+
+    def utm_forward(self, lats, lons, zone, x, y):
+        check(self.lib.plume_utm_forward(self._dev(lats, torch.float64, "lats"), self._dev(lons, torch.float64, "lons"),
+                                         lats.numel(), int(zone), self._dev(x, torch.float64, "x"),
+                                         self._dev(y, torch.float64, "y"), current_stream()), "plume_utm_forward")
+        self.launches += 1
+
+    def utm_inverse(self, x, y, zone, lats, lons):
+        check(self.lib.plume_utm_inverse(self._dev(x, torch.float64, "x"), self._dev(y, torch.float64, "y"), x.numel(),
+                                         int(zone), self._dev(lats, torch.float64, "lats"),
+                                         self._dev(lons, torch.float64, "lons"), current_stream()), "plume_utm_inverse")
+        self.launches += 1
+
+    def resample_nearest_index(self, src_lats, src_lons, zone, extent, x_size, y_size, radius, out_idx):
+        """extent = (min_x, min_y, max_x, max_y) outer edges of the x_size x y_size target area in UTM metres of `zone`;
+        out_idx int32 [y_size, x_size]: flat index of the nearest swath pixel within `radius` metres, else -1."""
+        n = src_lats.numel()
+        if src_lons.numel() != n or tuple(out_idx.shape) != (y_size, x_size):
+            raise ValueError("resample_nearest_index: swath arrays / out_idx do not agree")
+        ex = [float(v) for v in extent]
+        nbytes = int(self.lib.plume_resample_workspace_bytes(n, ex[0], ex[1], ex[2], ex[3], float(radius)))
+        ws = self._workspace(nbytes, src_lats.device)
+        check(self.lib.plume_resample_nearest_index(self._dev(src_lats, torch.float64, "src_lats"),
+                                                    self._dev(src_lons, torch.float64, "src_lons"), n, int(zone),
+                                                    ex[0], ex[1], ex[2], ex[3], int(x_size), int(y_size), float(radius),
+                                                    ptr(ws), nbytes, self._dev(out_idx, torch.int32, "out_idx"),
+                                                    current_stream()), "plume_resample_nearest_index")
+        self.launches += 4
+
+    def gather_fill(self, src, idx, fill_value, out):
+        if src.dtype not in (torch.float32, torch.float64) or out.dtype != src.dtype:
+            raise TypeError("gather_fill: float32 or float64 images")
+        check(self.lib.plume_gather_fill(self._dev(src, src.dtype, "src"), src.element_size(),
+                                         self._dev(idx, torch.int32, "idx"), idx.numel(), float(fill_value),
+                                         self._dev(out, out.dtype, "out"), current_stream()), "plume_gather_fill")
         self.launches += 1

@@ -65,7 +65,8 @@ class ScenePredictor:
         bt = min(self.batch_tiles, len(ys_l))
         cd = m.spec.cin_padded  # tiles are cut already zero padded to the first layer's K
         if self._tiles is None or self._tiles.shape[0] != bt or self._tiles.shape[1] != T:
-            self._tiles = torch.empty(bt, T, T, cd, dtype=m.act_dtype, device=dev)
+            shape = (bt, T, T, cd) if getattr(m, "planes", 1) == 1 else (bt, T, T, 2, cd)
+            self._tiles = torch.empty(*shape, dtype=m.act_dtype, device=dev)
         was = m.training
         m.eval()
         for b0 in range(0, len(ys_l), bt):

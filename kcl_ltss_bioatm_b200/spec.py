@@ -34,8 +34,18 @@ class UNetSpec:
     lr: float = 1e-3              # Adam
     betas: Tuple[float, float] = (0.9, 0.999)
     adam_eps: float = 1e-8
+    # Arithmetic of the GPU path (not part of the model definition; the oracle ignores it):
+    #   "bf16"  : bf16 activations and GEMM operands, fp32 accumulate -- north_star's 1e-2 logits bar;
+    #   "bf16x3": activations / operands as bf16 hi + lo pairs, three MMA passes (hi*hi + hi*lo + lo*hi), fp32
+    #             accumulate -- north_star's "tf32 mode" bar of 1e-3 ("tf32" is accepted as an alias; a single
+    #             kind::tf32 pass keeps 11 significant bits and does not reach 1e-3 on the 23-layer network).
+    precision: str = "bf16"
 
     def __post_init__(self):
+        if self.precision == "tf32":
+            object.__setattr__(self, "precision", "bf16x3")
+        if self.precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3' (alias 'tf32')")
         if self.n_classes != 1:
             raise ValueError("the plume segmenter is single-class (n_classes == 1)")
         if self.norm not in ("batch", "none"):

@@ -39,10 +39,15 @@ class UNetB200:
         if ops is None:
             from .ops import CudaOps  # fails loudly without the library / a GPU
 
-            ops = CudaOps()
+            ops = CudaOps(precision=spec.precision)
         self.spec, self.ops = spec, ops
         # bf16 on the GPU; the CPU operator oracle may ask for fp32 buffers to check the schedule exactly
         self.act_dtype = getattr(ops, "act_dtype", BF16)
+        # bf16x3 precision: every activation is [N, H, W, 2, C] (hi / lo planes) and every bf16 weight copy a hi
+        # matrix followed by a lo matrix; the schedule below is the same (channel slices index the last dim)
+        self.planes = getattr(ops, "planes", 1)
+        if spec.precision == "bf16x3" and self.planes != 2 and getattr(ops, "name", "") == "b200":
+            raise ValueError("spec.precision is 'bf16x3' but the operator layer was built for bf16")
         self.device = torch.device(device)
         self.layout = build_layout(spec)
         self.convs, self.ups = conv_layers(spec), up_layers(spec)
@@ -61,11 +66,11 @@ class UNetB200:
         off = 0
         self._wslot: Dict[str, tuple] = {}
         for name, L in self.convs.items():
-            n = L.cout * 9 * L.cin_k
+            n = self.planes * L.cout * 9 * L.cin_k
             self._wslot[name] = (off, n)
             off += (n + 127) // 128 * 128
         for name, U in self.ups.items():
-            n = 4 * U.cout * U.cin
+            n = self.planes * 4 * U.cout * U.cin
             self._wslot[name] = (off, n)
             off += (n + 127) // 128 * 128
         self.w_fwd = torch.zeros(off, dtype=self.act_dtype, device=dev)
@@ -306,10 +311,12 @@ class UNetB200:
             raise ValueError(f"tile height/width must be multiples of {div} (depth {d}); got {h}x{w}")
 
         def act(hh, ww, c):
+            if self.planes == 2:
+                return torch.empty(n, hh, ww, 2, c, dtype=self.act_dtype, device=dev)
             return torch.empty(n, hh, ww, c, dtype=self.act_dtype, device=dev)
 
         b = _Buffers(n, h, w)
-        b.x0 = act(h, w, spec.cin_padded) if spec.cin_padded != spec.in_channels else None
+        b.x0 = act(h, w, spec.cin_padded) if (spec.cin_padded != spec.in_channels or self.planes == 2) else None
         b.y1, b.a1, b.y2, b.cat, b.pool, b.am = [], [], [], [], [], []
         b.dy1, b.da1, b.dy2, b.da2 = [], [], [], []          # decoder activations (raw / activated)
         b.g_a, b.g_y, b.g_cat, b.g_pool = [], [], [], []       # gradient scratch per level
@@ -381,9 +388,11 @@ class UNetB200:
     # ------------------------------------------------------------------ forward
     def _prep_input(self, x: torch.Tensor, b: _Buffers) -> torch.Tensor:
         spec = self.spec
+        if x.dim() == 5 and self.planes == 2 and x.shape[-1] == spec.cin_padded and x.is_contiguous():
+            return x  # bf16x3 tiles already in the split format (ScenePredictor cuts them that way)
         if x.dtype != self.act_dtype or x.dim() != 4:
             raise ValueError(f"input must be a 4-D NHWC {self.act_dtype} tensor, got {x.dtype} {tuple(x.shape)}")
-        if x.shape[-1] == spec.cin_padded and x.is_contiguous():
+        if x.shape[-1] == spec.cin_padded and x.is_contiguous() and self.planes == 1:
             return x  # already zero padded to the first layer's K
         if x.shape[-1] != spec.in_channels:
             raise ValueError(f"input must have {spec.in_channels} channels, got {x.shape[-1]}")
@@ -430,7 +439,7 @@ class UNetB200:
         if `target` (uint8 [N,H,W]) is given the loss sums are accumulated.  Returns fp32 logits [N,H,W]."""
         spec, d, ops = self.spec, self.spec.depth, self.ops
         self._close_tail()
-        n, h, w, _ = x.shape
+        n, h, w = x.shape[:3]
         b = self._ensure_buffers(n, h, w)
         self.pack_weights()
         train = self.training
