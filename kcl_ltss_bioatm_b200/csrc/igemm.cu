@@ -92,15 +92,15 @@ struct FwdParams {
   double* stat_sq;
 };
 
-template <int BLOCK_N, int STAGES, int STAGING>
+template <int BLOCK_N, int STAGES, int STAGING, int EPI_WG = 1>
 struct FwdSmem {
   static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 bf16 (one 128-B swizzle row each)
   static constexpr int B_BYTES = BLOCK_N * 128;  // BLOCK_N out-channels x 64 bf16
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 128 * 128;    // 128 pixels x 64 bf16 outputs
-  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
-  static constexpr int OFF_PARAM = OFF_STG + STAGING * STG_BYTES;  // scale|shift|sum|sq, BLOCK_N each
-  static constexpr int OFF_BAR = OFF_PARAM + 4 * BLOCK_N * 4;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;              // STAGING buffers per epilogue warpgroup
+  static constexpr int OFF_PARAM = OFF_STG + EPI_WG * STAGING * STG_BYTES;  // per warpgroup: scale|shift|sum|sq
+  static constexpr int OFF_BAR = OFF_PARAM + EPI_WG * 4 * BLOCK_N * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEMPTR + 16 + 1024;  // + slack for the 1024-B alignment
@@ -170,13 +170,16 @@ __device__ __forceinline__ void epi_store_half_split(const uint32_t (&v)[32], in
 // weight matrix is followed by its lo matrix at row n_total, and the K loop runs three passes into the same
 // accumulator: x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (the dropped lo*lo term is 2^-18 relative).  The epilogue
 // splits the fp32 result again (STAGING == 2: one staging tile per plane).
-template <int BLOCK_N, int STAGES, int STAGING, bool SPLIT>
-__global__ void __launch_bounds__(256, 1)
+// EPI_WG = 2: two epilogue warpgroups (warps 4-7 and 8-11); warpgroup g drains TMEM accumulator g, i.e. every
+// other tile of the CTA, with its own staging buffers.  The transposed convolutions (K = Cin, one or four taps)
+// are bound by the epilogue, not by the MMAs: one warpgroup needs ~2.5 k cycles per 128 x 64 chunk.
+template <int BLOCK_N, int STAGES, int STAGING, bool SPLIT, int EPI_WG>
+__global__ void __launch_bounds__(128 + 128 * EPI_WG, 1)
     igemm_fwd_kernel(const __grid_constant__ TmapPack8 amaps,
                      const __grid_constant__ CUtensorMap bmap,
                      const __grid_constant__ TmapPack8 omaps, const FwdParams p) {
   static_assert(!SPLIT || STAGING == 2, "bf16x3 mode stages a hi and a lo tile");
-  using L = FwdSmem<BLOCK_N, STAGES, STAGING>;
+  using L = FwdSmem<BLOCK_N, STAGES, STAGING, EPI_WG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t sbase = (raw_addr + 1023u) & ~1023u;
@@ -293,18 +296,21 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    // ------------------------------------------------------------------ epilogue (4 warps per warpgroup)
+    const int wg = (warp - 4) >> 2;  // warpgroup: drains the tiles it = wg, wg + EPI_WG, ...
+    const int q = warp & 3;          // the TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;
-    float* s_scale = reinterpret_cast<float*>(gbase + L::OFF_PARAM);
+    const int et = threadIdx.x - 128 - wg * 128;
+    const uint32_t bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
+    const uint32_t off_stg = L::OFF_STG + wg * STAGING * L::STG_BYTES;
+    float* s_scale = reinterpret_cast<float*>(gbase + L::OFF_PARAM) + wg * 4 * BLOCK_N;
     float* s_shift = s_scale + BLOCK_N;
     float* s_sum = s_shift + BLOCK_N;
     float* s_sq = s_sum + BLOCK_N;
     const bool do_stats = p.stat_sum != nullptr;
-    int it = 0;
+    int it = wg;
     int chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x + wg * gridDim.x; tile < total_tiles; tile += EPI_WG * gridDim.x, it += EPI_WG) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int w0 = (m_tile % p.tiles_w) * p.TW;
@@ -349,9 +355,9 @@ __global__ void __launch_bounds__(256, 1)
         const int sb = (STAGING == 2 && !SPLIT) ? (chunk_ctr & 1) : 0;
         // staging buffer `sb` (bf16x3: both buffers) no longer being read by an earlier store
         if (et == 0) tma_store_wait_read<SPLIT ? 0 : STAGING - 1>();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_a, 128);
 
-        uint8_t* stg = gbase + L::OFF_STG + sb * L::STG_BYTES;
+        uint8_t* stg = gbase + off_stg + sb * L::STG_BYTES;
         if (SPLIT) {
           epi_store_half_split(v0, 0, s_scale + chunk * 64, s_shift + chunk * 64, p.relu, valid, stg,
                                stg + L::STG_BYTES, row);
@@ -363,13 +369,13 @@ __global__ void __launch_bounds__(256, 1)
                          stg, row);
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(bar_b, 128);
         if (et == 0) {
           const int col = col0 + chunk * 64;
-          tma_store_4d(&omaps.m[col / p.cout_per_view], sbase + L::OFF_STG + sb * L::STG_BYTES,
+          tma_store_4d(&omaps.m[col / p.cout_per_view], sbase + off_stg + sb * L::STG_BYTES,
                        col % p.cout_per_view, w0, h0, n0);
           if (SPLIT)
-            tma_store_4d(&omaps.m[4 + col / p.cout_per_view], sbase + L::OFF_STG + L::STG_BYTES,
+            tma_store_4d(&omaps.m[4 + col / p.cout_per_view], sbase + off_stg + L::STG_BYTES,
                          col % p.cout_per_view, w0, h0, n0);
           tma_store_commit();
         }
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(256, 1)
         }
       }
       if (do_stats) {
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_a, 128);
         for (int c = et; c < BLOCK_N; c += 128) {
           const int ch = (col0 + c) % p.cout_per_view;
           // fp64 accumulators: a channel with |mean| >> std loses its variance to cancellation in fp32
@@ -414,13 +420,14 @@ __global__ void __launch_bounds__(256, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  static_assert(EPI_WG == 1 || EPI_WG == 2, "one or two epilogue warpgroups");
 }
 
-template <int BLOCK_N, int STAGES, int STAGING, bool SPLIT = false>
+template <int BLOCK_N, int STAGES, int STAGING, bool SPLIT = false, int EPI_WG = 1>
 static int launch_fwd_inst(const TmapPack8& amaps, const CUtensorMap& bmap, const TmapPack8& omaps,
                            const FwdParams& p, int total_tiles, cudaStream_t stream) {
-  using L = FwdSmem<BLOCK_N, STAGES, STAGING>;
-  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES, STAGING, SPLIT>;
+  using L = FwdSmem<BLOCK_N, STAGES, STAGING, EPI_WG>;
+  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES, STAGING, SPLIT, EPI_WG>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -431,7 +438,7 @@ static int launch_fwd_inst(const TmapPack8& amaps, const CUtensorMap& bmap, cons
     return -2;
   }
   const int grid = std::min(total_tiles, num_sms());
-  kern<<<grid, 256, L::TOTAL, stream>>>(amaps, bmap, omaps, p);
+  kern<<<grid, 128 + 128 * EPI_WG, L::TOTAL, stream>>>(amaps, bmap, omaps, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error(std::string("igemm_fwd launch: ") + cudaGetErrorString(e));
@@ -1184,10 +1191,18 @@ int launch_igemm_fwd(const FwdDesc& d) {
       default:  return launch_fwd_inst<64, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
     }
   }
+  static const bool one_wg = getenv("PLUME_FWD_ONE_EPILOGUE_WG") != nullptr;   // A/B switch (scripts/time_convT.py)
+  if (one_wg) {
+    switch (block_n) {
+      case 256: return launch_fwd_inst<256, 4, 1>(amaps, bmap, omaps, p, (int)total, d.stream);
+      case 128: return launch_fwd_inst<128, 5, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+      default:  return launch_fwd_inst<64, 6, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+    }
+  }
   switch (block_n) {
-    case 256: return launch_fwd_inst<256, 4, 1>(amaps, bmap, omaps, p, (int)total, d.stream);
-    case 128: return launch_fwd_inst<128, 5, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
-    default:  return launch_fwd_inst<64, 6, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+    case 256: return launch_fwd_inst<256, 3, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+    case 128: return launch_fwd_inst<128, 4, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+    default:  return launch_fwd_inst<64, 6, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
   }
 }
 

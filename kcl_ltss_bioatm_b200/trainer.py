@@ -47,6 +47,35 @@ def init_distributed(device_type: str = "cuda"):
     return rank, world, local, dist.group.WORLD
 
 
+class LossLog:
+    """Reads every step's [loss, bce, dice] on the host without idling the GPU.  ``push(out)`` enqueues the
+    device->host copy of this step's result into a pinned ring slot (behind the step, on the current stream) and
+    returns the PREVIOUS step's values, waiting only for that older copy's event; the host can therefore launch
+    step i+1 before step i has finished.  ``flush()`` returns the last step's values.  Every step is read exactly
+    once, one step late."""
+
+    def __init__(self, depth: int = 2):
+        self._slots = [(torch.empty(3, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(max(2, depth))]
+        self._n = 0
+        self.bytes_per_step = 12
+
+    def _read(self, i: int):
+        buf, ev = self._slots[i % len(self._slots)]
+        ev.synchronize()
+        return buf.tolist()
+
+    def push(self, out: torch.Tensor):
+        prev = self._read(self._n - 1) if self._n else None
+        buf, ev = self._slots[self._n % len(self._slots)]
+        buf.copy_(out, non_blocking=True)
+        ev.record()
+        self._n += 1
+        return prev
+
+    def flush(self):
+        return self._read(self._n - 1) if self._n else None
+
+
 class Trainer:
     def __init__(self, spec: UNetSpec = UNetSpec(), device="cuda", process_group=None, ops=None,
                  seed: int = 0, micro_batches: int = 1, bucket_mb: float = 25.0):
@@ -182,9 +211,11 @@ class Trainer:
             g.clear()
 
     def fit(self, steps: int, batch_fn: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
-            log_every: int = 10, on_step: Optional[Callable[[int, float], None]] = None):
+            log_every: int = 10, on_step: Optional[Callable[[int, float], None]] = None, graphed: bool = False):
         """batch_fn(i) returns this rank's shard of batch i: device tensors, or (pinned) host tensors, which are
-        then copied `depth` batches ahead on a copy stream (DevicePrefetcher)."""
+        then copied `depth` batches ahead on a copy stream (DevicePrefetcher).  graphed=True replays the step from
+        a CUDA graph (step_graphed).  On a GPU every step's loss is read through a LossLog, one step late, so the
+        host never waits for the step it has just launched; `on_step(i, loss)` sees every step."""
         from .data import DevicePrefetcher
 
         losses = []
@@ -196,16 +227,29 @@ class Trainer:
                 yield batch_fn(it)
 
         stream = batches()
-        if first[0].device.type == "cpu" and self.model.device.type == "cuda":
+        on_gpu = self.model.device.type == "cuda"
+        if first[0].device.type == "cpu" and on_gpu:
             stream = DevicePrefetcher(stream, self.model.device)
-        for it, (x, t) in enumerate(stream):
-            out = self.step(x, t)
+        step_fn = self.step_graphed if graphed else self.step
+        ring = LossLog() if on_gpu else None
+
+        def report(it, v):
             if log_every and (it % log_every == 0 or it == steps - 1):
-                v = out.detach().float().cpu().tolist()  # host sync only when logging
                 losses.append((it, v[0]))
                 self.log.info("step %d loss %.5f (bce %.5f dice %.5f)", it, v[0], v[1], v[2])
-                if on_step:
-                    on_step(it, v[0])
+            if on_step:
+                on_step(it, v[0])
+
+        for it, (x, t) in enumerate(stream):
+            out = step_fn(x, t)
+            if ring is None:
+                report(it, out.detach().float().cpu().tolist())
+            else:
+                prev = ring.push(out)
+                if prev is not None:
+                    report(it - 1, prev)
+        if ring is not None and steps > 0:
+            report(steps - 1, ring.flush())
         return losses
 
     # ------------------------------------------------------------------ checkpoint / resume
