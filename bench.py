@@ -565,6 +565,40 @@ def run_config4(ranks, rank, world, pg, dev, peak_tf):
     return out
 
 
+def run_modes(ranks, rank, world, pg, dev):
+    """The headline step (configs[1]) in the two optional modes, at this N: deterministic reductions
+    (PLUME_DETERMINISTIC) and the bf16x3 high-precision arithmetic (north_star's "tf32 mode" bar)."""
+    import torch
+
+    from kcl_ltss_bioatm_b200.data import synthetic_batch
+    from kcl_ltss_bioatm_b200.spec import UNetSpec
+    from kcl_ltss_bioatm_b200.trainer import Trainer
+
+    out = {}
+    for name, spec, det, n in (("deterministic", UNetSpec(), True, BATCH), ("bf16x3", UNetSpec(precision="bf16x3"), False, 8)):
+        tr = Trainer(spec, device=dev, process_group=pg, seed=0)
+        tr.model.ops.set_deterministic(det)
+        try:
+            x, t = synthetic_batch(n, TILE, TILE, spec.in_channels, seed=900 + rank)
+            x, t = x.to(dev), t.to(dev)
+            graphed = pg is None or tr.graph_dp
+            step = tr.step_graphed if graphed else tr.step
+            ms = timed_steps(ranks, lambda i: step(x, t), 3, 6)
+            out[name] = {"workload": f"configs[1] network, {n} tiles of {TILE}x{TILE} per GPU, one training step",
+                         "n_gpus": world, "per_gpu_batch": n, "ms_per_step": ms, "tiles_per_s": world * n / (ms * 1e-3),
+                         "steps": 6, "warmup": 3, "final_loss": float(tr.model.loss_out[0].item())}
+            tr.release_graphs()
+        finally:
+            tr.model.ops.set_deterministic(False)
+        del tr, x, t
+        torch.cuda.empty_cache()
+    out["deterministic"]["note"] = ("ordered partial-sum reductions instead of fp atomics, one MMA issuer in the 3x3 "
+                                    "weight gradient: bit-identical runs (tests/test_gpu_determinism.py)")
+    out["bf16x3"]["note"] = ("activations / operands as bf16 hi+lo pairs, three tcgen05 passes per GEMM through the generic "
+                             "kernels: logits within 2e-5 of the fp32 oracle (tests/test_gpu_precise.py)")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
@@ -678,8 +712,9 @@ def _run_gpu(args):
     wanted = {c.strip() for c in args.configs.split(",") if c.strip()}
     for key, fn in (("configs[2]", lambda: run_config2(ranks, rank, world, pg, dev, peak_tf)),
                     ("configs[3]", lambda: run_config3(ranks, rank, world, dev, peak_tf)),
-                    ("configs[4]", lambda: run_config4(ranks, rank, world, pg, dev, peak_tf))):
-        if key[8] not in wanted:
+                    ("configs[4]", lambda: run_config4(ranks, rank, world, pg, dev, peak_tf)),
+                    ("modes", lambda: run_modes(ranks, rank, world, pg, dev))):
+        if (key[8] if key.startswith("configs") else "m") not in wanted:
             continue
         try:
             t0 = time.perf_counter()
@@ -782,8 +817,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--configs", default="2,3,4",
-                    help="which of the other BASELINE.json configs (indices 2, 3, 4) to measure as extra keys; '' = none")
+    ap.add_argument("--configs", default="2,3,4,m",
+                    help="which of the other BASELINE.json configs (indices 2, 3, 4; m = the deterministic and bf16x3 modes) to measure as extra keys; empty = none")
     ap.add_argument("--per-layer-out", default=None, help="also write the per-layer table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":

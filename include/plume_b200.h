@@ -32,6 +32,14 @@ const char* plume_version(void);
 const char* plume_last_error(void);
 /* Diagnostic word written by a kernel whose bounded barrier wait expired (0 = none). */
 int plume_debug_word(void);
+/* Deterministic mode (also PLUME_DETERMINISTIC=1 in the environment, read at the first call): every reduction
+ * that normally ends in floating-point atomics -- BatchNorm statistics, BatchNorm-backward / bias / head sums, the
+ * split-K weight gradients -- writes per-block partial sums to a library-owned scratch buffer and a second kernel
+ * adds them in block order; the 3x3 weight-gradient kernel runs a single MMA issuer.  Repeated runs are then
+ * bit-identical (tests/test_gpu_determinism.py).  The scratch grows with cudaMalloc on demand, which is not allowed
+ * inside a stream capture: run one un-captured step first (Trainer.step_graphed does). */
+void plume_set_deterministic(int on);
+int plume_get_deterministic(void);
 int plume_num_sms(void);
 /* Diagnostics: device buffer [num_sms][8] of int64 that the conv3x3 kernel fills with per-CTA cycle
  * counters of its producer / MMA / epilogue roles (NULL = off, the default). */
@@ -185,6 +193,22 @@ int plume_adam(float* param, const float* grad, float* m, float* v, long long n,
 int plume_adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,
                    plume_stream_t stream);
 
+/* ---- producers fused with the BatchNorm-backward reduction ----------------------------------------------------
+ * The gradient these two kernels write (dx of the pool backward, dfeat of the head backward) is the `da` of the
+ * BatchNorm layer in front of them.  The _bn variants also accumulate that layer's sum_g / sum_gx (exactly what
+ * plume_bn_bwd_reduce(da, y, ...) would add, computed from the rounded gradient they store), reading y once instead
+ * of running a separate pass over da and y.  Arguments: those of the plain function, then y / ldy / scale / shift /
+ * mean / invstd / relu / sum_g / sum_gx with plume_bn_bwd_reduce's meaning. */
+int plume_maxpool2x2_bwd_bn(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
+                            void* dx, int lddx, const void* y, int ldy, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, int relu, float* sum_g, float* sum_gx, int N,
+                            int H, int W, int C, plume_stream_t stream);
+int plume_head_bwd_bn(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                      const float* sums, float bce_weight, float dice_weight, float dice_eps, float grad_scale,
+                      void* dfeat, int lddf, float* dw, float* db, const void* y, int ldy, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
+                      float* sum_gx, long long pixels, int C, plume_stream_t stream);
+
 /* ---- bf16x3 high-precision mode (BASELINE.json's north_star: "1e-3 (tf32 mode)") ----------------------------
  * Every activation value is stored as hi + lo, two bf16 numbers (hi = bf16(v), lo = bf16(v - hi): 16 significant
  * bits, 4 bytes per value like fp32), in two channel planes per pixel: the pixel stride `ld*` (bf16 elements, a
@@ -228,6 +252,15 @@ int plume_head_bwd_x3(const void* feat, int ldf, const float* w, const float* lo
 int plume_extract_tiles_x3(const void* scene, int Hs, int Ws, int Cs, const int* ys, const int* xs,
                         int count, int T, void* tiles, int Cd, plume_stream_t stream);
 
+int plume_maxpool2x2_bwd_bn_x3(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
+                               void* dx, int lddx, const void* y, int ldy, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, int relu, float* sum_g, float* sum_gx, int N,
+                               int H, int W, int C, plume_stream_t stream);
+int plume_head_bwd_bn_x3(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                         const float* sums, float bce_weight, float dice_weight, float dice_eps, float grad_scale,
+                         void* dfeat, int lddf, float* dw, float* db, const void* y, int ldy, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
+                         float* sum_gx, long long pixels, int C, plume_stream_t stream);
 int plume_conv3x3_fwd_x3(const void* x, int ldx, const void* w, const float* scale, const float* shift,
                          int relu, void* y, int ldy, double* stat_sum, double* stat_sq, int N, int H, int W,
                          int Cin, int Cout, plume_stream_t stream);

@@ -59,6 +59,8 @@ const char* plume_version(void) { return "plume_b200 0.1 (sm_100a; tcgen05+TMA i
 const char* plume_last_error(void) { return g_last_error.c_str(); }
 int plume_debug_word(void) { return read_debug_word(); }
 void plume_debug_set_prof(long long* buf) { set_prof_buffer(buf); }
+void plume_set_deterministic(int on) { set_deterministic(on); }
+int plume_get_deterministic(void) { return deterministic() ? 1 : 0; }
 int plume_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -365,6 +367,55 @@ int plume_maxpool2x2_bwd_x3(const void* dy, int lddy, const uint8_t* argmax, con
                          int lddskip, void* dx, int lddx, int N, int H, int W, int C,
                          plume_stream_t stream) {
   return impl_maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, stream, 1);
+}
+
+static int impl_maxpool2x2_bwd_bn(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
+                                  void* dx, int lddx, const void* y, int ldy, const float* scale, const float* shift,
+                                  const float* mean, const float* invstd, int relu, float* sum_g, float* sum_gx,
+                                  int N, int H, int W, int C, plume_stream_t stream, int dt) {
+  PLUME_CHECK(dy && argmax && dx, "maxpool2x2_bwd_bn: null pointer");
+  BnReduceArgs bn{y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, nullptr};
+  return maxpool2x2_bwd(dy, lddy, argmax, dskip, lddskip, dx, lddx, N, H, W, C, dt, S(stream), &bn);
+}
+int plume_maxpool2x2_bwd_bn(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
+                            void* dx, int lddx, const void* y, int ldy, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, int relu, float* sum_g, float* sum_gx, int N,
+                            int H, int W, int C, plume_stream_t stream) {
+  return impl_maxpool2x2_bwd_bn(dy, lddy, argmax, dskip, lddskip, dx, lddx, y, ldy, scale, shift, mean, invstd, relu,
+                                sum_g, sum_gx, N, H, W, C, stream, 0);
+}
+int plume_maxpool2x2_bwd_bn_x3(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
+                               void* dx, int lddx, const void* y, int ldy, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, int relu, float* sum_g, float* sum_gx, int N,
+                               int H, int W, int C, plume_stream_t stream) {
+  return impl_maxpool2x2_bwd_bn(dy, lddy, argmax, dskip, lddskip, dx, lddx, y, ldy, scale, shift, mean, invstd, relu,
+                                sum_g, sum_gx, N, H, W, C, stream, 1);
+}
+static int impl_head_bwd_bn(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                            const float* sums, float bce_weight, float dice_weight, float dice_eps, float grad_scale,
+                            void* dfeat, int lddf, float* dw, float* db, const void* y, int ldy, const float* scale,
+                            const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
+                            float* sum_gx, long long pixels, int C, plume_stream_t stream, int dt) {
+  PLUME_CHECK(feat && w && logits && target && sums && dfeat && dw && db, "head_bwd_bn: null pointer");
+  BnReduceArgs bn{y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, nullptr};
+  return head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat, lddf, dw,
+                  db, pixels, C, dt, S(stream), &bn);
+}
+int plume_head_bwd_bn(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                      const float* sums, float bce_weight, float dice_weight, float dice_eps, float grad_scale,
+                      void* dfeat, int lddf, float* dw, float* db, const void* y, int ldy, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
+                      float* sum_gx, long long pixels, int C, plume_stream_t stream) {
+  return impl_head_bwd_bn(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat,
+                          lddf, dw, db, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C, stream, 0);
+}
+int plume_head_bwd_bn_x3(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
+                         const float* sums, float bce_weight, float dice_weight, float dice_eps, float grad_scale,
+                         void* dfeat, int lddf, float* dw, float* db, const void* y, int ldy, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
+                         float* sum_gx, long long pixels, int C, plume_stream_t stream) {
+  return impl_head_bwd_bn(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat,
+                          lddf, dw, db, y, ldy, scale, shift, mean, invstd, relu, sum_g, sum_gx, pixels, C, stream, 1);
 }
 
 static int impl_bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,

@@ -57,6 +57,84 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// ---- deterministic mode ---------------------------------------------------------------------------
+// PLUME_DETERMINISTIC=1 (or plume_set_deterministic): every reduction that normally ends in floating-point atomics
+// (no fixed order) instead writes per-block partial sums to a library-owned scratch buffer and a second small
+// kernel adds them up in block order, one thread per output element.  Inside a block the per-thread partials are
+// combined in thread order.  Two runs then produce bit-identical results.
+int g_det = -1;
+struct DetScratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+DetScratch g_scratch[2];
+}  // namespace
+
+bool deterministic() {
+  if (g_det < 0) {
+    const char* e = getenv("PLUME_DETERMINISTIC");
+    g_det = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_det == 1;
+}
+void set_deterministic(int on) { g_det = on ? 1 : 0; }
+
+// which: 0 = bandwidth-kernel and conv-statistics reductions (main / chain stream), 1 = weight gradients (side stream).
+// Grown with cudaMalloc when too small -- never inside a stream capture (the un-captured warm-up step sizes it).
+void* det_scratch(int which, size_t bytes) {
+  DetScratch& sc = g_scratch[which];
+  if (sc.bytes < bytes) {
+    // an outgrown buffer is NOT freed: a captured CUDA graph may still hold its address
+    sc.ptr = nullptr;
+    sc.bytes = 0;
+    const size_t want = std::max(bytes + bytes / 2, static_cast<size_t>(32) << 20);
+    if (cudaMalloc(&sc.ptr, want) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("deterministic mode: cannot allocate the partial-sum scratch (inside a stream capture?)");
+      return nullptr;
+    }
+    sc.bytes = want;
+  }
+  return sc.ptr;
+}
+
+// out[c] += sum over b (in order) of part[b * n + c], c < n
+__global__ void ordered_sum_kernel(const float* __restrict__ part, int blocks, int n, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += part[static_cast<size_t>(b) * n + c];
+  out[c] += s;
+}
+__global__ void ordered_sum_f64_kernel(const double* __restrict__ part, int blocks, int row, int n,
+                                       double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += part[static_cast<size_t>(b) * row + c];
+  out[c] += s;
+}
+int ordered_sum_f64(const double* part, int blocks, int row, int n, double* out, cudaStream_t s) {
+  ordered_sum_f64_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, blocks, row, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("ordered_sum_f64: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+int ordered_sum(const float* part, int blocks, int n, float* out, cudaStream_t s) {
+  ordered_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, blocks, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("ordered_sum: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+namespace {
+
 struct alignas(16) BF8 {
   uint32_t u[4];
 };
@@ -191,12 +269,37 @@ __device__ __forceinline__ void ld_f8(const float* p, float (&f)[8]) {
 // Threads with the same channel group first combine in shared memory, then one atomic per channel.
 template <int K>
 __device__ __forceinline__ void block_channel_reduce(float (&acc)[K][8], int cv_idx, int CV,
-                                                     float* const (&out)[K], float* s_acc) {
-  // s_acc: K * min(CV,256) * 8 floats, zeroed here
+                                                     float* const (&out)[K], float* s_acc,
+                                                     float* det_part = nullptr) {
   const int span = min(CV, kThreads);
+  const int slot = cv_idx % span;
+  const int cv_block_base = cv_idx - slot;  // identical for all threads of the block (see grid_for)
+  if (det_part != nullptr) {
+    // deterministic: s_acc holds every thread's partials (kThreads * K * 8 floats); output element (k, slot, e)
+    // is summed by ONE thread over the contributing threads in thread order (slot(t) = (slot(0) + t) % span),
+    // then stored to this block's row of the partial-sum scratch: part[block][k][C] (zeroed by the launcher)
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_acc[(threadIdx.x * K + k) * 8 + e] = acc[k][e];
+    __shared__ int s_slot0;
+    if (threadIdx.x == 0) s_slot0 = slot;
+    __syncthreads();
+    const int slot0 = s_slot0;
+    const int C = CV * 8;
+    for (int i = threadIdx.x; i < K * span * 8; i += kThreads) {
+      const int k = i / (span * 8);
+      const int r = i % (span * 8);
+      const int sl = r >> 3, e = r & 7;
+      float v = 0.f;
+      for (int t = (sl - slot0 + span) % span; t < kThreads; t += span) v += s_acc[(t * K + k) * 8 + e];
+      det_part[(static_cast<size_t>(blockIdx.x) * K + k) * C + cv_block_base * 8 + r] = v;
+    }
+    return;
+  }
+  // s_acc: K * min(CV,256) * 8 floats, zeroed here
   for (int i = threadIdx.x; i < K * span * 8; i += kThreads) s_acc[i] = 0.f;
   __syncthreads();
-  const int slot = cv_idx % span;
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -205,13 +308,59 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[K][8], int cv_
   // which global channel does smem slot s map to?  slot = cv % span and cv = (tid + const) % CV with
   // the loop-invariant mapping, so slot s holds channel group (cv0 - cv0 % span) + s where cv0 is this
   // block's first channel group; when CV <= 256, span == CV and the group is simply s.
-  const int cv_block_base = cv_idx - slot;  // identical for all threads of the block (see grid_for)
   for (int i = threadIdx.x; i < K * span * 8; i += kThreads) {
     const int k = i / (span * 8);
     const int r = i % (span * 8);
     const float v = s_acc[i];
     if (v != 0.f) atomicAdd(out[k] + cv_block_base * 8 + r, v);
   }
+}
+
+// Host side of a deterministic channel reduction: scratch for `grid` blocks x K x C partial sums (zeroed: a
+// block only writes the channel groups it covers), and the ordered final sums into out[k].
+struct DetReduce {
+  float* part = nullptr;
+  int grid = 0, K = 0, C = 0;
+  int begin(int grid_, int K_, int C_, cudaStream_t s) {
+    grid = grid_; K = K_; C = C_;
+    if (!deterministic()) return 0;
+    const size_t bytes = static_cast<size_t>(grid) * K * C * sizeof(float);
+    part = static_cast<float*>(det_scratch(0, bytes));
+    if (!part) return -2;
+    if (cudaMemsetAsync(part, 0, bytes, s) != cudaSuccess) {
+      set_error("deterministic reduction: cudaMemsetAsync failed");
+      return -2;
+    }
+    return 0;
+  }
+  // dynamic shared memory a reducing kernel needs
+  size_t smem(int CV) const {
+    return part ? static_cast<size_t>(kThreads) * K * 8 * sizeof(float)
+                : static_cast<size_t>(K) * std::min(CV, kThreads) * 8 * sizeof(float);
+  }
+  // out[k] += ordered sum; the K arrays are separate pointers
+  int finish(float* const* outs, cudaStream_t s) const {
+    if (!part) return 0;
+    for (int k = 0; k < K; ++k) {
+      if (!outs[k]) continue;
+      // row stride between blocks is K*C: view plane k as `grid` rows of K*C with offset k*C
+      ordered_sum_strided(k, outs[k], s);
+    }
+    return 0;
+  }
+  void ordered_sum_strided(int k, float* out, cudaStream_t s) const;
+};
+
+__global__ void ordered_sum_strided_kernel(const float* __restrict__ part, int blocks, int row, int n,
+                                           float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += part[static_cast<size_t>(b) * row + c];
+  out[c] += s;
+}
+void DetReduce::ordered_sum_strided(int k, float* out, cudaStream_t s) const {
+  ordered_sum_strided_kernel<<<(C + 255) / 256, 256, 0, s>>>(part + static_cast<size_t>(k) * C, grid, K * C, C, out);
 }
 
 }  // namespace
@@ -481,17 +630,54 @@ int maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, in
                      dt, s);
 }
 
+// Optional fused BatchNorm-backward reduction: the gradient a kernel has just produced (dx of the pool backward,
+// dfeat of the head backward) is the `da` of the BatchNorm in front of it, so the kernel can accumulate
+// sum(g) and sum(g * xhat) (g = da masked by ReLU) itself -- one extra read of y instead of a separate
+// bn_bwd_reduce pass over da AND y.  The sums use the ROUNDED gradient, i.e. what bn_bwd_apply will read back.
 template <typename T>
+struct BnReduceState {
+  float sc[8], sh[8], mu[8], is[8];
+  float acc[2][8];
+  __device__ __forceinline__ void init(const BnReduceArgs& a, int cv) {
+    ld_f8(a.scale + cv * 8, sc);
+    ld_f8(a.shift + cv * 8, sh);
+    ld_f8(a.mean + cv * 8, mu);
+    ld_f8(a.invstd + cv * 8, is);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+  }
+  // v: the stored (rounded) gradient of pixel p
+  __device__ __forceinline__ void add(const BnReduceArgs& a, const typename Act<T>::V8& v, long long p, int cv) {
+    float g[8], yy[8];
+    Act<T>::unpack(v, g);
+    Act<T>::unpack(Act<T>::ld_stream(static_cast<const T*>(a.y) + p * a.ldy + cv * 8, a.ldy >> 1), yy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gg = (!a.relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
+      acc[0][e] += gg;
+      acc[1][e] = fmaf(gg, (yy[e] - mu[e]) * is[e], acc[1][e]);
+    }
+  }
+  __device__ __forceinline__ void finish(const BnReduceArgs& a, int cv, int CV, float* s_acc) {
+    float* const outs[2] = {a.sum_g, a.sum_gx};
+    block_channel_reduce<2>(acc, cv, CV, outs, s_acc, a.det_part);
+  }
+};
+
+template <typename T, bool kReduce>
 __global__ void __launch_bounds__(kThreads)
     maxpool_bwd_kernel(const T* __restrict__ dy, long long lddy,
                        const uint8_t* __restrict__ argmax, const T* __restrict__ dskip,
                        long long lddskip, T* __restrict__ dx, long long lddx, int N, int Ho,
-                       int Wo, int CV) {
+                       int Wo, int CV, const BnReduceArgs bn) {
+  extern __shared__ float s_acc[];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
   const long long pstep = (1ll * gridDim.x * kThreads) / CV;
   const long long opix = 1ll * N * Ho * Wo;
   const int W = 2 * Wo;
+  BnReduceState<T> red;
+  if (kReduce) red.init(bn, cv);
   for (long long op = i0 / CV; op < opix; op += pstep) {
     const int wo = static_cast<int>(op % Wo);
     const long long t = op / Wo;
@@ -516,29 +702,64 @@ __global__ void __launch_bounds__(kThreads)
         const uint32_t bi = ((e < 4 ? am.x : am.y) >> (8 * (e & 3))) & 0xffu;
         if (bi == static_cast<uint32_t>(k)) o[e] += g[e];
       }
-      Act<T>::st(dx + off[k] * lddx + cv * 8, lddx >> 1, Act<T>::pack(o));
+      const typename Act<T>::V8 ov = Act<T>::pack(o);
+      Act<T>::st(dx + off[k] * lddx + cv * 8, lddx >> 1, ov);
+      if (kReduce) red.add(bn, ov, off[k], cv);
     }
   }
+  if (kReduce) red.finish(bn, cv, CV, s_acc);
+}
+
+static int bn_reduce_check(const BnReduceArgs* bn, const char* who) {
+  if (!bn) return 0;
+  if (!bn->y || !bn->scale || !bn->shift || !bn->mean || !bn->invstd || !bn->sum_g || !bn->sum_gx || bn->ldy % 8) {
+    set_error(std::string(who) + ": incomplete BatchNorm-reduction arguments");
+    return -1;
+  }
+  return 0;
 }
 
 int maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
-                   void* dx, int lddx, int N, int H, int W, int C, int dt, cudaStream_t s) {
+                   void* dx, int lddx, int N, int H, int W, int C, int dt, cudaStream_t s,
+                   const BnReduceArgs* bn_in) {
   if (C % 8 || lddy % 8 || lddx % 8 || (dskip && lddskip % 8) || C <= 0) {
     set_error("maxpool_bwd: channels/strides must be multiples of 8");
     return -1;
   }
-  if ((H & 1) || (W & 1)) {
+  if (H % 2 || W % 2) {
     set_error("maxpool_bwd: H and W must be even");
     return -1;
   }
+  if (bn_reduce_check(bn_in, "maxpool_bwd")) return -1;
   if (N <= 0 || H <= 0 || W <= 0) return 0;
   const int CV = C / 8;
   const long long work = 1ll * N * (H / 2) * (W / 2) * CV;
-  const int grid = grid_for(work, CV);
-  PLUME_ACT_DISPATCH(dt, (maxpool_bwd_kernel<T><<<grid, kThreads, 0, s>>>(
-                             static_cast<const T*>(dy), lddy, argmax, static_cast<const T*>(dskip), lddskip,
-                             static_cast<T*>(dx), lddx, N, H / 2, W / 2, CV)));
-  return check_launch("maxpool2x2_bwd");
+  BnReduceArgs bn{};
+  DetReduce dr;
+  int grid = grid_for(work, CV);
+  size_t smem = 0;
+  if (bn_in) {
+    bn = *bn_in;
+    grid = grid_for(work, CV, 4, 4);
+    if (dr.begin(grid, 2, C, s)) return -2;
+    bn.det_part = dr.part;
+    smem = dr.smem(CV);
+  }
+  PLUME_ACT_DISPATCH(dt, {
+    auto a0 = static_cast<const T*>(dy);
+    auto a1 = static_cast<const T*>(dskip);
+    auto a2 = static_cast<T*>(dx);
+    if (bn_in)
+      maxpool_bwd_kernel<T, true><<<grid, kThreads, smem, s>>>(a0, lddy, argmax, a1, lddskip, a2, lddx, N, H / 2,
+                                                               W / 2, CV, bn);
+    else
+      maxpool_bwd_kernel<T, false><<<grid, kThreads, 0, s>>>(a0, lddy, argmax, a1, lddskip, a2, lddx, N, H / 2,
+                                                             W / 2, CV, bn);
+  });
+  if (int r = check_launch("maxpool2x2_bwd")) return r;
+  if (!bn_in) return 0;
+  float* const outs[2] = {bn.sum_g, bn.sum_gx};
+  return dr.finish(outs, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -550,7 +771,7 @@ __global__ void __launch_bounds__(kThreads)
                          const T* __restrict__ y, long long ldy,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                         float* sum_g, float* sum_gx, long long pixels, int CV) {
+                         float* sum_g, float* sum_gx, long long pixels, int CV, float* det_part) {
   extern __shared__ float s_acc[];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
@@ -597,7 +818,7 @@ __global__ void __launch_bounds__(kThreads)
     }
   }
   float* const outs[2] = {sum_g, sum_gx};
-  block_channel_reduce<2>(acc, cv, CV, outs, s_acc);
+  block_channel_reduce<2>(acc, cv, CV, outs, s_acc, det_part);
 }
 
 int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
@@ -611,11 +832,15 @@ int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float*
   const int CV = C / 8;
   // two blocks per SM = what the 108 registers allow: one wave, no tail (244 -> 215 us over the five layer shapes)
   const int grid = grid_for(pixels * CV, CV, 2, 16);
-  const size_t smem = 2ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  DetReduce dr;
+  if (dr.begin(grid, 2, C, s)) return -2;
+  const size_t smem = dr.smem(CV);
   PLUME_ACT_DISPATCH(dt, (bn_bwd_reduce_kernel<T><<<grid, kThreads, smem, s>>>(
                              static_cast<const T*>(da), ldda, static_cast<const T*>(y), ldy, scale, shift, mean,
-                             invstd, relu, sum_g, sum_gx, pixels, CV)));
-  return check_launch("bn_bwd_reduce");
+                             invstd, relu, sum_g, sum_gx, pixels, CV, dr.part)));
+  if (int r = check_launch("bn_bwd_reduce")) return r;
+  float* const outs[2] = {sum_g, sum_gx};
+  return dr.finish(outs, s);
 }
 
 template <typename T>
@@ -626,7 +851,8 @@ __global__ void __launch_bounds__(kThreads)
                         const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                         const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
                         float inv_count, T* __restrict__ dy, long long lddy, float* sum_dy,
-                        float* dgamma, float* dbeta, int accumulate, long long pixels, int CV) {
+                        float* dgamma, float* dbeta, int accumulate, long long pixels, int CV,
+                        float* det_part) {
   extern __shared__ float s_acc[];
   // the finished per-channel sums are the BatchNorm parameter gradients; one block hands them over (sum_g /
   // sum_gx are a per-backward scratch, so that micro-batch accumulation never feeds stale sums into this pass)
@@ -689,7 +915,7 @@ __global__ void __launch_bounds__(kThreads)
     one(Act<T>::ld_stream(da + p * ldda + cv * 8, ldda >> 1), Act<T>::ld_stream(y + p * ldy + cv * 8, ldy >> 1), p);
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
-    block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+    block_channel_reduce<1>(acc, cv, CV, outs, s_acc, det_part);
   }
 }
 
@@ -708,12 +934,16 @@ int bn_bwd_apply(const void* da, int ldda, const void* y, int ldy, const float* 
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 2, 16);  // one wave at the kernel's occupancy (see bn_bwd_reduce)
-  const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  DetReduce dr;
+  if (sum_dy && dr.begin(grid, 1, C, s)) return -2;
+  const size_t smem = dr.part ? dr.smem(CV) : 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
   PLUME_ACT_DISPATCH(dt, (bn_bwd_apply_kernel<T><<<grid, kThreads, smem, s>>>(
                              static_cast<const T*>(da), ldda, static_cast<const T*>(y), ldy, scale, shift, mean,
                              invstd, relu, sum_g, sum_gx, 1.f / static_cast<float>(pixels), static_cast<T*>(dy),
-                             lddy, sum_dy, dgamma, dbeta, accumulate, pixels, CV)));
-  return check_launch("bn_bwd_apply");
+                             lddy, sum_dy, dgamma, dbeta, accumulate, pixels, CV, dr.part)));
+  if (int r = check_launch("bn_bwd_apply")) return r;
+  float* const outs[1] = {sum_dy};
+  return dr.finish(outs, s);
 }
 
 template <typename T>
@@ -721,7 +951,7 @@ __global__ void __launch_bounds__(kThreads)
     relu_bwd_kernel(const T* __restrict__ da, long long ldda,
                     const T* __restrict__ a, long long lda,
                     T* __restrict__ dy, long long lddy, float* sum_dy, long long pixels,
-                    int CV) {
+                    int CV, float* det_part) {
   extern __shared__ float s_acc[];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
@@ -742,7 +972,7 @@ __global__ void __launch_bounds__(kThreads)
   }
   if (sum_dy) {
     float* const outs[1] = {sum_dy};
-    block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+    block_channel_reduce<1>(acc, cv, CV, outs, s_acc, det_part);
   }
 }
 
@@ -755,17 +985,21 @@ int relu_bwd(const void* da, int ldda, const void* a, int lda, void* dy, int ldd
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4);
-  const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  DetReduce dr;
+  if (sum_dy && dr.begin(grid, 1, C, s)) return -2;
+  const size_t smem = dr.part ? dr.smem(CV) : 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
   PLUME_ACT_DISPATCH(dt, (relu_bwd_kernel<T><<<grid, kThreads, smem, s>>>(
                              static_cast<const T*>(da), ldda, static_cast<const T*>(a), lda, static_cast<T*>(dy),
-                             lddy, sum_dy, pixels, CV)));
-  return check_launch("relu_bwd");
+                             lddy, sum_dy, pixels, CV, dr.part)));
+  if (int r = check_launch("relu_bwd")) return r;
+  float* const outs[1] = {sum_dy};
+  return dr.finish(outs, s);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     channel_sum_kernel(const T* __restrict__ x, long long ldx, float* out,
-                       long long pixels, int CV) {
+                       long long pixels, int CV, float* det_part) {
   extern __shared__ float s_acc[];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
@@ -780,7 +1014,7 @@ __global__ void __launch_bounds__(kThreads)
     for (int e = 0; e < 8; ++e) acc[0][e] += f[e];
   }
   float* const outs[1] = {out};
-  block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+  block_channel_reduce<1>(acc, cv, CV, outs, s_acc, det_part);
 }
 
 int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, int dt, cudaStream_t s) {
@@ -791,10 +1025,14 @@ int channel_sum(const void* x, int ldx, float* out, long long pixels, int C, int
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4, 16);
-  const size_t smem = 1ull * std::min(CV, kThreads) * 8 * sizeof(float);
+  DetReduce dr;
+  if (dr.begin(grid, 1, C, s)) return -2;
+  const size_t smem = dr.smem(CV);
   PLUME_ACT_DISPATCH(dt, (channel_sum_kernel<T><<<grid, kThreads, smem, s>>>(static_cast<const T*>(x), ldx, out,
-                                                                            pixels, CV)));
-  return check_launch("channel_sum");
+                                                                            pixels, CV, dr.part)));
+  if (int r = check_launch("channel_sum")) return r;
+  float* const outs[1] = {out};
+  return dr.finish(outs, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -808,7 +1046,7 @@ __global__ void __launch_bounds__(kThreads)
     head_fwd_kernel(const T* __restrict__ feat, long long ldf,
                     const float* __restrict__ w, const float* __restrict__ b,
                     const uint8_t* __restrict__ target, float* __restrict__ logits, float* sums,
-                    long long pixels, int CV) {
+                    long long pixels, int CV, float* det_part) {
   __shared__ float s_red[4][kThreads / 32];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
   const int cv = static_cast<int>(i0 % CV);
@@ -882,7 +1120,8 @@ __global__ void __launch_bounds__(kThreads)
   if (threadIdx.x < 4) {
     float v = 0.f;
     for (int k = 0; k < kThreads / 32; ++k) v += s_red[threadIdx.x][k];
-    atomicAdd(sums + threadIdx.x, v);
+    if (det_part) det_part[blockIdx.x * 4 + threadIdx.x] = v;   // deterministic: summed in block order afterwards
+    else atomicAdd(sums + threadIdx.x, v);
   }
 }
 
@@ -900,9 +1139,15 @@ int head_fwd(const void* feat, int ldf, const float* w, const float* b, const ui
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4);
+  float* part = nullptr;
+  if (target && deterministic()) {
+    part = static_cast<float*>(det_scratch(0, static_cast<size_t>(grid) * 4 * sizeof(float)));
+    if (!part) return -2;
+  }
   PLUME_ACT_DISPATCH(dt, (head_fwd_kernel<T><<<grid, kThreads, 0, s>>>(static_cast<const T*>(feat), ldf, w, b,
-                                                                      target, logits, sums, pixels, CV)));
-  return check_launch("head_fwd");
+                                                                      target, logits, sums, pixels, CV, part)));
+  if (int r = check_launch("head_fwd")) return r;
+  return part ? ordered_sum(part, grid, 4, sums, s) : 0;
 }
 
 __global__ void head_loss_kernel(const float* sums, float inv_pixels, float bce_w, float dice_w,
@@ -924,14 +1169,14 @@ int head_loss(const float* sums, long long pixels, float bce_w, float dice_w, fl
   return check_launch("head_loss");
 }
 
-template <typename T>
+template <typename T, bool kReduce>
 __global__ void __launch_bounds__(kThreads)
     head_bwd_kernel(const T* __restrict__ feat, long long ldf,
                     const float* __restrict__ w, const float* __restrict__ logits,
                     const uint8_t* __restrict__ target, const float* __restrict__ sums, float inv_pixels,
                     float bce_w, float dice_w, float eps, float grad_scale,
                     T* __restrict__ dfeat, long long lddf, float* dw, float* db,
-                    long long pixels, int CV) {
+                    long long pixels, int CV, float* det_part, float* det_db, const BnReduceArgs bn) {
   extern __shared__ float s_acc[];
   __shared__ float s_db[kThreads / 32];
   const long long i0 = 1ll * blockIdx.x * kThreads + threadIdx.x;
@@ -947,6 +1192,8 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[0][e] = 0.f;
   float a_db = 0.f;
+  BnReduceState<T> red;
+  if (kReduce) red.init(bn, cv);
   auto one = [&](long long p, const typename Act<T>::V8& fv, float z, float t) {
     const float pr = sigmoidf_(z);
     const float ddice = -(2.f * t * S - I2) * invS2;
@@ -958,7 +1205,9 @@ __global__ void __launch_bounds__(kThreads)
       o[e] = dz * wv[e];
       acc[0][e] = fmaf(dz, f[e], acc[0][e]);
     }
-    Act<T>::st(dfeat + p * lddf + cv * 8, lddf >> 1, Act<T>::pack(o));
+    const typename Act<T>::V8 ov = Act<T>::pack(o);
+    Act<T>::st(dfeat + p * lddf + cv * 8, lddf >> 1, ov);
+    if (kReduce) red.add(bn, ov, p, cv);
     if (cv == 0) a_db += dz;
   };
   constexpr int U = 4;
@@ -978,33 +1227,77 @@ __global__ void __launch_bounds__(kThreads)
   for (; p < pixels; p += pstep)
     one(p, Act<T>::ld_stream(feat + p * ldf + cv * 8, ldf >> 1), __ldg(logits + p), target[p] ? 1.f : 0.f);
   float* const outs[1] = {dw};
-  block_channel_reduce<1>(acc, cv, CV, outs, s_acc);
+  block_channel_reduce<1>(acc, cv, CV, outs, s_acc, det_part);
+  if (kReduce) {
+    __syncthreads();   // s_acc is reused
+    red.finish(bn, cv, CV, s_acc);
+  }
   a_db = warp_sum(a_db);
   if ((threadIdx.x & 31) == 0) s_db[threadIdx.x >> 5] = a_db;
   __syncthreads();
   if (threadIdx.x == 0) {
     float v = 0.f;
     for (int k = 0; k < kThreads / 32; ++k) v += s_db[k];
-    atomicAdd(db, v);
+    if (det_db) det_db[blockIdx.x] = v;
+    else atomicAdd(db, v);
   }
 }
 
 int head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
              const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
-             int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s) {
+             int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s,
+             const BnReduceArgs* bn_in) {
   if (!head_cv_ok(C) || ldf % 8 || lddf % 8) {
     set_error("head_bwd: C must be 8*2^k <= 256 and strides multiples of 8");
     return -1;
   }
+  if (bn_reduce_check(bn_in, "head_bwd")) return -1;
   if (pixels <= 0) return 0;
   const int CV = C / 8;
   const int grid = grid_for(pixels * CV, CV, 4);
-  const size_t smem = 1ull * CV * 8 * sizeof(float);
-  PLUME_ACT_DISPATCH(dt, (head_bwd_kernel<T><<<grid, kThreads, smem, s>>>(
-                             static_cast<const T*>(feat), ldf, w, logits, target, sums,
-                             1.f / static_cast<float>(pixels), bce_w, dice_w, eps, grad_scale, static_cast<T*>(dfeat),
-                             lddf, dw, db, pixels, CV)));
-  return check_launch("head_bwd");
+  BnReduceArgs bn{};
+  if (bn_in) bn = *bn_in;
+  // deterministic mode: scratch = [grid][C] partial dw rows | [grid] partial db | [grid][2][C] BatchNorm sums
+  float *part_dw = nullptr, *part_db = nullptr;
+  const bool det = deterministic();
+  if (det) {
+    const size_t n_dw = static_cast<size_t>(grid) * C, n_db = grid, n_bn = bn_in ? 2 * n_dw : 0;
+    part_dw = static_cast<float*>(det_scratch(0, (n_dw + n_db + n_bn) * sizeof(float)));
+    if (!part_dw) return -2;
+    if (cudaMemsetAsync(part_dw, 0, (n_dw + n_db + n_bn) * sizeof(float), s) != cudaSuccess) {
+      set_error("head_bwd: cudaMemsetAsync failed");
+      return -2;
+    }
+    part_db = part_dw + n_dw;
+    bn.det_part = bn_in ? part_db + n_db : nullptr;
+  }
+  const int K = bn_in ? 2 : 1;
+  const size_t smem = det ? static_cast<size_t>(kThreads) * K * 8 * sizeof(float)
+                          : static_cast<size_t>(K) * CV * 8 * sizeof(float);
+  PLUME_ACT_DISPATCH(dt, {
+    auto f0 = static_cast<const T*>(feat);
+    auto f1 = static_cast<T*>(dfeat);
+    const float ip = 1.f / static_cast<float>(pixels);
+    if (bn_in)
+      head_bwd_kernel<T, true><<<grid, kThreads, smem, s>>>(f0, ldf, w, logits, target, sums, ip, bce_w, dice_w, eps,
+                                                            grad_scale, f1, lddf, dw, db, pixels, CV, part_dw, part_db,
+                                                            bn);
+    else
+      head_bwd_kernel<T, false><<<grid, kThreads, smem, s>>>(f0, ldf, w, logits, target, sums, ip, bce_w, dice_w, eps,
+                                                             grad_scale, f1, lddf, dw, db, pixels, CV, part_dw, part_db,
+                                                             bn);
+  });
+  if (int r = check_launch("head_bwd")) return r;
+  if (!det) return 0;
+  if (int r = ordered_sum(part_dw, grid, C, dw, s)) return r;
+  if (int r = ordered_sum(part_db, grid, 1, db, s)) return r;
+  if (bn_in) {
+    DetReduce dr;
+    dr.part = bn.det_part; dr.grid = grid; dr.K = 2; dr.C = C;
+    float* const outs[2] = {bn.sum_g, bn.sum_gx};
+    return dr.finish(outs, s);
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,15 @@ namespace plume {
 
 void set_error(const std::string& msg);
 
+// Deterministic mode (PLUME_DETERMINISTIC=1 / plume_set_deterministic): reductions write per-block partial sums to
+// a library-owned scratch (`which`: 0 = main / chain stream users, 1 = weight gradients on the side stream) and a
+// second kernel adds them in block order instead of floating-point atomics.
+bool deterministic();
+void set_deterministic(int on);
+void* det_scratch(int which, size_t bytes);
+int ordered_sum(const float* part, int blocks, int n, float* out, cudaStream_t s);          // out[c] += sum_b part[b*n+c]
+int ordered_sum_f64(const double* part, int blocks, int row, int n, double* out, cudaStream_t s);  // rows `row` apart
+
 int pad_channels(const void* in, int Cs, void* out, int Cd, long long pixels, int dt, cudaStream_t s);
 int bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean,
@@ -26,8 +35,18 @@ int scale_shift_act_pool(const void* y, int ldy, const float* scale, const float
                          int H, int W, int C, int dt, cudaStream_t s);
 int maxpool2x2_fwd(const void* x, int ldx, void* y, int ldy, uint8_t* argmax, int N, int H, int W,
                    int C, int dt, cudaStream_t s);
+// Optional fused BatchNorm-backward reduction of the gradient a kernel produces (see bandwidth.cu)
+struct BnReduceArgs {
+  const void* y;            // raw conv output of the BatchNorm layer (activation storage format), pixel stride ldy
+  long long ldy;
+  const float *scale, *shift, *mean, *invstd;
+  int relu;
+  float *sum_g, *sum_gx;    // added to (zeroed per backward pass by the caller)
+  float* det_part;          // internal: deterministic-mode scratch
+};
 int maxpool2x2_bwd(const void* dy, int lddy, const uint8_t* argmax, const void* dskip, int lddskip,
-                   void* dx, int lddx, int N, int H, int W, int C, int dt, cudaStream_t s);
+                   void* dx, int lddx, int N, int H, int W, int C, int dt, cudaStream_t s,
+                   const BnReduceArgs* bn = nullptr);
 int bn_bwd_reduce(const void* da, int ldda, const void* y, int ldy, const float* scale,
                   const float* shift, const float* mean, const float* invstd, int relu, float* sum_g,
                   float* sum_gx, long long pixels, int C, int dt, cudaStream_t s);
@@ -44,7 +63,8 @@ int head_loss(const float* sums, long long pixels, float bce_w, float dice_w, fl
               cudaStream_t s);
 int head_bwd(const void* feat, int ldf, const float* w, const float* logits, const uint8_t* target,
              const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
-             int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s);
+             int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s,
+             const BnReduceArgs* bn = nullptr);
 int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
          double beta2, double eps, int step, float grad_scale, cudaStream_t s);
 int adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,

@@ -15,6 +15,7 @@
 //
 // No reference counterpart: the reference repository has no model code.
 #include "igemm.cuh"
+#include "bandwidth.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -56,6 +57,22 @@ static int num_sms() {
   return n;
 }
 
+// Deterministic BatchNorm statistics: `rows` rows of [sum | sq] (c doubles each) in the scratch, zeroed; after the
+// launch the rows are added into stat_sum / stat_sq in row order.
+static double* det_stats_begin(int rows, int c, cudaStream_t s) {
+  const size_t bytes = static_cast<size_t>(rows) * 2 * c * sizeof(double);
+  double* part = static_cast<double*>(det_scratch(0, bytes));
+  if (part && cudaMemsetAsync(part, 0, bytes, s) != cudaSuccess) {
+    set_error("deterministic statistics: cudaMemsetAsync failed");
+    return nullptr;
+  }
+  return part;
+}
+static int det_stats_finish(const double* part, int rows, int c, double* stat_sum, double* stat_sq, cudaStream_t s) {
+  if (int r = ordered_sum_f64(part, rows, 2 * c, c, stat_sum, s)) return r;
+  return ordered_sum_f64(part + c, rows, 2 * c, c, stat_sq, s);
+}
+
 static int pow2_floor(int v) {
   int p = 1;
   while (p * 2 <= v) p *= 2;
@@ -90,6 +107,8 @@ struct FwdParams {
   int relu;
   double* stat_sum;
   double* stat_sq;
+  double* det_part;               // deterministic mode: per-(CTA, warpgroup) rows [sum | sq] of det_c doubles each
+  int det_c;
 };
 
 template <int BLOCK_N, int STAGES, int STAGING, int EPI_WG = 1>
@@ -398,10 +417,22 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WG, 1)
             q0 = fmaf(f.x, f.x, q0);
             q1 = fmaf(f.y, f.y, q1);
           }
-          atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
-          atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
-          atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
-          atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
+          if (p.det_part) {
+            for (int turn = 0; turn < 4; ++turn) {   // deterministic: the four warps take turns
+              if (q == turn) {
+                s_sum[chunk * 64 + 2 * lane] += s0;
+                s_sum[chunk * 64 + 2 * lane + 1] += s1;
+                s_sq[chunk * 64 + 2 * lane] += q0;
+                s_sq[chunk * 64 + 2 * lane + 1] += q1;
+              }
+              named_bar_sync(bar_a, 128);
+            }
+          } else {
+            atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
+            atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
+            atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
+            atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
+          }
         }
       }
       if (do_stats) {
@@ -409,8 +440,16 @@ __global__ void __launch_bounds__(128 + 128 * EPI_WG, 1)
         for (int c = et; c < BLOCK_N; c += 128) {
           const int ch = (col0 + c) % p.cout_per_view;
           // fp64 accumulators: a channel with |mean| >> std loses its variance to cancellation in fp32
-          atomicAdd(p.stat_sum + ch, static_cast<double>(s_sum[c]));
-          atomicAdd(p.stat_sq + ch, static_cast<double>(s_sq[c]));
+          if (p.det_part) {
+            // deterministic: this warpgroup's row of the scratch; successive tiles of a warpgroup are ordered by
+            // the named barriers above, and within a tile every channel has one writer
+            double* rowp = p.det_part + (EPI_WG * blockIdx.x + wg) * 2ll * p.det_c;
+            rowp[ch] += static_cast<double>(s_sum[c]);
+            rowp[p.det_c + ch] += static_cast<double>(s_sq[c]);
+          } else {
+            atomicAdd(p.stat_sum + ch, static_cast<double>(s_sum[c]));
+            atomicAdd(p.stat_sq + ch, static_cast<double>(s_sq[c]));
+          }
         }
       }
     }
@@ -491,6 +530,8 @@ struct Conv3Params {
   int relu;
   double* stat_sum;
   double* stat_sq;
+  double* det_part;               // deterministic mode: per-(CTA, warpgroup) rows [sum | sq] of `cout` doubles each
+  int cout;
   long long* prof;                // optional [grid][8] cycle counters (plume_debug_set_prof)
 };
 
@@ -849,8 +890,16 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       for (int i = 0; i < ACC_PER_THREAD; ++i) {
         const int c = et + 128 * i;
         if (c < BLOCK_N) {
-          atomicAdd(p.stat_sum + acc_ch0 + c, acc_s[i]);
-          atomicAdd(p.stat_sq + acc_ch0 + c, acc_q[i]);
+          if (p.det_part) {
+            // deterministic: this warpgroup's own row of the scratch (zeroed by the launcher); thread et is the
+            // only writer of its channels, flushes of one warpgroup are sequential
+            double* rowp = p.det_part + (2 * blockIdx.x + g) * 2ll * p.cout;
+            rowp[acc_ch0 + c] += acc_s[i];
+            rowp[p.cout + acc_ch0 + c] += acc_q[i];
+          } else {
+            atomicAdd(p.stat_sum + acc_ch0 + c, acc_s[i]);
+            atomicAdd(p.stat_sq + acc_ch0 + c, acc_q[i]);
+          }
         }
         acc_s[i] = acc_q[i] = 0.0;
       }
@@ -960,10 +1009,23 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
               q0 = fmaf(f.x, f.x, q0);
               q1 = fmaf(f.y, f.y, q1);
             }
-            atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
-            atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
-            atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
-            atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
+            if (p.det_part) {
+              // deterministic: the four warps add their row groups' sums one after the other
+              for (int turn = 0; turn < 4; ++turn) {
+                if (q == turn) {
+                  s_sum[chunk * 64 + 2 * lane] += s0;
+                  s_sum[chunk * 64 + 2 * lane + 1] += s1;
+                  s_sq[chunk * 64 + 2 * lane] += q0;
+                  s_sq[chunk * 64 + 2 * lane + 1] += q1;
+                }
+                named_bar_sync(bar_a, 128);
+              }
+            } else {
+              atomicAdd(&s_sum[chunk * 64 + 2 * lane], s0);
+              atomicAdd(&s_sum[chunk * 64 + 2 * lane + 1], s1);
+              atomicAdd(&s_sq[chunk * 64 + 2 * lane], q0);
+              atomicAdd(&s_sq[chunk * 64 + 2 * lane + 1], q1);
+            }
           }
         }
       }
@@ -1046,6 +1108,8 @@ static int try_launch_conv3(const FwdDesc& d) {
   p.div_tiles_w = make_fastdiv(p.tiles_w);
   p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
   p.stat_sum = d.stat_sum; p.stat_sq = d.stat_sq;
+  p.det_part = nullptr;
+  p.cout = cout;
   p.prof = g_prof_buf;
 
   // mode 0: weights resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (a slot is
@@ -1087,15 +1151,23 @@ static int try_launch_conv3(const FwdDesc& d) {
     return -1;
   }
   const int tt = static_cast<int>(total);
+  const int det_rows = 2 * std::min(tt, num_sms());   // one row per (CTA, epilogue warpgroup)
+  if (d.stat_sum && deterministic()) {
+    p.det_part = det_stats_begin(det_rows, cout, d.stream);
+    if (!p.det_part) return -2;
+  }
+  int r;
   if (mode == 0) {
-    if (block_n == 128) return launch_conv3_inst<128, 0>(amap, bmap, omap, p, smem, tt, d.stream);
-    return launch_conv3_inst<64, 0>(amap, bmap, omap, p, smem, tt, d.stream);
+    r = block_n == 128 ? launch_conv3_inst<128, 0>(amap, bmap, omap, p, smem, tt, d.stream)
+                       : launch_conv3_inst<64, 0>(amap, bmap, omap, p, smem, tt, d.stream);
+  } else if (mode == 1) {
+    r = block_n == 128 ? launch_conv3_inst<128, 1>(amap, bmap, omap, p, smem, tt, d.stream)
+                       : launch_conv3_inst<64, 1>(amap, bmap, omap, p, smem, tt, d.stream);
+  } else {
+    r = launch_conv3_inst<256, 2>(amap, bmap, omap, p, smem, tt, d.stream);
   }
-  if (mode == 1) {
-    if (block_n == 128) return launch_conv3_inst<128, 1>(amap, bmap, omap, p, smem, tt, d.stream);
-    return launch_conv3_inst<64, 1>(amap, bmap, omap, p, smem, tt, d.stream);
-  }
-  return launch_conv3_inst<256, 2>(amap, bmap, omap, p, smem, tt, d.stream);
+  if (r == 0 && p.det_part) r = det_stats_finish(p.det_part, det_rows, cout, d.stat_sum, d.stat_sq, d.stream);
+  return r;
 }
 
 int launch_igemm_fwd(const FwdDesc& d) {
@@ -1179,31 +1251,35 @@ int launch_igemm_fwd(const FwdDesc& d) {
   p.relu = d.relu;
   p.stat_sum = d.stat_sum;
   p.stat_sq = d.stat_sq;
+  p.det_part = nullptr;
+  p.det_c = d.cout_per_view;
   const long long total = 1ll * p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   if (total > 0x7fffffffll) {
     set_error("igemm_fwd: too many tiles");
     return -1;
   }
-  if (d.split) {
-    switch (block_n) {
-      case 256: return launch_fwd_inst<256, 3, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
-      case 128: return launch_fwd_inst<128, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
-      default:  return launch_fwd_inst<64, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
-    }
+  const int det_rows = 2 * std::min(static_cast<int>(total), num_sms());   // (CTA, epilogue warpgroup), at most two
+  if (d.stat_sum && deterministic()) {
+    p.det_part = det_stats_begin(det_rows, p.det_c, d.stream);
+    if (!p.det_part) return -2;
   }
   static const bool one_wg = getenv("PLUME_FWD_ONE_EPILOGUE_WG") != nullptr;   // A/B switch (scripts/time_convT.py)
-  if (one_wg) {
-    switch (block_n) {
-      case 256: return launch_fwd_inst<256, 4, 1>(amaps, bmap, omaps, p, (int)total, d.stream);
-      case 128: return launch_fwd_inst<128, 5, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
-      default:  return launch_fwd_inst<64, 6, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
-    }
+  int r;
+  if (d.split) {
+    r = block_n == 256   ? launch_fwd_inst<256, 3, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream)
+        : block_n == 128 ? launch_fwd_inst<128, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream)
+                         : launch_fwd_inst<64, 4, 2, true>(amaps, bmap, omaps, p, (int)total, d.stream);
+  } else if (one_wg) {
+    r = block_n == 256   ? launch_fwd_inst<256, 4, 1>(amaps, bmap, omaps, p, (int)total, d.stream)
+        : block_n == 128 ? launch_fwd_inst<128, 5, 2>(amaps, bmap, omaps, p, (int)total, d.stream)
+                         : launch_fwd_inst<64, 6, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
+  } else {
+    r = block_n == 256   ? launch_fwd_inst<256, 3, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream)
+        : block_n == 128 ? launch_fwd_inst<128, 4, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream)
+                         : launch_fwd_inst<64, 6, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
   }
-  switch (block_n) {
-    case 256: return launch_fwd_inst<256, 3, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
-    case 128: return launch_fwd_inst<128, 4, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
-    default:  return launch_fwd_inst<64, 6, 2, false, 2>(amaps, bmap, omaps, p, (int)total, d.stream);
-  }
+  if (r == 0 && p.det_part) r = det_stats_finish(p.det_part, det_rows, p.det_c, d.stat_sum, d.stat_sq, d.stream);
+  return r;
 }
 
 // =================================================================================================
@@ -1220,6 +1296,8 @@ struct WgradParams {
   int splits, ktiles_per_split;
   float* dw;                      // fp32 weight gradient, element (tap t, ci, co) at co*s_co + t*s_t + ci
   long long s_co, s_t;
+  float* det_part;                // deterministic mode: [splits][dw_numel] partial sums (stored, not added)
+  long long dw_numel;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -1365,15 +1443,21 @@ __global__ void __launch_bounds__(256, 1)
     // split-K partial sums are added straight into dW with fp32 reductions (RED.ADD): consecutive lanes are
     // consecutive input channels = consecutive addresses, so every warp instruction is one 128-byte line
     const int t = grow / p.cin, ci = grow - t * p.cin;
-    float* dst = p.dw + t * p.s_t + ci + static_cast<long long>(n_tile * BLOCK_N) * p.s_co;
+    float* base = p.det_part ? p.det_part + split * p.dw_numel : p.dw;
+    float* dst = base + t * p.s_t + ci + static_cast<long long>(n_tile * BLOCK_N) * p.s_co;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
       tmem_ld_wait();
       if (row_ok) {
+        if (p.det_part) {   // deterministic: this split's own copy, summed over the splits in order afterwards
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * p.s_co, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) dst[(c + j) * p.s_co] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * p.s_co, __uint_as_float(v[j]));
+        }
       }
     }
   }
@@ -1462,6 +1546,9 @@ static WgradConfig wgrad_config(int N, int H, int W, int num_taps, int Cin, int 
 int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout) {
   return wgrad_config(N, H, W, num_taps, Cin, Cout, num_taps == 9 ? 1 : 4).splits;
 }
+static int wgrad_plan_views(int N, int H, int W, int num_taps, int Cin, int Cout, int dy_views) {
+  return wgrad_config(N, H, W, num_taps, Cin, Cout, dy_views).splits;
+}
 
 // =================================================================================================
 // 3x3 weight gradient with halo reuse ("wgrad3").  K tile = 8 (w) x 8 (h) pixels; with MN-major
@@ -1481,6 +1568,8 @@ struct Wgrad3Params {
   int stages;
   float* dw;                      // fp32, element (tap t, ci, co) at co*s_co + t*s_t + ci
   long long s_co, s_t;
+  float* det_part;                // deterministic mode: [splits][dw_numel] partial sums, one MMA issuer
+  long long dw_numel;
 };
 
 constexpr int kXBox = 10 * 1024;  // 8 w x 10 h pixels x 64 channels
@@ -1540,7 +1629,7 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tfull_bar, nk > 1 ? 2 : 1);  // every issuer that has a stage commits once
+    mbar_init(tfull_bar, (nk > 1 && !p.det_part) ? 2 : 1);  // every issuer that has a stage commits once
     ctr[0] = 0;
     ctr[1] = 0;
     fence_mbar_init();
@@ -1593,12 +1682,14 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
     }
   } else if (warp == kWarpMma0 || warp == kWarpMma1) {
     const int me = warp == kWarpMma0 ? 0 : 1;
-    if (lane == 0 && me < nk) {
+    // deterministic mode: one issuer takes every stage, so the accumulation order inside the CTA is fixed
+    const int istep = p.det_part ? 1 : 2;
+    if (lane == 0 && me < nk && (me == 0 || !p.det_part)) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       if (me == 1) wait_counter(ctr + 1, 1, 8);  // the zeroing stage has been issued
       int stage = me % p.stages;
-      for (int i = me; i < nk; i += 2) {
+      for (int i = me; i < nk; i += istep) {
         wait_counter(ctr, i + 1, 6);
         tc_fence_after();
         const uint32_t x_addr = sbase + stage * stage_bytes;
@@ -1630,7 +1721,7 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
         }
         umma_commit(empty_bar(stage));
         if (i == 0) ctr[1] = 1;
-        stage += 2;
+        stage += istep;
         while (stage >= p.stages) stage -= p.stages;
       }
       umma_commit(tfull_bar);
@@ -1653,15 +1744,21 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
         ci = cb * 128 + row;
       }
       // fp32 reductions straight into dW: lanes = consecutive ci = one 128-byte line per instruction
-      float* dst = p.dw + wt * p.s_t + ci + static_cast<long long>(n_tile * BLOCK_N) * p.s_co;
+      float* base = p.det_part ? p.det_part + split * p.dw_numel : p.dw;
+      float* dst = base + wt * p.s_t + ci + static_cast<long long>(n_tile * BLOCK_N) * p.s_co;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * BLOCK_N + c, v);
         tmem_ld_wait();
         if (ok) {
+          if (p.det_part) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * p.s_co, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) dst[(c + j) * p.s_co] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * p.s_co, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -1714,6 +1811,8 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   p.dw = d.dw;
   p.s_co = d.s_co;
   p.s_t = d.s_t;
+  p.det_part = d.det_part;
+  p.dw_numel = 9ll * d.Cin * d.Cout;
   const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (c.block_n / 64) * 8192;
   const int overhead = 8 * (2 * kMaxSlots + 3) + 16 + 1024;
   // Leave room beside a CTA for one block of a bandwidth kernel on another stream (see unet.py).
@@ -1755,7 +1854,27 @@ static int launch_wgrad_inst(const TmapPack2& xmap, const TmapPack8& dymaps, con
   return 0;
 }
 
-int launch_igemm_wgrad(const WgradDesc& d) {
+static int launch_igemm_wgrad_impl(const WgradDesc& d);
+
+// Deterministic mode: every K split stores its partial sums to its own slice of the scratch (zeroed first: a CTA
+// writes only the rows it owns) and `ordered_sum` adds the slices to dW in split order.
+int launch_igemm_wgrad(const WgradDesc& d0) {
+  if (!deterministic()) return launch_igemm_wgrad_impl(d0);
+  WgradDesc d = d0;
+  const int splits = wgrad_plan_views(d.x.N, d.x.H, d.x.W, d.num_taps, d.Cin, d.Cout, d.split ? 4 : d.num_dy_views);
+  const long long numel = 1ll * d.num_taps * d.Cin * d.Cout;
+  const size_t bytes = static_cast<size_t>(splits) * numel * sizeof(float);
+  d.det_part = static_cast<float*>(det_scratch(1, bytes));
+  if (!d.det_part) return -2;
+  if (cudaMemsetAsync(d.det_part, 0, bytes, d.stream) != cudaSuccess) {
+    set_error("deterministic wgrad: cudaMemsetAsync failed");
+    return -2;
+  }
+  if (int r = launch_igemm_wgrad_impl(d)) return r;
+  return ordered_sum(d.det_part, splits, static_cast<int>(numel), d.dw, d.stream);
+}
+
+static int launch_igemm_wgrad_impl(const WgradDesc& d) {
   if (d.Cin == 64 && d.num_dy_views > 1) {
     set_error("igemm_wgrad: per-tap dY views need Cin to be a multiple of 128");
     return -1;
@@ -1834,6 +1953,8 @@ int launch_igemm_wgrad(const WgradDesc& d) {
   p.dw = d.dw;
   p.s_co = d.s_co;
   p.s_t = d.s_t;
+  p.det_part = d.det_part;
+  p.dw_numel = 1ll * d.num_taps * d.Cin * d.Cout;
   if (d.split) {
     switch (block_n) {
       case 256: return launch_wgrad_inst<256, 4, true>(xmap, dymaps, p, d.stream);

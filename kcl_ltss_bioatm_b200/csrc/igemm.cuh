@@ -45,6 +45,7 @@ struct WgradDesc {
   long long s_co, s_t;
   cudaStream_t stream;
   int split;          // bf16x3 mode (see FwdDesc): x and dy are hi/lo plane pairs
+  float* det_part;    // set by launch_igemm_wgrad in deterministic mode: [splits][taps*Cin*Cout] partial sums
 };
 // Chooses the K split for a problem; returns the number of splits (>=1).
 int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout);

@@ -77,6 +77,14 @@ SIGNATURES = {
     "plume_threshold_masks": (_I, [_P, _I, _I, _P, _I, _P, _P]),
     "plume_label_components": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "plume_fire_extents": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
+    "plume_maxpool2x2_bwd_bn": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "plume_maxpool2x2_bwd_bn_x3": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "plume_head_bwd_bn": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P,
+                               _LL, _I, _P]),
+    "plume_head_bwd_bn_x3": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P,
+                                  _P, _LL, _I, _P]),
+    "plume_set_deterministic": (None, [_I]),
+    "plume_get_deterministic": (_I, []),
     "plume_utm_zone_histogram": (_I, [_P, _LL, _P, _P]),
     "plume_utm_forward": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "plume_utm_inverse": (_I, [_P, _P, _LL, _I, _P, _P, _P]),

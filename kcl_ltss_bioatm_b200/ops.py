@@ -91,6 +91,14 @@ class CudaOps:
     def _fn(self, name: str):
         return getattr(self.lib, name + self._sfx)
 
+    def set_deterministic(self, on: bool) -> None:
+        """Library-wide switch (also PLUME_DETERMINISTIC=1): ordered partial-sum reductions instead of fp atomics."""
+        self.lib.plume_set_deterministic(int(bool(on)))
+
+    @property
+    def is_deterministic(self) -> bool:
+        return bool(self.lib.plume_get_deterministic())
+
     def _a(self, t: torch.Tensor, name: str):
         return _act(t, name, self.planes)
 
@@ -260,14 +268,28 @@ class CudaOps:
               "plume_maxpool2x2_fwd")
         self.launches += 1
 
-    def maxpool_bwd(self, dy, argmax, dskip, dx):
+    def _bn_args(self, bn, c):
+        """bn = (y, scale, shift, mean, invstd, relu, sum_g, sum_gx): the BatchNorm layer whose `da` a producer
+        kernel writes; returns the C-ABI argument tuple of the fused reduction."""
+        y, scale, shift, mean, invstd, relu, sum_g, sum_gx = bn
+        yp, ldy, *_ = self._a(y, "bn.y")
+        return (yp, ldy, _f32(scale, "scale", c), _f32(shift, "shift", c), _f32(mean, "mean", c),
+                _f32(invstd, "invstd", c), int(bool(relu)), _f32(sum_g, "sum_g", c), _f32(sum_gx, "sum_gx", c))
+
+    def maxpool_bwd(self, dy, argmax, dskip, dx, bn=None):
+        """bn: optional (y, scale, shift, mean, invstd, relu, sum_g, sum_gx) -- also accumulate the BatchNorm-backward
+        sums of dx (what bn_bwd_reduce(dx, y, ...) would add)."""
         dyp, lddy, *_ = self._a(dy, "dy")
         dxp, lddx, n, h, w, c = self._a(dx, "dx")
         sp, lds = (ptr(None), 0)
         if dskip is not None:
             sp, lds, *_ = self._a(dskip, "dskip")
-        check(self._fn("plume_maxpool2x2_bwd")(dyp, lddy, ptr(argmax), sp, lds, dxp, lddx, n, h, w, c,
-                                            current_stream()), "plume_maxpool2x2_bwd")
+        if bn is None:
+            check(self._fn("plume_maxpool2x2_bwd")(dyp, lddy, ptr(argmax), sp, lds, dxp, lddx, n, h, w, c,
+                                                   current_stream()), "plume_maxpool2x2_bwd")
+        else:
+            check(self._fn("plume_maxpool2x2_bwd_bn")(dyp, lddy, ptr(argmax), sp, lds, dxp, lddx, *self._bn_args(bn, c),
+                                                      n, h, w, c, current_stream()), "plume_maxpool2x2_bwd_bn")
         self.launches += 1
 
     def bn_bwd_reduce(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx):
@@ -321,13 +343,17 @@ class CudaOps:
               "plume_head_loss")
         self.launches += 1
 
-    def head_bwd(self, feat, w, logits, target, sums, bce_w, dice_w, eps, grad_scale, dfeat, dw, db):
+    def head_bwd(self, feat, w, logits, target, sums, bce_w, dice_w, eps, grad_scale, dfeat, dw, db, bn=None):
+        """bn: see maxpool_bwd -- the BatchNorm layer that produced `feat`; its sums are accumulated from dfeat."""
         fp, ldf, n, h, wd, c = self._a(feat, "feat")
         dfp, lddf, *_ = self._a(dfeat, "dfeat")
-        check(self._fn("plume_head_bwd")(fp, ldf, _f32(w, "w", c), _f32(logits, "logits"), ptr(target),
-                                      _f32(sums, "sums", 4), float(bce_w), float(dice_w), float(eps),
-                                      float(grad_scale), dfp, lddf, _f32(dw, "dw", c), _f32(db, "db", 1),
-                                      n * h * wd, c, current_stream()), "plume_head_bwd")
+        head = (fp, ldf, _f32(w, "w", c), _f32(logits, "logits"), ptr(target), _f32(sums, "sums", 4), float(bce_w),
+                float(dice_w), float(eps), float(grad_scale), dfp, lddf, _f32(dw, "dw", c), _f32(db, "db", 1))
+        if bn is None:
+            check(self._fn("plume_head_bwd")(*head, n * h * wd, c, current_stream()), "plume_head_bwd")
+        else:
+            check(self._fn("plume_head_bwd_bn")(*head, *self._bn_args(bn, c), n * h * wd, c, current_stream()),
+                  "plume_head_bwd_bn")
         self.launches += 1
 
     def adam(self, param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):

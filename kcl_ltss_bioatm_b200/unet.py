@@ -137,6 +137,7 @@ class UNetB200:
         self._tail_event: Optional["torch.cuda.Event"] = None  # side stream: all wgrads before enc0's are done
         self._tail_open = False                                # backward returned without joining the side stream
         self._defer_ok = not os.environ.get("PLUME_NO_DEFER_TAIL")
+        self.fuse_bn_reduce = not os.environ.get("PLUME_NO_FUSED_BN_REDUCE")   # A/B switch
         self._tail_offset = min(s.offset for k, s in self.layout.slots.items() if k.startswith("enc0."))
 
         if seed is not None:
@@ -512,9 +513,18 @@ class UNetB200:
         ev.record(torch.cuda.current_stream(self.device))
         return ev
 
-    def _conv_block_bwd(self, name: str, x_in, y, a, g_a, g_y, g_in, acc=False):
+    def _bn_reduce_args(self, name: str, y):
+        """The (y, scale, shift, mean, invstd, relu, sum_g, sum_gx) tuple a producer kernel needs to accumulate the
+        BatchNorm-backward sums of layer `name` while it writes that layer's incoming gradient (None: not fused)."""
+        if not self.use_bn or not self.fuse_bn_reduce:
+            return None
+        st = self._bn[name]
+        return (y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, st["sum_g"], st["sum_gx"])
+
+    def _conv_block_bwd(self, name: str, x_in, y, a, g_a, g_y, g_in, acc=False, reduced=False):
         """Backward of conv -> [BN] -> ReLU.  g_a: gradient w.r.t. the activated output; g_y: scratch for
-        the gradient w.r.t. the raw conv output; g_in: where the input gradient goes (None = not needed)."""
+        the gradient w.r.t. the raw conv output; g_in: where the input gradient goes (None = not needed).
+        reduced=True: the kernel that produced g_a has already accumulated this layer's sum_g / sum_gx."""
         ops = self.ops
         L = self.convs[name]
         busy = self._gy_busy.pop(g_y.data_ptr(), None)
@@ -522,8 +532,9 @@ class UNetB200:
             torch.cuda.current_stream(self.device).wait_event(busy)
         if self.use_bn:
             st = self._bn[name]
-            ops.bn_bwd_reduce(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, st["sum_g"],
-                              st["sum_gx"])
+            if not reduced:
+                ops.bn_bwd_reduce(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, st["sum_g"],
+                                  st["sum_gx"])
             ops.bn_bwd_apply(g_a, y, st["scale"], st["shift"], st["mean"], st["invstd"], 1, st["sum_g"],
                              st["sum_gx"], g_y, self.g(f"{name}.bias"), self.g(f"{L.bn}.weight"),
                              self.g(f"{L.bn}.bias"), acc)
@@ -587,13 +598,17 @@ class UNetB200:
         self._gy_busy = {}
         self._tail_event = None
         feat = b.da2[0]
+        # the head's and the pools' backward kernels write the incoming gradient of a BatchNorm layer: they also
+        # accumulate that layer's backward sums (one read of y instead of a separate pass over the gradient and y)
+        bn0 = self._bn_reduce_args("dec0.conv2", b.dy2[0])
         ops.head_bwd(feat, self.p("head.weight"), b.logits, b.target, self.head_sums, spec.bce_weight,
                      spec.dice_weight, spec.dice_eps, loss_scale / self.world, b.g_a[0], self.g("head.weight"),
-                     self.g("head.bias"))
+                     self.g("head.bias"), **({"bn": bn0} if bn0 else {}))
         self._grads_ready("head.bias")
         for l in range(d):
             c = spec.channels(l)
-            self._conv_block_bwd(f"dec{l}.conv2", b.da1[l], b.dy2[l], b.da2[l], b.g_a[l], b.g_y[l][0], b.g_a[l], acc)
+            self._conv_block_bwd(f"dec{l}.conv2", b.da1[l], b.dy2[l], b.da2[l], b.g_a[l], b.g_y[l][0], b.g_a[l], acc,
+                                 reduced=(l == 0 and bn0 is not None))
             self._conv_block_bwd(f"dec{l}.conv1", b.cat[l], b.dy1[l], b.da1[l], b.g_a[l], b.g_y[l][1], b.g_cat[l], acc)
             du = b.g_cat[l][..., c:]
             x_up = b.ba2 if l == d - 1 else b.da2[l + 1]
@@ -609,8 +624,10 @@ class UNetB200:
         for l in reversed(range(d)):
             c = spec.channels(l)
             skip = b.cat[l][..., :c]
-            ops.maxpool_bwd(b.g_pool[l], b.am[l], b.g_cat[l][..., :c], b.g_a[l])
-            self._conv_block_bwd(f"enc{l}.conv2", b.a1[l], b.y2[l], skip, b.g_a[l], b.g_y[l][0], b.g_a[l], acc)
+            bnl = self._bn_reduce_args(f"enc{l}.conv2", b.y2[l])
+            ops.maxpool_bwd(b.g_pool[l], b.am[l], b.g_cat[l][..., :c], b.g_a[l], **({"bn": bnl} if bnl else {}))
+            self._conv_block_bwd(f"enc{l}.conv2", b.a1[l], b.y2[l], skip, b.g_a[l], b.g_y[l][0], b.g_a[l], acc,
+                                 reduced=bnl is not None)
             x_in = b.x_in if l == 0 else b.pool[l - 1]
             g_in = None if l == 0 else b.g_pool[l - 1]
             self._conv_block_bwd(f"enc{l}.conv1", x_in, b.y1[l], b.a1[l], b.g_a[l], b.g_y[l][1], g_in, acc)

@@ -184,7 +184,7 @@ class RefOps:
         y.copy_(best.to(self.act_dtype))
         argmax.view_as(idx).copy_(idx)
 
-    def maxpool_bwd(self, dy, argmax, dskip, dx):
+    def maxpool_bwd(self, dy, argmax, dskip, dx, bn=None):
         n, h, w, c = dx.shape
         g = dy.float()
         idx = argmax.view(n, h // 2, w // 2, c).long()
@@ -194,6 +194,9 @@ class RefOps:
         if dskip is not None:
             out = out + dskip.float()
         dx.copy_(out.to(self.act_dtype))
+        if bn is not None:   # fused BatchNorm-backward reduction of the stored gradient
+            y, scale, shift, mean, invstd, relu, sum_g, sum_gx = bn
+            self.bn_bwd_reduce(dx, y, scale, shift, mean, invstd, relu, sum_g, sum_gx)
 
     def bn_bwd_reduce(self, da, y, scale, shift, mean, invstd, relu, sum_g, sum_gx):
         yf = y.float()
@@ -253,7 +256,7 @@ class RefOps:
         loss_out[1] = bce
         loss_out[2] = dice
 
-    def head_bwd(self, feat, w, logits, target, sums, bce_w, dice_w, eps, grad_scale, dfeat, dw, db):
+    def head_bwd(self, feat, w, logits, target, sums, bce_w, dice_w, eps, grad_scale, dfeat, dw, db, bn=None):
         n, h, wd, c = feat.shape
         z = logits.view(n, h, wd)
         t = (target.view(n, h, wd) != 0).float()
@@ -266,6 +269,9 @@ class RefOps:
         dfeat.copy_((dz.unsqueeze(-1) * w).to(self.act_dtype))
         dw += (dz.unsqueeze(-1) * feat.float()).sum(dim=(0, 1, 2))
         db += dz.sum()
+        if bn is not None:
+            y, scale, shift, mean, invstd, relu, sum_g, sum_gx = bn
+            self.bn_bwd_reduce(dfeat, y, scale, shift, mean, invstd, relu, sum_g, sum_gx)
 
     def adam(self, param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
         g = grad * grad_scale

@@ -477,3 +477,46 @@ def test_batchnorm_statistics_survive_large_mean_over_std(ops, ratio):
     assert ((mean - mean_true).abs() / mean_true.abs()).max().item() < 1e-6
     assert ((1 / invstd ** 2 - 1e-5 - var_true).abs() / var_true).max().item() < 2e-3
     assert relmax(y, y_ref) < 1.6e-2
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 24, 64), (3, 8, 8, 256), (1, 64, 64, 128)])
+def test_pool_and_head_backward_fused_with_bn_reduction(ops, n, h, w, c):
+    """plume_maxpool2x2_bwd_bn / plume_head_bwd_bn: the gradient they store is bit-identical to the plain kernels',
+    and the BatchNorm-backward sums they accumulate equal a separate bn_bwd_reduce over that stored gradient."""
+    cu, _ = ops
+    g = torch.Generator().manual_seed(11)
+    dy = torch.randn(n, h // 2, w // 2, c, generator=g).to(BF).to(DEV)
+    am = torch.randint(0, 4, (n, h // 2, w // 2, c), generator=g, dtype=torch.uint8).to(DEV)
+    dskip = torch.randn(n, h, w, c, generator=g).to(BF).to(DEV)
+    y = torch.randn(n, h, w, c, generator=g).to(BF).to(DEV)
+    scale, shift = (1 + 0.1 * rnd(c, seed=3)).to(DEV), (0.1 * rnd(c, seed=4)).to(DEV)
+    mean, invstd = (0.1 * rnd(c, seed=5)).to(DEV), (1 + 0.1 * rnd(c, seed=6)).abs().to(DEV)
+    dx0, dx1 = (torch.empty(n, h, w, c, dtype=BF, device=DEV) for _ in range(2))
+    sg0, sx0, sg1, sx1 = (torch.zeros(c, device=DEV) for _ in range(4))
+    cu.maxpool_bwd(dy, am, dskip, dx0)
+    cu.bn_bwd_reduce(dx0, y, scale, shift, mean, invstd, 1, sg0, sx0)
+    cu.maxpool_bwd(dy, am, dskip, dx1, bn=(y, scale, shift, mean, invstd, 1, sg1, sx1))
+    torch.cuda.synchronize()
+    assert torch.equal(dx0, dx1)
+    assert relmax(sg1, sg0) < 1e-4 and relmax(sx1, sx0) < 1e-4
+    if c <= 256:   # the head takes C = 8 * 2^k <= 256 feature channels
+        feat = torch.randn(n, h, w, c, generator=g).to(BF).to(DEV)
+        wh, logits = (0.1 * rnd(c, seed=7)).to(DEV), rnd(n, h, w, seed=8).to(DEV)
+        target = (torch.rand(n, h, w, generator=g) > 0.7).to(torch.uint8).to(DEV)
+        sums = torch.tensor([1.0, 2.0, 30.0, 40.0], device=DEV)
+        outs = []
+        for fused in (False, True):
+            df = torch.empty(n, h, w, c, dtype=BF, device=DEV)
+            dw, db, sg, sx = torch.zeros(c, device=DEV), torch.zeros(1, device=DEV), torch.zeros(c, device=DEV), \
+                torch.zeros(c, device=DEV)
+            if fused:
+                cu.head_bwd(feat, wh, logits, target, sums, 1.0, 1.0, 1.0, 0.5, df, dw, db,
+                            bn=(y, scale, shift, mean, invstd, 1, sg, sx))
+            else:
+                cu.head_bwd(feat, wh, logits, target, sums, 1.0, 1.0, 1.0, 0.5, df, dw, db)
+                cu.bn_bwd_reduce(df, y, scale, shift, mean, invstd, 1, sg, sx)
+            torch.cuda.synchronize()
+            outs.append((df, dw, db, sg, sx))
+        assert torch.equal(outs[0][0], outs[1][0])
+        for a, b in zip(outs[0][1:], outs[1][1:]):
+            assert relmax(b, a) < 1e-4
