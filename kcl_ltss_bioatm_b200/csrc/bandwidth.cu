@@ -646,11 +646,16 @@ struct BnReduceState {
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
   }
-  // v: the stored (rounded) gradient of pixel p
-  __device__ __forceinline__ void add(const BnReduceArgs& a, const typename Act<T>::V8& v, long long p, int cv) {
+  __device__ __forceinline__ typename Act<T>::V8 load_y(const BnReduceArgs& a, long long p, int cv) const {
+    return Act<T>::ld_stream(static_cast<const T*>(a.y) + p * a.ldy + cv * 8, a.ldy >> 1);
+  }
+  // v: the stored (rounded) gradient of a pixel, yv: the layer's raw conv output there (load_y, issued early so
+  // that the loads of several pixels are in flight together)
+  __device__ __forceinline__ void add(const BnReduceArgs& a, const typename Act<T>::V8& v,
+                                      const typename Act<T>::V8& yv) {
     float g[8], yy[8];
     Act<T>::unpack(v, g);
-    Act<T>::unpack(Act<T>::ld_stream(static_cast<const T*>(a.y) + p * a.ldy + cv * 8, a.ldy >> 1), yy);
+    Act<T>::unpack(yv, yy);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float gg = (!a.relu || fmaf(yy[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
@@ -688,11 +693,17 @@ __global__ void __launch_bounds__(kThreads)
     Act<T>::unpack(Act<T>::ld_stream(dy + op * lddy + cv * 8, lddy >> 1), g);
     const uint2 am = *reinterpret_cast<const uint2*>(argmax + (op * CV + cv) * 8);
     const long long off[4] = {ip, ip + 1, ip + W, ip + W + 1};
+    typename Act<T>::V8 sv[4], yv[4];   // all loads of the 2 x 2 window first: up to 8 vectors in flight
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (dskip) sv[k] = Act<T>::ld_stream(dskip + off[k] * lddskip + cv * 8, lddskip >> 1);
+      if (kReduce) yv[k] = red.load_y(bn, off[k], cv);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float o[8];
       if (dskip) {
-        Act<T>::unpack(Act<T>::ld_stream(dskip + off[k] * lddskip + cv * 8, lddskip >> 1), o);
+        Act<T>::unpack(sv[k], o);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.f;
@@ -704,7 +715,7 @@ __global__ void __launch_bounds__(kThreads)
       }
       const typename Act<T>::V8 ov = Act<T>::pack(o);
       Act<T>::st(dx + off[k] * lddx + cv * 8, lddx >> 1, ov);
-      if (kReduce) red.add(bn, ov, off[k], cv);
+      if (kReduce) red.add(bn, ov, yv[k]);
     }
   }
   if (kReduce) red.finish(bn, cv, CV, s_acc);
@@ -1194,7 +1205,7 @@ __global__ void __launch_bounds__(kThreads)
   float a_db = 0.f;
   BnReduceState<T> red;
   if (kReduce) red.init(bn, cv);
-  auto one = [&](long long p, const typename Act<T>::V8& fv, float z, float t) {
+  auto one = [&](long long p, const typename Act<T>::V8& fv, const typename Act<T>::V8& yv, float z, float t) {
     const float pr = sigmoidf_(z);
     const float ddice = -(2.f * t * S - I2) * invS2;
     const float dz = grad_scale * (bce_w * (pr - t) * inv_pixels + dice_w * ddice * pr * (1.f - pr));
@@ -1207,25 +1218,29 @@ __global__ void __launch_bounds__(kThreads)
     }
     const typename Act<T>::V8 ov = Act<T>::pack(o);
     Act<T>::st(dfeat + p * lddf + cv * 8, lddf >> 1, ov);
-    if (kReduce) red.add(bn, ov, p, cv);
+    if (kReduce) red.add(bn, ov, yv);
     if (cv == 0) a_db += dz;
   };
   constexpr int U = 4;
   long long p = i0 / CV;
   for (; p + (U - 1) * pstep < pixels; p += U * pstep) {
-    typename Act<T>::V8 fv[U];
+    typename Act<T>::V8 fv[U], yv[U];
     float zz[U], tt[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       fv[u] = Act<T>::ld_stream(feat + (p + u * pstep) * ldf + cv * 8, ldf >> 1);
+      if (kReduce) yv[u] = red.load_y(bn, p + u * pstep, cv);
       zz[u] = __ldg(logits + p + u * pstep);
       tt[u] = target[p + u * pstep] ? 1.f : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) one(p + u * pstep, fv[u], zz[u], tt[u]);
+    for (int u = 0; u < U; ++u) one(p + u * pstep, fv[u], yv[u], zz[u], tt[u]);
   }
-  for (; p < pixels; p += pstep)
-    one(p, Act<T>::ld_stream(feat + p * ldf + cv * 8, ldf >> 1), __ldg(logits + p), target[p] ? 1.f : 0.f);
+  for (; p < pixels; p += pstep) {
+    typename Act<T>::V8 yv1;
+    if (kReduce) yv1 = red.load_y(bn, p, cv);
+    one(p, Act<T>::ld_stream(feat + p * ldf + cv * 8, ldf >> 1), yv1, __ldg(logits + p), target[p] ? 1.f : 0.f);
+  }
   float* const outs[1] = {dw};
   block_channel_reduce<1>(acc, cv, CV, outs, s_acc, det_part);
   if (kReduce) {

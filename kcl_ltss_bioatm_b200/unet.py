@@ -138,6 +138,7 @@ class UNetB200:
         self._tail_open = False                                # backward returned without joining the side stream
         self._defer_ok = not os.environ.get("PLUME_NO_DEFER_TAIL")
         self.fuse_bn_reduce = not os.environ.get("PLUME_NO_FUSED_BN_REDUCE")   # A/B switch
+        self.fuse_head_bn = bool(os.environ.get("PLUME_FUSE_HEAD_BN"))
         self._tail_offset = min(s.offset for k, s in self.layout.slots.items() if k.startswith("enc0."))
 
         if seed is not None:
@@ -600,7 +601,9 @@ class UNetB200:
         feat = b.da2[0]
         # the head's and the pools' backward kernels write the incoming gradient of a BatchNorm layer: they also
         # accumulate that layer's backward sums (one read of y instead of a separate pass over the gradient and y)
-        bn0 = self._bn_reduce_args("dec0.conv2", b.dy2[0])
+        # (measured on configs[1], one box: pools 0.42 -> 0.36 ms per step fused; the head kernel is compute-heavier
+        # and LOSES 0.03 ms when it also carries the reduction, so it stays separate unless PLUME_FUSE_HEAD_BN=1)
+        bn0 = self._bn_reduce_args("dec0.conv2", b.dy2[0]) if self.fuse_head_bn else None
         ops.head_bwd(feat, self.p("head.weight"), b.logits, b.target, self.head_sums, spec.bce_weight,
                      spec.dice_weight, spec.dice_eps, loss_scale / self.world, b.g_a[0], self.g("head.weight"),
                      self.g("head.bias"), **({"bn": bn0} if bn0 else {}))
