@@ -40,6 +40,11 @@ int plume_debug_word(void);
  * inside a stream capture: run one un-captured step first (Trainer.step_graphed does). */
 void plume_set_deterministic(int on);
 int plume_get_deterministic(void);
+/* SMs left free by the persistent GEMM kernels (default 0; also PLUME_SM_MARGIN).  Data-parallel training sets it to
+ * the number of CTAs NCCL may use: a one-CTA-per-SM persistent kernel that finds some SMs held by an all-reduce
+ * runs its last CTAs as a second wave. */
+void plume_set_sm_margin(int sms);
+int plume_get_sm_margin(void);
 int plume_num_sms(void);
 /* Diagnostics: device buffer [num_sms][8] of int64 that the conv3x3 kernel fills with per-CTA cycle
  * counters of its producer / MMA / epilogue roles (NULL = off, the default). */

@@ -59,6 +59,8 @@ const char* plume_version(void) { return "plume_b200 0.1 (sm_100a; tcgen05+TMA i
 const char* plume_last_error(void) { return g_last_error.c_str(); }
 int plume_debug_word(void) { return read_debug_word(); }
 void plume_debug_set_prof(long long* buf) { set_prof_buffer(buf); }
+void plume_set_sm_margin(int sms) { set_sm_margin(sms); }
+int plume_get_sm_margin(void) { return get_sm_margin(); }
 void plume_set_deterministic(int on) { set_deterministic(on); }
 int plume_get_deterministic(void) { return deterministic() ? 1 : 0; }
 int plume_num_sms(void) {

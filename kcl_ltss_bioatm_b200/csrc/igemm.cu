@@ -46,6 +46,19 @@ struct TmapPack2 {
   CUtensorMap m[2];
 };
 
+// SMs left to the persistent GEMM kernels.  Under data parallelism NCCL's all-reduce kernels hold a few SMs for
+// milliseconds; a persistent kernel with one CTA per SM and statically assigned tiles then runs its last CTAs as a
+// second wave and takes up to twice as long.  plume_set_sm_margin(k) (PLUME_SM_MARGIN) sizes the persistent grids
+// and the split-K wave arithmetic for `SMs - k`, so every CTA is resident from the start.
+static int g_sm_margin = -1;
+void set_sm_margin(int k) { g_sm_margin = k < 0 ? 0 : k; }
+int get_sm_margin() {
+  if (g_sm_margin < 0) {
+    const char* e = getenv("PLUME_SM_MARGIN");
+    g_sm_margin = e ? std::max(0, atoi(e)) : 0;
+  }
+  return g_sm_margin;
+}
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -54,7 +67,7 @@ static int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return std::max(8, n - get_sm_margin());
 }
 
 // Deterministic BatchNorm statistics: `rows` rows of [sum | sq] (c doubles each) in the scratch, zeroed; after the
@@ -1489,7 +1502,8 @@ static int split_for(int ctas, int ktiles, int min_ktiles, int* per_out) {
   // extra wave (measured: 99 splits x 3 CTAs = 297 CTAs ran 401 us, 148 x 3 = 444 CTAs 299 us).  Cost of a
   // candidate in K-tile units = waves * (K tiles per CTA + kEpilogue), kEpilogue ~ pipeline fill + the
   // fp32 reductions of one CTA (about 6 us per extra wave measured on the 64 -> 64 layer).
-  constexpr int kSms = 148, kEpilogue = 10, kMaxWaves = 4;
+  const int kSms = num_sms();
+  constexpr int kEpilogue = 10, kMaxWaves = 4;
   static const int force_waves = [] {  // diagnostics: PLUME_WGRAD_WAVES=n -> the most splits that fit n waves
     const char* e = getenv("PLUME_WGRAD_WAVES");
     const int v = e ? atoi(e) : 0;

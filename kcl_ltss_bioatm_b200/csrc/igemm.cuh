@@ -51,6 +51,10 @@ struct WgradDesc {
 int wgrad_plan(int N, int H, int W, int num_taps, int Cin, int Cout);
 int launch_igemm_wgrad(const WgradDesc& d);
 
+// SMs to leave free for concurrent collective kernels (see igemm.cu)
+void set_sm_margin(int k);
+int get_sm_margin();
+
 int read_debug_word();
 // Diagnostics: when set, conv3 launches write per-CTA cycle counters ([grid][8] int64) there.
 void set_prof_buffer(long long* buf);  // last watchdog tag written by a trapped kernel (0 if none)

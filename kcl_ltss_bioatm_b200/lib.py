@@ -83,6 +83,8 @@ SIGNATURES = {
                                _LL, _I, _P]),
     "plume_head_bwd_bn_x3": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P,
                                   _P, _LL, _I, _P]),
+    "plume_set_sm_margin": (None, [_I]),
+    "plume_get_sm_margin": (_I, []),
     "plume_set_deterministic": (None, [_I]),
     "plume_get_deterministic": (_I, []),
     "plume_utm_zone_histogram": (_I, [_P, _LL, _P, _P]),

@@ -41,7 +41,13 @@ def init_distributed(device_type: str = "cuda"):
     os.environ.setdefault("MASTER_PORT", "29500")
     if device_type == "cuda":
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        # PLUME_NCCL_HIGH_PRIORITY=1: NCCL's stream outranks the compute streams, so an all-reduce kernel gets its
+        # CTAs resident at the next kernel boundary instead of waiting behind the backward pass's pending CTAs
+        opts = None
+        if os.environ.get("PLUME_NCCL_HIGH_PRIORITY", "0") == "1":
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local),
+                                pg_options=opts)
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     return rank, world, local, dist.group.WORLD
