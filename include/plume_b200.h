@@ -282,6 +282,11 @@ int plume_convT2x2_wgrad_x3(const void* x, int ldx, const void* du, int lddu, fl
                             void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout,
                             plume_stream_t stream);
 
+/* Flat fp32 <-> bf16 casts (round to nearest even): gradient buckets compressed for the data-parallel all-reduce
+ * (opt-in, PLUME_GRAD_COMM=bf16).  `in` / `out` 32-byte (fp32) and 16-byte (bf16) aligned. */
+int plume_cast_f32_bf16(const float* in, void* out, long long n, plume_stream_t stream);
+int plume_cast_bf16_f32(const void* in, float* out, long long n, plume_stream_t stream);
+
 /* ---- tiled large-scene inference -------------------------------------------------------------- */
 /* Cut `count` tiles of T x T (NHWC bf16, Cd channels, zero padded past Cs and past the scene edge)
  * out of a scene [Hs][Ws][Cs] bf16; tile k covers origin (ys[k], xs[k]) given as int32 device arrays. */

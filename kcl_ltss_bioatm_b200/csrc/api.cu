@@ -529,6 +529,15 @@ int plume_head_bwd_x3(const void* feat, int ldf, const float* w, const float* lo
   return impl_head_bwd(feat, ldf, w, logits, target, sums, bce_weight, dice_weight, dice_eps, grad_scale, dfeat, lddf, dw, db, pixels, C, stream, 1);
 }
 
+int plume_cast_f32_bf16(const float* in, void* out, long long n, plume_stream_t stream) {
+  PLUME_CHECK(n <= 0 || (in && out), "cast_f32_bf16: null pointer");
+  return cast_f32_bf16(in, out, n, S(stream));
+}
+int plume_cast_bf16_f32(const void* in, float* out, long long n, plume_stream_t stream) {
+  PLUME_CHECK(n <= 0 || (in && out), "cast_bf16_f32: null pointer");
+  return cast_bf16_f32(in, out, n, S(stream));
+}
+
 int plume_adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
                double beta2, double eps, int step, float grad_scale, plume_stream_t stream) {
   PLUME_CHECK(param && grad && m && v, "adam: null pointer");

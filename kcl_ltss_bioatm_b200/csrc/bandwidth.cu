@@ -1316,6 +1316,51 @@ int head_bwd(const void* feat, int ldf, const float* w, const float* logits, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 <-> bf16 casts of flat buffers (gradient buckets compressed for the data-parallel all-reduce)
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  const long long n8 = n / 8;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += step) {
+    float f[8];
+    ld_f8(in + i * 8, f);
+    st_bf8(out + i * 8, pack8(f));
+  }
+  for (long long i = n8 * 8 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long step = 1ll * gridDim.x * blockDim.x;
+  const long long n8 = n / 8;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += step) {
+    float f[8];
+    unpack8(ld_bf8(in + i * 8), f);
+    *reinterpret_cast<float4*>(out + i * 8) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(out + i * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  for (long long i = n8 * 8 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+    out[i] = __bfloat162float(in[i]);
+}
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) & 31) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    set_error("cast_f32_bf16: buffers must be 32- / 16-byte aligned");
+    return -1;
+  }
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 1), kThreads, 0, s>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  return check_launch("cast_f32_bf16");
+}
+int cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(out) & 31) || (reinterpret_cast<uintptr_t>(in) & 15)) {
+    set_error("cast_bf16_f32: buffers must be 16- / 32-byte aligned");
+    return -1;
+  }
+  cast_bf16_f32_kernel<<<grid_for(n / 8 + 1, 1), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  return check_launch("cast_bf16_f32");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Adam
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)

@@ -65,6 +65,8 @@ int head_bwd(const void* feat, int ldf, const float* w, const float* logits, con
              const float* sums, float bce_w, float dice_w, float eps, float grad_scale, void* dfeat,
              int lddf, float* dw, float* db, long long pixels, int C, int dt, cudaStream_t s,
              const BnReduceArgs* bn = nullptr);
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
+int cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t s);
 int adam(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
          double beta2, double eps, int step, float grad_scale, cudaStream_t s);
 int adam_dev(float* param, const float* grad, float* m, float* v, long long n, const float* coef,

@@ -83,6 +83,8 @@ SIGNATURES = {
                                _LL, _I, _P]),
     "plume_head_bwd_bn_x3": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P,
                                   _P, _LL, _I, _P]),
+    "plume_cast_f32_bf16": (_I, [_P, _P, _LL, _P]),
+    "plume_cast_bf16_f32": (_I, [_P, _P, _LL, _P]),
     "plume_set_sm_margin": (None, [_I]),
     "plume_get_sm_margin": (_I, []),
     "plume_set_deterministic": (None, [_I]),

@@ -356,6 +356,16 @@ class CudaOps:
                   "plume_head_bwd_bn")
         self.launches += 1
 
+    def cast_f32_bf16(self, src, dst):
+        assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+        check(self.lib.plume_cast_f32_bf16(_f32(src, "src"), ptr(dst), src.numel(), current_stream()), "plume_cast_f32_bf16")
+        self.launches += 1
+
+    def cast_bf16_f32(self, src, dst):
+        assert src.dtype == torch.bfloat16 and dst.dtype == torch.float32 and src.numel() == dst.numel()
+        check(self.lib.plume_cast_bf16_f32(ptr(src), _f32(dst, "dst"), src.numel(), current_stream()), "plume_cast_bf16_f32")
+        self.launches += 1
+
     def adam(self, param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
         n = param.numel()
         check(self.lib.plume_adam(_f32(param, "param"), _f32(grad, "grad", n), _f32(m, "m", n),

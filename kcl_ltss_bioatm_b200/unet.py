@@ -139,6 +139,10 @@ class UNetB200:
         self._defer_ok = not os.environ.get("PLUME_NO_DEFER_TAIL")
         self.fuse_bn_reduce = not os.environ.get("PLUME_NO_FUSED_BN_REDUCE")   # A/B switch
         self.fuse_head_bn = bool(os.environ.get("PLUME_FUSE_HEAD_BN"))
+        # PLUME_GRAD_COMM=bf16: gradient buckets are rounded to bf16 for the all-reduce (half the bytes on the wire,
+        # summed in bf16 by NCCL) and widened back into the fp32 gradient buffer; default fp32
+        self.grad_comm_bf16 = os.environ.get("PLUME_GRAD_COMM", "fp32").lower() == "bf16" and self.world > 1
+        self._comm_buf: Optional[torch.Tensor] = None
         self._tail_offset = min(s.offset for k, s in self.layout.slots.items() if k.startswith("enc0."))
 
         if seed is not None:
@@ -686,19 +690,30 @@ class UNetB200:
             a, e = self._buckets[self._next_bucket]
             if e > upto and not (last_key is None):
                 break
+            def reduce_bucket():
+                if not self.grad_comm_bf16:
+                    return dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True), None
+                if self._comm_buf is None:
+                    self._comm_buf = torch.empty(self.layout.total, dtype=torch.bfloat16, device=self.device)
+                self.ops.cast_f32_bf16(self.grads[a:e], self._comm_buf[a:e])
+                return (dist.all_reduce(self._comm_buf[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True),
+                        (a, e))
+
             if self.overlap_wgrad:
                 # the bucket's weight gradients are on the side stream, the rest on this one
                 self._side.wait_event(self._mark())
                 with torch.cuda.stream(self._side):
-                    wk = dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                    wk = reduce_bucket()
             else:
-                wk = dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                wk = reduce_bucket()
             self._pending.append(wk)
             self._next_bucket += 1
 
     def wait_grads(self) -> None:
-        for wk in self._pending:
+        for wk, widen in self._pending:
             wk.wait()
+            if widen is not None:   # bf16 wire format: back into the fp32 gradient buffer
+                self.ops.cast_bf16_f32(self._comm_buf[widen[0]:widen[1]], self.grads[widen[0]:widen[1]])
         self._pending = []
 
     # ------------------------------------------------------------------ optimizer / step

@@ -273,6 +273,12 @@ class RefOps:
             y, scale, shift, mean, invstd, relu, sum_g, sum_gx = bn
             self.bn_bwd_reduce(dfeat, y, scale, shift, mean, invstd, relu, sum_g, sum_gx)
 
+    def cast_f32_bf16(self, src, dst):
+        dst.copy_(src.to(torch.bfloat16))
+
+    def cast_bf16_f32(self, src, dst):
+        dst.copy_(src.float())
+
     def adam(self, param, grad, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
         g = grad * grad_scale
         m.mul_(beta1).add_((1 - beta1) * g)
