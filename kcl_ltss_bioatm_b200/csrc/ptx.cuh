@@ -193,14 +193,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// Instruction descriptor for kind::tf32: fp32 operands in shared memory consumed as TF32, FP32 accumulate.
-//   a_format = b_format = 2 (TF32); one MMA covers K = 8 elements (32 bytes of a K-major row).
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
-         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
-}
-
 // Split form of the same descriptor for lean issue loops: the high word is a per-kernel constant and the
 // low word is (address >> 4) | (LBO >> 4) << 16, so stepping along K is one 32-bit add (the issuing thread,
 // not the tensor pipe, limits small-N MMAs otherwise: scripts/bench_mma.cu measures 48 / 64 / 128 cycles
@@ -221,19 +213,6 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
-                                               uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -30,13 +30,11 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// A strided NHWC view (bf16, or fp32 when esize == 4): `ptr` addresses channel 0 of pixel (0,0,0); strides are in
-// elements.
+// A strided NHWC bf16 view: `ptr` addresses channel 0 of pixel (0,0,0); strides are in elements.
 struct ActView {
   const void* ptr;
   int C, W, H, N;
   long long pix_stride, row_stride, img_stride;
-  int esize = 2;  // bytes per element (bf16)
   long long plane = 0;  // bf16x3 mode: element offset from `ptr` (the hi plane) to the lo plane of the same view
 };
 // The lo plane of a bf16x3 view as a view of its own.
@@ -56,12 +54,12 @@ inline ActView dense_view(const void* ptr, int N, int H, int W, int C_total, int
   return v;
 }
 
-// 4-D map (C, W, H, N) of a bf16 / fp32 view, 128-byte swizzle, zero fill outside the tensor.
+// bf16 4-D map (C, W, H, N), 128-byte swizzle, zero fill outside the tensor.
 inline int make_act_map(CUtensorMap* m, const ActView& v, int box_c, int box_w, int box_h,
                         int box_n) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
-  const cuuint64_t es = static_cast<cuuint64_t>(v.esize);
+  const cuuint64_t es = 2;  // bytes per bf16 element
   cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t strides[3] = {(cuuint64_t)v.pix_stride * es, (cuuint64_t)v.row_stride * es,
                            (cuuint64_t)v.img_stride * es};
@@ -72,8 +70,7 @@ inline int make_act_map(CUtensorMap* m, const ActView& v, int box_c, int box_w, 
     set_error("activation view is not 16-byte aligned (channel offsets/strides must be multiples of 8)");
     return -1;
   }
-  CUresult r = enc(m, v.esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                   const_cast<void*>(v.ptr), dims, strides,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -89,22 +86,20 @@ inline int make_act_map(CUtensorMap* m, const ActView& v, int box_c, int box_w, 
   return 0;
 }
 
-// Row-major matrix [rows][cols] (cols contiguous; bf16, or fp32 with esize 4), 128-byte swizzle;
-// box = (box_cols, box_rows).
+// bf16 row-major matrix [rows][cols] (cols contiguous), 128-byte swizzle; box = (box_cols, box_rows).
 inline int make_mat_map(CUtensorMap* m, const void* ptr, long long rows, long long cols,
-                        int box_cols, int box_rows, int esize = 2) {
+                        int box_cols, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * (cuuint64_t)esize};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15)) {
     set_error("weight matrix is not 16-byte aligned");
     return -1;
   }
-  CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(ptr), dims, strides,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -111,12 +111,19 @@ def _file_batches(folder, per_rank, rank, world, device, spec):
 @click.option("--resume/--no-resume", default=False)
 @click.option("--seed", default=0, show_default=True)
 @click.option("--log-every", default=10, show_default=True)
+@click.option("--precision", default="bf16", type=click.Choice(["bf16", "bf16x3", "tf32"]), show_default=True,
+              help="bf16x3 (alias tf32): hi+lo bf16 storage, three tensor-core passes, logits within 1e-3 of fp32")
+@click.option("--graph/--no-graph", default=True, show_default=True, help="replay the step from a CUDA graph")
+@click.option("--deterministic/--no-deterministic", default=False, show_default=True,
+              help="ordered reductions instead of floating-point atomics: bit-identical runs")
 def main(steps, batch, tile, micro_batches, base_filters, depth, in_channels, norm, lr, name, resume, seed,
-         log_every):
+         log_every, precision, graph, deterministic):
     rank, world, local, pg = init_distributed("cuda")
     device = torch.device("cuda", local)
-    spec = UNetSpec(in_channels=in_channels, base_filters=base_filters, depth=depth, norm=norm, lr=lr)
+    spec = UNetSpec(in_channels=in_channels, base_filters=base_filters, depth=depth, norm=norm, lr=lr,
+                    precision=precision)
     trainer = Trainer(spec, device=device, process_group=pg, seed=seed, micro_batches=micro_batches)
+    trainer.model.ops.set_deterministic(deterministic)
     if resume:
         trainer.load_checkpoint(fp.path_to_model_folder, name)
         logger.info("resumed %s at step %d", name, trainer.model.step_count)
@@ -127,7 +134,7 @@ def main(steps, batch, tile, micro_batches, base_filters, depth, in_channels, no
                 for i in range(4)]
         batch_fn = lambda it: pool[it % len(pool)]  # noqa: E731
     t0 = time.time()
-    trainer.fit(steps, batch_fn, log_every=log_every if rank == 0 else 0)
+    trainer.fit(steps, batch_fn, log_every=log_every if rank == 0 else 0, graphed=graph)
     torch.cuda.synchronize()
     dt = time.time() - t0
     if rank == 0:
