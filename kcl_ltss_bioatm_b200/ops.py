@@ -470,7 +470,7 @@ class CudaOps:
                                               self._dev(labels, torch.int32, "labels"),
                                               self._dev(sizes, torch.int32, "sizes"), current_stream()),
               "plume_label_components")
-        self.launches += 3
+        self.launches += 4
 
     def fire_extents(self, labels, sizes, fire_rc, win, extents):
         """fire_rc int32 [n, 2] -> extents int32 [T, n]: size of the component nearest to each fire in its window."""

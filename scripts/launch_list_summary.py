@@ -1,7 +1,7 @@
 """Turns an ncu launch list of bench.py (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
---csv) into the committed artefacts: a compact per-launch CSV, a per-kernel summary and profiles/r1_traffic.json (the
+--csv) into the committed artefacts: a compact per-launch CSV, a per-kernel summary and a traffic JSON (the
 per-family DRAM traffic bench.py reports as roofline.traffic).
-Usage: python scripts/launch_list_summary.py gpurun_out/launches.csv profiles/r1_launches_step3_final"""
+Usage: python scripts/launch_list_summary.py gpurun_out/launches.csv profiles/r2_launches_final [profiles/r2_traffic.json] ["what was profiled"]"""
 import collections
 import csv
 import json
@@ -9,6 +9,8 @@ import re
 import sys
 
 src, stem = sys.argv[1], sys.argv[2]
+traffic_path = sys.argv[3] if len(sys.argv) > 3 else "profiles/r2_traffic.json"
+what = sys.argv[4] if len(sys.argv) > 4 else "python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 rows = list(csv.DictReader(l for l in open(src) if not l.startswith("==")))
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 by = collections.OrderedDict()
@@ -36,10 +38,8 @@ for d in L:
     a[0] += 1
     a[1] += d["us"]
     a[2] += d["dram_read_bytes"] + d["dram_write_bytes"]
-out = ["ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 3000 "
-       "python bench.py --steps 2 --warmup 1 --no-cpu-baseline",
-       f"{len(L)} launches (all legs of the bench: warm-up, graph-capture warm-ups, timed graph replays, eager roofline "
-       f"leg, end-to-end leg = about 14 training steps), {tot:.1f} us total; serialised, cold cache: compare SHARES",
+out = ["ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none " + what,
+       f"{len(L)} launches, {tot:.1f} us total; serialised, cold cache: compare SHARES",
        f"{'us total':>12} {'share':>6} {'n':>5} {'us/launch':>10} {'DRAM MB/launch':>15}  kernel"]
 for n, (c, v, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{v:12.1f} {100 * v / tot:5.1f}% {c:5d} {v / c:10.1f} {b / c / 1e6:15.2f}  {n[:90]}")
@@ -55,5 +55,5 @@ for f_, keys in fam.items():
     out.append(f"family {f_}: {len(sel)} launches, {traffic[f_]['share_of_step'] * 100:.1f}% of the time, "
                f"{traffic[f_]['dram_bytes_per_launch'] / 1e6:.1f} MB DRAM traffic per launch")
 open(stem + ".txt", "w").write("\n".join(out) + "\n")
-json.dump(traffic, open("profiles/r1_traffic.json", "w"), indent=1)
+json.dump(traffic, open(traffic_path, "w"), indent=1)
 print("\n".join(out[:14] + out[-2:]))
