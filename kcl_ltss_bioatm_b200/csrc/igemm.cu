@@ -626,7 +626,7 @@ __device__ __forceinline__ void wait_counter(const volatile uint32_t* ctr, uint3
 // MODE 0: weights resident in shared memory (whole [BLOCK_N][9*Cin] slice), group = one halo slot
 // MODE 1: weight ring of "triples" (the three vertical taps of one halo slot share a barrier)
 // MODE 2: weight ring of single tiles (BLOCK_N = 256), group = one tap
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool HALF_STAGE>
 __global__ void __launch_bounds__(kConv3Threads, 1)
     igemm_conv3_kernel(const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap bmap,
@@ -637,9 +637,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   constexpr uint32_t ISSUERS = MODE == 2 ? 1 : 2;  // 512-cycle groups of N=256 MMAs hide a single issuer's sync
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int BSLOT_BYTES = TPG * B_BYTES;
-  // 128-wide tiles in triple mode need a third weight slot more than a full staging tile: stage 64 rows
-  // (half a tile) at a time there
-  constexpr bool HALF_STAGE = (BLOCK_N == 128 && MODE == 1);
+  // HALF_STAGE: stage 64 rows (half a tile) at a time.  128-wide tiles in triple mode need a third weight slot more
+  // than a full staging tile; resident weight slices of 144 KB (64 -> 128 and 128 -> 64 channels) fit beside three
+  // halo slots only with the smaller staging buffers.
   constexpr int STG_ROWS = HALF_STAGE ? 64 : 128;
   constexpr int STG_BYTES = STG_ROWS * 128;
   constexpr int kWarpAlloc = 8, kWarpProducer = 9, kWarpInit = 10, kWarpMma0 = 11, kWarpRelayB = 12,
@@ -1072,10 +1072,10 @@ static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles, bool half_
          2 * (half_stage ? 8192 : 16384) + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool HALF_STAGE>
 static int launch_conv3_inst(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
                              const Conv3Params& p, size_t smem, int total_tiles, cudaStream_t stream) {
-  auto kern = igemm_conv3_kernel<BLOCK_N, MODE>;
+  auto kern = igemm_conv3_kernel<BLOCK_N, MODE, HALF_STAGE>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -1128,12 +1128,23 @@ static int try_launch_conv3(const FwdDesc& d) {
   // mode 0: weights resident when the whole [block_n][9*Cin] slice fits beside >= 4 halo slots (a slot is
   //         12 MMAs of work; fewer cannot cover the TMA latency)
   // mode 1: weight triples (block_n <= 128), mode 2: single weight tiles (block_n == 256)
+  // (PLUME_CONV3_RESIDENT_HALF=0 disables the second form: A/B switch)
+  static const bool resident_half = !(getenv("PLUME_CONV3_RESIDENT_HALF") && atoi(getenv("PLUME_CONV3_RESIDENT_HALF")) == 0);
   int mode, b_tiles;
+  bool half_stage = false;
   if (n_tiles == 1 && block_n <= 128 && conv3_smem_bytes(block_n, 4, 9 * kb) <= limit) {
     mode = 0;
     p.b_slots = 0;
     b_tiles = 9 * kb;
     p.a_slots = 4;
+  } else if (resident_half && n_tiles == 1 && block_n <= 128 && conv3_smem_bytes(block_n, 3, 9 * kb, true) <= limit) {
+    // 144 KB slices (64 -> 128, 128 -> 64): resident beside three halo slots when the staging buffers are halved;
+    // streaming them through the ring instead re-writes 144 KB of weights into shared memory for every tile
+    mode = 0;
+    half_stage = true;
+    p.b_slots = 0;
+    b_tiles = 9 * kb;
+    p.a_slots = 3;
   } else if (block_n <= 128) {
     mode = 1;
     p.b_slots = block_n == 128 ? 3 : 4;   // triples of 48 KB / 24 KB
@@ -1145,7 +1156,7 @@ static int try_launch_conv3(const FwdDesc& d) {
     b_tiles = 4;
     p.a_slots = 3;
   }
-  const bool half_stage = mode == 1 && block_n == 128;  // must match HALF_STAGE in the kernel
+  if (mode == 1 && block_n == 128) half_stage = true;   // selects the HALF_STAGE instantiation below
   while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles, half_stage) <= limit) ++p.a_slots;
   const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles, half_stage);
   if (smem > limit) return 1;
@@ -1170,14 +1181,17 @@ static int try_launch_conv3(const FwdDesc& d) {
     if (!p.det_part) return -2;
   }
   int r;
-  if (mode == 0) {
-    r = block_n == 128 ? launch_conv3_inst<128, 0>(amap, bmap, omap, p, smem, tt, d.stream)
-                       : launch_conv3_inst<64, 0>(amap, bmap, omap, p, smem, tt, d.stream);
+  if (mode == 0 && half_stage) {
+    r = block_n == 128 ? launch_conv3_inst<128, 0, true>(amap, bmap, omap, p, smem, tt, d.stream)
+                       : launch_conv3_inst<64, 0, true>(amap, bmap, omap, p, smem, tt, d.stream);
+  } else if (mode == 0) {
+    r = block_n == 128 ? launch_conv3_inst<128, 0, false>(amap, bmap, omap, p, smem, tt, d.stream)
+                       : launch_conv3_inst<64, 0, false>(amap, bmap, omap, p, smem, tt, d.stream);
   } else if (mode == 1) {
-    r = block_n == 128 ? launch_conv3_inst<128, 1>(amap, bmap, omap, p, smem, tt, d.stream)
-                       : launch_conv3_inst<64, 1>(amap, bmap, omap, p, smem, tt, d.stream);
+    r = block_n == 128 ? launch_conv3_inst<128, 1, true>(amap, bmap, omap, p, smem, tt, d.stream)
+                       : launch_conv3_inst<64, 1, false>(amap, bmap, omap, p, smem, tt, d.stream);
   } else {
-    r = launch_conv3_inst<256, 2>(amap, bmap, omap, p, smem, tt, d.stream);
+    r = launch_conv3_inst<256, 2, false>(amap, bmap, omap, p, smem, tt, d.stream);
   }
   if (r == 0 && p.det_part) r = det_stats_finish(p.det_part, det_rows, cout, d.stat_sum, d.stat_sq, d.stream);
   return r;

@@ -178,42 +178,19 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Flatten in two passes.  Only run starts take part in unions (every other pixel points at its run's start since
-// init), so only they can sit on long parent chains: pass A resolves the run starts and writes their roots back,
-// pass B gives every other pixel its run start's root with two loads.  (One pass in which every pixel walked its
-// run start's chain by itself repeated that walk once per pixel of the run.)
-__device__ __forceinline__ int run_start_lane(uint32_t bits, int lane) {
-  const uint32_t zeros = ~bits & ((1u << lane) - 1u);   // unset pixels to the left, inside the segment
-  return zeros ? 32 - __clz(zeros) : 0;
-}
-
-__global__ void __launch_bounds__(256)
-    ccl_flatten_starts_kernel(int T, int H, int W, int* __restrict__ parent_all) {
-  const RowSeg r = row_segment(H, W, T);
-  const int lane = threadIdx.x & 31;
-  const long long plane = 1ll * H * W;
-  int* parent = parent_all + (r.valid ? r.t * plane : 0);
-  const int i = r.y * W + r.x;
-  const bool set = r.valid && parent[i] >= 0;
-  const uint32_t bits = __ballot_sync(0xffffffffu, set);
-  if (!set || run_start_lane(bits, lane) != lane) return;
-  parent[i] = uf_find(parent, i);   // racing readers see the old parent or the root: both are ancestors
-}
-
 __global__ void __launch_bounds__(256)
     ccl_flatten_kernel(int T, int H, int W, int* __restrict__ parent_all, int* __restrict__ sizes_all) {
   const RowSeg r = row_segment(H, W, T);
   const int lane = threadIdx.x & 31;
   const long long plane = 1ll * H * W;
-  int* parent = parent_all + (r.valid ? r.t * plane : 0);
-  const int i = r.y * W + r.x;
-  const bool set = r.valid && parent[i] >= 0;
-  const uint32_t bits = __ballot_sync(0xffffffffu, set);
   int root = -1;
-  if (set) {
-    const int start = run_start_lane(bits, lane);
-    root = parent[i - lane + start];   // the run start's root (pass A); for the run start itself its own entry
-    parent[i] = root;
+  if (r.valid) {
+    int* parent = parent_all + r.t * plane;
+    const int i = r.y * W + r.x;
+    if (parent[i] >= 0) {
+      root = uf_find(parent, i);
+      parent[i] = root;   // readers that race with this see the old parent or the root: both are ancestors
+    }
   }
   const uint32_t active = __ballot_sync(0xffffffffu, root >= 0);
   if (root < 0) return;
@@ -237,7 +214,6 @@ int label_components(const uint8_t* masks, int T, int H, int W, int* labels, int
   const unsigned grid = static_cast<unsigned>(blocks);
   ccl_init_kernel<<<grid, 256, 0, s>>>(masks, T, H, W, labels, sizes);
   ccl_merge_kernel<<<grid, 256, 0, s>>>(masks, T, H, W, labels);
-  ccl_flatten_starts_kernel<<<grid, 256, 0, s>>>(T, H, W, labels);
   ccl_flatten_kernel<<<grid, 256, 0, s>>>(T, H, W, labels, sizes);
   return check_launch_sweep("label_components");
 }

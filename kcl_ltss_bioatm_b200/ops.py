@@ -470,7 +470,7 @@ class CudaOps:
                                               self._dev(labels, torch.int32, "labels"),
                                               self._dev(sizes, torch.int32, "sizes"), current_stream()),
               "plume_label_components")
-        self.launches += 4
+        self.launches += 3
 
     def fire_extents(self, labels, sizes, fire_rc, win, extents):
         """fire_rc int32 [n, 2] -> extents int32 [T, n]: size of the component nearest to each fire in its window."""
@@ -518,7 +518,7 @@ class CudaOps:
                                                     ex[0], ex[1], ex[2], ex[3], int(x_size), int(y_size), float(radius),
                                                     ptr(ws), nbytes, self._dev(out_idx, torch.int32, "out_idx"),
                                                     current_stream()), "plume_resample_nearest_index")
-        self.launches += 4
+        self.launches += 3
 
     def gather_fill(self, src, idx, fill_value, out):
         if src.dtype not in (torch.float32, torch.float64) or out.dtype != src.dtype:

@@ -38,6 +38,8 @@ CONV_SHAPES = [  # N, H, W, Cin, Cout
     (1, 4, 4, 64, 64),      # one GEMM tile spans several images (and is mostly out of bounds)
     (5, 4, 4, 128, 64),
     (1, 16, 16, 1024, 256), (2, 48, 24, 128, 128),
+    (2, 32, 16, 128, 64),   # 144 KB weight slice resident beside three halo slots (half-tile staging), kb = 2
+    (1, 40, 24, 64, 128),   # the same for a 128-wide tile, ragged
 ]
 
 
@@ -61,7 +63,7 @@ def test_conv3x3_fwd_epilogue_stats(ops, n, h, w, cin, cout):
             assert relmax(ss, ss_r) < 5e-3 and relmax(sq, sq_r) < 5e-3
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES[:6])
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES[:6] + CONV_SHAPES[-2:])
 def test_conv3x3_concat_slices_and_dgrad(ops, n, h, w, cin, cout):
     cu, rf = ops
     x = rnd(n, h, w, cin, seed=1).to(BF)
