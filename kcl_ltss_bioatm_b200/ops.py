@@ -518,7 +518,7 @@ class CudaOps:
                                                     ex[0], ex[1], ex[2], ex[3], int(x_size), int(y_size), float(radius),
                                                     ptr(ws), nbytes, self._dev(out_idx, torch.int32, "out_idx"),
                                                     current_stream()), "plume_resample_nearest_index")
-        self.launches += 3
+        self.launches += 4
 
     def gather_fill(self, src, idx, fill_value, out):
         if src.dtype not in (torch.float32, torch.float64) or out.dtype != src.dtype:
