@@ -1137,9 +1137,12 @@ static int try_launch_conv3(const FwdDesc& d) {
     p.b_slots = 0;
     b_tiles = 9 * kb;
     p.a_slots = 4;
-  } else if (resident_half && n_tiles == 1 && block_n <= 128 && conv3_smem_bytes(block_n, 3, 9 * kb, true) <= limit) {
-    // 144 KB slices (64 -> 128, 128 -> 64): resident beside three halo slots when the staging buffers are halved;
-    // streaming them through the ring instead re-writes 144 KB of weights into shared memory for every tile
+  } else if (resident_half && n_tiles == 1 && block_n == 128 && conv3_smem_bytes(block_n, 3, 9 * kb, true) <= limit) {
+    // the 144 KB slice of a 64 -> 128 layer: resident beside three halo slots when the staging buffers are halved;
+    // streaming it through the ring instead re-writes 144 KB of weights into shared memory for every tile.
+    // Measured on one box (gpurun_out/r2u): 64 -> 128 @128x128 125 -> 117 us, @256x256 (a dgrad) 317 -> 290 us.  The
+    // same for 128 -> 64 (64-wide tiles, kb = 2) is SLOWER, 349 -> 402 us: three halo slots are 1.7 k cycles of
+    // 48-cycle MMAs, too little look-ahead, where the ring configuration affords six -- so 128-wide tiles only.
     mode = 0;
     half_stage = true;
     p.b_slots = 0;
