@@ -121,3 +121,61 @@ def test_two_rank_graphed_steps_match_eager_steps(tmp_path):
             assert abs(a - b) <= 1e-2 * abs(a), (r["le"], r["lg"])
     d = (r0["pe"] - r0["pg"]).abs()
     assert d.median().item() <= 1e-4 and (d.norm() / r0["pe"].norm()).item() <= 2e-2
+
+
+def _worker_bf16_wire(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      PLUME_GRAD_COMM="bf16")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from kcl_ltss_bioatm_b200.data import synthetic_batch
+    from kcl_ltss_bioatm_b200.trainer import Trainer
+
+    spec = _spec()
+    tr = Trainer(spec, device=f"cuda:{rank}", process_group=dist.group.WORLD, seed=rank, bucket_mb=0.5)
+    assert tr.model.grad_comm_bf16
+    x, t = synthetic_batch(4, 64, 64, spec.in_channels, seed=11)
+    half = slice(rank * 2, rank * 2 + 2)
+    m = tr.model
+    m.train(True)
+    m.forward(x[half].cuda(), t[half].cuda())
+    m.backward()
+    m.wait_grads()
+    torch.cuda.synchronize()
+    g_eager = m.grads.cpu().clone()
+    # and the same through the captured-graph step (casts + all-reduces inside the graph)
+    losses = [float(tr.step_graphed(x[half].cuda(), t[half].cuda())[0].item()) for _ in range(3)]
+    torch.cuda.synchronize()
+    torch.save({"grads": g_eager, "params": m.params.cpu(), "losses": losses}, os.path.join(out_dir, f"b{rank}.pt"))
+    dist.barrier()
+    tr.release_graphs()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_bf16_gradient_wire_format(tmp_path):
+    """PLUME_GRAD_COMM=bf16: buckets are rounded to bf16 for the all-reduce and widened back.  Both ranks end with the
+    same gradients; they equal the single-GPU gradient of the full batch to bf16 rounding (2^-8 relative per
+    element); graphed steps run and keep the replicas identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29700 + os.getpid() % 90
+    mp.spawn(_worker_bf16_wire, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    assert torch.equal(r0["grads"], r1["grads"]) and torch.equal(r0["params"], r1["params"])
+    assert r0["losses"][-1] < r0["losses"][0] and all(abs(a - a) == 0 for a in r0["losses"])
+    from kcl_ltss_bioatm_b200.data import synthetic_batch
+    from kcl_ltss_bioatm_b200.unet import UNetB200
+
+    spec = _spec()
+    single = UNetB200(spec, device="cuda:0", seed=0)     # rank 0's seed: the replicas were broadcast from rank 0
+    x, t = synthetic_batch(4, 64, 64, spec.in_channels, seed=11)
+    single.train(True)
+    single.forward(x.cuda(), t.cuda())
+    single.backward()
+    torch.cuda.synchronize()
+    g = single.grads.cpu()
+    rel = ((r0["grads"] - g).norm() / g.norm()).item()
+    print(f"bf16 wire format: all-reduced gradient vs single-GPU gradient rel L2 {rel:.2e}")
+    assert rel < 8e-3
