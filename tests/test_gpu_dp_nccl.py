@@ -164,7 +164,7 @@ def test_two_rank_bf16_gradient_wire_format(tmp_path):
     mp.spawn(_worker_bf16_wire, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
     assert torch.equal(r0["grads"], r1["grads"]) and torch.equal(r0["params"], r1["params"])
-    assert r0["losses"][-1] < r0["losses"][0] and all(abs(a - a) == 0 for a in r0["losses"])
+    assert r0["losses"][-1] < r0["losses"][0] and r1["losses"][-1] < r1["losses"][0]   # three steps on one batch
     from kcl_ltss_bioatm_b200.data import synthetic_batch
     from kcl_ltss_bioatm_b200.unet import UNetB200
 
