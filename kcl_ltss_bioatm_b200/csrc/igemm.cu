@@ -626,7 +626,15 @@ __device__ __forceinline__ void wait_counter(const volatile uint32_t* ctr, uint3
 // MODE 0: weights resident in shared memory (whole [BLOCK_N][9*Cin] slice), group = one halo slot
 // MODE 1: weight ring of "triples" (the three vertical taps of one halo slot share a barrier)
 // MODE 2: weight ring of single tiles (BLOCK_N = 256), group = one tap
-template <int BLOCK_N, int MODE, bool HALF_STAGE>
+// PAIR (MODE 2 only, launched as clusters of two CTAs): tcgen05.mma.cta_group::2.  The two CTAs of a pair work on two
+// adjacent M tiles with the same N tile; each loads its own halo boxes and HALF of every weight tile (128 of the 256
+// rows), both CTAs' TMA loads complete on the LEADER's "full" barriers (rank 0), the leader's relays and its single
+// issuer thread see them and issue M = 256 MMAs that read A from both CTAs and the two halves of B, commits are
+// multicast to both CTAs' "empty" / "accumulator full" barriers, each CTA's epilogue drains its own TMEM and
+// arrives on the leader's "accumulator drained" barrier.  Per SM the operand traffic of an N = 256 MMA drops from
+// 21.5 KB to 13.5 KB per 128 cycles, i.e. below what shared memory delivers (scripts/test_2cta.cu: 128.1 cycles per
+// pair MMA, correct against a CPU matmul).
+template <int BLOCK_N, int MODE, bool HALF_STAGE, bool PAIR = false>
 __global__ void __launch_bounds__(kConv3Threads, 1)
     igemm_conv3_kernel(const __grid_constant__ CUtensorMap amap,
                        const __grid_constant__ CUtensorMap bmap,
@@ -635,7 +643,8 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   constexpr int TPG = MODE == 2 ? 1 : 3;   // taps per MMA group
   constexpr int GPS = 3 / TPG;             // groups per halo slot
   constexpr uint32_t ISSUERS = MODE == 2 ? 1 : 2;  // 512-cycle groups of N=256 MMAs hide a single issuer's sync
-  constexpr int B_BYTES = BLOCK_N * 128;
+  static_assert(!PAIR || MODE == 2, "CTA pairs are implemented for the 256-wide ring mode");
+  constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // PAIR: this CTA's half of the weight tile
   constexpr int BSLOT_BYTES = TPG * B_BYTES;
   // HALF_STAGE: stage 64 rows (half a tile) at a time.  128-wide tiles in triple mode need a third weight slot more
   // than a full staging tile; resident weight slices of 144 KB (64 -> 128 and 128 -> 64 channels) fit beside three
@@ -651,6 +660,11 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // position in the CTA pair; rank 0 is the leader
+  const bool leader = rank == 0;
+  // virtual CTA index / count over which work items are distributed (PAIR: the pair)
+  const int vcta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int vgrid = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   const uint32_t b_region = RESIDENT ? 9u * p.kb * B_BYTES : static_cast<uint32_t>(p.b_slots) * BSLOT_BYTES;
   const uint32_t off_a = 0;
@@ -685,7 +699,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), ISSUERS);  // every issuer commits after its last group of the tile
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), PAIR ? 256 : 128);   // PAIR: both CTAs' epilogue warpgroups arrive on the leader's
     }
     mbar_init(bres_full, 1);
     ctr[0] = 0;
@@ -694,24 +708,31 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     fence_mbar_init();
   }
   if (warp == kWarpAlloc) {
-    tmem_alloc(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * ISSUERS * BLOCK_N);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2cta(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * ISSUERS * BLOCK_N);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(sbase + off_bar + 8 * (4 * kMaxSlots + 5), 2 * ISSUERS * BLOCK_N);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int tiles_img = p.tiles_w * p.tiles_h;
-  const int total_tiles = tiles_img * p.N * p.n_tiles;
-  const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                       static_cast<int>(gridDim.x);
+  // work items: tiles, or (PAIR) pairs of adjacent M tiles with the same N tile (the host guarantees an even count)
+  const int total_tiles = PAIR ? (tiles_img * p.N / 2) * p.n_tiles : tiles_img * p.N * p.n_tiles;
+  const int my_tiles = (total_tiles - vcta + vgrid - 1) / vgrid;
   const int slots_per_tile = 3 * p.kb;  // halo slots per tile
 
-  // tile -> (n tile, image, w0, h0) without integer divides
+  // work item -> (n tile, image, w0, h0) of THIS CTA's tile, without integer divides
   auto decode = [&](int tile, int& n_tile, int& img, int& w0, int& h0) {
-    const uint32_t m_tile = fdiv(tile, p.div_ntiles);
+    uint32_t m_tile = fdiv(tile, p.div_ntiles);
     n_tile = tile - m_tile * p.n_tiles;
+    if (PAIR) m_tile = 2 * m_tile + rank;
     img = fdiv(m_tile, p.div_tiles_img);
     const uint32_t rem = m_tile - img * tiles_img;
     const uint32_t ty = fdiv(rem, p.div_tiles_w);
@@ -732,7 +753,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
       }
       int sa = 0, pa = 0, sb = 0, pb = 0;
       long long t_wait = 0, t_begin = clock64();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = vcta; tile < total_tiles; tile += vgrid) {
         int n_tile, img, w0, h0;
         decode(tile, n_tile, img, w0, h0);
         for (int kb = 0; kb < p.kb; ++kb) {
@@ -740,20 +761,34 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
             const long long tw0 = p.prof ? clock64() : 0;
             mbar_wait_relaxed(a_empty(sa), pa ^ 1, 1, &g_dbg_word);
             if (p.prof) t_wait += clock64() - tw0;
-            mbar_expect_tx(a_full(sa), kHaloBytes);
-            tma_load_4d(sbase + off_a + sa * kHaloBytes, &amap, a_full(sa), kb * 64, w0 + dwi - 1,
-                        h0 - 1, img);
+            if (PAIR) {
+              // the leader's barrier counts both CTAs' bytes; the peer only issues its load
+              if (leader) mbar_expect_tx(a_full(sa), 2 * kHaloBytes);
+              tma_load_4d_2cta(sbase + off_a + sa * kHaloBytes, &amap, a_full(sa), kb * 64, w0 + dwi - 1, h0 - 1, img);
+            } else {
+              mbar_expect_tx(a_full(sa), kHaloBytes);
+              tma_load_4d(sbase + off_a + sa * kHaloBytes, &amap, a_full(sa), kb * 64, w0 + dwi - 1,
+                          h0 - 1, img);
+            }
             if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
             if (!RESIDENT) {
 #pragma unroll
               for (int g = 0; g < GPS; ++g) {
                 mbar_wait_relaxed(b_empty(sb), pb ^ 1, 8, &g_dbg_word);
-                mbar_expect_tx(b_full(sb), BSLOT_BYTES);
+                if (PAIR) {
+                  if (leader) mbar_expect_tx(b_full(sb), 2 * BSLOT_BYTES);
+                } else {
+                  mbar_expect_tx(b_full(sb), BSLOT_BYTES);
+                }
 #pragma unroll
                 for (int t = 0; t < TPG; ++t) {
                   const int dhi = g * TPG + t;
-                  tma_load_2d(sbase + off_b + sb * BSLOT_BYTES + t * B_BYTES, &bmap, b_full(sb),
-                              (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N);
+                  if (PAIR)   // this CTA's half of the weight tile: rows [rank * 128, +128) of the 256
+                    tma_load_2d_2cta(sbase + off_b + sb * BSLOT_BYTES + t * B_BYTES, &bmap, b_full(sb),
+                                     (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N + rank * (BLOCK_N / 2));
+                  else
+                    tma_load_2d(sbase + off_b + sb * BSLOT_BYTES + t * B_BYTES, &bmap, b_full(sb),
+                                (dhi * 3 + dwi) * p.cin + kb * 64, n_tile * BLOCK_N);
                 }
                 if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
               }
@@ -768,7 +803,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     }
   } else if (warp == kWarpInit) {
     // ------------------------------------------------------------------ relay: halo slots full
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int sa = 0, pa = 0;
       const uint32_t n = static_cast<uint32_t>(my_tiles) * slots_per_tile;
       for (uint32_t i = 0; i < n; ++i) {
@@ -779,7 +814,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     }
   } else if (warp == kWarpRelayB) {
     // ------------------------------------------------------------------ relay: weight slots full
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       if (RESIDENT) {
         mbar_wait(bres_full, 0, 9, &g_dbg_word);
         ctr[1] = 1;
@@ -795,7 +830,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     }
   } else if (warp == kWarpAlloc) {
     // ------------------------------------------------------------------ relay: accumulators drained
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       for (int it = 0; it < my_tiles; ++it) {
         // tile `it` may start once the epilogue drained the previous user of accumulator it & 1
         mbar_wait(tempty_bar(it & 1), ((it >> 1) & 1) ^ 1, 13, &g_dbg_word);
@@ -804,9 +839,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     }
   } else if (warp == kWarpMma0 || warp == kWarpMma1) {
     // ------------------------------------------------------------------ MMA issuers (one lane each)
-    if (lane == 0 && (warp == kWarpMma0 || ISSUERS == 2)) {
+    if (lane == 0 && leader && (warp == kWarpMma0 || ISSUERS == 2)) {
       const uint32_t me = warp == kWarpMma0 ? 0u : 1u;
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BLOCK_N, 0, 0);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       const long long t_begin = clock64();
       const uint32_t a_lo_base = umma_desc_lo(sbase + off_a, 16);
@@ -848,13 +883,21 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
                   const int dhi = g * TPG + t;   // vertical tap = one 1024-byte atom further into the halo
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    umma_bf16_lohi(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
+                    if (PAIR)
+                      umma_bf16_lohi_2cta(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
+                    else
+                      umma_bf16_lohi(d_tmem, a_lo + dhi * 64 + 2 * k, hi, b_lo + 2 * k, hi, idesc, accumulate);
                     accumulate = 1;
                   }
                   b_lo += RESIDENT ? b_tap_step : kBUnits;
                 }
-                if (!RESIDENT) umma_commit(b_empty(sb));
-                umma_commit(a_empty(sa));
+                if (PAIR) {   // both CTAs' producers get their slots back
+                  umma_commit_2cta(b_empty(sb), 3u);
+                  umma_commit_2cta(a_empty(sa), 3u);
+                } else {
+                  if (!RESIDENT) umma_commit(b_empty(sb));
+                  umma_commit(a_empty(sa));
+                }
               }
               if (!RESIDENT) {
                 if (++sb == p.b_slots) sb = 0;
@@ -863,7 +906,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
             if (++sa == p.a_slots) sa = 0;
           }
         }
-        umma_commit(tfull_bar(it & 1));   // arrives once this thread's MMAs of the tile are complete
+        // arrives once this thread's MMAs of the tile are complete (PAIR: in both CTAs)
+        if (PAIR) umma_commit_2cta(tfull_bar(it & 1), 3u);
+        else umma_commit(tfull_bar(it & 1));
       }
       if (p.prof && me == 0) p.prof[blockIdx.x * 8 + 2] = clock64() - t_begin;  // MMA issuer: total
     }
@@ -917,7 +962,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
         acc_s[i] = acc_q[i] = 0.0;
       }
     };
-    for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+    for (int tile = vcta + g * vgrid; tile < total_tiles; tile += 2 * vgrid, it += 2) {
       int n_tile, img, w0, h0;
       decode(tile, n_tile, img, w0, h0);
       const int acc_phase = (it >> 1) & 1;
@@ -971,7 +1016,8 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
         }
         if (chunk == BLOCK_N / 64 - 1) {
           tc_fence_before();
-          mbar_arrive(tempty_bar(g));
+          if (PAIR) mbar_arrive_leader(tempty_bar(g));   // the issuer lives in the leader CTA
+          else mbar_arrive(tempty_bar(g));
         }
         const float* sc = s_scale + chunk * 64;
         const float* sh = s_shift + chunk * 64;
@@ -1064,12 +1110,50 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 2 * ISSUERS * BLOCK_N);
+  if (PAIR) {
+    cluster_sync_all();   // the leader's MMAs read the peer's shared memory and commit to its barriers until the end
+    if (warp == kWarpAlloc) tmem_dealloc_2cta(tmem_base, 2 * ISSUERS * BLOCK_N);
+  } else {
+    if (warp == kWarpAlloc) tmem_dealloc(tmem_base, 2 * ISSUERS * BLOCK_N);
+  }
 }
 
-static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles, bool half_stage = false) {
-  return static_cast<size_t>(a_slots) * kHaloBytes + static_cast<size_t>(b_tiles) * block_n * 128 +
+static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles, bool half_stage = false, bool pair = false) {
+  return static_cast<size_t>(a_slots) * kHaloBytes + static_cast<size_t>(b_tiles) * (pair ? block_n / 2 : block_n) * 128 +
          2 * (half_stage ? 8192 : 16384) + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
+}
+
+// CTA-pair launch of the 256-wide kernel: clusters of two CTAs, an even grid, work items = tile pairs.
+static int launch_conv3_pair(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
+                             const Conv3Params& p, size_t smem, int total_pairs, cudaStream_t stream) {
+  auto kern = igemm_conv3_kernel<256, 2, false, true>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(igemm_conv3 pair): ") + cudaGetErrorString(attr_err));
+    return -2;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2u * static_cast<unsigned>(std::min(total_pairs, num_sms() / 2)), 1, 1);
+  cfg.blockDim = dim3(kConv3Threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, amap, bmap, omap, p);
+  if (e != cudaSuccess) {
+    set_error(std::string("igemm_conv3 pair launch: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
 }
 
 template <int BLOCK_N, int MODE, bool HALF_STAGE>
@@ -1159,9 +1243,22 @@ static int try_launch_conv3(const FwdDesc& d) {
     b_tiles = 4;
     p.a_slots = 3;
   }
+  // 256-wide tiles as CTA pairs (cta_group::2) when the M tiles pair up; PLUME_CONV3_PAIR=0 keeps single CTAs
+  static const bool pair_on = !(getenv("PLUME_CONV3_PAIR") && atoi(getenv("PLUME_CONV3_PAIR")) == 0);
+  const long long m_tiles = 1ll * p.tiles_w * p.tiles_h * N;
+  const bool pair = pair_on && mode == 2 && m_tiles % 2 == 0 && m_tiles * n_tiles >= 4;
+  if (pair) {   // a CTA holds half of every weight tile (16 KB): more ring slots in the same shared memory
+    p.a_slots = 4;
+    p.b_slots = 6;
+    b_tiles = 6;
+    while (p.b_slots < kMaxSlots && conv3_smem_bytes(block_n, p.a_slots, b_tiles + 1, false, true) <= limit) {
+      ++p.b_slots;
+      ++b_tiles;
+    }
+  }
   if (mode == 1 && block_n == 128) half_stage = true;   // selects the HALF_STAGE instantiation below
-  while (p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles, half_stage) <= limit) ++p.a_slots;
-  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles, half_stage);
+  while (!pair && p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles, half_stage) <= limit) ++p.a_slots;
+  const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles, half_stage, pair);
   if (smem > limit) return 1;
 
   CUtensorMap amap, bmap, omap;
@@ -1171,14 +1268,14 @@ static int try_launch_conv3(const FwdDesc& d) {
   }
   if (make_act_map(&amap, d.in[0], 64, 8, 18, 1)) return -1;
   if (make_act_map(&omap, d.out[0], 64, 8, half_stage ? 8 : 16, 1)) return -1;
-  if (make_mat_map(&bmap, d.wmat, cout, 9ll * d.Cin, 64, block_n)) return -1;
+  if (make_mat_map(&bmap, d.wmat, cout, 9ll * d.Cin, 64, pair ? block_n / 2 : block_n)) return -1;
   const long long total = 1ll * p.tiles_w * p.tiles_h * N * n_tiles;
   if (total > 0x7fffffffll) {
     set_error("igemm_conv3: too many tiles");
     return -1;
   }
   const int tt = static_cast<int>(total);
-  const int det_rows = 2 * std::min(tt, num_sms());   // one row per (CTA, epilogue warpgroup)
+  const int det_rows = 2 * std::min(tt, num_sms()) + 2;   // one row per (CTA, epilogue warpgroup)
   if (d.stat_sum && deterministic()) {
     p.det_part = det_stats_begin(det_rows, cout, d.stream);
     if (!p.det_part) return -2;
@@ -1193,6 +1290,8 @@ static int try_launch_conv3(const FwdDesc& d) {
   } else if (mode == 1) {
     r = block_n == 128 ? launch_conv3_inst<128, 1, true>(amap, bmap, omap, p, smem, tt, d.stream)
                        : launch_conv3_inst<64, 1, false>(amap, bmap, omap, p, smem, tt, d.stream);
+  } else if (pair) {
+    r = launch_conv3_pair(amap, bmap, omap, p, smem, tt / 2, d.stream);
   } else {
     r = launch_conv3_inst<256, 2, false>(amap, bmap, omap, p, smem, tt, d.stream);
   }

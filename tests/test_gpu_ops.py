@@ -434,6 +434,45 @@ def test_conv3_repeated_launches_are_bit_identical(ops, cin, cout, mode):
     assert int(bad.item()) == 0, f"{mode}: {int(bad.item())} differing elements over 200 launches"
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 48, 40, 256, 512), (2, 32, 32, 128, 256), (2, 64, 24, 512, 256)])
+def test_conv3_cta_pairs_match_oracle_and_repeat_bit_identically(ops, n, h, w, cin, cout):
+    """256-wide tiles run as CTA pairs (tcgen05.mma.cta_group::2) when the M tiles pair up: forward with epilogue and
+    BatchNorm statistics against the oracle, dgrad against the oracle, and 100 repeated launches bit-identical (both
+    CTAs' TMA loads complete on the leader's barriers; a visibility race would show as run-to-run differences)."""
+    cu, rf = ops
+    x = rnd(n, h, w, cin, seed=21).to(BF)
+    wt = (rnd(cout, 3, 3, cin, seed=22) / (9 * cin) ** 0.5).to(BF)
+    scale, shift = 1 + 0.1 * rnd(cout, seed=23), 0.1 * rnd(cout, seed=24)
+    y_ref = torch.empty(n, h, w, cout, dtype=BF)
+    ss_r, sq_r = torch.zeros(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64)
+    rf.conv3x3_fwd(x, wt, scale, shift, 1, y_ref, ss_r, sq_r)
+    xd, wd_, scd, shd = x.to(DEV), wt.to(DEV), scale.to(DEV), shift.to(DEV)
+    first = torch.full((n, h, w, cout), float("nan"), dtype=BF, device=DEV)
+    ss, sq = (torch.zeros(cout, dtype=torch.float64, device=DEV) for _ in range(2))
+    cu.conv3x3_fwd(xd, wd_, scd, shd, 1, first, ss, sq)
+    torch.cuda.synchronize()
+    assert relmax(first, y_ref) < 1.6e-2
+    assert relmax(ss, ss_r) < 2e-3 and relmax(sq, sq_r) < 2e-3
+    y = torch.empty_like(first)
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    for _ in range(100):
+        y.fill_(float("nan"))
+        cu.conv3x3_fwd(xd, wd_, scd, shd, 1, y)
+        bad += (y.view(torch.int16) != first.view(torch.int16)).sum()
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0, f"{int(bad.item())} differing elements over 100 launches"
+    # dgrad: cout -> cin through the rotated weights (cin >= 256 also runs as pairs)
+    wf_r, wd_r = torch.empty(cout, 3, 3, cin, dtype=BF), torch.empty(cin, 3, 3, cout, dtype=BF)
+    rf.pack_conv3x3(wt.float(), wf_r, wd_r)
+    dy = rnd(n, h, w, cout, seed=25).to(BF)
+    dx_ref = torch.empty(n, h, w, cin, dtype=BF)
+    rf.conv3x3_dgrad(dy, wd_r, dx_ref)
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=BF, device=DEV)
+    cu.conv3x3_dgrad(dy.to(DEV), wd_r.to(DEV), dx)
+    torch.cuda.synchronize()
+    assert relmax(dx, dx_ref) < 1.6e-2
+
+
 def test_wgrad3_repeated_launches_agree_to_rounding(ops):
     """The split-K weight gradient adds its partial sums with fp32 atomics (order not fixed): repeated launches must
     agree to fp32 rounding of the sum, nothing more."""
