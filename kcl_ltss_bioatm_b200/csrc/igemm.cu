@@ -643,7 +643,6 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   constexpr int TPG = MODE == 2 ? 1 : 3;   // taps per MMA group
   constexpr int GPS = 3 / TPG;             // groups per halo slot
   constexpr uint32_t ISSUERS = MODE == 2 ? 1 : 2;  // 512-cycle groups of N=256 MMAs hide a single issuer's sync
-  static_assert(!PAIR || MODE == 2, "CTA pairs are implemented for the 256-wide ring mode");
   constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // PAIR: this CTA's half of the weight tile
   constexpr int BSLOT_BYTES = TPG * B_BYTES;
   // HALF_STAGE: stage 64 rows (half a tile) at a time.  128-wide tiles in triple mode need a third weight slot more
@@ -744,12 +743,19 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
     // ------------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
       if (RESIDENT) {
-        // n_tiles == 1 in this mode: the CTA's weight slice never changes
-        mbar_expect_tx(bres_full, b_region);
+        // n_tiles == 1 in this mode: the CTA's weight slice never changes (PAIR: this CTA's half of its rows;
+        // the leader's barrier counts both halves)
+        if (!PAIR) mbar_expect_tx(bres_full, b_region);
+        else if (leader) mbar_expect_tx(bres_full, 2 * b_region);
         for (int t = 0; t < 9; ++t)
-          for (int kb = 0; kb < p.kb; ++kb)
-            tma_load_2d(sbase + off_b + (t * p.kb + kb) * B_BYTES, &bmap, bres_full,
-                        t * p.cin + kb * 64, 0);
+          for (int kb = 0; kb < p.kb; ++kb) {
+            if (PAIR)
+              tma_load_2d_2cta(sbase + off_b + (t * p.kb + kb) * B_BYTES, &bmap, bres_full, t * p.cin + kb * 64,
+                               rank * (BLOCK_N / 2));
+            else
+              tma_load_2d(sbase + off_b + (t * p.kb + kb) * B_BYTES, &bmap, bres_full,
+                          t * p.cin + kb * 64, 0);
+          }
       }
       int sa = 0, pa = 0, sb = 0, pb = 0;
       long long t_wait = 0, t_begin = clock64();
@@ -1123,10 +1129,11 @@ static size_t conv3_smem_bytes(int block_n, int a_slots, int b_tiles, bool half_
          2 * (half_stage ? 8192 : 16384) + 2 * 4 * block_n * 4 + 8 * (4 * kMaxSlots + 8) + 16 + 1024;
 }
 
-// CTA-pair launch of the 256-wide kernel: clusters of two CTAs, an even grid, work items = tile pairs.
+// CTA-pair launch: clusters of two CTAs, an even grid, work items = tile pairs.
+template <int BLOCK_N, int MODE, bool HALF_STAGE>
 static int launch_conv3_pair(const CUtensorMap& amap, const CUtensorMap& bmap, const CUtensorMap& omap,
                              const Conv3Params& p, size_t smem, int total_pairs, cudaStream_t stream) {
-  auto kern = igemm_conv3_kernel<256, 2, false, true>;
+  auto kern = igemm_conv3_kernel<BLOCK_N, MODE, HALF_STAGE, true>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -1214,19 +1221,30 @@ static int try_launch_conv3(const FwdDesc& d) {
   // mode 1: weight triples (block_n <= 128), mode 2: single weight tiles (block_n == 256)
   // (PLUME_CONV3_RESIDENT_HALF=0 disables the second form: A/B switch)
   static const bool resident_half = !(getenv("PLUME_CONV3_RESIDENT_HALF") && atoi(getenv("PLUME_CONV3_RESIDENT_HALF")) == 0);
+  // CTA pairs (tcgen05.mma.cta_group::2) when the M tiles pair up: each CTA holds HALF of every weight tile, so weight
+  // slices that are resident halve, ring slots halve, and an MMA reads half of B per SM.  PLUME_CONV3_PAIR: 0 = never,
+  // 1 = only the 256-wide ring mode, 2 (default) = every mode.
+  static const int pair_level = getenv("PLUME_CONV3_PAIR") ? atoi(getenv("PLUME_CONV3_PAIR")) : 2;
+  const long long m_tiles = 1ll * p.tiles_w * p.tiles_h * N;
+  const bool can_pair = m_tiles % 2 == 0 && m_tiles * n_tiles >= 4;
+  bool pair = can_pair && ((pair_level >= 2) || (pair_level == 1 && block_n == 256));
+  auto fits = [&](int a_slots, int b_tiles_, bool half) {
+    return conv3_smem_bytes(block_n, a_slots, b_tiles_, half, pair) <= limit;
+  };
   int mode, b_tiles;
   bool half_stage = false;
-  if (n_tiles == 1 && block_n <= 128 && conv3_smem_bytes(block_n, 4, 9 * kb) <= limit) {
+  if (n_tiles == 1 && block_n <= 128 && fits(4, 9 * kb, false)) {
     mode = 0;
     p.b_slots = 0;
     b_tiles = 9 * kb;
     p.a_slots = 4;
-  } else if (resident_half && n_tiles == 1 && block_n == 128 && conv3_smem_bytes(block_n, 3, 9 * kb, true) <= limit) {
-    // the 144 KB slice of a 64 -> 128 layer: resident beside three halo slots when the staging buffers are halved;
-    // streaming it through the ring instead re-writes 144 KB of weights into shared memory for every tile.
-    // Measured on one box (gpurun_out/r2u): 64 -> 128 @128x128 125 -> 117 us, @256x256 (a dgrad) 317 -> 290 us.  The
-    // same for 128 -> 64 (64-wide tiles, kb = 2) is SLOWER, 349 -> 402 us: three halo slots are 1.7 k cycles of
-    // 48-cycle MMAs, too little look-ahead, where the ring configuration affords six -- so 128-wide tiles only.
+  } else if (resident_half && n_tiles == 1 && block_n == 128 && fits(3, 9 * kb, true)) {
+    // a 144 KB slice (64 -> 128 layer; as a CTA pair: the 128 -> 128 layers): resident beside three halo slots when
+    // the staging buffers are halved; streaming it through the ring instead re-writes the weights into shared memory
+    // for every tile.  Measured on one box (gpurun_out/r2u): 64 -> 128 @128x128 125 -> 117 us, @256x256 (a dgrad)
+    // 317 -> 290 us.  The same for 128 -> 64 (64-wide tiles, kb = 2, single CTAs) is SLOWER, 349 -> 402 us: three
+    // halo slots are 1.7 k cycles of 48-cycle MMAs, too little look-ahead, where the ring configuration affords six --
+    // so 128-wide tiles only.
     mode = 0;
     half_stage = true;
     p.b_slots = 0;
@@ -1234,30 +1252,23 @@ static int try_launch_conv3(const FwdDesc& d) {
     p.a_slots = 3;
   } else if (block_n <= 128) {
     mode = 1;
-    p.b_slots = block_n == 128 ? 3 : 4;   // triples of 48 KB / 24 KB
+    p.b_slots = block_n == 128 ? 3 : 4;   // triples of 48 KB / 24 KB (half of that per CTA of a pair)
     b_tiles = 3 * p.b_slots;
     p.a_slots = 3;
   } else {
     mode = 2;
-    p.b_slots = 4;
-    b_tiles = 4;
-    p.a_slots = 3;
-  }
-  // 256-wide tiles as CTA pairs (cta_group::2) when the M tiles pair up; PLUME_CONV3_PAIR=0 keeps single CTAs
-  static const bool pair_on = !(getenv("PLUME_CONV3_PAIR") && atoi(getenv("PLUME_CONV3_PAIR")) == 0);
-  const long long m_tiles = 1ll * p.tiles_w * p.tiles_h * N;
-  const bool pair = pair_on && mode == 2 && m_tiles % 2 == 0 && m_tiles * n_tiles >= 4;
-  if (pair) {   // a CTA holds half of every weight tile (16 KB): more ring slots in the same shared memory
-    p.a_slots = 4;
-    p.b_slots = 6;
-    b_tiles = 6;
-    while (p.b_slots < kMaxSlots && conv3_smem_bytes(block_n, p.a_slots, b_tiles + 1, false, true) <= limit) {
-      ++p.b_slots;
-      ++b_tiles;
-    }
+    p.b_slots = pair ? 6 : 4;
+    b_tiles = p.b_slots;
+    p.a_slots = pair ? 4 : 3;
   }
   if (mode == 1 && block_n == 128) half_stage = true;   // selects the HALF_STAGE instantiation below
-  while (!pair && p.a_slots < 6 && conv3_smem_bytes(block_n, p.a_slots + 1, b_tiles, half_stage) <= limit) ++p.a_slots;
+  if (mode == 2 && pair) {
+    while (p.b_slots < kMaxSlots && fits(p.a_slots, b_tiles + 1, false)) { ++p.b_slots; ++b_tiles; }
+  } else {
+    while (p.a_slots < 6 && fits(p.a_slots + 1, b_tiles, half_stage)) ++p.a_slots;
+    if (mode == 1 && pair)   // the halved triples leave room for a deeper weight ring
+      while (p.b_slots < kMaxSlots && fits(p.a_slots, b_tiles + 3, half_stage)) { ++p.b_slots; b_tiles += 3; }
+  }
   const size_t smem = conv3_smem_bytes(block_n, p.a_slots, b_tiles, half_stage, pair);
   if (smem > limit) return 1;
 
@@ -1281,7 +1292,20 @@ static int try_launch_conv3(const FwdDesc& d) {
     if (!p.det_part) return -2;
   }
   int r;
-  if (mode == 0 && half_stage) {
+  if (pair) {
+    const int tp = tt / 2;
+    if (mode == 0 && half_stage)
+      r = block_n == 128 ? launch_conv3_pair<128, 0, true>(amap, bmap, omap, p, smem, tp, d.stream)
+                         : launch_conv3_pair<64, 0, true>(amap, bmap, omap, p, smem, tp, d.stream);
+    else if (mode == 0)
+      r = block_n == 128 ? launch_conv3_pair<128, 0, false>(amap, bmap, omap, p, smem, tp, d.stream)
+                         : launch_conv3_pair<64, 0, false>(amap, bmap, omap, p, smem, tp, d.stream);
+    else if (mode == 1)
+      r = block_n == 128 ? launch_conv3_pair<128, 1, true>(amap, bmap, omap, p, smem, tp, d.stream)
+                         : launch_conv3_pair<64, 1, false>(amap, bmap, omap, p, smem, tp, d.stream);
+    else
+      r = launch_conv3_pair<256, 2, false>(amap, bmap, omap, p, smem, tp, d.stream);
+  } else if (mode == 0 && half_stage) {
     r = block_n == 128 ? launch_conv3_inst<128, 0, true>(amap, bmap, omap, p, smem, tt, d.stream)
                        : launch_conv3_inst<64, 0, true>(amap, bmap, omap, p, smem, tt, d.stream);
   } else if (mode == 0) {
@@ -1290,8 +1314,6 @@ static int try_launch_conv3(const FwdDesc& d) {
   } else if (mode == 1) {
     r = block_n == 128 ? launch_conv3_inst<128, 1, true>(amap, bmap, omap, p, smem, tt, d.stream)
                        : launch_conv3_inst<64, 1, false>(amap, bmap, omap, p, smem, tt, d.stream);
-  } else if (pair) {
-    r = launch_conv3_pair(amap, bmap, omap, p, smem, tt / 2, d.stream);
   } else {
     r = launch_conv3_inst<256, 2, false>(amap, bmap, omap, p, smem, tt, d.stream);
   }

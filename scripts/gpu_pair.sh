@@ -9,6 +9,7 @@ timeout 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_determinism.p
 tail -4 $O/pytest_net.log
 for rep in 1 2; do
 PLUME_CONV3_PAIR=0 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --configs '' > $O/bench_off_$rep.json 2>> $O/bench.err
+PLUME_CONV3_PAIR=1 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --configs '' > $O/bench_p256_$rep.json 2>> $O/bench.err
 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --configs '' > $O/bench_on_$rep.json 2>> $O/bench.err
 done
 python - <<'PY'
@@ -18,7 +19,7 @@ for f in sorted(glob.glob(O+"/bench_*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         pl={(r["layer"],r["pass"]):r["us"] for r in d["per_layer"]}
-        print(os.path.basename(f),"ms/step",round(d["ms_per_step"],3),"fwd TF/s",round(d["roofline"]["achieved"]), {k:round(pl[k],1) for k in (("enc2.conv2","fwd"),("dec3.conv1","fwd"),("bottleneck.conv2","fwd"),("dec2.conv1","dgrad"),("enc3.conv1","fwd"))})
+        print(os.path.basename(f),"ms/step",round(d["ms_per_step"],3),"fwd TF/s",round(d["roofline"]["achieved"]), {k:round(pl[k],1) for k in (("enc0.conv2","fwd"),("enc1.conv1","fwd"),("enc1.conv2","fwd"),("dec0.conv1","fwd"),("dec1.conv1","fwd"),("dec0.conv1","dgrad"),("enc2.conv2","fwd"))})
     except Exception as e: print(f,"ERR",e)
 PY
 fi

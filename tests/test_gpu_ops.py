@@ -434,9 +434,13 @@ def test_conv3_repeated_launches_are_bit_identical(ops, cin, cout, mode):
     assert int(bad.item()) == 0, f"{mode}: {int(bad.item())} differing elements over 200 launches"
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 48, 40, 256, 512), (2, 32, 32, 128, 256), (2, 64, 24, 512, 256)])
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (4, 48, 40, 256, 512), (2, 32, 32, 128, 256), (2, 64, 24, 512, 256),       # 256-wide ring of single weight tiles
+    (4, 48, 40, 64, 64), (2, 40, 24, 128, 64),                                 # 64-wide, weights resident (kb = 1, 2)
+    (2, 32, 32, 64, 128), (2, 48, 24, 128, 128),                               # 128-wide resident, full / half staging
+    (2, 32, 32, 256, 128), (2, 32, 16, 256, 64)])                              # rings of weight triples
 def test_conv3_cta_pairs_match_oracle_and_repeat_bit_identically(ops, n, h, w, cin, cout):
-    """256-wide tiles run as CTA pairs (tcgen05.mma.cta_group::2) when the M tiles pair up: forward with epilogue and
+    """Tiles run as CTA pairs (tcgen05.mma.cta_group::2) when the M tiles pair up: forward with epilogue and
     BatchNorm statistics against the oracle, dgrad against the oracle, and 100 repeated launches bit-identical (both
     CTAs' TMA loads complete on the leader's barriers; a visibility race would show as run-to-run differences)."""
     cu, rf = ops
