@@ -1238,13 +1238,14 @@ static int try_launch_conv3(const FwdDesc& d) {
     p.b_slots = 0;
     b_tiles = 9 * kb;
     p.a_slots = 4;
-  } else if (resident_half && n_tiles == 1 && block_n == 128 && fits(3, 9 * kb, true)) {
-    // a 144 KB slice (64 -> 128 layer; as a CTA pair: the 128 -> 128 layers): resident beside three halo slots when
-    // the staging buffers are halved; streaming it through the ring instead re-writes the weights into shared memory
-    // for every tile.  Measured on one box (gpurun_out/r2u): 64 -> 128 @128x128 125 -> 117 us, @256x256 (a dgrad)
-    // 317 -> 290 us.  The same for 128 -> 64 (64-wide tiles, kb = 2, single CTAs) is SLOWER, 349 -> 402 us: three
-    // halo slots are 1.7 k cycles of 48-cycle MMAs, too little look-ahead, where the ring configuration affords six --
-    // so 128-wide tiles only.
+  } else if (resident_half && !pair && n_tiles == 1 && block_n == 128 && fits(3, 9 * kb, true)) {
+    // single CTAs, the 144 KB slice of a 64 -> 128 layer: resident beside three halo slots when the staging buffers
+    // are halved; streaming it through the ring instead re-writes the weights into shared memory for every tile.
+    // Measured on one box (gpurun_out/r2u): 64 -> 128 @128x128 125 -> 117 us, @256x256 (a dgrad) 317 -> 290 us.  The
+    // same for 128 -> 64 (64-wide tiles, kb = 2) is SLOWER, 349 -> 402 us: three halo slots are 1.7 k cycles of
+    // 48-cycle MMAs, too little look-ahead, where the ring configuration affords six -- so 128-wide tiles only.  As a
+    // CTA pair the 64 -> 128 slice fits with full staging (branch above); for the 128 -> 128 slice (144 KB per CTA of
+    // a pair) the ring with six halo slots wins again: 146 -> 133 us forward, 139 -> 116 us dgrad (gpurun_out/r2z).
     mode = 0;
     half_stage = true;
     p.b_slots = 0;

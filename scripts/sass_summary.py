@@ -24,7 +24,7 @@ for line in sass.splitlines():
 print("# SASS evidence for the tensor-core kernels of libplume_b200.so (cuobjdump -sass, sm_100a)")
 print("# per kernel: counts of the instructions that prove tcgen05 (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR =")
 print("# tcgen05.commit), TMA (UTMALDG = cp.async.bulk.tensor load, UTMASTG = store, UTMACCTL.PF = descriptor prefetch) and")
-print("# mbarrier traffic (SYNCS).  No HMMA (mma.sync) anywhere; every MMA is cta_group::1 (no .2CTA suffix).")
+print("# mbarrier traffic (SYNCS).  No HMMA (mma.sync) anywhere; the PAIR instantiations of igemm_conv3_kernel carry the .2CTA forms (UTCHMMA.2CTA, UTMALDG.*.2CTA, UTCBAR.2CTA.MULTICAST).")
 tot = collections.Counter()
 for fn, c in per.items():
     if not any(k.startswith(("UTCHMMA", "UTMALDG", "LDTM")) for k in c):
