@@ -1735,11 +1735,17 @@ constexpr int kXBox = 10 * 1024;  // 8 w x 10 h pixels x 64 channels
 // the zeroing stage 0 must come first, which issuer 1 waits for (ctr[1]).
 constexpr int kWgrad3Threads = 288;
 
-template <int BLOCK_N>
+// PAIR (Cin >= 256, 128 output channels per CTA pair, launched as clusters of two CTAs along x): the two CTAs take two
+// units (horizontal tap x 128-channel slice) of the same N tile and K split, so they share dY -- each loads HALF of
+// the dY tile (64 of its 128 channels) and the leader issues M = 256 MMAs (cta_group::2); see igemm_conv3_kernel.
+template <int BLOCK_N, bool PAIR = false>
 __global__ void __launch_bounds__(kWgrad3Threads, 1)
     igemm_wgrad3_kernel(const __grid_constant__ CUtensorMap xmap,
                         const __grid_constant__ CUtensorMap dymap, const Wgrad3Params p) {
-  constexpr int DY_BYTES = (BLOCK_N / 64) * 8192;
+  static_assert(!PAIR || BLOCK_N == 128, "CTA pairs: 128-wide tiles");
+  constexpr int DY_BYTES = (PAIR ? BLOCK_N / 128 : BLOCK_N / 64) * 8192;   // PAIR: this CTA's half of the dY tile
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   constexpr int kWarpAlloc = 4, kWarpProducer = 5, kWarpRelay = 6, kWarpMma0 = 7, kWarpMma1 = 8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -1761,9 +1767,10 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
   const int nblocks = p.mode9 ? 5 : 3;
   const uint32_t tmem_cols = (nblocks * BLOCK_N <= 256) ? 256u : 512u;
 
-  // work item: blockIdx.x = (unit, n tile), blockIdx.y = K split
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int unit = blockIdx.x / p.n_tiles;
+  // work item: blockIdx.x = (unit, n tile) -- PAIR: ((unit pair, n tile), rank) --, blockIdx.y = K split
+  const int item = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_tile = item % p.n_tiles;
+  const int unit = PAIR ? 2 * (item / p.n_tiles) + static_cast<int>(rank) : item / p.n_tiles;
   const int split = blockIdx.y;
   const int dwi = p.mode9 ? 0 : unit / p.ci_blocks;   // horizontal tap of this CTA (mode 3)
   const int cb = p.mode9 ? 0 : unit % p.ci_blocks;    // 128-channel slice of this CTA (mode 3)
@@ -1788,11 +1795,17 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
     fence_mbar_init();
   }
   if (warp == kWarpAlloc) {
-    tmem_alloc(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2cta(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(sbase + off_bar + 8 * (2 * kMaxSlots + 1), tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -1807,6 +1820,16 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
         mbar_wait_relaxed(empty_bar(stage), phase ^ 1, 5, &g_dbg_word);
         const uint32_t x_addr = sbase + stage * stage_bytes;
         const uint32_t dy_addr = x_addr + x_bytes;
+        if (PAIR) {
+          // both CTAs' bytes are counted on the leader's barrier; this CTA loads its own X boxes and its half of dY
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * stage_bytes);
+          tma_load_4d_2cta(x_addr, &xmap, full_bar(stage), cb * 128, w0 + dwi - 1, h0 - 1, img);
+          tma_load_4d_2cta(x_addr + kXBox, &xmap, full_bar(stage), cb * 128 + 64, w0 + dwi - 1, h0 - 1, img);
+          tma_load_4d_2cta(dy_addr, &dymap, full_bar(stage), n_tile * BLOCK_N + static_cast<int>(rank) * 64, w0, h0,
+                           img);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_expect_tx(full_bar(stage), stage_bytes);
         if (p.mode9) {
 #pragma unroll
@@ -1825,7 +1848,7 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
       }
     }
   } else if (warp == kWarpRelay) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0, phase = 0;
       for (int i = 0; i < nk; ++i) {
         mbar_wait(full_bar(stage), phase, 6, &g_dbg_word);
@@ -1837,8 +1860,8 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
     const int me = warp == kWarpMma0 ? 0 : 1;
     // deterministic mode: one issuer takes every stage, so the accumulation order inside the CTA is fixed
     const int istep = p.det_part ? 1 : 2;
-    if (lane == 0 && me < nk && (me == 0 || !p.det_part)) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 1, 1);
+    if (lane == 0 && leader && me < nk && (me == 0 || !p.det_part)) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BLOCK_N, 1, 1);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       if (me == 1) wait_counter(ctr + 1, 1, 8);  // the zeroing stage has been issued
       int stage = me % p.stages;
@@ -1867,17 +1890,24 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
           for (int blk = 0; blk < 3; ++blk) {
             const uint32_t a_lo = umma_desc_lo(x_addr + blk * 1024, kXBox);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_lohi(tmem_base + blk * BLOCK_N, a_lo + 128 * k, hi, b_lo + 128 * k, hi, idesc,
-                             k == 0 ? accflag : 1u);
+            for (int k = 0; k < 4; ++k) {
+              if (PAIR)
+                umma_bf16_lohi_2cta(tmem_base + blk * BLOCK_N, a_lo + 128 * k, hi, b_lo + 128 * k, hi, idesc,
+                                    k == 0 ? accflag : 1u);
+              else
+                umma_bf16_lohi(tmem_base + blk * BLOCK_N, a_lo + 128 * k, hi, b_lo + 128 * k, hi, idesc,
+                               k == 0 ? accflag : 1u);
+            }
           }
         }
-        umma_commit(empty_bar(stage));
+        if (PAIR) umma_commit_2cta(empty_bar(stage), 3u);
+        else umma_commit(empty_bar(stage));
         if (i == 0) ctr[1] = 1;
         stage += istep;
         while (stage >= p.stages) stage -= p.stages;
       }
-      umma_commit(tfull_bar);
+      if (PAIR) umma_commit_2cta(tfull_bar, 3u);
+      else umma_commit(tfull_bar);
     }
   } else if (warp < 4) {
     const int q = warp;
@@ -1918,7 +1948,47 @@ __global__ void __launch_bounds__(kWgrad3Threads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpAlloc) tmem_dealloc(tmem_base, tmem_cols);
+  if (PAIR) {
+    cluster_sync_all();
+    if (warp == kWarpAlloc) tmem_dealloc_2cta(tmem_base, tmem_cols);
+  } else {
+    if (warp == kWarpAlloc) tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+static int launch_wgrad3_pair(const CUtensorMap& xmap, const CUtensorMap& dymap, const Wgrad3Params& p, size_t smem,
+                              int ctas_mn, cudaStream_t stream) {
+  auto kern = igemm_wgrad3_kernel<128, true>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(igemm_wgrad3 pair): ") + cudaGetErrorString(attr_err));
+    return -2;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas_mn, p.splits, 1);     // ctas_mn is even: clusters of two along x
+  cfg.blockDim = dim3(kWgrad3Threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xmap, dymap, p);
+  if (e != cudaSuccess) {
+    set_error(std::string("igemm_wgrad3 pair launch: ") + cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
 }
 
 template <int BLOCK_N>
@@ -1966,7 +2036,11 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   p.s_t = d.s_t;
   p.det_part = d.det_part;
   p.dw_numel = 9ll * d.Cin * d.Cout;
-  const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (c.block_n / 64) * 8192;
+  // CTA pairs when two units of the same N tile exist for every pair (an even number of 128-channel slices);
+  // PLUME_WGRAD3_PAIR=0 keeps single CTAs
+  static const bool pair_on = !(getenv("PLUME_WGRAD3_PAIR") && atoi(getenv("PLUME_WGRAD3_PAIR")) == 0);
+  const bool pair = pair_on && !p.mode9 && c.block_n == 128 && p.ci_blocks % 2 == 0;
+  const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (pair ? 1 : c.block_n / 64) * 8192;
   const int overhead = 8 * (2 * kMaxSlots + 3) + 16 + 1024;
   // Leave room beside a CTA for one block of a bandwidth kernel on another stream (see unet.py).
   static const int smem_budget = [] {
@@ -1979,6 +2053,7 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   CUtensorMap xmap, dymap;
   if (make_act_map(&xmap, d.x, 64, 8, 10, 1)) return -1;
   if (make_act_map(&dymap, d.dy[0], 64, 8, 8, 1)) return -1;
+  if (pair) return launch_wgrad3_pair(xmap, dymap, p, smem, c.ctas_mn, d.stream);
   if (c.block_n == 128) return launch_wgrad3_inst<128>(xmap, dymap, p, smem, c.ctas_mn, d.stream);
   return launch_wgrad3_inst<64>(xmap, dymap, p, smem, c.ctas_mn, d.stream);
 }

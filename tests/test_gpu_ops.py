@@ -96,7 +96,8 @@ def test_conv3x3_concat_slices_and_dgrad(ops, n, h, w, cin, cout):
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [
     (1, 16, 16, 64, 64), (2, 16, 16, 64, 128), (2, 16, 16, 128, 64), (1, 32, 32, 128, 256),
-    (4, 8, 8, 256, 128), (3, 24, 40, 64, 64), (5, 4, 4, 128, 64), (8, 64, 64, 64, 64), (2, 16, 16, 512, 256)])
+    (4, 8, 8, 256, 128), (3, 24, 40, 64, 64), (5, 4, 4, 128, 64), (8, 64, 64, 64, 64), (2, 16, 16, 512, 256),
+    (3, 24, 40, 256, 256), (2, 32, 32, 1024, 128)])   # CTA pairs (Cin >= 256): ragged tiles, many channel slices
 def test_conv3x3_wgrad_splitk(ops, n, h, w, cin, cout):
     cu, rf = ops
     x, dy = rnd(n, h, w, cin, seed=1).to(BF), rnd(n, h, w, cout, seed=2).to(BF)
