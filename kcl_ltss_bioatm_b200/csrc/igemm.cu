@@ -2036,9 +2036,11 @@ static int launch_wgrad3(const WgradDesc& d, const WgradConfig& c) {
   p.s_t = d.s_t;
   p.det_part = d.det_part;
   p.dw_numel = 9ll * d.Cin * d.Cout;
-  // CTA pairs when two units of the same N tile exist for every pair (an even number of 128-channel slices);
-  // PLUME_WGRAD3_PAIR=0 keeps single CTAs
-  static const bool pair_on = !(getenv("PLUME_WGRAD3_PAIR") && atoi(getenv("PLUME_WGRAD3_PAIR")) == 0);
+  // CTA pairs when two units of the same N tile exist for every pair (an even number of 128-channel slices).  OFF by
+  // default (PLUME_WGRAD3_PAIR=1 enables it): correct (tests/test_gpu_ops.py) but measured no faster on any layer
+  // (gpurun_out/r2aa: 202.1 vs 201.8, 107.6 vs 107.6, 205.4 vs 205.5 us ...) -- the 128-wide weight-gradient tiles
+  // already run at 80-86 % of the tensor pipe and are not bound by the dY reads the pairing halves.
+  static const bool pair_on = getenv("PLUME_WGRAD3_PAIR") && atoi(getenv("PLUME_WGRAD3_PAIR")) != 0;
   const bool pair = pair_on && !p.mode9 && c.block_n == 128 && p.ci_blocks % 2 == 0;
   const int stage_bytes = (p.mode9 ? 3 : 2) * kXBox + (pair ? 1 : c.block_n / 64) * 8192;
   const int overhead = 8 * (2 * kMaxSlots + 3) + 16 + 1024;

@@ -99,6 +99,28 @@ def test_conv3x3_concat_slices_and_dgrad(ops, n, h, w, cin, cout):
     (4, 8, 8, 256, 128), (3, 24, 40, 64, 64), (5, 4, 4, 128, 64), (8, 64, 64, 64, 64), (2, 16, 16, 512, 256),
     (3, 24, 40, 256, 256), (2, 32, 32, 1024, 128)])   # CTA pairs (Cin >= 256): ragged tiles, many channel slices
 def test_conv3x3_wgrad_splitk(ops, n, h, w, cin, cout):
+    _wgrad_splitk(ops, n, h, w, cin, cout)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 8, 8, 256, 128), (3, 24, 40, 256, 256), (2, 32, 32, 1024, 128)])
+def test_conv3x3_wgrad_cta_pairs(n, h, w, cin, cout):
+    """The opt-in CTA-pair weight gradient (PLUME_WGRAD3_PAIR=1, read once per process: run in a child process)."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests.test_gpu_ops import _wgrad_splitk\n"
+            "from kcl_ltss_bioatm_b200.ops import CudaOps\n"
+            "from oracle.ops_ref import RefOps\n"
+            "_wgrad_splitk((CudaOps(), RefOps()), %d, %d, %d, %d, %d)\nprint('pair wgrad ok')\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n, h, w, cin, cout))
+    env = dict(os.environ, PLUME_WGRAD3_PAIR="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "pair wgrad ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def _wgrad_splitk(ops, n, h, w, cin, cout):
     cu, rf = ops
     x, dy = rnd(n, h, w, cin, seed=1).to(BF), rnd(n, h, w, cout, seed=2).to(BF)
     dw_ref = torch.zeros(cout, 3, 3, cin)
