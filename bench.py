@@ -202,11 +202,13 @@ def conv_variant(op: str, cin: int, cout: int, h: int, w: int) -> str:
     n = cout  # GEMM N of the launch (dgrad: the layer's input channels, passed as cout here)
     bn = 256 if n % 256 == 0 else (128 if n % 128 == 0 else 64)
     if h >= 16 and w >= 8:
+        # CTA pairs (cta_group::2) whenever the M tiles pair up -- always for the even batches measured here; a CTA
+        # of a pair holds half of every weight tile, which decides whether the slice is resident
         kb = cin // 64
         resident = n == bn and bn <= 128 and \
-            (4 * 18432 + 9 * kb * bn * 128 + 2 * 16384 + 32 * bn + 8 * 40 + 16 + 1024) <= 232448
+            (4 * 18432 + 9 * kb * (bn // 2) * 128 + 2 * 16384 + 32 * bn + 8 * 40 + 16 + 1024) <= 232448
         mode = 0 if resident else (1 if bn <= 128 else 2)
-        return f"igemm_conv3_kernel<{bn},{mode}>"
+        return f"igemm_conv3_kernel<{bn},{mode}> CTA pair"
     return f"igemm_fwd_kernel<{bn}>"
 
 
