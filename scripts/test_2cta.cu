@@ -17,7 +17,7 @@ using namespace plume;
 
 __device__ int g_dbg = 0;
 
-template <int KB>   // K = 64 * KB
+template <int KB, int N>   // K = 64 * KB; D is 256 x N
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     pair_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ D,
               int iters, long long* cycles) {
@@ -28,7 +28,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128;   // per CTA: 128 rows of A, 128 of the 256 rows of B
+  constexpr int A_BYTES = 128 * 128, B_BYTES = (N / 2) * 128;   // per CTA: 128 rows of A, half of the N rows of B
   if (threadIdx.x == 0) {
     for (int k = 0; k < KB; ++k) mbar_init(smem_u32(&bar_full[k]), 1);
     mbar_init(smem_u32(&bar_tfull), 1);
@@ -49,11 +49,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       const uint32_t a = sbase + k * (A_BYTES + B_BYTES), b = a + A_BYTES;
       if (rank == 0) mbar_expect_tx(smem_u32(&bar_full[k]), 2 * (A_BYTES + B_BYTES));   // both CTAs' bytes
       tma_load_2d_2cta(a, &mapA, smem_u32(&bar_full[k]), k * 64, rank * 128);
-      tma_load_2d_2cta(b, &mapB, smem_u32(&bar_full[k]), k * 64, rank * 128);
+      tma_load_2d_2cta(b, &mapB, smem_u32(&bar_full[k]), k * 64, rank * (N / 2));
     }
   }
   if (warp == 2 && lane == 0 && rank == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(256, N, 0, 0);
     constexpr uint32_t hi = umma_desc_hi_sw128(1024);
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < KB; ++k) {
@@ -73,7 +73,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     tc_fence_after();
     if (threadIdx.x == 0 && cycles) cycles[rank] = clock64() - t0;
     const int row = rank * 128 + warp * 32 + lane;
-    for (int c = 0; c < 256; c += 32) {
+    for (int c = 0; c < N; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tm + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
       tmem_ld_wait();
@@ -88,8 +88,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-int main() {
+template <int N>
+static int run(const std::vector<float>& Af, const std::vector<float>& Bf, __nv_bfloat16* dA, __nv_bfloat16* dB, float* dD,
+               long long* dC) {
   constexpr int KB = 2, K = 64 * KB;
+  CUtensorMap mapA, mapB;
+  if (make_mat_map(&mapA, dA, 256, K, 64, 128) || make_mat_map(&mapB, dB, 256, K, 64, N / 2)) return 1;
+  const int smem = KB * (16384 + (N / 2) * 128) + 1024;
+  cudaFuncSetAttribute(pair_gemm<KB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaMemset(dD, 0xff, 256 * 256 * 4);
+  pair_gemm<KB, N><<<2, 192, smem>>>(mapA, mapB, dD, 1, dC);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    int dbg = 0;
+    cudaMemcpyFromSymbol(&dbg, g_dbg, 4);
+    printf("N=%d kernel failed: %s (watchdog tag 0x%x)\n", N, cudaGetErrorString(e), dbg);
+    return 2;
+  }
+  std::vector<float> D(256 * 256);
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double worst = 0;
+  int bad = 0;
+  for (int m = 0; m < 256; ++m)
+    for (int n = 0; n < N; ++n) {
+      double r = 0;
+      for (int k = 0; k < K; ++k) r += double(Af[m * K + k]) * Bf[n * K + k];
+      const double d = fabs(D[m * 256 + n] - r);
+      if (!(d <= 1e-3)) ++bad;
+      worst = d > worst ? d : worst;
+    }
+  printf("pair GEMM 256x%dx%d: max |err| %.3e, %d mismatching elements -> %s\n", N, K, worst, bad, bad ? "FAIL" : "OK");
+  if (bad) return 3;
+  long long h[2];
+  pair_gemm<KB, N><<<148, 192, smem>>>(mapA, mapB, dD, 2000, dC);
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("timing run failed: %s\n", cudaGetErrorString(e)); return 4; }
+  cudaMemcpy(h, dC, 16, cudaMemcpyDeviceToHost);
+  printf("  74 pairs, 2000 x %d MMAs per pair: %.1f cycles per M=256,N=%d,K=16 pair MMA (single CTA, M=128: %d)\n", 4 * KB,
+         double(h[0]) / (2000 * 4.0 * KB), N, N == 64 ? 48 : (N == 128 ? 64 : 128));
+  return 0;
+}
+
+int main() {
+  constexpr int K = 128;
   std::vector<__nv_bfloat16> A(256 * K), B(256 * K);
   std::vector<float> Af(256 * K), Bf(256 * K);
   srand(1);
@@ -108,48 +149,8 @@ int main() {
   cudaMalloc(&dC, 16);
   cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
-  cudaMemset(dD, 0xff, 256 * 256 * 4);
-  CUtensorMap mapA, mapB;
-  if (make_mat_map(&mapA, dA, 256, K, 64, 128) || make_mat_map(&mapB, dB, 256, K, 64, 128)) return 1;
-  const int smem = KB * 32768 + 1024;
-  cudaFuncSetAttribute(pair_gemm<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_gemm<KB><<<2, 192, smem>>>(mapA, mapB, dD, 1, dC);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) {
-    int dbg = 0;
-    cudaMemcpyFromSymbol(&dbg, g_dbg, 4);
-    printf("kernel failed: %s (watchdog tag 0x%x)\n", cudaGetErrorString(e), dbg);
-    return 2;
-  }
-  std::vector<float> D(256 * 256);
-  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-  double worst = 0, ref_max = 0;
-  int bad = 0;
-  for (int m = 0; m < 256; ++m)
-    for (int n = 0; n < 256; ++n) {
-      double r = 0;
-      for (int k = 0; k < K; ++k) r += double(Af[m * K + k]) * Bf[n * K + k];
-      const double d = fabs(D[m * 256 + n] - r);
-      if (!(d <= 1e-3)) ++bad;
-      worst = d > worst ? d : worst;
-      ref_max = fabs(r) > ref_max ? fabs(r) : ref_max;
-    }
-  printf("pair GEMM 256x256x%d: max |err| %.3e (max |ref| %.2f), %d mismatching elements -> %s\n", K, worst, ref_max, bad,
-         bad ? "FAIL" : "OK");
-  if (bad) {
-    printf("D[0][0..3] = %g %g %g %g ; D[128][0..3] = %g %g %g %g ; D[0][128..131] = %g %g %g %g\n", D[0], D[1], D[2], D[3],
-           D[128 * 256], D[128 * 256 + 1], D[128 * 256 + 2], D[128 * 256 + 3], D[128], D[129], D[130], D[131]);
-    return 3;
-  }
-  // issue rate of the pair MMA: M = 256 (two SMs), N = 256, K = 16 per instruction
-  long long h[2];
-  for (int iters : {1, 2000}) {
-    pair_gemm<KB><<<148, 192, smem>>>(mapA, mapB, dD, iters, dC);
-    e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("timing run failed: %s\n", cudaGetErrorString(e)); return 4; }
-    cudaMemcpy(h, dC, 16, cudaMemcpyDeviceToHost);
-    printf("grid 148 (74 pairs), %d x %d MMAs per pair: %lld cycles -> %.1f cycles per M=256,N=256,K=16 MMA\n", iters,
-           4 * KB, h[0], double(h[0]) / (iters * 4.0 * KB));
-  }
-  return 0;
+  int rc = run<256>(Af, Bf, dA, dB, dD, dC);
+  if (!rc) rc = run<128>(Af, Bf, dA, dB, dD, dC);
+  if (!rc) rc = run<64>(Af, Bf, dA, dB, dD, dC);
+  return rc;
 }
