@@ -22,6 +22,10 @@
 #include <cstdlib>
 #include <mutex>
 
+#ifndef PLUME_PAIR_ISSUERS
+#define PLUME_PAIR_ISSUERS 2   // MMA issuer threads of the CTA-pair conv3 kernels in the resident / triple modes
+#endif
+
 namespace plume {
 
 __device__ int g_dbg_word = 0;
@@ -642,7 +646,11 @@ __global__ void __launch_bounds__(kConv3Threads, 1)
   constexpr bool RESIDENT = MODE == 0;
   constexpr int TPG = MODE == 2 ? 1 : 3;   // taps per MMA group
   constexpr int GPS = 3 / TPG;             // groups per halo slot
-  constexpr uint32_t ISSUERS = MODE == 2 ? 1 : 2;  // 512-cycle groups of N=256 MMAs hide a single issuer's sync
+  // 512-cycle groups of N=256 MMAs hide a single issuer's sync.  The pair kernels of the other modes keep two issuers:
+  // with one (-DPLUME_PAIR_ISSUERS=1, A/B of two builds on one box, gpurun_out/r2ab) the 64-wide layers slow down from
+  // 190 to 240 us and 128 -> 64 from 318 to 431 us -- they run at the pair instruction's floor of ~80 cycles
+  // (scripts/test_2cta.cu) only when the issue overhead of one thread hides behind the other's MMAs.
+  constexpr uint32_t ISSUERS = MODE == 2 ? 1 : (PAIR ? PLUME_PAIR_ISSUERS : 2);
   constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // PAIR: this CTA's half of the weight tile
   constexpr int BSLOT_BYTES = TPG * B_BYTES;
   // HALF_STAGE: stage 64 rows (half a tile) at a time.  128-wide tiles in triple mode need a third weight slot more
