@@ -323,8 +323,8 @@ int plume_locate_fires(const double* lats, const double* lons, int H, int W, con
 
 /* ---- threshold sweep (replaces plume_identifier_gaussian_profile.py:142-202) ------------------------------ */
 /* masks[t][y][x] (uint8 0/1) = binary_dilation(binary_erosion(aod > thresholds[t])) with the cross-shaped
- * footprint (erosion treats pixels beyond the border as set, dilation as unset); aod float32 [H][W], compared
- * in float64 against the float64 thresholds (T <= 64), every threshold from one read of the image. */
+ * footprint (erosion treats pixels beyond the border as set, dilation as unset); aod float32 [H][W]; decides exactly
+ * like numpy's float64 comparison against the float64 thresholds (T <= 64), every threshold from one read of the image. */
 int plume_threshold_masks(const float* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
                           plume_stream_t stream);
 /* 8-connected components of every mask plane.  labels[t][i] = -1 for background, else the smallest row-major
@@ -337,6 +337,24 @@ int plume_label_components(const uint8_t* masks, int T, int H, int W, int* label
  * the window holds no component: find_plume_extents / extract_label of the reference. */
 int plume_fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_row_col,
                        int n_fires, int win, int* extents, plume_stream_t stream);
+/* Bit-plane form of the same sweep: masks packed 32 pixels per word, components found over runs of set bits, no
+ * dense label plane.  bits is uint32 [T][H][ceil(W / 32)], bit i of word s <-> pixel x = 32 s + i, bits beyond W zero.
+ *   plume_threshold_mask_bits : the masks of plume_threshold_masks as bit planes (any T; fp32 comparison against the
+ *                               thresholds rounded down to float32, which decides exactly like the float64 comparison).
+ *   plume_pack_mask_bits      : byte masks [T][H][W] (non-zero = set) -> bit planes.
+ *   plume_bits_extents        : plume_label_components + plume_fire_extents on bit planes: extents[t][f] only.
+ *   plume_sweep_extents       : generate_mask_dict + find_plume_extents (gaussian_profile.py:142-179) in one call,
+ *                               aod float32 [H][W] -> extents int32 [T][n_fires]; the bit planes live in the workspace.
+ * workspace: device memory of at least plume_sweep_workspace_bytes(H, W, T) bytes for both calls that take one. */
+size_t plume_sweep_workspace_bytes(int H, int W, int T);
+int plume_threshold_mask_bits(const float* aod, int H, int W, const double* thresholds, int T, uint32_t* bits,
+                              plume_stream_t stream);
+int plume_pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, plume_stream_t stream);
+int plume_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_row_col, int n_fires, int win,
+                       void* workspace, size_t workspace_bytes, int* extents, plume_stream_t stream);
+int plume_sweep_extents(const float* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
+                        int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
+                        plume_stream_t stream);
 
 /* ---- UTM projection and nearest-neighbour swath -> grid resampling ------------
  * Replaces /root/reference/src/features/tools.py:9-64 (class utm_resampler), which calls pyproj and

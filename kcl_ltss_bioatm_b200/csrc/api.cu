@@ -612,6 +612,29 @@ int plume_fire_extents(const int* labels, const int* sizes, int T, int H, int W,
   PLUME_CHECK(T <= 0 || n_fires <= 0 || (labels && sizes && fire_row_col && extents), "fire_extents: null pointer");
   return fire_extents(labels, sizes, T, H, W, fire_row_col, n_fires, win, extents, S(stream));
 }
+size_t plume_sweep_workspace_bytes(int H, int W, int T) { return sweep_workspace_bytes(H, W, T); }
+int plume_threshold_mask_bits(const float* aod, int H, int W, const double* thresholds, int T, uint32_t* bits,
+                              plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || (aod && thresholds && bits), "threshold_mask_bits: null pointer");
+  return threshold_mask_bits(aod, H, W, thresholds, T, bits, S(stream));
+}
+int plume_pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || (masks && bits), "pack_mask_bits: null pointer");
+  return pack_mask_bits(masks, T, H, W, bits, S(stream));
+}
+int plume_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_row_col, int n_fires, int win,
+                       void* workspace, size_t workspace_bytes, int* extents, plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || n_fires <= 0 || (bits && fire_row_col && workspace && extents), "bits_extents: null pointer");
+  return bits_extents(bits, T, H, W, fire_row_col, n_fires, win, workspace, workspace_bytes, extents, S(stream));
+}
+int plume_sweep_extents(const float* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
+                        int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
+                        plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || n_fires <= 0 || (aod && thresholds && fire_row_col && workspace && extents),
+              "sweep_extents: null pointer");
+  return sweep_extents(aod, H, W, thresholds, T, fire_row_col, n_fires, win, workspace, workspace_bytes, extents,
+                       S(stream));
+}
 
 int plume_utm_zone_histogram(const double* lon, long long n, int* hist64, plume_stream_t stream) {
   PLUME_CHECK(hist64 && (n <= 0 || lon), "utm_zone_histogram: null pointer");

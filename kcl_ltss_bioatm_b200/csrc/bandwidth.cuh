@@ -92,6 +92,14 @@ int threshold_masks(const float* aod, int H, int W, const double* thr, int T, ui
 int label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes, cudaStream_t s);
 int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_rc, int n_fires, int win,
                  int* extents, cudaStream_t s);
+// bit-plane form (32 pixels per word; sweep_bits.cuh)
+size_t sweep_workspace_bytes(int H, int W, int T);
+int threshold_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, cudaStream_t s);
+int pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, cudaStream_t s);
+int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
+                 size_t workspace_bytes, int* extents, cudaStream_t s);
+int sweep_extents(const float* aod, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
+                  void* workspace, size_t workspace_bytes, int* extents, cudaStream_t s);
 
 // UTM projection + nearest-neighbour swath -> grid resampling (resample.cu)
 int utm_zone_histogram(const double* lon, long long n, int* hist64, cudaStream_t s);

@@ -5,6 +5,7 @@
 //   fire_extents_kernel    : per (threshold, fire) the size of the component nearest to the fire in its window
 // Integer / boolean work; results are exact against oracle/sweep_ref.py.
 #include "bandwidth.cuh"
+#include "sweep_bits.cuh"
 
 #include <algorithm>
 #include <cstdint>
@@ -28,39 +29,53 @@ constexpr int kMaxThresholds = 64;
 // masks[t][y][x] = dilate(erode(aod > thr[t])).  With the cross footprint that is
 //   OR over q in cross(p), q inside the image, of  AND over r in cross(q) of (r outside the image or aod[r] > t)
 // (erosion sees set pixels beyond the border, dilation unset ones).  A thread loads the 13 values of the
-// diamond around its pixel once and evaluates every threshold from registers; the comparison is done in
-// float64 because the reference compares a float32 image with float64 thresholds.
+// diamond around its pixel once and evaluates every threshold from registers.
+// The reference compares a float32 image with float64 thresholds (`float32(0.48) > 0.48`).  For a float32 v and a
+// double t,  v > t  <=>  v > rd(t)  with rd(t) the largest float32 <= t: if t is a float32 itself nothing changes;
+// otherwise t lies strictly between two consecutive float32 a < t < b and v > t <=> v >= b <=> v > a = rd(t).  So the
+// thresholds are rounded DOWN once (__double2float_rd) and the 13 x T comparisons per pixel run in fp32 -- the fp64
+// comparisons made this kernel compute bound (112 us per 25-threshold sweep of a 1200 x 1200 image).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     threshold_masks_kernel(const float* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
                            uint8_t* __restrict__ masks) {
-  __shared__ double s_thr[kMaxThresholds];
-  if (threadIdx.x < T) s_thr[threadIdx.x] = thr[threadIdx.x];
+  __shared__ float s_thr[kMaxThresholds];
+  if (threadIdx.x < T) s_thr[threadIdx.x] = __double2float_rd(thr[threadIdx.x]);
   __syncthreads();
   const long long pixels = 1ll * H * W;
   const long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels) return;
   const int y = static_cast<int>(i / W), x = static_cast<int>(i % W);
-  // diamond offsets: index = (dy + 2) * 5 + (dx + 2); only |dy| + |dx| <= 2 are used
-  double v[5][5];
-  bool inb[5][5];
+  // the 13 diamond positions, bit index = (dy + 2) * 5 + (dx + 2); only |dy| + |dx| <= 2 are used
+  float v[25];
+  uint32_t outside = 0;   // bit set: position outside the image (counts as set for the erosion)
 #pragma unroll
   for (int dy = -2; dy <= 2; ++dy)
 #pragma unroll
     for (int dx = -2; dx <= 2; ++dx) {
       if ((dy < 0 ? -dy : dy) + (dx < 0 ? -dx : dx) > 2) continue;
+      const int b = (dy + 2) * 5 + (dx + 2);
       const int yy = y + dy, xx = x + dx;
       const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-      inb[dy + 2][dx + 2] = in;
-      v[dy + 2][dx + 2] = in ? static_cast<double>(aod[1ll * yy * W + xx]) : 0.0;
+      if (!in) outside |= 1u << b;
+      v[b] = in ? aod[1ll * yy * W + xx] : 0.0f;
     }
   for (int t = 0; t < T; ++t) {
-    const double th = s_thr[t];
-    // set[dy][dx]: pixel counts as set for the erosion (outside the image = set)
-    auto set = [&](int dy, int dx) { return !inb[dy + 2][dx + 2] || v[dy + 2][dx + 2] > th; };
-    auto eroded = [&](int dy, int dx) {   // q = p + (dy, dx), |dy| + |dx| <= 1; outside the image = unset
-      if (!inb[dy + 2][dx + 2]) return false;
-      return set(dy, dx) && set(dy - 1, dx) && set(dy + 1, dx) && set(dy, dx - 1) && set(dy, dx + 1);
+    const float th = s_thr[t];
+    uint32_t set = outside;   // bit b: position counts as set for the erosion
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
+        if ((dy < 0 ? -dy : dy) + (dx < 0 ? -dx : dx) > 2) continue;
+        const int b = (dy + 2) * 5 + (dx + 2);
+        if (v[b] > th) set |= 1u << b;
+      }
+    // eroded(q): q inside the image and the cross around q all set; q = p + (dy, dx), |dy| + |dx| <= 1
+    auto eroded = [&](int dy, int dx) {
+      const int b = (dy + 2) * 5 + (dx + 2);
+      const uint32_t cross = (1u << b) | (1u << (b - 5)) | (1u << (b + 5)) | (1u << (b - 1)) | (1u << (b + 1));
+      return ((outside >> b) & 1u) == 0 && (set & cross) == cross;
     };
     const bool m = eroded(0, 0) || eroded(-1, 0) || eroded(1, 0) || eroded(0, -1) || eroded(0, 1);
     masks[1ll * t * pixels + i] = m ? 1 : 0;
@@ -269,6 +284,271 @@ int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const
   fire_extents_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(labels, sizes, T, H, W, fire_rc,
                                                                                     n_fires, win, extents);
   return check_launch_sweep("fire_extents");
+}
+
+// ================================================================================================
+// Bit-plane sweep: the same three steps on masks packed 32 pixels per word (sweep_bits.cuh holds the per-thread
+// bodies, shared with the CPU emulation test).  The byte-mask / int32-label kernels above stay for callers that
+// want dense planes; ThresholdSweep.extents and find_plume_extents use this path.
+//   mask_bits_kernel    : a warp walks down a 32-column strip of the image.  Per row one coalesced load; per
+//                         threshold ONE comparison per pixel and two ballots; lane t keeps the ballots of threshold
+//                         t and runs erosion and dilation for its threshold on 36-bit row windows (bit-parallel
+//                         over the 32 columns), a sliding window of two rows of B and of E in registers.
+//   bits_init / merge / flatten : union-find over word-local runs (<= 16 per word, typically 1), one thread per
+//                         word; parent / size entries only exist at run starts.
+//   bits_extents_kernel : one warp per (threshold, fire), one window row per lane, nearest set bit per row by clz / ffs.
+// ================================================================================================
+using namespace sweepbits;
+
+constexpr int kStripRows = 16;      // output rows per warp of mask_bits_kernel (+ 4 halo rows)
+constexpr int kMaskWarps = 4;
+
+__global__ void __launch_bounds__(kMaskWarps * 32)
+    mask_bits_kernel(const float* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
+                     uint32_t* __restrict__ bits) {
+  __shared__ float s_thr[32];
+  const int chunk = blockIdx.y;                       // 32 thresholds per chunk, lane = threshold
+  const int Tc = min(32, T - 32 * chunk);
+  if (threadIdx.x < Tc) s_thr[threadIdx.x] = __double2float_rd(thr[32 * chunk + threadIdx.x]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int segs = (W + 31) / 32;
+  const int strips = (H + kStripRows - 1) / kStripRows;
+  const long long wg = 1ll * blockIdx.x * kMaskWarps + (threadIdx.x >> 5);
+  if (wg >= 1ll * segs * strips) return;
+  const int seg = static_cast<int>(wg % segs), y0 = static_cast<int>(wg / segs) * kStripRows;
+  const int y_end = min(y0 + kStripRows, H);          // output rows y0 .. y_end - 1
+  const uint64_t colmask = window_colmask(seg, W);
+  const uint64_t outcols = ~colmask & kWin36;
+  // lane l: pixel column 32 seg + l; lanes 0..3 also the window's extra columns -2, -1, +32, +33
+  const int x = 32 * seg + lane;
+  const int xe = lane < 2 ? 32 * seg - 2 + lane : 32 * seg + 30 + lane;
+  const bool in_x = x < W, in_xe = lane < 4 && xe >= 0 && xe < W;
+  OpenState st;
+  st.b1 = st.b2 = st.e1 = st.e2 = 0;
+  float v_next = 0.f, ve_next = 0.f;
+  if (y0 - 2 >= 0) {
+    const float* row = aod + 1ll * (y0 - 2) * W;
+    if (in_x) v_next = __ldg(row + x);
+    if (in_xe) ve_next = __ldg(row + xe);
+  }
+  uint32_t* out = bits + (1ll * (32 * chunk + lane) * H) * segs + seg;   // plane of this lane's threshold
+  for (int yy = y0 - 2; yy <= y_end + 1; ++yy) {
+    const float v = v_next, ve = ve_next;
+    const bool row_in = yy >= 0 && yy < H;
+    if (yy + 1 >= 0 && yy + 1 < H && yy + 1 <= y_end + 1) {              // next row's loads fly during this row's loop
+      const float* row = aod + 1ll * (yy + 1) * W;
+      v_next = in_x ? __ldg(row + x) : 0.f;
+      ve_next = in_xe ? __ldg(row + xe) : 0.f;
+    }
+    uint64_t b = kWin36;                                                 // rows beyond the border: all set
+    if (row_in) {                                                        // warp-uniform
+      uint32_t selc = 0, sele = 0;
+#pragma unroll 4
+      for (int t = 0; t < Tc; ++t) {
+        const float th = s_thr[t];
+        const uint32_t c = __ballot_sync(0xffffffffu, v > th);
+        const uint32_t e = __ballot_sync(0xffffffffu, ve > th);
+        if (lane == t) {
+          selc = c;
+          sele = e;
+        }
+      }
+      b = (static_cast<uint64_t>(selc) << 2) | (sele & 3u) | (static_cast<uint64_t>((sele >> 2) & 3u) << 34) | outcols;
+    }
+    const uint32_t word = open_step(st, b, yy - 1 >= 0 && yy - 1 < H, colmask);
+    const int r = yy - 2;
+    if (r >= y0 && lane < Tc) out[1ll * r * segs] = word;
+  }
+}
+
+int threshold_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, cudaStream_t s) {
+  if (H <= 0 || W <= 0 || T <= 0) return 0;
+  const Geom g = make_geom(H, W);
+  if (g.ent_per_plane >= 0x7FFFFFFFll) {
+    set_error("threshold_mask_bits: plane too large");
+    return -1;
+  }
+  const long long warps = 1ll * g.segs * ((H + kStripRows - 1) / kStripRows);
+  const dim3 grid(static_cast<unsigned>((warps + kMaskWarps - 1) / kMaskWarps), static_cast<unsigned>((T + 31) / 32));
+  if (grid.y > 65535u) {
+    set_error("threshold_mask_bits: too many thresholds");
+    return -1;
+  }
+  mask_bits_kernel<<<grid, kMaskWarps * 32, 0, s>>>(aod, H, W, thr, T, bits);
+  return check_launch_sweep("threshold_mask_bits");
+}
+
+// byte masks [T][H][W] -> bit planes (one warp per word)
+__global__ void __launch_bounds__(256)
+    pack_mask_bits_kernel(const uint8_t* __restrict__ masks, long long words, int W, int segs,
+                          uint32_t* __restrict__ bits) {
+  const long long word = (1ll * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (word >= words) return;
+  const int lane = threadIdx.x & 31;
+  const long long row = word / segs;                       // t * H + y
+  const int x = static_cast<int>(word % segs) * 32 + lane;
+  const uint32_t w = __ballot_sync(0xffffffffu, x < W && masks[row * W + x] != 0);
+  if (lane == 0) bits[word] = w;
+}
+
+int pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, cudaStream_t s) {
+  if (T <= 0 || H <= 0 || W <= 0) return 0;
+  const Geom g = make_geom(H, W);
+  const long long words = g.words_per_plane * T;
+  const long long blocks = (words * 32 + 255) / 256;
+  if (blocks >= 0x7FFFFFFFll) {
+    set_error("pack_mask_bits: too many pixels for one call");
+    return -1;
+  }
+  pack_mask_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(masks, words, W, g.segs, bits);
+  return check_launch_sweep("pack_mask_bits");
+}
+
+struct WordPos {
+  long long idx;   // word index over all planes
+  int t, y, seg;
+  bool valid;
+};
+__device__ __forceinline__ WordPos word_pos(const Geom& g, int T) {
+  WordPos p;
+  p.idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  p.valid = p.idx < g.words_per_plane * T;
+  p.t = static_cast<int>(p.idx / g.words_per_plane);
+  const int rem = static_cast<int>(p.idx % g.words_per_plane);
+  p.y = rem / g.segs;
+  p.seg = rem % g.segs;
+  return p;
+}
+
+__global__ void __launch_bounds__(256)
+    bits_init_kernel(const uint32_t* __restrict__ bits, int T, Geom g, int2* __restrict__ ent) {
+  const WordPos p = word_pos(g, T);
+  if (!p.valid) return;
+  const uint32_t w = bits[p.idx];
+  if (w) init_word(w, ent + p.t * g.ent_per_plane, g, p.y, p.seg);
+}
+
+__global__ void __launch_bounds__(256)
+    bits_merge_kernel(const uint32_t* __restrict__ bits, int T, Geom g, int2* __restrict__ ent) {
+  const WordPos p = word_pos(g, T);
+  if (!p.valid) return;
+  const uint32_t w = bits[p.idx];
+  if (!w) return;
+  const uint32_t left = p.seg > 0 ? bits[p.idx - 1] : 0u;
+  uint32_t up_l = 0, up_c = 0, up_r = 0;
+  if (p.y > 0) {
+    const uint32_t* up = bits + p.idx - g.segs;
+    up_c = up[0];
+    if (p.seg > 0) up_l = up[-1];
+    if (p.seg + 1 < g.segs) up_r = up[1];
+  }
+  merge_word(w, left, up_l, up_c, up_r, ent + p.t * g.ent_per_plane, g, p.y, p.seg);
+}
+
+// Every run looks up its root and stores it as its parent; the size counters are bumped once per (warp, root)
+// and round: a large component would otherwise serialise tens of thousands of atomics on one address.
+__global__ void __launch_bounds__(256)
+    bits_flatten_kernel(const uint32_t* __restrict__ bits, int T, Geom g, int2* __restrict__ ent_all) {
+  const WordPos p = word_pos(g, T);
+  const int lane = threadIdx.x & 31;
+  uint32_t rest = p.valid ? bits[p.idx] : 0u;
+  int2* ent = ent_all + p.t * g.ent_per_plane;
+  while (true) {
+    const uint32_t active = __ballot_sync(0xffffffffu, rest != 0u);
+    if (!active) break;
+    if (rest != 0u) {
+      int len;
+      const int e = pop_run(rest, g, p.y, p.seg, len);
+      const int root = uf_root(ent, e);
+      if (root != e) ent[e].x = root;   // readers racing with this see the old parent or the root: both ancestors
+      const unsigned long long key = (static_cast<unsigned long long>(p.t) << 32) | static_cast<unsigned>(root);
+      const uint32_t same = __match_any_sync(active, key);
+      int total = 0;
+      for (uint32_t m = same; m; m &= m - 1u) total += __shfl_sync(same, len, __ffs(m) - 1);
+      if (lane == __ffs(same) - 1) atomicAdd(&ent[root].y, total);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    bits_extents_kernel(const uint32_t* __restrict__ bits, const int2* __restrict__ ent_all, int T, Geom g,
+                        const int* __restrict__ fire_rc, int n_fires, int win, int* __restrict__ extents) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= T * n_fires) return;
+  const int t = warp / n_fires, f = warp % n_fires;
+  const int r = fire_rc[2 * f], c = fire_rc[2 * f + 1];
+  const uint32_t* plane = bits + t * g.words_per_plane;
+  unsigned long long best = kNoKey;
+  for (int dy = -win + lane; dy <= win; dy += 32) {
+    const int y = r + dy;
+    if (y < 0 || y >= g.H) continue;
+    const unsigned long long k = best_in_row(plane + 1ll * y * g.segs, g, c, dy, win);
+    best = k < best ? k : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0) extents[t * n_fires + f] = extent_of_key(best, plane, ent_all + t * g.ent_per_plane, g, r, c, win);
+}
+
+namespace {
+size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+}  // namespace
+
+size_t sweep_workspace_bytes(int H, int W, int T) {
+  if (H <= 0 || W <= 0 || T <= 0) return 0;
+  const Geom g = make_geom(H, W);
+  return align256(static_cast<size_t>(g.ent_per_plane) * T * sizeof(int2)) +
+         align256(static_cast<size_t>(g.words_per_plane) * T * sizeof(uint32_t));
+}
+
+int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
+                 size_t workspace_bytes, int* extents, cudaStream_t s) {
+  if (T <= 0 || H <= 0 || W <= 0 || n_fires <= 0) return 0;
+  const Geom g = make_geom(H, W);
+  if (g.ent_per_plane >= 0x7FFFFFFFll) {
+    set_error("bits_extents: plane too large");
+    return -1;
+  }
+  if (win < 0 || win > 1000) {
+    set_error("bits_extents: bad window");
+    return -1;
+  }
+  if (workspace_bytes < sweep_workspace_bytes(H, W, T)) {
+    set_error("bits_extents: workspace smaller than plume_sweep_workspace_bytes(H, W, T)");
+    return -1;
+  }
+  const long long blocks = (g.words_per_plane * T + 255) / 256;
+  if (blocks >= 0x7FFFFFFFll || 1ll * T * n_fires * 32 >= 0x7FFFFFFFll) {
+    set_error("bits_extents: too many pixels / fires for one call");
+    return -1;
+  }
+  int2* ent = static_cast<int2*>(workspace);
+  const unsigned grid = static_cast<unsigned>(blocks);
+  bits_init_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
+  bits_merge_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
+  bits_flatten_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
+  bits_extents_kernel<<<static_cast<unsigned>((1ll * T * n_fires * 32 + 255) / 256), 256, 0, s>>>(
+      bits, ent, T, g, fire_rc, n_fires, win, extents);
+  return check_launch_sweep("bits_extents");
+}
+
+int sweep_extents(const float* aod, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
+                  void* workspace, size_t workspace_bytes, int* extents, cudaStream_t s) {
+  if (T <= 0 || H <= 0 || W <= 0 || n_fires <= 0) return 0;
+  if (workspace_bytes < sweep_workspace_bytes(H, W, T)) {
+    set_error("sweep_extents: workspace smaller than plume_sweep_workspace_bytes(H, W, T)");
+    return -1;
+  }
+  const Geom g = make_geom(H, W);
+  uint32_t* bits = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) +
+                                               align256(static_cast<size_t>(g.ent_per_plane) * T * sizeof(int2)));
+  const int rc = threshold_mask_bits(aod, H, W, thr, T, bits, s);
+  if (rc) return rc;
+  return bits_extents(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, s);
 }
 
 }  // namespace plume

@@ -484,6 +484,61 @@ class CudaOps:
               "plume_fire_extents")
         self.launches += 1
 
+    # bit-plane form: masks packed 32 pixels per word (int32 tensors [T, H, ceil(W / 32)], bit i of a word = pixel 32 s + i)
+    def sweep_workspace_bytes(self, h, w, t) -> int:
+        return int(self.lib.plume_sweep_workspace_bytes(int(h), int(w), int(t)))
+
+    def threshold_mask_bits(self, aod, thresholds, bits):
+        """aod float32 [H, W], thresholds float64 [T] -> bits int32 [T, H, ceil(W / 32)] = dilate(erode(aod > t))."""
+        h, w = aod.shape
+        t = thresholds.numel()
+        if tuple(bits.shape) != (t, h, (w + 31) // 32):
+            raise ValueError("bits must be [T, H, ceil(W / 32)]")
+        check(self.lib.plume_threshold_mask_bits(self._dev(aod, torch.float32, "aod"), h, w,
+                                                 self._dev(thresholds, torch.float64, "thresholds"), t,
+                                                 self._dev(bits, torch.int32, "bits"), current_stream()),
+              "plume_threshold_mask_bits")
+        self.launches += 1
+
+    def pack_mask_bits(self, masks, bits):
+        """masks uint8 [T, H, W] -> bits int32 [T, H, ceil(W / 32)]."""
+        t, h, w = masks.shape
+        if tuple(bits.shape) != (t, h, (w + 31) // 32):
+            raise ValueError("bits must be [T, H, ceil(W / 32)]")
+        check(self.lib.plume_pack_mask_bits(self._dev(masks, torch.uint8, "masks"), t, h, w,
+                                            self._dev(bits, torch.int32, "bits"), current_stream()),
+              "plume_pack_mask_bits")
+        self.launches += 1
+
+    def bits_extents(self, bits, w, fire_rc, win, workspace, extents):
+        """bits int32 [T, H, ceil(W / 32)] -> extents int32 [T, n]: components over runs of set bits + nearest
+        component per fire; workspace: uint8 tensor of at least sweep_workspace_bytes(H, W, T)."""
+        t, h, segs = bits.shape
+        n = fire_rc.shape[0]
+        if segs != (w + 31) // 32 or tuple(extents.shape) != (t, n) or fire_rc.dim() != 2 or fire_rc.shape[1] != 2:
+            raise ValueError("bits must be [T, H, ceil(W / 32)], extents [T, n_fires], fire_rc [n_fires, 2]")
+        check(self.lib.plume_bits_extents(self._dev(bits, torch.int32, "bits"), t, h, int(w),
+                                          self._dev(fire_rc, torch.int32, "fire_rc"), n, int(win),
+                                          self._dev(workspace, torch.uint8, "workspace"), workspace.numel(),
+                                          self._dev(extents, torch.int32, "extents"), current_stream()),
+              "plume_bits_extents")
+        self.launches += 4 if n and t else 0
+
+    def sweep_extents(self, aod, thresholds, fire_rc, win, workspace, extents):
+        """aod float32 [H, W], thresholds float64 [T], fire_rc int32 [n, 2] -> extents int32 [T, n] in one call."""
+        h, w = aod.shape
+        t = thresholds.numel()
+        n = fire_rc.shape[0]
+        if tuple(extents.shape) != (t, n) or fire_rc.dim() != 2 or fire_rc.shape[1] != 2:
+            raise ValueError("extents must be [T, n_fires], fire_rc [n_fires, 2]")
+        check(self.lib.plume_sweep_extents(self._dev(aod, torch.float32, "aod"), h, w,
+                                           self._dev(thresholds, torch.float64, "thresholds"), t,
+                                           self._dev(fire_rc, torch.int32, "fire_rc"), n, int(win),
+                                           self._dev(workspace, torch.uint8, "workspace"), workspace.numel(),
+                                           self._dev(extents, torch.int32, "extents"), current_stream()),
+              "plume_sweep_extents")
+        self.launches += 5 if n and t else 0
+
     # ------------------------------------------------------------------ UTM projection / nearest-neighbour resampling
     def utm_zone_histogram(self, lons, hist):
         """lons float64 (any shape) -> hist int32 [64]: hist[z] = pixels whose UTM zone is z (tools.py:27-28)."""

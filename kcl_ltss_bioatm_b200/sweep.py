@@ -8,7 +8,8 @@ Reference-named functions (same arguments and results):
     find_plume_extents(masks_dict, fire_rows, fire_cols)         gaussian_profile.py:157-179
     find_threshold_index(plume_extents_across_all_fires)         gaussian_profile.py:204-240  (host, numpy)
 
-``ThresholdSweep.extents`` is the fused form that keeps masks, labels and sizes on the device.  The masks use the
+``ThresholdSweep.extents`` is the fused form: masks as bit planes (32 pixels per word), components over runs of set
+bits, only the [T, n_fires] extents leave the device.  ``masks`` / ``label`` give dense byte / int32 planes.  The masks use the
 cross-shaped footprint with scikit-image's border rules (erosion: set beyond the border; dilation: unset) and the
 labelling is 8-connected, scikit-image's default for 2-D.  There is no CPU path.
 """
@@ -46,21 +47,89 @@ class ThresholdSweep:
         self.ops.label_components(masks, labels, sizes)
         return labels, sizes
 
-    def extents_of_masks(self, masks: torch.Tensor, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
-        h, w = masks.shape[1:]
-        rc = np.stack([np.asarray(fire_rows, dtype=np.int64), np.asarray(fire_cols, dtype=np.int64)], 1)
+    # ---- bit-plane path (32 pixels per word; csrc/sweep_bits.cuh): what extents / find_plume_extents run on
+    def _workspace(self, h, w, t) -> torch.Tensor:
+        need = self.ops.sweep_workspace_bytes(h, w, t)
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need:
+            self._ws = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def _fires(self, fire_rows, fire_cols, h, w, win) -> torch.Tensor:
+        rc = np.stack([np.asarray(fire_rows, dtype=np.int64).reshape(-1), np.asarray(fire_cols, dtype=np.int64).reshape(-1)], 1)
         if len(rc) and (rc[:, 0].min() < win or rc[:, 0].max() > h - win - 1 or rc[:, 1].min() < win
                         or rc[:, 1].max() > w - win - 1):
             raise ValueError("a fire is closer than the window to the image edge (locate_fire_in_image filters these)")
+        return torch.tensor(rc, dtype=torch.int32).to(self.device)
+
+    def mask_bits(self, aod, thresholds) -> torch.Tensor:
+        """int32 [T, H, ceil(W / 32)] on the device: bit i of word s = masks[t, y, 32 s + i]."""
+        a = torch.as_tensor(np.asarray(aod, dtype=np.float32) if not torch.is_tensor(aod) else aod,
+                            dtype=torch.float32).to(self.device).contiguous()
+        thr = torch.tensor(np.asarray(thresholds, dtype=np.float64).reshape(-1)).to(self.device)
+        bits = torch.empty(thr.numel(), a.shape[0], (a.shape[1] + 31) // 32, dtype=torch.int32, device=self.device)
+        if bits.numel():
+            self.ops.threshold_mask_bits(a, thr, bits)
+        return bits
+
+    @staticmethod
+    def unpack_bits(bits: torch.Tensor, w: int) -> np.ndarray:
+        """bool [T, H, W] on the host from device bit planes (the device -> host copy is 8 x smaller than byte masks)."""
+        b = bits.cpu().numpy()
+        t, h, segs = b.shape
+        return np.unpackbits(b.view(np.uint8).reshape(t, h, segs * 4), axis=2, bitorder="little")[:, :, :w].astype(bool)
+
+    def pack_bits_host(self, masks: np.ndarray) -> torch.Tensor:
+        """bool [T, H, W] on the host -> device bit planes (packed on the host: the copy is 8 x smaller)."""
+        t, h, w = masks.shape
+        segs = (w + 31) // 32
+        padded = np.zeros((t, h, segs * 32), dtype=bool)
+        padded[:, :, :w] = masks
+        words = np.packbits(padded, axis=2, bitorder="little").view("<u4").view(np.int32)
+        return torch.from_numpy(np.ascontiguousarray(words)).to(self.device)
+
+    def extents_of_bits(self, bits: torch.Tensor, w: int, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
+        """device bit planes [T, H, ceil(W / 32)] -> float64 [T, n_fires] (find_plume_extents)."""
+        t, h, _ = bits.shape
+        rc = self._fires(fire_rows, fire_cols, h, w, win)
+        out = torch.zeros(t, len(rc), dtype=torch.int32, device=bits.device)
+        if len(rc) and t:
+            self.ops.bits_extents(bits, w, rc, win, self._workspace(h, w, t), out)
+        return out.cpu().numpy().astype(np.float64)
+
+    def extents_of_masks(self, masks: torch.Tensor, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
+        """uint8 masks [T, H, W] on the device -> float64 [T, n_fires] (find_plume_extents)."""
+        t, h, w = masks.shape
+        rc = self._fires(fire_rows, fire_cols, h, w, win)
+        out = torch.zeros(t, len(rc), dtype=torch.int32, device=masks.device)
+        if len(rc) and t:
+            bits = torch.empty(t, h, (w + 31) // 32, dtype=torch.int32, device=masks.device)
+            self.ops.pack_mask_bits(masks.contiguous(), bits)
+            self.ops.bits_extents(bits, w, rc, win, self._workspace(h, w, t), out)
+        return out.cpu().numpy().astype(np.float64)
+
+    def extents_dense(self, masks: torch.Tensor, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
+        """The same through the dense int32 label planes (label + fire_extents)."""
+        h, w = masks.shape[1:]
+        rc = self._fires(fire_rows, fire_cols, h, w, win)
         labels, sizes = self.label(masks)
         out = torch.zeros(masks.shape[0], len(rc), dtype=torch.int32, device=masks.device)
         if len(rc):
-            self.ops.fire_extents(labels, sizes, torch.tensor(rc, dtype=torch.int32).to(masks.device), win, out)
+            self.ops.fire_extents(labels, sizes, rc, win, out)
         return out.cpu().numpy().astype(np.float64)
 
     def extents(self, aod, thresholds, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
-        """float64 [T, n_fires]: generate_mask_dict + find_plume_extents in one pass on the device."""
-        return self.extents_of_masks(self.masks(aod, thresholds), fire_rows, fire_cols, win)
+        """float64 [T, n_fires]: generate_mask_dict + find_plume_extents in one call on the device (any T: the
+        reference's three sweeps of a timestamp can be passed as one concatenated threshold list)."""
+        a = torch.as_tensor(np.asarray(aod, dtype=np.float32) if not torch.is_tensor(aod) else aod,
+                            dtype=torch.float32).to(self.device).contiguous()
+        thr = torch.tensor(np.asarray(thresholds, dtype=np.float64).reshape(-1)).to(self.device)
+        h, w = a.shape
+        rc = self._fires(fire_rows, fire_cols, h, w, win)
+        out = torch.zeros(thr.numel(), len(rc), dtype=torch.int32, device=self.device)
+        if len(rc) and thr.numel():
+            self.ops.sweep_extents(a, thr, rc, win, self._workspace(h, w, thr.numel()), out)
+        return out.cpu().numpy().astype(np.float64)
 
 
 _default: Optional[ThresholdSweep] = None
@@ -75,16 +144,18 @@ def _sweep() -> ThresholdSweep:
 
 def generate_mask_dict(aod, threshold_range) -> Dict[float, np.ndarray]:
     """{threshold: bool mask [H, W]} -- aod > t with singleton pixels removed (erosion then dilation)."""
-    m = _sweep().masks(aod, threshold_range).cpu().numpy().astype(bool)
+    threshold_range = list(threshold_range)
+    s = _sweep()
+    m = s.unpack_bits(s.mask_bits(aod, threshold_range), np.shape(aod)[1])
     return {t: m[i] for i, t in enumerate(threshold_range)}
 
 
 def find_plume_extents(masks_dict, fire_rows, fire_cols) -> np.ndarray:
     """[len(masks_dict), len(fires)]: per threshold (dict order) and fire the pixel count of the labelled region
     nearest to the fire within its 31 x 31 window, 0 where there is none."""
-    stack = np.stack([np.asarray(masks_dict[k]) for k in masks_dict]).astype(np.uint8)
+    stack = np.stack([np.asarray(masks_dict[k]) for k in masks_dict]) != 0
     s = _sweep()
-    return s.extents_of_masks(torch.from_numpy(stack).to(s.device), fire_rows, fire_cols)
+    return s.extents_of_bits(s.pack_bits_host(stack), stack.shape[2], fire_rows, fire_cols)
 
 
 def find_threshold_index(plume_extents_across_all_fires) -> List[Optional[int]]:

@@ -1,0 +1,152 @@
+// TEST INFRASTRUCTURE.  Sequential CPU run of the per-thread bodies of the bit-plane sweep kernels
+// (kcl_ltss_bioatm_b200/csrc/sweep_bits.cuh, the same source the CUDA kernels compile) so that the bit logic is
+// checked against the oracle without a GPU (tests/test_sweep_bits_emu.py builds this with g++).  The warp-level
+// parts of the kernels (ballots, shuffles) are replaced by loops over 32 lanes with the kernel's own index
+// arithmetic; threads run one after the other in an order the caller can permute.  Nothing in the package links this.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../kcl_ltss_bioatm_b200/csrc/sweep_bits.cuh"
+
+using namespace plume::sweepbits;
+
+namespace {
+float round_down_to_float(double t) {          // __double2float_rd
+  float f = static_cast<float>(t);
+  if (static_cast<double>(f) > t) f = std::nextafterf(f, -INFINITY);
+  return f;
+}
+constexpr int kStripRows = 16;
+
+void mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits) {
+  const int segs = (W + 31) / 32;
+  const int strips = (H + kStripRows - 1) / kStripRows;
+  for (int t = 0; t < T; ++t) {
+    const float th = round_down_to_float(thr[t]);
+    for (int wg = 0; wg < segs * strips; ++wg) {
+      const int seg = wg % segs, y0 = (wg / segs) * kStripRows;
+      const int y_end = y0 + kStripRows < H ? y0 + kStripRows : H;
+      const uint64_t colmask = window_colmask(seg, W);
+      const uint64_t outcols = ~colmask & kWin36;
+      OpenState st;
+      st.b1 = st.b2 = st.e1 = st.e2 = 0;
+      for (int yy = y0 - 2; yy <= y_end + 1; ++yy) {
+        uint64_t b = kWin36;
+        if (yy >= 0 && yy < H) {
+          uint32_t selc = 0, sele = 0;
+          for (int lane = 0; lane < 32; ++lane) {
+            const int x = 32 * seg + lane;
+            const int xe = lane < 2 ? 32 * seg - 2 + lane : 32 * seg + 30 + lane;
+            const bool in_x = x < W, in_xe = lane < 4 && xe >= 0 && xe < W;
+            const float v = in_x ? aod[1ll * yy * W + x] : 0.f;
+            const float ve = in_xe ? aod[1ll * yy * W + xe] : 0.f;
+            if (v > th) selc |= 1u << lane;
+            if (ve > th) sele |= 1u << lane;
+          }
+          b = (static_cast<uint64_t>(selc) << 2) | (sele & 3u) | (static_cast<uint64_t>((sele >> 2) & 3u) << 34) | outcols;
+        }
+        const uint32_t word = open_step(st, b, yy - 1 >= 0 && yy - 1 < H, colmask);
+        const int r = yy - 2;
+        if (r >= y0) bits[(1ll * t * H + r) * segs + seg] = word;
+      }
+    }
+  }
+}
+
+// a fixed pseudo-random permutation of 0..n-1 (seed 0: identity) -- thread order must not matter
+std::vector<long long> order(long long n, unsigned seed) {
+  std::vector<long long> o(n);
+  for (long long i = 0; i < n; ++i) o[i] = i;
+  if (seed) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1;
+    for (long long i = n - 1; i > 0; --i) {
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      const long long j = static_cast<long long>((s >> 33) % static_cast<uint64_t>(i + 1));
+      std::swap(o[i], o[j]);
+    }
+  }
+  return o;
+}
+}  // namespace
+
+extern "C" {
+
+void emu_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits) {
+  mask_bits(aod, H, W, thr, T, bits);
+}
+
+void emu_pack_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits) {
+  const int segs = (W + 31) / 32;
+  for (long long row = 0; row < 1ll * T * H; ++row)
+    for (int sg = 0; sg < segs; ++sg) {
+      uint32_t w = 0;
+      for (int l = 0; l < 32; ++l)
+        if (32 * sg + l < W && masks[row * W + 32 * sg + l]) w |= 1u << l;
+      bits[row * segs + sg] = w;
+    }
+}
+
+// init + merge + flatten + extents; `ent` is scratch of T * H * 16 * segs int2 (garbage-filled by the caller on purpose)
+void emu_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, int2* ent_all,
+                      int* extents, unsigned seed) {
+  const Geom g = make_geom(H, W);
+  const long long words = g.words_per_plane * T;
+  auto pos = [&](long long idx, int& t, int& y, int& seg) {
+    t = static_cast<int>(idx / g.words_per_plane);
+    const int rem = static_cast<int>(idx % g.words_per_plane);
+    y = rem / g.segs;
+    seg = rem % g.segs;
+  };
+  for (long long idx : order(words, seed)) {
+    int t, y, seg;
+    pos(idx, t, y, seg);
+    if (bits[idx]) init_word(bits[idx], ent_all + t * g.ent_per_plane, g, y, seg);
+  }
+  for (long long idx : order(words, seed ? seed + 1 : 0)) {
+    int t, y, seg;
+    pos(idx, t, y, seg);
+    const uint32_t w = bits[idx];
+    if (!w) continue;
+    const uint32_t left = seg > 0 ? bits[idx - 1] : 0u;
+    uint32_t up_l = 0, up_c = 0, up_r = 0;
+    if (y > 0) {
+      const uint32_t* up = bits + idx - g.segs;
+      up_c = up[0];
+      if (seg > 0) up_l = up[-1];
+      if (seg + 1 < g.segs) up_r = up[1];
+    }
+    merge_word(w, left, up_l, up_c, up_r, ent_all + t * g.ent_per_plane, g, y, seg);
+  }
+  for (long long idx : order(words, seed ? seed + 2 : 0)) {
+    int t, y, seg;
+    pos(idx, t, y, seg);
+    uint32_t rest = bits[idx];
+    int2* ent = ent_all + t * g.ent_per_plane;
+    while (rest) {
+      int len;
+      const int e = pop_run(rest, g, y, seg, len);
+      const int root = uf_root(ent, e);
+      if (root != e) ent[e].x = root;
+      ent[root].y += len;
+    }
+  }
+  for (int t = 0; t < T; ++t)
+    for (int f = 0; f < n_fires; ++f) {
+      const int r = fire_rc[2 * f], c = fire_rc[2 * f + 1];
+      const uint32_t* plane = bits + t * g.words_per_plane;
+      unsigned long long best = kNoKey;
+      for (int lane = 0; lane < 32; ++lane)
+        for (int dy = -win + lane; dy <= win; dy += 32) {
+          const int y = r + dy;
+          if (y < 0 || y >= H) continue;
+          const unsigned long long k = best_in_row(plane + 1ll * y * g.segs, g, c, dy, win);
+          best = k < best ? k : best;
+        }
+      extents[t * n_fires + f] = extent_of_key(best, plane, ent_all + t * g.ent_per_plane, g, r, c, win);
+    }
+}
+
+long long emu_ent_count(int H, int W, int T) { return make_geom(H, W).ent_per_plane * T; }
+}

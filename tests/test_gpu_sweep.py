@@ -34,8 +34,11 @@ def test_sweep_equals_reference_golden(sw, i):
     aod, fires, thr, masks, extents, index = case(i)
     m = sw.masks(aod, thr)
     assert np.array_equal(m.cpu().numpy().astype(bool), masks)
-    ext = sw.extents(aod, thr, fires[:, 0], fires[:, 1])
+    assert np.array_equal(sw.unpack_bits(sw.mask_bits(aod, thr), aod.shape[1]), masks)      # bit planes
+    ext = sw.extents(aod, thr, fires[:, 0], fires[:, 1])                                    # fused bit-plane path
     assert ext.dtype == np.float64 and np.array_equal(ext, extents)
+    assert np.array_equal(sw.extents_dense(m, fires[:, 0], fires[:, 1]), extents)           # dense label planes
+    assert np.array_equal(sw.extents_of_masks(m, fires[:, 0], fires[:, 1]), extents)        # byte masks -> bit planes
     idx = [-1 if v is None else v for v in sweep.find_threshold_index(ext)]
     assert idx == index.tolist()
 
@@ -90,3 +93,72 @@ def test_fire_too_close_to_edge_is_rejected(sw):
     aod, _, thr, _, _, _ = case(0)
     with pytest.raises(ValueError):
         sw.extents(aod, thr, [3], [40])
+
+
+def spiral(h, w):
+    sp = np.zeros((h, w), dtype=bool)
+    y0, x0, y1, x1 = 0, 0, h - 1, w - 1
+    while y1 - y0 > 3 and x1 - x0 > 3:
+        sp[y0, x0:x1 + 1] = True
+        sp[y0:y1 + 1, x1] = True
+        sp[y1, x0 + 2:x1 + 1] = True
+        sp[y0 + 2:y1 + 1, x0 + 2] = True
+        y0, x0, y1, x1 = y0 + 2, x0 + 2, y1 - 2, x1 - 2
+    return sp
+
+
+@pytest.mark.parametrize("h,w,density", [(1, 1, 1.0), (7, 300, 0.5), (64, 64, 0.62), (97, 129, 0.4), (257, 333, 0.55),
+                                         (600, 800, 0.6)])
+def test_bit_plane_extents_equal_oracle_on_random_masks(sw, h, w, density):
+    """The run-based union-find on percolation-like masks, a spiral, a full and an empty plane."""
+    rng = np.random.default_rng(h * 1000 + w)
+    masks = rng.random((5, h, w)) < density
+    masks[1] = ~masks[1] if h > 1 else masks[1]
+    masks[3] = True
+    masks[4] = False
+    if h >= 8 and w >= 8:
+        masks[2] = spiral(h, w)
+    win = min(sweep_ref.P_ID_WIN_SIZE, (h - 1) // 2, (w - 1) // 2)
+    rows = rng.integers(win, h - win, 40)
+    cols = rng.integers(win, w - win, 40)
+    ref = sweep_ref.find_plume_extents_ref(masks, rows, cols, win)
+    dev = torch.from_numpy(masks.astype(np.uint8)).cuda()
+    for _ in range(3):                                                     # atomics: every run must agree
+        assert np.array_equal(sw.extents_of_masks(dev, rows, cols, win), ref)
+    assert np.array_equal(sw.extents_of_bits(sw.pack_bits_host(masks), w, rows, cols, win), ref)
+    assert np.array_equal(sw.extents_dense(dev, rows, cols, win), ref)
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (2, 31), (3, 32), (5, 33), (7, 300), (40, 64), (33, 65), (61, 97), (300, 1200)])
+def test_mask_bits_equal_oracle_on_noisy_images(sw, h, w):
+    rng = np.random.default_rng(h * 131 + w)
+    aod = rng.random((h, w)).astype(np.float32)
+    aod[rng.random((h, w)) < 0.02] = np.nan
+    thr = np.concatenate([[0.1, 0.25, 0.5, float(np.float32(0.3)), 0.3, 0.9, -1.0, 2.0], rng.random(33)])   # two chunks
+    ref = sweep_ref.threshold_masks_ref(aod, thr)
+    assert np.array_equal(sw.unpack_bits(sw.mask_bits(aod, thr), w), ref)
+    assert np.array_equal(sw.masks(aod, thr[:40]).cpu().numpy().astype(bool), ref[:40])
+    blobs = (rng.random((h, w)) < 0.8).astype(np.float32)
+    assert np.array_equal(sw.unpack_bits(sw.mask_bits(blobs, [0.5]), w), sweep_ref.threshold_masks_ref(blobs, [0.5]))
+
+
+def test_threshold_rounding_decides_like_float64(sw):
+    x = np.float32(0.48)
+    for t in (0.48, float(x), float(np.nextafter(x, np.float32(1))), float(np.nextafter(x, np.float32(0))), 1e-50, -1e-50, 1e300):
+        aod = np.full((6, 7), x, dtype=np.float32)
+        want = bool(np.float64(x) > t)
+        assert sw.unpack_bits(sw.mask_bits(aod, [t]), 7).all() == want
+        assert bool(sw.masks(aod, [t]).cpu().numpy().all()) == want
+
+
+def test_full_size_timestamp_bit_planes_agree_with_dense_planes(sw):
+    """1200 x 1200, the reference's three sweeps (75 thresholds) in ONE call against the dense-plane path per sweep."""
+    aod, _ = synthetic_aod(1200, 1200, 5)
+    rng = np.random.default_rng(3)
+    rows, cols = rng.integers(16, 1184, 64), rng.integers(16, 1184, 64)
+    sweeps = [np.abs(np.arange(0, tmax, step) - tmax) for step, tmax in [(0.02, 0.5), (0.03, 0.75), (0.04, 1)]]
+    fused = sw.extents(aod, np.concatenate(sweeps), rows, cols)
+    dense = np.concatenate([sw.extents_dense(sw.masks(aod, t), rows, cols) for t in sweeps])
+    assert fused.shape == (75, 64) and np.array_equal(fused, dense)
+    assert np.array_equal(np.concatenate([sw.extents(aod, t, rows, cols) for t in sweeps]), fused)
+    assert fused.max() > 1000 and (fused == 0).any()
