@@ -290,10 +290,10 @@ int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const
 // Bit-plane sweep: the same three steps on masks packed 32 pixels per word (sweep_bits.cuh holds the per-thread
 // bodies, shared with the CPU emulation test).  The byte-mask / int32-label kernels above stay for callers that
 // want dense planes; ThresholdSweep.extents and find_plume_extents use this path.
-//   mask_bits_kernel    : a warp walks down a 32-column strip of the image.  Per row one coalesced load; per
-//                         threshold ONE comparison per pixel and two ballots; lane t keeps the ballots of threshold
-//                         t and runs erosion and dilation for its threshold on 36-bit row windows (bit-parallel
-//                         over the 32 columns), a sliding window of two rows of B and of E in registers.
+//   mask_bits_kernel    : a warp walks down a 64-column strip of the image.  Per row coalesced loads; per threshold
+//                         ONE comparison per pixel and three ballots; lane t takes the ballots of threshold t and
+//                         runs erosion and dilation for its threshold on 36-bit row windows (bit-parallel over
+//                         the 32 columns of a word), a sliding window of two rows of B and of E in registers.
 //   bits_init / merge / flatten : union-find over word-local runs (<= 16 per word, typically 1), one thread per
 //                         word; parent / size entries only exist at run starts.
 //   bits_extents_kernel : one warp per (threshold, fire), one window row per lane, nearest set bit per row by clz / ffs.
@@ -303,80 +303,108 @@ using namespace sweepbits;
 constexpr int kStripRows = 16;      // output rows per warp of mask_bits_kernel (+ 4 halo rows)
 constexpr int kMaskWarps = 4;
 
+// A warp takes two adjacent 32-column strips and kStripRows rows: three ballots per threshold serve 64 columns (the
+// two extra window columns between the strips are ordinary pixels of the other strip; lanes 0..3 load the four
+// outer ones), and lane 0 parks the ballots in shared memory, from where the lane that owns the threshold picks
+// them up after the loop (no per-threshold select).
 __global__ void __launch_bounds__(kMaskWarps * 32)
     mask_bits_kernel(const float* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
-                     uint32_t* __restrict__ bits) {
+                     uint32_t* __restrict__ bits, int2* __restrict__ ent_all) {
   __shared__ float s_thr[32];
-  const int chunk = blockIdx.y;                       // 32 thresholds per chunk, lane = threshold
+  __shared__ uint4 s_sel[kMaskWarps][32];
+  const int chunk = blockIdx.y;
   const int Tc = min(32, T - 32 * chunk);
   if (threadIdx.x < Tc) s_thr[threadIdx.x] = __double2float_rd(thr[32 * chunk + threadIdx.x]);
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int segs = (W + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int segs = (W + 31) / 32, pairs = (segs + 1) / 2;
   const int strips = (H + kStripRows - 1) / kStripRows;
-  const long long wg = 1ll * blockIdx.x * kMaskWarps + (threadIdx.x >> 5);
-  if (wg >= 1ll * segs * strips) return;
-  const int seg = static_cast<int>(wg % segs), y0 = static_cast<int>(wg / segs) * kStripRows;
-  const int y_end = min(y0 + kStripRows, H);          // output rows y0 .. y_end - 1
-  const uint64_t colmask = window_colmask(seg, W);
-  const uint64_t outcols = ~colmask & kWin36;
-  // lane l: pixel column 32 seg + l; lanes 0..3 also the window's extra columns -2, -1, +32, +33
-  const int x = 32 * seg + lane;
-  const int xe = lane < 2 ? 32 * seg - 2 + lane : 32 * seg + 30 + lane;
-  const bool in_x = x < W, in_xe = lane < 4 && xe >= 0 && xe < W;
-  OpenState st;
-  st.b1 = st.b2 = st.e1 = st.e2 = 0;
-  float v_next = 0.f, ve_next = 0.f;
+  const long long wg = 1ll * blockIdx.x * kMaskWarps + warp;
+  if (wg >= 1ll * pairs * strips) return;
+  const int sp = static_cast<int>(wg % pairs), y0 = static_cast<int>(wg / pairs) * kStripRows;
+  const int y_end = min(y0 + kStripRows, H);
+  const int seg0 = 2 * sp, seg1 = 2 * sp + 1;
+  const uint64_t colmask0 = window_colmask(seg0, W), colmask1 = window_colmask(seg1, W);
+  const uint64_t outcols0 = ~colmask0 & kWin36, outcols1 = ~colmask1 & kWin36;
+  const int x0 = 64 * sp + lane, x1 = x0 + 32;
+  const int xe = lane < 2 ? 64 * sp - 2 + lane : 64 * sp + 62 + lane;          // lanes 0..3: columns -2, -1, +64, +65
+  const bool in0 = x0 < W, in1 = x1 < W, ine = lane < 4 && xe >= 0 && xe < W;
+  OpenState st0, st1;
+  st0.b1 = st0.b2 = st0.e1 = st0.e2 = 0;
+  st1 = st0;
+  float n0 = 0.f, n1 = 0.f, ne = 0.f;
   if (y0 - 2 >= 0) {
     const float* row = aod + 1ll * (y0 - 2) * W;
-    if (in_x) v_next = __ldg(row + x);
-    if (in_xe) ve_next = __ldg(row + xe);
+    if (in0) n0 = __ldg(row + x0);
+    if (in1) n1 = __ldg(row + x1);
+    if (ine) ne = __ldg(row + xe);
   }
-  uint32_t* out = bits + (1ll * (32 * chunk + lane) * H) * segs + seg;   // plane of this lane's threshold
+  uint32_t* out = bits + (1ll * (32 * chunk + lane) * H) * segs + seg0;
+  // fused call: the lane that owns a threshold also creates the union-find entries of the runs it emits (bits_init)
+  const Geom g = make_geom(H, W);
+  int2* ent = ent_all ? ent_all + (32 * chunk + lane) * g.ent_per_plane : nullptr;
   for (int yy = y0 - 2; yy <= y_end + 1; ++yy) {
-    const float v = v_next, ve = ve_next;
+    const float v0 = n0, v1 = n1, ve = ne;
     const bool row_in = yy >= 0 && yy < H;
-    if (yy + 1 >= 0 && yy + 1 < H && yy + 1 <= y_end + 1) {              // next row's loads fly during this row's loop
+    if (yy + 1 >= 0 && yy + 1 < H && yy + 1 <= y_end + 1) {
       const float* row = aod + 1ll * (yy + 1) * W;
-      v_next = in_x ? __ldg(row + x) : 0.f;
-      ve_next = in_xe ? __ldg(row + xe) : 0.f;
+      n0 = in0 ? __ldg(row + x0) : 0.f;
+      n1 = in1 ? __ldg(row + x1) : 0.f;
+      ne = ine ? __ldg(row + xe) : 0.f;
     }
-    uint64_t b = kWin36;                                                 // rows beyond the border: all set
+    uint64_t b0 = kWin36, b1 = kWin36;
     if (row_in) {                                                        // warp-uniform
-      uint32_t selc = 0, sele = 0;
-#pragma unroll 4
+#pragma unroll 5
       for (int t = 0; t < Tc; ++t) {
         const float th = s_thr[t];
-        const uint32_t c = __ballot_sync(0xffffffffu, v > th);
+        const uint32_t c0 = __ballot_sync(0xffffffffu, v0 > th);
+        const uint32_t c1 = __ballot_sync(0xffffffffu, v1 > th);
         const uint32_t e = __ballot_sync(0xffffffffu, ve > th);
-        if (lane == t) {
-          selc = c;
-          sele = e;
-        }
+        if (lane == 0) s_sel[warp][t] = make_uint4(c0, c1, e, 0u);
       }
-      b = (static_cast<uint64_t>(selc) << 2) | (sele & 3u) | (static_cast<uint64_t>((sele >> 2) & 3u) << 34) | outcols;
+      __syncwarp();
+      const uint4 sel = s_sel[warp][lane];                               // lanes >= Tc read stale words, never used
+      __syncwarp();
+      b0 = (static_cast<uint64_t>(sel.x) << 2) | (sel.z & 3u) | (static_cast<uint64_t>(sel.y & 3u) << 34) | outcols0;
+      b1 = (static_cast<uint64_t>(sel.y) << 2) | (sel.x >> 30) | (static_cast<uint64_t>((sel.z >> 2) & 3u) << 34) | outcols1;
     }
-    const uint32_t word = open_step(st, b, yy - 1 >= 0 && yy - 1 < H, colmask);
+    const bool prev_in = yy - 1 >= 0 && yy - 1 < H;
+    const uint32_t w0 = open_step(st0, b0, prev_in, colmask0);
+    const uint32_t w1 = open_step(st1, b1, prev_in, colmask1);
     const int r = yy - 2;
-    if (r >= y0 && lane < Tc) out[1ll * r * segs] = word;
+    if (r >= y0 && lane < Tc) {
+      out[1ll * r * segs] = w0;
+      if (seg1 < segs) out[1ll * r * segs + 1] = w1;
+      if (ent) {
+        init_word(w0, ent, g, r, seg0);
+        init_word(w1, ent, g, r, seg1);                                 // zero when seg1 is beyond the image
+      }
+    }
   }
 }
 
-int threshold_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, cudaStream_t s) {
+namespace {
+int mask_bits_launch(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, int2* ent,
+                     cudaStream_t s) {
   if (H <= 0 || W <= 0 || T <= 0) return 0;
   const Geom g = make_geom(H, W);
   if (g.ent_per_plane >= 0x7FFFFFFFll) {
     set_error("threshold_mask_bits: plane too large");
     return -1;
   }
-  const long long warps = 1ll * g.segs * ((H + kStripRows - 1) / kStripRows);
+  const long long warps = 1ll * ((g.segs + 1) / 2) * ((H + kStripRows - 1) / kStripRows);
   const dim3 grid(static_cast<unsigned>((warps + kMaskWarps - 1) / kMaskWarps), static_cast<unsigned>((T + 31) / 32));
   if (grid.y > 65535u) {
     set_error("threshold_mask_bits: too many thresholds");
     return -1;
   }
-  mask_bits_kernel<<<grid, kMaskWarps * 32, 0, s>>>(aod, H, W, thr, T, bits);
+  mask_bits_kernel<<<grid, kMaskWarps * 32, 0, s>>>(aod, H, W, thr, T, bits, ent);
   return check_launch_sweep("threshold_mask_bits");
+}
+}  // namespace
+
+int threshold_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, cudaStream_t s) {
+  return mask_bits_launch(aod, H, W, thr, T, bits, nullptr, s);
 }
 
 // byte masks [T][H][W] -> bit planes (one warp per word)
@@ -505,8 +533,9 @@ size_t sweep_workspace_bytes(int H, int W, int T) {
          align256(static_cast<size_t>(g.words_per_plane) * T * sizeof(uint32_t));
 }
 
-int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
-                 size_t workspace_bytes, int* extents, cudaStream_t s) {
+namespace {
+int bits_extents_launch(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win,
+                        void* workspace, size_t workspace_bytes, int* extents, bool entries_ready, cudaStream_t s) {
   if (T <= 0 || H <= 0 || W <= 0 || n_fires <= 0) return 0;
   const Geom g = make_geom(H, W);
   if (g.ent_per_plane >= 0x7FFFFFFFll) {
@@ -528,12 +557,18 @@ int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, 
   }
   int2* ent = static_cast<int2*>(workspace);
   const unsigned grid = static_cast<unsigned>(blocks);
-  bits_init_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
+  if (!entries_ready) bits_init_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
   bits_merge_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
   bits_flatten_kernel<<<grid, 256, 0, s>>>(bits, T, g, ent);
   bits_extents_kernel<<<static_cast<unsigned>((1ll * T * n_fires * 32 + 255) / 256), 256, 0, s>>>(
       bits, ent, T, g, fire_rc, n_fires, win, extents);
   return check_launch_sweep("bits_extents");
+}
+}  // namespace
+
+int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
+                 size_t workspace_bytes, int* extents, cudaStream_t s) {
+  return bits_extents_launch(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, false, s);
 }
 
 int sweep_extents(const float* aod, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
@@ -546,9 +581,9 @@ int sweep_extents(const float* aod, int H, int W, const double* thr, int T, cons
   const Geom g = make_geom(H, W);
   uint32_t* bits = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) +
                                                align256(static_cast<size_t>(g.ent_per_plane) * T * sizeof(int2)));
-  const int rc = threshold_mask_bits(aod, H, W, thr, T, bits, s);
+  const int rc = mask_bits_launch(aod, H, W, thr, T, bits, static_cast<int2*>(workspace), s);
   if (rc) return rc;
-  return bits_extents(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, s);
+  return bits_extents_launch(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, true, s);
 }
 
 }  // namespace plume

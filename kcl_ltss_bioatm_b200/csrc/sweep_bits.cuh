@@ -119,6 +119,21 @@ PLUME_HD int uf_root(const int2* ent, int x) {
   }
   return x;
 }
+// the same with path halving: every visited entry is re-pointed at its grandparent by a plain store.  Safe next to
+// the atomicMin of uf_unite: only non-roots are written, always with an ancestor (a smaller index of the same set);
+// a lost atomicMin result is harmless because the thread that issued it goes on uniting the previous parent with its
+// target (uf_unite).  Measured on 1200 x 1200 x 75 planes: merge + flatten 163 -> 80 us; a band-local phase in shared
+// memory and skipping unions the left neighbour also makes gained nothing on top (gpurun_out/r2ab).
+PLUME_HD int uf_root_halving(int2* ent, int x) {
+  int p = ent[x].x;
+  while (p != x) {
+    const int gp = ent[p].x;
+    if (gp != p) ent[x].x = gp;
+    x = p;
+    p = gp;
+  }
+  return x;
+}
 PLUME_HD int uf_atomic_min(int2* ent, int a, int b) {
 #if defined(__CUDA_ARCH__)
   return atomicMin(&ent[a].x, b);
@@ -130,8 +145,8 @@ PLUME_HD int uf_atomic_min(int2* ent, int a, int b) {
 }
 PLUME_HD void uf_unite(int2* ent, int a, int b) {
   while (true) {
-    a = uf_root(ent, a);
-    b = uf_root(ent, b);
+    a = uf_root_halving(ent, a);
+    b = uf_root_halving(ent, b);
     if (a == b) return;
     if (a < b) {
       const int t = a;

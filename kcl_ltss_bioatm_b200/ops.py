@@ -537,7 +537,7 @@ class CudaOps:
                                            self._dev(workspace, torch.uint8, "workspace"), workspace.numel(),
                                            self._dev(extents, torch.int32, "extents"), current_stream()),
               "plume_sweep_extents")
-        self.launches += 5 if n and t else 0
+        self.launches += 4 if n and t else 0
 
     # ------------------------------------------------------------------ UTM projection / nearest-neighbour resampling
     def utm_zone_histogram(self, lons, hist):

@@ -7,6 +7,8 @@ Reference-named functions (same arguments and results):
     generate_mask_dict(aod, threshold_range)                     gaussian_profile.py:142-154
     find_plume_extents(masks_dict, fire_rows, fire_cols)         gaussian_profile.py:157-179
     find_threshold_index(plume_extents_across_all_fires)         gaussian_profile.py:204-240  (host, numpy)
+    cluster_fires(aod, fire_rows, fire_cols)                     gaussian_profile.py:126-139
+    fire_cluster_centroids(fire_labels)                          gaussian_profile.py:474-477  (host, numpy)
 
 ``ThresholdSweep.extents`` is the fused form: masks as bit planes (32 pixels per word), components over runs of set
 bits, only the [T, n_fires] extents leave the device.  ``masks`` / ``label`` give dense byte / int32 planes.  The masks use the
@@ -132,6 +134,32 @@ class ThresholdSweep:
         return out.cpu().numpy().astype(np.float64)
 
 
+    def cluster_fires(self, shape, fire_rows, fire_cols, min_size: int = 3) -> np.ndarray:
+        """int64 [H, W]: the fire pixels labelled by 8-connected cluster, numbered 1..n in raster order of each
+        cluster's first pixel, clusters smaller than ``min_size`` removed (their numbers stay unused).  The labelling
+        runs on the device (label_components on the fire grid); only the labels and sizes AT the fire pixels come
+        back, and the numbering -- a rank over a handful of roots -- is done on the host."""
+        h, w = int(shape[0]), int(shape[1])
+        rows = torch.as_tensor(np.asarray(fire_rows, dtype=np.int64).reshape(-1)).to(self.device)
+        cols = torch.as_tensor(np.asarray(fire_cols, dtype=np.int64).reshape(-1)).to(self.device)
+        out = np.zeros((h, w), dtype=np.int64)
+        if rows.numel() == 0:
+            return out
+        if int(rows.min()) < 0 or int(rows.max()) >= h or int(cols.min()) < 0 or int(cols.max()) >= w:
+            raise IndexError("a fire lies outside the image")
+        grid = torch.zeros(1, h, w, dtype=torch.uint8, device=self.device)
+        grid[0, rows, cols] = 1
+        labels, sizes = self.label(grid)
+        root = labels[0, rows, cols].to(torch.int64)                     # canonical label = first pixel of the cluster
+        size = sizes.view(-1)[root].cpu().numpy()
+        root = root.cpu().numpy()
+        ranks = {r: k + 1 for k, r in enumerate(np.unique(root))}         # raster order of first pixels = label numbers
+        keep = size >= min_size
+        r, c = rows.cpu().numpy()[keep], cols.cpu().numpy()[keep]
+        out[r, c] = [ranks[v] for v in root[keep]]
+        return out
+
+
 _default: Optional[ThresholdSweep] = None
 
 
@@ -176,3 +204,20 @@ def find_threshold_index(plume_extents_across_all_fires) -> List[Optional[int]]:
             continue
         best.append(None if k == ratios.size else k)
     return best
+
+
+def cluster_fires(aod, fire_rows, fire_cols) -> np.ndarray:
+    """Label image of the fire clusters (8-connected, at least 3 pixels), shaped like ``aod``."""
+    return _sweep().cluster_fires(np.shape(aod), fire_rows, fire_cols)
+
+
+def fire_cluster_centroids(fire_labels):
+    """``[r.centroid for r in regionprops(fire_labels)]`` as integer (rows, cols) arrays, labels ascending --
+    what ``identify`` feeds to the sweep (a few dozen pixels: host numpy)."""
+    fire_labels = np.asarray(fire_labels)
+    r, c = np.nonzero(fire_labels)
+    lab = fire_labels[r, c]
+    ids, inv, cnt = np.unique(lab, return_inverse=True, return_counts=True)
+    rows = np.bincount(inv, weights=r, minlength=len(ids)) / np.maximum(cnt, 1)
+    cols = np.bincount(inv, weights=c, minlength=len(ids)) / np.maximum(cnt, 1)
+    return rows.astype(int), cols.astype(int)

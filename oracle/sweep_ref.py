@@ -88,3 +88,25 @@ def find_threshold_index_ref(extents: np.ndarray):
             continue
         best.append(None if k == ratio.size else k)
     return best
+
+
+def cluster_fires_ref(shape, fire_rows, fire_cols, min_size: int = 3) -> np.ndarray:
+    """gaussian_profile.py:126-139: the fire pixels as an 8-connected label image (labels 1..n in raster order of each
+    cluster's first pixel, scikit-image's numbering), clusters of fewer than ``min_size`` pixels set to 0 with the
+    other labels unchanged (``remove_small_objects`` on a label image)."""
+    grid = np.zeros(shape, dtype=bool)
+    grid[np.asarray(fire_rows, dtype=np.int64), np.asarray(fire_cols, dtype=np.int64)] = True
+    lab, _ = ndi.label(grid, structure=np.ones((3, 3), dtype=int))
+    lab = lab.astype(np.int64)
+    small = np.bincount(lab.ravel()) < min_size
+    lab[small[lab]] = 0
+    return lab
+
+
+def cluster_centroids_ref(labels: np.ndarray):
+    """gaussian_profile.py:474-477: ``[r.centroid for r in regionprops(labels)]`` truncated to int -- per remaining
+    label in ascending order the mean row and mean column of its pixels."""
+    ids = np.unique(labels[labels > 0])
+    rows = np.array([np.nonzero(labels == i)[0].mean() for i in ids]).astype(int)
+    cols = np.array([np.nonzero(labels == i)[1].mean() for i in ids]).astype(int)
+    return rows, cols

@@ -1,8 +1,10 @@
 """Drop-in for the fire-geolocation and threshold-sweep functions of the reference's
 ``src/features/plume_identifier_gaussian_profile.py`` (same names, same arguments): the per-fire nearest-pixel
 search runs on the GPU through ``plume_locate_fires``, mask generation / labelling / plume extents through
-``plume_threshold_masks``, ``plume_label_components`` and ``plume_fire_extents``.  The rest of the reference file
+``plume_sweep_extents`` (bit planes; ``plume_threshold_masks``, ``plume_label_components`` and ``plume_fire_extents``
+for dense planes), fire clustering through ``plume_label_components``.  The rest of the reference file
 (plume acceptance tests, hull extraction, :243-649) is not part of this path."""
 from kcl_ltss_bioatm_b200.fires import (P_ID_WIN_SIZE, grid_indexes, haversine, locate_fire_in_image,  # noqa: F401
                                         subset_fires_to_image)
-from kcl_ltss_bioatm_b200.sweep import find_plume_extents, find_threshold_index, generate_mask_dict  # noqa: F401,E402
+from kcl_ltss_bioatm_b200.sweep import (cluster_fires, find_plume_extents, find_threshold_index,  # noqa: F401,E402
+                                        fire_cluster_centroids, generate_mask_dict)

@@ -20,36 +20,44 @@ float round_down_to_float(double t) {          // __double2float_rd
 }
 constexpr int kStripRows = 16;
 
+// mask_bits_kernel: two adjacent strips per warp, three ballots per threshold
 void mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits) {
-  const int segs = (W + 31) / 32;
+  const int segs = (W + 31) / 32, pairs = (segs + 1) / 2;
   const int strips = (H + kStripRows - 1) / kStripRows;
   for (int t = 0; t < T; ++t) {
     const float th = round_down_to_float(thr[t]);
-    for (int wg = 0; wg < segs * strips; ++wg) {
-      const int seg = wg % segs, y0 = (wg / segs) * kStripRows;
+    for (int wg = 0; wg < pairs * strips; ++wg) {
+      const int sp = wg % pairs, y0 = (wg / pairs) * kStripRows;
       const int y_end = y0 + kStripRows < H ? y0 + kStripRows : H;
-      const uint64_t colmask = window_colmask(seg, W);
-      const uint64_t outcols = ~colmask & kWin36;
-      OpenState st;
-      st.b1 = st.b2 = st.e1 = st.e2 = 0;
+      const int seg0 = 2 * sp, seg1 = 2 * sp + 1;
+      const uint64_t colmask0 = window_colmask(seg0, W), colmask1 = window_colmask(seg1, W);
+      const uint64_t outcols0 = ~colmask0 & kWin36, outcols1 = ~colmask1 & kWin36;
+      OpenState st0, st1;
+      st0.b1 = st0.b2 = st0.e1 = st0.e2 = 0;
+      st1 = st0;
       for (int yy = y0 - 2; yy <= y_end + 1; ++yy) {
-        uint64_t b = kWin36;
+        uint64_t b0 = kWin36, b1 = kWin36;
         if (yy >= 0 && yy < H) {
-          uint32_t selc = 0, sele = 0;
+          uint32_t c0 = 0, c1 = 0, e = 0;
           for (int lane = 0; lane < 32; ++lane) {
-            const int x = 32 * seg + lane;
-            const int xe = lane < 2 ? 32 * seg - 2 + lane : 32 * seg + 30 + lane;
-            const bool in_x = x < W, in_xe = lane < 4 && xe >= 0 && xe < W;
-            const float v = in_x ? aod[1ll * yy * W + x] : 0.f;
-            const float ve = in_xe ? aod[1ll * yy * W + xe] : 0.f;
-            if (v > th) selc |= 1u << lane;
-            if (ve > th) sele |= 1u << lane;
+            const int x0 = 64 * sp + lane, x1 = x0 + 32;
+            const int xe = lane < 2 ? 64 * sp - 2 + lane : 64 * sp + 62 + lane;
+            const bool in0 = x0 < W, in1 = x1 < W, ine = lane < 4 && xe >= 0 && xe < W;
+            if ((in0 ? aod[1ll * yy * W + x0] : 0.f) > th) c0 |= 1u << lane;
+            if ((in1 ? aod[1ll * yy * W + x1] : 0.f) > th) c1 |= 1u << lane;
+            if ((ine ? aod[1ll * yy * W + xe] : 0.f) > th) e |= 1u << lane;
           }
-          b = (static_cast<uint64_t>(selc) << 2) | (sele & 3u) | (static_cast<uint64_t>((sele >> 2) & 3u) << 34) | outcols;
+          b0 = (static_cast<uint64_t>(c0) << 2) | (e & 3u) | (static_cast<uint64_t>(c1 & 3u) << 34) | outcols0;
+          b1 = (static_cast<uint64_t>(c1) << 2) | (c0 >> 30) | (static_cast<uint64_t>((e >> 2) & 3u) << 34) | outcols1;
         }
-        const uint32_t word = open_step(st, b, yy - 1 >= 0 && yy - 1 < H, colmask);
+        const bool prev_in = yy - 1 >= 0 && yy - 1 < H;
+        const uint32_t w0 = open_step(st0, b0, prev_in, colmask0);
+        const uint32_t w1 = open_step(st1, b1, prev_in, colmask1);
         const int r = yy - 2;
-        if (r >= y0) bits[(1ll * t * H + r) * segs + seg] = word;
+        if (r >= y0) {
+          bits[(1ll * t * H + r) * segs + seg0] = w0;
+          if (seg1 < segs) bits[(1ll * t * H + r) * segs + seg1] = w1;
+        }
       }
     }
   }

@@ -22,3 +22,21 @@ def synthetic_aod(h, w, seed):
     # extra fires: far from any plume (no label in the window), and on a plume edge
     fires += [(16, 16), (h - 17, w - 17), (h // 2, w // 2)]
     return aod.astype(np.float32), np.array(fires, dtype=np.int64)
+
+
+def synthetic_fire_pixels(h, w, seed):
+    """Active-fire detections as (rows, cols): clumps of touching pixels (some below the 3-pixel minimum), diagonal
+    chains, isolated pixels and duplicates (a pixel detected twice)."""
+    rng = np.random.default_rng(1000 + seed)
+    rows, cols = [], []
+    for _ in range(max(2, h * w // 400)):
+        cy, cx = int(rng.integers(0, h)), int(rng.integers(0, w))
+        for _ in range(int(rng.integers(1, 9))):
+            rows.append(int(np.clip(cy + rng.integers(-2, 3), 0, h - 1)))
+            cols.append(int(np.clip(cx + rng.integers(-2, 3), 0, w - 1)))
+    for k in range(min(h, w, 6)):                                   # a diagonal chain: 8-connected only
+        rows.append(k)
+        cols.append(k)
+    rows += rows[:3]
+    cols += cols[:3]
+    return np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64)

@@ -162,3 +162,20 @@ def test_full_size_timestamp_bit_planes_agree_with_dense_planes(sw):
     assert fused.shape == (75, 64) and np.array_equal(fused, dense)
     assert np.array_equal(np.concatenate([sw.extents(aod, t, rows, cols) for t in sweeps]), fused)
     assert fused.max() > 1000 and (fused == 0).any()
+
+
+GC = np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_cases.npz"))
+
+
+@pytest.mark.parametrize("i", range(int(GC["n_cases"])))
+def test_cluster_fires_equals_reference_golden(sw, i):
+    from tests.sweep_data import synthetic_fire_pixels
+    h, w, seed = (int(v) for v in GC[f"c{i}_hws"])
+    rows, cols = synthetic_fire_pixels(h, w, seed)
+    got = sw.cluster_fires((h, w), rows, cols)
+    assert got.dtype == np.int64 and np.array_equal(got, GC[f"c{i}_labels"])
+    assert np.array_equal(got, sweep_ref.cluster_fires_ref((h, w), rows, cols))
+    assert not sw.cluster_fires((h, w), [], []).any()
+    r, c = sweep.fire_cluster_centroids(got)
+    rr, cc = sweep_ref.cluster_centroids_ref(got)
+    assert np.array_equal(r, rr) and np.array_equal(c, cc)

@@ -22,3 +22,4 @@ def test_reference_named_module_reexports():
     assert ref_named.find_threshold_index is sweep.find_threshold_index
     assert ref_named.generate_mask_dict is sweep.generate_mask_dict
     assert ref_named.find_plume_extents is sweep.find_plume_extents
+    assert ref_named.cluster_fires is sweep.cluster_fires

@@ -51,3 +51,25 @@ def test_label_canonical_form():
     m = np.array([[1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 0, 0], [1, 1, 0, 1]], dtype=bool)
     lab = sweep_ref.label_ref(m)
     assert lab.tolist() == [[1, 0, 0, 4], [0, 1, 0, 4], [0, 0, 0, 0], [13, 13, 0, 16]]   # diagonal joins (8-conn.)
+
+
+GC = np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_cases.npz"))
+
+
+@pytest.mark.parametrize("i", range(int(GC["n_cases"])))
+def test_cluster_fires_oracle_equals_reference_golden(i):
+    """oracle cluster_fires against the reference's own function (scripts/make_cluster_golden.py)."""
+    from tests.sweep_data import synthetic_fire_pixels
+    h, w, seed = (int(v) for v in GC[f"c{i}_hws"])
+    rows, cols = synthetic_fire_pixels(h, w, seed)
+    got = sweep_ref.cluster_fires_ref((h, w), rows, cols)
+    assert got.dtype == np.int64 and np.array_equal(got, GC[f"c{i}_labels"])
+
+
+def test_cluster_centroids_host_equals_oracle():
+    from kcl_ltss_bioatm_b200 import sweep
+    for i in range(int(GC["n_cases"])):
+        lab = GC[f"c{i}_labels"].astype(np.int64)
+        r, c = sweep.fire_cluster_centroids(lab)
+        rr, cc = sweep_ref.cluster_centroids_ref(lab)
+        assert np.array_equal(r, rr) and np.array_equal(c, cc) and r.dtype == rr.dtype
