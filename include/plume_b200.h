@@ -327,6 +327,10 @@ int plume_locate_fires(const double* lats, const double* lons, int H, int W, con
  * like numpy's float64 comparison against the float64 thresholds (T <= 64), every threshold from one read of the image. */
 int plume_threshold_masks(const float* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
                           plume_stream_t stream);
+/* The same for a float64 image (the reference's MAIAC AOD is int16 * 0.001 = float64, tools.py:88): compared in float64.
+ * Every aod-taking call of this section has an _f64 twin. */
+int plume_threshold_masks_f64(const double* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
+                              plume_stream_t stream);
 /* 8-connected components of every mask plane.  labels[t][i] = -1 for background, else the smallest row-major
  * pixel index of the pixel's component (a canonical label); sizes[t][i] = pixel count of the component whose
  * canonical label is i (0 elsewhere).  labels / sizes are int32 [T][H][W]. */
@@ -349,12 +353,30 @@ int plume_fire_extents(const int* labels, const int* sizes, int T, int H, int W,
 size_t plume_sweep_workspace_bytes(int H, int W, int T);
 int plume_threshold_mask_bits(const float* aod, int H, int W, const double* thresholds, int T, uint32_t* bits,
                               plume_stream_t stream);
+int plume_threshold_mask_bits_f64(const double* aod, int H, int W, const double* thresholds, int T, uint32_t* bits,
+                                  plume_stream_t stream);
 int plume_pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, plume_stream_t stream);
 int plume_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_row_col, int n_fires, int win,
                        void* workspace, size_t workspace_bytes, int* extents, plume_stream_t stream);
 int plume_sweep_extents(const float* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
                         int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
                         plume_stream_t stream);
+int plume_sweep_extents_f64(const double* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
+                            int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
+                            plume_stream_t stream);
+
+/* ---- nearest-valid fill (replaces plume_identifier_gaussian_profile.py:451-461, interpolate_aod_nearest) ----------
+ * out[y][x] = aod[y][x] where aod != null_value, else the value of the nearest pixel (Euclidean pixel distance) whose
+ * value != null_value -- scipy's NearestNDInterpolator over the valid pixels, evaluated on the whole grid.  Among
+ * equidistant valid pixels the first in row-major order is taken (scipy's kd-tree returns one of them in traversal
+ * order).  NaN counts as valid (NaN != null_value).  An image without any valid pixel is returned unchanged; the host
+ * wrapper raises, as the reference does.  aod / out float32 (or float64: _f64) [H][W], out must not alias aod;
+ * workspace: device memory of plume_fill_nearest_workspace_bytes(H, W) bytes. */
+size_t plume_fill_nearest_workspace_bytes(int H, int W);
+int plume_fill_nearest(const float* aod, int H, int W, float null_value, void* workspace, size_t workspace_bytes,
+                       float* out, plume_stream_t stream);
+int plume_fill_nearest_f64(const double* aod, int H, int W, double null_value, void* workspace, size_t workspace_bytes,
+                           double* out, plume_stream_t stream);
 
 /* ---- UTM projection and nearest-neighbour swath -> grid resampling ------------
  * Replaces /root/reference/src/features/tools.py:9-64 (class utm_resampler), which calls pyproj and

@@ -600,7 +600,12 @@ int plume_locate_fires(const double* lats, const double* lons, int H, int W, con
 int plume_threshold_masks(const float* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
                           plume_stream_t stream) {
   PLUME_CHECK(T <= 0 || (aod && thresholds && masks), "threshold_masks: null pointer");
-  return threshold_masks(aod, H, W, thresholds, T, masks, S(stream));
+  return threshold_masks(aod, 0, H, W, thresholds, T, masks, S(stream));
+}
+int plume_threshold_masks_f64(const double* aod, int H, int W, const double* thresholds, int T, uint8_t* masks,
+                              plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || (aod && thresholds && masks), "threshold_masks_f64: null pointer");
+  return threshold_masks(aod, 1, H, W, thresholds, T, masks, S(stream));
 }
 int plume_label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes,
                            plume_stream_t stream) {
@@ -616,7 +621,12 @@ size_t plume_sweep_workspace_bytes(int H, int W, int T) { return sweep_workspace
 int plume_threshold_mask_bits(const float* aod, int H, int W, const double* thresholds, int T, uint32_t* bits,
                               plume_stream_t stream) {
   PLUME_CHECK(T <= 0 || (aod && thresholds && bits), "threshold_mask_bits: null pointer");
-  return threshold_mask_bits(aod, H, W, thresholds, T, bits, S(stream));
+  return threshold_mask_bits(aod, 0, H, W, thresholds, T, bits, S(stream));
+}
+int plume_threshold_mask_bits_f64(const double* aod, int H, int W, const double* thresholds, int T, uint32_t* bits,
+                                  plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || (aod && thresholds && bits), "threshold_mask_bits_f64: null pointer");
+  return threshold_mask_bits(aod, 1, H, W, thresholds, T, bits, S(stream));
 }
 int plume_pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, plume_stream_t stream) {
   PLUME_CHECK(T <= 0 || (masks && bits), "pack_mask_bits: null pointer");
@@ -632,8 +642,28 @@ int plume_sweep_extents(const float* aod, int H, int W, const double* thresholds
                         plume_stream_t stream) {
   PLUME_CHECK(T <= 0 || n_fires <= 0 || (aod && thresholds && fire_row_col && workspace && extents),
               "sweep_extents: null pointer");
-  return sweep_extents(aod, H, W, thresholds, T, fire_row_col, n_fires, win, workspace, workspace_bytes, extents,
+  return sweep_extents(aod, 0, H, W, thresholds, T, fire_row_col, n_fires, win, workspace, workspace_bytes, extents,
                        S(stream));
+}
+int plume_sweep_extents_f64(const double* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
+                            int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
+                            plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || n_fires <= 0 || (aod && thresholds && fire_row_col && workspace && extents),
+              "sweep_extents_f64: null pointer");
+  return sweep_extents(aod, 1, H, W, thresholds, T, fire_row_col, n_fires, win, workspace, workspace_bytes, extents,
+                       S(stream));
+}
+
+size_t plume_fill_nearest_workspace_bytes(int H, int W) { return fill_nearest_workspace_bytes(H, W); }
+int plume_fill_nearest(const float* aod, int H, int W, float null_value, void* workspace, size_t workspace_bytes,
+                       float* out, plume_stream_t stream) {
+  PLUME_CHECK(H <= 0 || W <= 0 || (aod && workspace && out), "fill_nearest: null pointer");
+  return fill_nearest(aod, 0, H, W, null_value, workspace, workspace_bytes, out, S(stream));
+}
+int plume_fill_nearest_f64(const double* aod, int H, int W, double null_value, void* workspace, size_t workspace_bytes,
+                           double* out, plume_stream_t stream) {
+  PLUME_CHECK(H <= 0 || W <= 0 || (aod && workspace && out), "fill_nearest_f64: null pointer");
+  return fill_nearest(aod, 1, H, W, null_value, workspace, workspace_bytes, out, S(stream));
 }
 
 int plume_utm_zone_histogram(const double* lon, long long n, int* hist64, plume_stream_t stream) {

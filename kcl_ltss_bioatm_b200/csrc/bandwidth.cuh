@@ -88,18 +88,25 @@ int locate_fires(const double* lats, const double* lons, int H, int W, const dou
                  const double* fire_lon, int n_fires, double half_box, void* workspace, size_t workspace_bytes,
                  int* out_rc, cudaStream_t s);
 
-int threshold_masks(const float* aod, int H, int W, const double* thr, int T, uint8_t* masks, cudaStream_t s);
+// aod: float32 (f64 = 0) or float64 (f64 = 1) image
+int threshold_masks(const void* aod, int f64, int H, int W, const double* thr, int T, uint8_t* masks, cudaStream_t s);
 int label_components(const uint8_t* masks, int T, int H, int W, int* labels, int* sizes, cudaStream_t s);
 int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const int* fire_rc, int n_fires, int win,
                  int* extents, cudaStream_t s);
 // bit-plane form (32 pixels per word; sweep_bits.cuh)
 size_t sweep_workspace_bytes(int H, int W, int T);
-int threshold_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, cudaStream_t s);
+int threshold_mask_bits(const void* aod, int f64, int H, int W, const double* thr, int T, uint32_t* bits,
+                        cudaStream_t s);
 int pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, cudaStream_t s);
 int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
                  size_t workspace_bytes, int* extents, cudaStream_t s);
-int sweep_extents(const float* aod, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
+int sweep_extents(const void* aod, int f64, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
                   void* workspace, size_t workspace_bytes, int* extents, cudaStream_t s);
+
+// nearest-valid fill of the AOD grid (fill.cu)
+size_t fill_nearest_workspace_bytes(int H, int W);
+int fill_nearest(const void* aod, int f64, int H, int W, double null_value, void* workspace, size_t workspace_bytes,
+                 void* out, cudaStream_t s);
 
 // UTM projection + nearest-neighbour swath -> grid resampling (resample.cu)
 int utm_zone_histogram(const double* lon, long long n, int* hist64, cudaStream_t s);

@@ -25,29 +25,42 @@ int check_launch_sweep(const char* what) {
 constexpr int kMaxThresholds = 64;
 }  // namespace
 
+// The image is float32 or float64 (the reference's MAIAC AOD is int16 * 0.001 = float64, tools.py:88); thresholds are
+// float64.  A float64 image is compared in float64.  For a float32 v and a double t,  v > t  <=>  v > rd(t)  with
+// rd(t) the largest float32 <= t: if t is a float32 itself nothing changes; otherwise t lies strictly between two
+// consecutive float32 a < t < b and v > t <=> v >= b <=> v > a = rd(t).  So for float32 images the thresholds are
+// rounded DOWN once (__double2float_rd) and the comparisons run in fp32.
+template <typename V>
+__device__ __forceinline__ V image_threshold(double t);
+template <>
+__device__ __forceinline__ float image_threshold<float>(double t) {
+  return __double2float_rd(t);
+}
+template <>
+__device__ __forceinline__ double image_threshold<double>(double t) {
+  return t;
+}
+
 // ------------------------------------------------------------------------------------------------
 // masks[t][y][x] = dilate(erode(aod > thr[t])).  With the cross footprint that is
 //   OR over q in cross(p), q inside the image, of  AND over r in cross(q) of (r outside the image or aod[r] > t)
 // (erosion sees set pixels beyond the border, dilation unset ones).  A thread loads the 13 values of the
 // diamond around its pixel once and evaluates every threshold from registers.
-// The reference compares a float32 image with float64 thresholds (`float32(0.48) > 0.48`).  For a float32 v and a
-// double t,  v > t  <=>  v > rd(t)  with rd(t) the largest float32 <= t: if t is a float32 itself nothing changes;
-// otherwise t lies strictly between two consecutive float32 a < t < b and v > t <=> v >= b <=> v > a = rd(t).  So the
-// thresholds are rounded DOWN once (__double2float_rd) and the 13 x T comparisons per pixel run in fp32 -- the fp64
-// comparisons made this kernel compute bound (112 us per 25-threshold sweep of a 1200 x 1200 image).
+// Comparison: image_threshold<V> above.
 // ------------------------------------------------------------------------------------------------
+template <typename V>
 __global__ void __launch_bounds__(256)
-    threshold_masks_kernel(const float* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
+    threshold_masks_kernel(const V* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
                            uint8_t* __restrict__ masks) {
-  __shared__ float s_thr[kMaxThresholds];
-  if (threadIdx.x < T) s_thr[threadIdx.x] = __double2float_rd(thr[threadIdx.x]);
+  __shared__ V s_thr[kMaxThresholds];
+  if (threadIdx.x < T) s_thr[threadIdx.x] = image_threshold<V>(thr[threadIdx.x]);
   __syncthreads();
   const long long pixels = 1ll * H * W;
   const long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels) return;
   const int y = static_cast<int>(i / W), x = static_cast<int>(i % W);
   // the 13 diamond positions, bit index = (dy + 2) * 5 + (dx + 2); only |dy| + |dx| <= 2 are used
-  float v[25];
+  V v[25];
   uint32_t outside = 0;   // bit set: position outside the image (counts as set for the erosion)
 #pragma unroll
   for (int dy = -2; dy <= 2; ++dy)
@@ -58,10 +71,10 @@ __global__ void __launch_bounds__(256)
       const int yy = y + dy, xx = x + dx;
       const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
       if (!in) outside |= 1u << b;
-      v[b] = in ? aod[1ll * yy * W + xx] : 0.0f;
+      v[b] = in ? aod[1ll * yy * W + xx] : V(0);
     }
   for (int t = 0; t < T; ++t) {
-    const float th = s_thr[t];
+    const V th = s_thr[t];
     uint32_t set = outside;   // bit b: position counts as set for the erosion
 #pragma unroll
     for (int dy = -2; dy <= 2; ++dy)
@@ -82,14 +95,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int threshold_masks(const float* aod, int H, int W, const double* thr, int T, uint8_t* masks, cudaStream_t s) {
+int threshold_masks(const void* aod, int f64, int H, int W, const double* thr, int T, uint8_t* masks, cudaStream_t s) {
   if (H <= 0 || W <= 0 || T <= 0) return 0;
   if (T > kMaxThresholds) {
     set_error("threshold_masks: at most 64 thresholds per call");
     return -1;
   }
   const long long pixels = 1ll * H * W;
-  threshold_masks_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, s>>>(aod, H, W, thr, T, masks);
+  const unsigned grid = static_cast<unsigned>((pixels + 255) / 256);
+  if (f64) threshold_masks_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(aod), H, W, thr, T, masks);
+  else threshold_masks_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(aod), H, W, thr, T, masks);
   return check_launch_sweep("threshold_masks");
 }
 
@@ -307,14 +322,15 @@ constexpr int kMaskWarps = 4;
 // two extra window columns between the strips are ordinary pixels of the other strip; lanes 0..3 load the four
 // outer ones), and lane 0 parks the ballots in shared memory, from where the lane that owns the threshold picks
 // them up after the loop (no per-threshold select).
+template <typename V>
 __global__ void __launch_bounds__(kMaskWarps * 32)
-    mask_bits_kernel(const float* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
+    mask_bits_kernel(const V* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
                      uint32_t* __restrict__ bits, int2* __restrict__ ent_all) {
-  __shared__ float s_thr[32];
+  __shared__ V s_thr[32];
   __shared__ uint4 s_sel[kMaskWarps][32];
   const int chunk = blockIdx.y;
   const int Tc = min(32, T - 32 * chunk);
-  if (threadIdx.x < Tc) s_thr[threadIdx.x] = __double2float_rd(thr[32 * chunk + threadIdx.x]);
+  if (threadIdx.x < Tc) s_thr[threadIdx.x] = image_threshold<V>(thr[32 * chunk + threadIdx.x]);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int segs = (W + 31) / 32, pairs = (segs + 1) / 2;
@@ -332,9 +348,9 @@ __global__ void __launch_bounds__(kMaskWarps * 32)
   OpenState st0, st1;
   st0.b1 = st0.b2 = st0.e1 = st0.e2 = 0;
   st1 = st0;
-  float n0 = 0.f, n1 = 0.f, ne = 0.f;
+  V n0 = 0, n1 = 0, ne = 0;
   if (y0 - 2 >= 0) {
-    const float* row = aod + 1ll * (y0 - 2) * W;
+    const V* row = aod + 1ll * (y0 - 2) * W;
     if (in0) n0 = __ldg(row + x0);
     if (in1) n1 = __ldg(row + x1);
     if (ine) ne = __ldg(row + xe);
@@ -344,19 +360,19 @@ __global__ void __launch_bounds__(kMaskWarps * 32)
   const Geom g = make_geom(H, W);
   int2* ent = ent_all ? ent_all + (32 * chunk + lane) * g.ent_per_plane : nullptr;
   for (int yy = y0 - 2; yy <= y_end + 1; ++yy) {
-    const float v0 = n0, v1 = n1, ve = ne;
+    const V v0 = n0, v1 = n1, ve = ne;
     const bool row_in = yy >= 0 && yy < H;
     if (yy + 1 >= 0 && yy + 1 < H && yy + 1 <= y_end + 1) {
-      const float* row = aod + 1ll * (yy + 1) * W;
-      n0 = in0 ? __ldg(row + x0) : 0.f;
-      n1 = in1 ? __ldg(row + x1) : 0.f;
-      ne = ine ? __ldg(row + xe) : 0.f;
+      const V* row = aod + 1ll * (yy + 1) * W;
+      n0 = in0 ? __ldg(row + x0) : V(0);
+      n1 = in1 ? __ldg(row + x1) : V(0);
+      ne = ine ? __ldg(row + xe) : V(0);
     }
     uint64_t b0 = kWin36, b1 = kWin36;
     if (row_in) {                                                        // warp-uniform
 #pragma unroll 5
       for (int t = 0; t < Tc; ++t) {
-        const float th = s_thr[t];
+        const V th = s_thr[t];
         const uint32_t c0 = __ballot_sync(0xffffffffu, v0 > th);
         const uint32_t c1 = __ballot_sync(0xffffffffu, v1 > th);
         const uint32_t e = __ballot_sync(0xffffffffu, ve > th);
@@ -384,7 +400,7 @@ __global__ void __launch_bounds__(kMaskWarps * 32)
 }
 
 namespace {
-int mask_bits_launch(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, int2* ent,
+int mask_bits_launch(const void* aod, int f64, int H, int W, const double* thr, int T, uint32_t* bits, int2* ent,
                      cudaStream_t s) {
   if (H <= 0 || W <= 0 || T <= 0) return 0;
   const Geom g = make_geom(H, W);
@@ -398,13 +414,15 @@ int mask_bits_launch(const float* aod, int H, int W, const double* thr, int T, u
     set_error("threshold_mask_bits: too many thresholds");
     return -1;
   }
-  mask_bits_kernel<<<grid, kMaskWarps * 32, 0, s>>>(aod, H, W, thr, T, bits, ent);
+  if (f64) mask_bits_kernel<double><<<grid, kMaskWarps * 32, 0, s>>>(static_cast<const double*>(aod), H, W, thr, T, bits, ent);
+  else mask_bits_kernel<float><<<grid, kMaskWarps * 32, 0, s>>>(static_cast<const float*>(aod), H, W, thr, T, bits, ent);
   return check_launch_sweep("threshold_mask_bits");
 }
 }  // namespace
 
-int threshold_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, cudaStream_t s) {
-  return mask_bits_launch(aod, H, W, thr, T, bits, nullptr, s);
+int threshold_mask_bits(const void* aod, int f64, int H, int W, const double* thr, int T, uint32_t* bits,
+                        cudaStream_t s) {
+  return mask_bits_launch(aod, f64, H, W, thr, T, bits, nullptr, s);
 }
 
 // byte masks [T][H][W] -> bit planes (one warp per word)
@@ -571,7 +589,7 @@ int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, 
   return bits_extents_launch(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, false, s);
 }
 
-int sweep_extents(const float* aod, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
+int sweep_extents(const void* aod, int f64, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
                   void* workspace, size_t workspace_bytes, int* extents, cudaStream_t s) {
   if (T <= 0 || H <= 0 || W <= 0 || n_fires <= 0) return 0;
   if (workspace_bytes < sweep_workspace_bytes(H, W, T)) {
@@ -581,7 +599,7 @@ int sweep_extents(const float* aod, int H, int W, const double* thr, int T, cons
   const Geom g = make_geom(H, W);
   uint32_t* bits = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) +
                                                align256(static_cast<size_t>(g.ent_per_plane) * T * sizeof(int2)));
-  const int rc = mask_bits_launch(aod, H, W, thr, T, bits, static_cast<int2*>(workspace), s);
+  const int rc = mask_bits_launch(aod, f64, H, W, thr, T, bits, static_cast<int2*>(workspace), s);
   if (rc) return rc;
   return bits_extents_launch(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, true, s);
 }

@@ -75,13 +75,19 @@ SIGNATURES = {
     "plume_stitch_threshold": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I, _P]),
     "plume_rasterize_hulls": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "plume_threshold_masks": (_I, [_P, _I, _I, _P, _I, _P, _P]),
+    "plume_threshold_masks_f64": (_I, [_P, _I, _I, _P, _I, _P, _P]),
     "plume_label_components": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "plume_fire_extents": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "plume_sweep_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "plume_fill_nearest_workspace_bytes": (c_size_t, [_I, _I]),
+    "plume_fill_nearest": (_I, [_P, _I, _I, _F, _P, c_size_t, _P, _P]),
+    "plume_fill_nearest_f64": (_I, [_P, _I, _I, _D, _P, c_size_t, _P, _P]),
     "plume_threshold_mask_bits": (_I, [_P, _I, _I, _P, _I, _P, _P]),
+    "plume_threshold_mask_bits_f64": (_I, [_P, _I, _I, _P, _I, _P, _P]),
     "plume_pack_mask_bits": (_I, [_P, _I, _I, _I, _P, _P]),
     "plume_bits_extents": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, c_size_t, _P, _P]),
     "plume_sweep_extents": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P, c_size_t, _P, _P]),
+    "plume_sweep_extents_f64": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P, c_size_t, _P, _P]),
     "plume_maxpool2x2_bwd_bn": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "plume_maxpool2x2_bwd_bn_x3": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "plume_head_bwd_bn": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P,

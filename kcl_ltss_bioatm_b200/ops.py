@@ -448,16 +448,21 @@ class CudaOps:
             raise TypeError(f"{name}: expected a contiguous {dtype} CUDA tensor")
         return ptr(t)
 
+    def _image(self, aod, name):
+        """(pointer, '_f64' or '') of a float32 / float64 image: the float64 entry points compare in float64."""
+        if aod.dtype == torch.float64:
+            return self._dev(aod, torch.float64, "aod"), name + "_f64"
+        return self._dev(aod, torch.float32, "aod"), name
+
     def threshold_masks(self, aod, thresholds, masks):
-        """aod float32 [H, W], thresholds float64 [T] -> masks uint8 [T, H, W] = dilate(erode(aod > t))."""
+        """aod float32 / float64 [H, W], thresholds float64 [T] -> masks uint8 [T, H, W] = dilate(erode(aod > t))."""
         h, w = aod.shape
         t = thresholds.numel()
         if tuple(masks.shape) != (t, h, w):
             raise ValueError("masks must be [T, H, W]")
-        check(self.lib.plume_threshold_masks(self._dev(aod, torch.float32, "aod"), h, w,
-                                             self._dev(thresholds, torch.float64, "thresholds"), t,
-                                             self._dev(masks, torch.uint8, "masks"), current_stream()),
-              "plume_threshold_masks")
+        a, fn = self._image(aod, "plume_threshold_masks")
+        check(getattr(self.lib, fn)(a, h, w, self._dev(thresholds, torch.float64, "thresholds"), t,
+                                    self._dev(masks, torch.uint8, "masks"), current_stream()), fn)
         self.launches += 1
 
     def label_components(self, masks, labels, sizes):
@@ -489,15 +494,14 @@ class CudaOps:
         return int(self.lib.plume_sweep_workspace_bytes(int(h), int(w), int(t)))
 
     def threshold_mask_bits(self, aod, thresholds, bits):
-        """aod float32 [H, W], thresholds float64 [T] -> bits int32 [T, H, ceil(W / 32)] = dilate(erode(aod > t))."""
+        """aod float32 / float64 [H, W], thresholds float64 [T] -> bits int32 [T, H, ceil(W / 32)]."""
         h, w = aod.shape
         t = thresholds.numel()
         if tuple(bits.shape) != (t, h, (w + 31) // 32):
             raise ValueError("bits must be [T, H, ceil(W / 32)]")
-        check(self.lib.plume_threshold_mask_bits(self._dev(aod, torch.float32, "aod"), h, w,
-                                                 self._dev(thresholds, torch.float64, "thresholds"), t,
-                                                 self._dev(bits, torch.int32, "bits"), current_stream()),
-              "plume_threshold_mask_bits")
+        a, fn = self._image(aod, "plume_threshold_mask_bits")
+        check(getattr(self.lib, fn)(a, h, w, self._dev(thresholds, torch.float64, "thresholds"), t,
+                                    self._dev(bits, torch.int32, "bits"), current_stream()), fn)
         self.launches += 1
 
     def pack_mask_bits(self, masks, bits):
@@ -525,19 +529,32 @@ class CudaOps:
         self.launches += 4 if n and t else 0
 
     def sweep_extents(self, aod, thresholds, fire_rc, win, workspace, extents):
-        """aod float32 [H, W], thresholds float64 [T], fire_rc int32 [n, 2] -> extents int32 [T, n] in one call."""
+        """aod float32 / float64 [H, W], thresholds float64 [T], fire_rc int32 [n, 2] -> extents int32 [T, n]."""
         h, w = aod.shape
         t = thresholds.numel()
         n = fire_rc.shape[0]
         if tuple(extents.shape) != (t, n) or fire_rc.dim() != 2 or fire_rc.shape[1] != 2:
             raise ValueError("extents must be [T, n_fires], fire_rc [n_fires, 2]")
-        check(self.lib.plume_sweep_extents(self._dev(aod, torch.float32, "aod"), h, w,
-                                           self._dev(thresholds, torch.float64, "thresholds"), t,
-                                           self._dev(fire_rc, torch.int32, "fire_rc"), n, int(win),
-                                           self._dev(workspace, torch.uint8, "workspace"), workspace.numel(),
-                                           self._dev(extents, torch.int32, "extents"), current_stream()),
-              "plume_sweep_extents")
+        a, fn = self._image(aod, "plume_sweep_extents")
+        check(getattr(self.lib, fn)(a, h, w, self._dev(thresholds, torch.float64, "thresholds"), t,
+                                    self._dev(fire_rc, torch.int32, "fire_rc"), n, int(win),
+                                    self._dev(workspace, torch.uint8, "workspace"), workspace.numel(),
+                                    self._dev(extents, torch.int32, "extents"), current_stream()), fn)
         self.launches += 4 if n and t else 0
+
+    # ------------------------------------------------------------------ nearest-valid fill (interpolate_aod_nearest)
+    def fill_nearest_workspace_bytes(self, h, w) -> int:
+        return int(self.lib.plume_fill_nearest_workspace_bytes(int(h), int(w)))
+
+    def fill_nearest(self, aod, null_value, workspace, out):
+        """aod float32 / float64 [H, W] -> out (same dtype): null pixels take the value of the nearest valid pixel."""
+        h, w = aod.shape
+        if out.shape != aod.shape or out.dtype != aod.dtype or out.data_ptr() == aod.data_ptr():
+            raise ValueError("out must be a distinct tensor with the image's shape and dtype")
+        a, fn = self._image(aod, "plume_fill_nearest")
+        check(getattr(self.lib, fn)(a, h, w, float(null_value), self._dev(workspace, torch.uint8, "workspace"),
+                                    workspace.numel(), self._dev(out, aod.dtype, "out"), current_stream()), fn)
+        self.launches += 3
 
     # ------------------------------------------------------------------ UTM projection / nearest-neighbour resampling
     def utm_zone_histogram(self, lons, hist):

@@ -9,6 +9,7 @@ Reference-named functions (same arguments and results):
     find_threshold_index(plume_extents_across_all_fires)         gaussian_profile.py:204-240  (host, numpy)
     cluster_fires(aod, fire_rows, fire_cols)                     gaussian_profile.py:126-139
     fire_cluster_centroids(fire_labels)                          gaussian_profile.py:474-477  (host, numpy)
+    interpolate_aod_nearest(aod)                                 gaussian_profile.py:451-461
 
 ``ThresholdSweep.extents`` is the fused form: masks as bit planes (32 pixels per word), components over runs of set
 bits, only the [T, n_fires] extents leave the device.  ``masks`` / ``label`` give dense byte / int32 planes.  The masks use the
@@ -25,6 +26,7 @@ import torch
 from .ops import CudaOps
 
 P_ID_WIN_SIZE = 15  # gaussian_profile.py:37
+NULL_VALUE = -999   # gaussian_profile.py:41
 
 
 class ThresholdSweep:
@@ -32,10 +34,18 @@ class ThresholdSweep:
         self.device = torch.device(device)
         self.ops = ops if ops is not None else CudaOps()
 
+    def _image(self, aod) -> torch.Tensor:
+        """The image on the device in its own precision: float64 stays float64 (the reference's AOD is int16 * 0.001 in
+        float64 and is compared in float64, tools.py:88), everything else becomes float32."""
+        if torch.is_tensor(aod):
+            dt = torch.float64 if aod.dtype == torch.float64 else torch.float32
+            return aod.to(device=self.device, dtype=dt).contiguous()
+        a = np.asarray(aod)
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if a.dtype == np.float64 else np.float32)).to(self.device)
+
     def masks(self, aod, thresholds) -> torch.Tensor:
         """uint8 [T, H, W] on the device."""
-        a = torch.as_tensor(np.asarray(aod, dtype=np.float32) if not torch.is_tensor(aod) else aod,
-                            dtype=torch.float32).to(self.device).contiguous()
+        a = self._image(aod)
         thr = torch.tensor(np.asarray(thresholds, dtype=np.float64)).to(self.device)
         out = torch.empty(thr.numel(), *a.shape, dtype=torch.uint8, device=self.device)
         self.ops.threshold_masks(a, thr, out)
@@ -66,8 +76,7 @@ class ThresholdSweep:
 
     def mask_bits(self, aod, thresholds) -> torch.Tensor:
         """int32 [T, H, ceil(W / 32)] on the device: bit i of word s = masks[t, y, 32 s + i]."""
-        a = torch.as_tensor(np.asarray(aod, dtype=np.float32) if not torch.is_tensor(aod) else aod,
-                            dtype=torch.float32).to(self.device).contiguous()
+        a = self._image(aod)
         thr = torch.tensor(np.asarray(thresholds, dtype=np.float64).reshape(-1)).to(self.device)
         bits = torch.empty(thr.numel(), a.shape[0], (a.shape[1] + 31) // 32, dtype=torch.int32, device=self.device)
         if bits.numel():
@@ -123,8 +132,7 @@ class ThresholdSweep:
     def extents(self, aod, thresholds, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
         """float64 [T, n_fires]: generate_mask_dict + find_plume_extents in one call on the device (any T: the
         reference's three sweeps of a timestamp can be passed as one concatenated threshold list)."""
-        a = torch.as_tensor(np.asarray(aod, dtype=np.float32) if not torch.is_tensor(aod) else aod,
-                            dtype=torch.float32).to(self.device).contiguous()
+        a = self._image(aod)
         thr = torch.tensor(np.asarray(thresholds, dtype=np.float64).reshape(-1)).to(self.device)
         h, w = a.shape
         rc = self._fires(fire_rows, fire_cols, h, w, win)
@@ -133,6 +141,18 @@ class ThresholdSweep:
             self.ops.sweep_extents(a, thr, rc, win, self._workspace(h, w, thr.numel()), out)
         return out.cpu().numpy().astype(np.float64)
 
+
+    def fill_nearest(self, aod, null_value=NULL_VALUE) -> torch.Tensor:
+        """The image (device tensor, float32 or float64 like the input) with every pixel == null_value replaced by the
+        value of the nearest pixel != null_value (Euclidean pixel distance; among equidistant ones the first in
+        row-major order)."""
+        a = self._image(aod)
+        if not bool((a != null_value).any()):
+            raise ValueError("no valid pixel to interpolate from (NearestNDInterpolator needs at least one point)")
+        ws = torch.empty(self.ops.fill_nearest_workspace_bytes(*a.shape), dtype=torch.uint8, device=self.device)
+        out = torch.empty_like(a)
+        self.ops.fill_nearest(a, null_value, ws, out)
+        return out
 
     def cluster_fires(self, shape, fire_rows, fire_cols, min_size: int = 3) -> np.ndarray:
         """int64 [H, W]: the fire pixels labelled by 8-connected cluster, numbered 1..n in raster order of each
@@ -209,6 +229,12 @@ def find_threshold_index(plume_extents_across_all_fires) -> List[Optional[int]]:
 def cluster_fires(aod, fire_rows, fire_cols) -> np.ndarray:
     """Label image of the fire clusters (8-connected, at least 3 pixels), shaped like ``aod``."""
     return _sweep().cluster_fires(np.shape(aod), fire_rows, fire_cols)
+
+
+def interpolate_aod_nearest(aod) -> np.ndarray:
+    """The AOD grid with its NULL_VALUE pixels filled from the nearest valid pixel; float64 like scipy's result
+    (values are copied: a float32 image is widened exactly)."""
+    return _sweep().fill_nearest(aod).cpu().numpy().astype(np.float64)
 
 
 def fire_cluster_centroids(fire_labels):

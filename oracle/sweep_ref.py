@@ -110,3 +110,30 @@ def cluster_centroids_ref(labels: np.ndarray):
     rows = np.array([np.nonzero(labels == i)[0].mean() for i in ids]).astype(int)
     cols = np.array([np.nonzero(labels == i)[1].mean() for i in ids]).astype(int)
     return rows, cols
+
+
+NULL_VALUE = -999   # gaussian_profile.py:41
+
+
+def interpolate_aod_nearest_ref(aod: np.ndarray, null_value=NULL_VALUE, return_unique: bool = False):
+    """gaussian_profile.py:451-461 by brute force: every pixel takes the value of the nearest pixel != null_value
+    (Euclidean distance in pixel units; valid pixels are their own nearest).  scipy's NearestNDInterpolator answers a
+    query that has several equidistant nearest points with whichever its kd-tree visits first; this restatement takes
+    the first in row-major order (np.argmin), and ``return_unique`` also returns the mask of pixels whose nearest
+    valid pixel is unique -- where both must agree (tests/test_sweep_oracle.py pins exactly that against scipy)."""
+    aod = np.asarray(aod)
+    good = aod != null_value
+    if not good.any():
+        raise ValueError("no valid pixel")
+    gy, gx = np.nonzero(good)                                   # row-major order
+    vals = aod[gy, gx]
+    out = aod.copy()
+    unique = np.ones(aod.shape, dtype=bool)
+    by, bx = np.nonzero(~good)
+    for lo in range(0, len(by), 2048):
+        y, x = by[lo:lo + 2048, None].astype(np.int64), bx[lo:lo + 2048, None].astype(np.int64)
+        d2 = (y - gy[None, :]) ** 2 + (x - gx[None, :]) ** 2
+        k = np.argmin(d2, axis=1)
+        out[by[lo:lo + 2048], bx[lo:lo + 2048]] = vals[k]
+        unique[by[lo:lo + 2048], bx[lo:lo + 2048]] = (d2 == d2.min(axis=1, keepdims=True)).sum(axis=1) == 1
+    return (out, unique) if return_unique else out

@@ -98,6 +98,25 @@ small = sweep_ref.find_plume_extents_ref(sweep_ref.threshold_masks_ref(aod[:300,
 ok = ok and bool(np.array_equal(small, c_ref.plume_extents(c_ref.threshold_masks(aod[:300, :300], sweeps[0][:5]),
                                                              np.clip(rows[:8], 16, 283), np.clip(cols[:8], 16, 283))))
 
+# the step before the sweep in the reference's loop: interpolate_aod_nearest (gaussian_profile.py:613)
+from tests.sweep_data import synthetic_null_aod  # noqa: E402
+from scipy import interpolate  # noqa: E402
+nul = synthetic_null_aod(H, W, 9)
+nul_dev = torch.from_numpy(nul).cuda()
+fill_ws = torch.empty(sw.ops.fill_nearest_workspace_bytes(H, W), dtype=torch.uint8, device="cuda")
+fill_out = torch.empty_like(nul_dev)
+ms_fill = timed(lambda: sw.ops.fill_nearest(nul_dev, -999, fill_ws, fill_out))
+one = torch.full((H, W), -999.0, dtype=torch.float64, device="cuda")
+one[7, 11] = 0.5                                                      # worst case: every pixel walks all rows
+ms_fill_worst = timed(lambda: sw.ops.fill_nearest(one, -999, fill_ws, fill_out))
+sw.ops.fill_nearest(nul_dev, -999, fill_ws, fill_out)
+t0 = time.perf_counter()
+good = nul != -999
+xx, yy = np.meshgrid(np.arange(W), np.arange(H))
+scipy_filled = interpolate.NearestNDInterpolator(np.vstack((xx[good], yy[good])).T, nul[good])(np.ravel(xx), np.ravel(yy)).reshape(H, W)
+fill_cpu_s = time.perf_counter() - t0
+fill_agree = float((fill_out.cpu().numpy() == scipy_filled).mean())          # < 1 only by distance ties
+
 peaks = {}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(p):
@@ -117,5 +136,9 @@ line = {
     "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "timestamps/s", "cores": 1, "kind": "port",
                      "sample": f"plain-C oracle (two-pass union-find labelling), all three sweeps of the timestamp ({cpu_s:.2f} s)"},
     "parity_on_sample": ok,
+    "nearest_fill": {"ms": ms_fill, "ms_single_valid_pixel": ms_fill_worst, "null_fraction": float((~good).mean()), "dtype": "f64",
+                     "gbps": (H * W * 8 * 2 + H * W * 4 * 2) / (ms_fill * 1e-3) / 1e9,
+                     "bytes_definition": "image read + written (8 B each) and the row-offset plane written + read (4 B each)",
+                     "cpu_scipy_s": fill_cpu_s, "cpu_cores": 1, "agreement_with_scipy": fill_agree},
 }
 print(json.dumps(line))

@@ -40,3 +40,23 @@ def synthetic_fire_pixels(h, w, seed):
     rows += rows[:3]
     cols += cols[:3]
     return np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64)
+
+
+def synthetic_null_aod(h, w, seed, dtype=np.float64):
+    """AOD as the reference reads it (int16 * 0.001, float64) with NULL_VALUE (-999) gaps: cloud-like blobs, salt,
+    a fully null band and a null border."""
+    rng = np.random.default_rng(2000 + seed)
+    aod = (rng.integers(0, 1500, (h, w)).astype(np.int16) * 0.001).astype(dtype)
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    null = rng.random((h, w)) < 0.05
+    for _ in range(min(200, max(1, h * w // 1500))):
+        cy, cx, r = rng.integers(0, h), rng.integers(0, w), rng.integers(2, min(40, max(3, min(h, w) // 3)))
+        null |= (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+    if h > 6:
+        null[h // 2:h // 2 + 2, :] = True
+    null[0, :] = True
+    null[:, -1] = True
+    if null.all():
+        null[h // 3, w // 3] = False
+    aod[null] = -999
+    return aod

@@ -179,3 +179,77 @@ def test_cluster_fires_equals_reference_golden(sw, i):
     r, c = sweep.fire_cluster_centroids(got)
     rr, cc = sweep_ref.cluster_centroids_ref(got)
     assert np.array_equal(r, rr) and np.array_equal(c, cc)
+
+
+def test_float64_image_is_compared_in_float64(sw):
+    """MAIAC AOD as the reference reads it: int16 * 0.001 in float64 (tools.py:88), thresholds from np.arange -- the
+    image values sit exactly on or next to the thresholds, where a float32 copy of the image decides differently."""
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 1000, (90, 140)).astype(np.int16)
+    raw[20:60, 30:100] = rng.integers(470, 490, (40, 70))                 # a plateau straddling 0.48
+    aod = raw * 0.001
+    assert aod.dtype == np.float64
+    thr = np.abs(np.arange(0, 0.5, 0.02) - 0.5)                           # gaussian_profile.py:492
+    ref = sweep_ref.threshold_masks_ref(aod, thr)
+    assert not np.array_equal(sweep_ref.threshold_masks_ref(aod.astype(np.float32), thr), ref)   # float32 would differ
+    assert np.array_equal(sw.unpack_bits(sw.mask_bits(aod, thr), 140), ref)
+    assert np.array_equal(sw.masks(aod, thr).cpu().numpy().astype(bool), ref)
+    rows, cols = rng.integers(16, 74, 9), rng.integers(16, 124, 9)
+    assert np.array_equal(sw.extents(aod, thr, rows, cols), sweep_ref.find_plume_extents_ref(ref, rows, cols))
+    d = sweep.generate_mask_dict(aod, thr)
+    assert all(np.array_equal(d[t], ref[k]) for k, t in enumerate(thr))
+
+
+GF = np.load(os.path.join(os.path.dirname(__file__), "golden", "fill_cases.npz"))
+
+
+@pytest.mark.parametrize("i", range(int(GF["n_cases"])))
+def test_nearest_fill_equals_oracle_and_reference_golden(sw, i):
+    from tests.sweep_data import synthetic_null_aod
+    h, w, seed = (int(v) for v in GF[f"c{i}_hws"])
+    aod = synthetic_null_aod(h, w, seed, np.dtype(str(GF[f"c{i}_dtype"])))
+    ref, unique = sweep_ref.interpolate_aod_nearest_ref(aod, return_unique=True)
+    got = sw.fill_nearest(aod)
+    assert got.dtype == (torch.float64 if aod.dtype == np.float64 else torch.float32)
+    assert np.array_equal(got.cpu().numpy(), ref)                                   # every pixel, ties included
+    named = sweep.interpolate_aod_nearest(aod)
+    assert named.dtype == np.float64 and np.array_equal(named[unique], GF[f"c{i}_filled"][unique])
+
+
+def test_nearest_fill_edge_cases(sw):
+    aod = np.full((5, 70), -999.0)
+    with pytest.raises(ValueError):
+        sw.fill_nearest(aod)
+    aod[3, 40] = 0.25                                                     # a single valid pixel fills everything
+    assert (sw.fill_nearest(aod).cpu().numpy() == 0.25).all()
+    aod = np.arange(12, dtype=np.float32).reshape(3, 4)                   # nothing to fill
+    assert np.array_equal(sw.fill_nearest(aod).cpu().numpy(), aod)
+    aod = np.full((1, 1), 0.5)
+    assert sw.fill_nearest(aod).item() == 0.5
+    aod = np.full((4, 33), -999.0)
+    aod[0, 0], aod[3, 32] = 1.0, np.nan                                   # NaN != -999: a valid pixel, as in numpy
+    out = sw.fill_nearest(aod).cpu().numpy()
+    assert np.array_equal(out, sweep_ref.interpolate_aod_nearest_ref(aod), equal_nan=True) and np.isnan(out).any()
+
+
+def test_nearest_fill_full_size_properties(sw):
+    """1200 x 1200 (too large for the brute-force oracle): valid pixels unchanged, idempotent, every filled value is
+    the value of a valid pixel at the distance scipy's exact Euclidean distance transform reports."""
+    import scipy.ndimage as ndi
+    from tests.sweep_data import synthetic_null_aod
+    aod = synthetic_null_aod(1200, 1200, 9)
+    good = aod != -999
+    out = sw.fill_nearest(aod)
+    o = out.cpu().numpy()
+    assert np.array_equal(o[good], aod[good]) and not (o == -999).any()
+    assert np.array_equal(sw.fill_nearest(out).cpu().numpy(), o)
+    dist, idx = ndi.distance_transform_edt(~good, return_indices=True)
+    same = o == aod[idx[0], idx[1]]                                       # differs only where ties were broken differently
+    assert same.mean() > 0.9
+    yy, xx = np.nonzero(~same)
+    for y, x in list(zip(yy, xx))[:200]:                                  # at a tie: some valid pixel at exactly that distance holds our value
+        r = int(np.ceil(dist[y, x]))
+        y0, x0 = max(0, y - r), max(0, x - r)
+        win = aod[y0:y + r + 1, x0:x + r + 1]
+        wy, wx = np.nonzero(win == o[y, x])
+        assert (np.round(dist[y, x] ** 2) == (wy + y0 - y) ** 2 + (wx + x0 - x) ** 2).any()
