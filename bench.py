@@ -601,6 +601,56 @@ def run_modes(ranks, rank, world, pg, dev):
     return out
 
 
+def run_label_generation(dev, peak_bw):
+    """the label-generation kernels next to the UNet path, on one GPU (no collective: timestamps are
+    independent).  One MAIAC-sized timestamp (1200 x 1200 float64 AOD, 64 fire clusters): nearest-valid fill
+    (interpolate_aod_nearest), then the reference's three threshold sweeps (75 thresholds: masks, components, per-fire
+    plume extents) in one call on bit planes; CUDA events, inputs resident, 10 repetitions after 2."""
+    import numpy as np
+    import torch
+
+    from kcl_ltss_bioatm_b200 import sweep
+    from tests.sweep_data import synthetic_aod, synthetic_null_aod
+
+    h = w = 1200
+    sw = sweep.ThresholdSweep(dev)
+    aod = torch.from_numpy(synthetic_aod(h, w, 5)[0].astype(np.float64)).to(dev)
+    nul = torch.from_numpy(synthetic_null_aod(h, w, 9)).to(dev)
+    rng = np.random.default_rng(3)
+    rc = torch.tensor(np.stack([rng.integers(16, h - 16, 64), rng.integers(16, w - 16, 64)], 1), dtype=torch.int32).to(dev)
+    thr = torch.tensor(np.concatenate([np.abs(np.arange(0, tmax, step) - tmax)
+                                       for step, tmax in [(0.02, 0.5), (0.03, 0.75), (0.04, 1)]])).to(dev)
+    ws = torch.empty(sw.ops.sweep_workspace_bytes(h, w, thr.numel()), dtype=torch.uint8, device=dev)
+    ext = torch.empty(thr.numel(), 64, dtype=torch.int32, device=dev)
+    fws = torch.empty(sw.ops.fill_nearest_workspace_bytes(h, w), dtype=torch.uint8, device=dev)
+    filled = torch.empty_like(nul)
+
+    def timed(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_sweep = timed(lambda: sw.ops.sweep_extents(aod, thr, rc, sweep.P_ID_WIN_SIZE, ws, ext))
+    ms_fill = timed(lambda: sw.ops.fill_nearest(nul, sweep.NULL_VALUE, fws, filled))
+    segs = (w + 31) // 32
+    sweep_bytes = h * w * 8 + thr.numel() * h * segs * 4 * 4          # image once; bit plane written, read by merge / flatten / extents
+    fill_bytes = h * w * (8 + 8 + 4 + 4)
+    return {"workload": f"{h}x{w} float64 AOD timestamp, 64 fire clusters: nearest-valid fill + 75-threshold sweep (one call)",
+            "n_gpus": 1, "sweep_ms": ms_sweep, "fill_ms": ms_fill, "timestamps_per_s": 1e3 / (ms_sweep + ms_fill),
+            "sweep_bit_plane_gbps": sweep_bytes / (ms_sweep * 1e-3) / 1e9, "fill_gbps": fill_bytes / (ms_fill * 1e-3) / 1e9,
+            "hbm_peak_gbps": peak_bw or None, "extents_checksum": int(ext.sum().item()),
+            "null_fraction": float((nul == sweep.NULL_VALUE).float().mean().item()),
+            "note": "latency / atomic bound union-find, not streaming: the bit planes are 32 x smaller than label planes "
+                    "(profiles/r2_bench_sweep.json holds the comparison with the dense-plane path and the C oracle)"}
+
+
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
@@ -718,8 +768,11 @@ def _run_gpu(args):
     for key, fn in (("configs[2]", lambda: run_config2(ranks, rank, world, pg, dev, peak_tf)),
                     ("configs[3]", lambda: run_config3(ranks, rank, world, dev, peak_tf)),
                     ("configs[4]", lambda: run_config4(ranks, rank, world, pg, dev, peak_tf)),
-                    ("modes", lambda: run_modes(ranks, rank, world, pg, dev))):
-        if (key[8] if key.startswith("configs") else "m") not in wanted:
+                    ("modes", lambda: run_modes(ranks, rank, world, pg, dev)),
+                    ("label_generation", lambda: run_label_generation(dev, peak_bw))):
+        if (key[8] if key.startswith("configs") else key[0]) not in wanted:
+            continue
+        if key == "label_generation" and rank != 0:
             continue
         try:
             t0 = time.perf_counter()
@@ -822,8 +875,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--configs", default="2,3,4,m",
-                    help="which of the other BASELINE.json configs (indices 2, 3, 4; m = the deterministic and bf16x3 modes) to measure as extra keys; empty = none")
+    ap.add_argument("--configs", default="2,3,4,m,l",
+                    help="which of the other BASELINE.json configs (indices 2, 3, 4; m = the deterministic and bf16x3 modes; "
+                         "l = the label-generation kernels of SURVEY 8(f)) to measure as extra keys; empty = none")
     ap.add_argument("--per-layer-out", default=None, help="also write the per-layer table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
