@@ -90,6 +90,33 @@ PLUME_HD uint64_t window_colmask(int seg, int W) {
   return upto_hi & ~((1ull << lo) - 1ull);
 }
 
+// Thresholds of a chunk as an ascending 32-entry table (padded with +inf): the number of entries below v, by a
+// branch-free binary search.  A pixel's comparison results against all thresholds are then the low `count` bits.
+template <typename V>
+PLUME_HD int count_below(const V* s, V v) {
+  int k = 0;
+  if (v > s[15]) k = 16;
+  if (v > s[k + 7]) k += 8;
+  if (v > s[k + 3]) k += 4;
+  if (v > s[k + 1]) k += 2;
+  if (v > s[k]) k += 1;
+  if (k == 31 && v > s[31]) k = 32;
+  return k;
+}
+// position of threshold i in the ascending order of th[0..n) (equal values keep their order)
+template <typename V>
+PLUME_HD int rank_of(const V* th, int n, int i) {
+  int r = 0;
+  for (int j = 0; j < n; ++j) r += (th[j] < th[i] || (th[j] == th[i] && j < i)) ? 1 : 0;
+  return r;
+}
+// One stage of the 32 x 32 bit-matrix transpose across a warp (lane l holds row l; stages j = 16, 8, 4, 2, 1;
+// y = the word of lane l ^ j).  Afterwards lane t holds column t: bit l = bit t of lane l's original word.
+PLUME_HD uint32_t transpose32_step(uint32_t x, uint32_t y, int lane, int j) {
+  const uint32_t mask = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+  return (lane & j) ? ((x & ~mask) | ((y >> j) & mask)) : ((x & mask) | ((y << j) & ~mask));
+}
+
 struct OpenState {
   uint64_t b1, b2;   // B of the previous row and of the one before
   uint64_t e1, e2;   // E of (row - 2) and (row - 3)

@@ -20,43 +20,74 @@ float round_down_to_float(double t) {          // __double2float_rd
 }
 constexpr int kStripRows = 16;
 
-// mask_bits_kernel: two adjacent strips per warp, three ballots per threshold
+// mask_bits_kernel<float, true>: two adjacent strips per warp; per lane the count of thresholds below its pixel, a
+// 32 x 32 bit transpose across the "warp", lane r owns the r-th smallest threshold of the chunk
 void mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits) {
   const int segs = (W + 31) / 32, pairs = (segs + 1) / 2;
   const int strips = (H + kStripRows - 1) / kStripRows;
-  for (int t = 0; t < T; ++t) {
-    const float th = round_down_to_float(thr[t]);
+  for (int chunk = 0; chunk < (T + 31) / 32; ++chunk) {
+    const int Tc = T - 32 * chunk < 32 ? T - 32 * chunk : 32;
+    float raw[32], sorted[32];
+    int plane_of[32];
+    for (int i = 0; i < 32; ++i) {
+      float mine = i < Tc ? round_down_to_float(thr[32 * chunk + i]) : INFINITY;
+      if (mine != mine) mine = INFINITY;
+      raw[i] = mine;
+      sorted[i] = INFINITY;
+    }
+    for (int i = 0; i < Tc; ++i) {
+      const int r = rank_of(raw, Tc, i);
+      sorted[r] = raw[i];
+      plane_of[r] = i;
+    }
     for (int wg = 0; wg < pairs * strips; ++wg) {
       const int sp = wg % pairs, y0 = (wg / pairs) * kStripRows;
       const int y_end = y0 + kStripRows < H ? y0 + kStripRows : H;
       const int seg0 = 2 * sp, seg1 = 2 * sp + 1;
       const uint64_t colmask0 = window_colmask(seg0, W), colmask1 = window_colmask(seg1, W);
       const uint64_t outcols0 = ~colmask0 & kWin36, outcols1 = ~colmask1 & kWin36;
-      OpenState st0, st1;
-      st0.b1 = st0.b2 = st0.e1 = st0.e2 = 0;
-      st1 = st0;
+      OpenState st0[32], st1[32];
+      std::memset(st0, 0, sizeof(st0));
+      std::memset(st1, 0, sizeof(st1));
       for (int yy = y0 - 2; yy <= y_end + 1; ++yy) {
-        uint64_t b0 = kWin36, b1 = kWin36;
-        if (yy >= 0 && yy < H) {
-          uint32_t c0 = 0, c1 = 0, e = 0;
+        uint32_t c0[32], c1[32], me[32];
+        const bool row_in = yy >= 0 && yy < H;
+        if (row_in) {
           for (int lane = 0; lane < 32; ++lane) {
             const int x0 = 64 * sp + lane, x1 = x0 + 32;
             const int xe = lane < 2 ? 64 * sp - 2 + lane : 64 * sp + 62 + lane;
             const bool in0 = x0 < W, in1 = x1 < W, ine = lane < 4 && xe >= 0 && xe < W;
-            if ((in0 ? aod[1ll * yy * W + x0] : 0.f) > th) c0 |= 1u << lane;
-            if ((in1 ? aod[1ll * yy * W + x1] : 0.f) > th) c1 |= 1u << lane;
-            if ((ine ? aod[1ll * yy * W + xe] : 0.f) > th) e |= 1u << lane;
+            c0[lane] = low_mask32(count_below(sorted, in0 ? aod[1ll * yy * W + x0] : 0.f));
+            c1[lane] = low_mask32(count_below(sorted, in1 ? aod[1ll * yy * W + x1] : 0.f));
+            me[lane] = low_mask32(count_below(sorted, ine ? aod[1ll * yy * W + xe] : 0.f));
           }
-          b0 = (static_cast<uint64_t>(c0) << 2) | (e & 3u) | (static_cast<uint64_t>(c1 & 3u) << 34) | outcols0;
-          b1 = (static_cast<uint64_t>(c1) << 2) | (c0 >> 30) | (static_cast<uint64_t>((e >> 2) & 3u) << 34) | outcols1;
+          for (int j = 16; j > 0; j >>= 1) {
+            uint32_t n0[32], n1[32];
+            for (int lane = 0; lane < 32; ++lane) {
+              n0[lane] = transpose32_step(c0[lane], c0[lane ^ j], lane, j);
+              n1[lane] = transpose32_step(c1[lane], c1[lane ^ j], lane, j);
+            }
+            std::memcpy(c0, n0, sizeof(c0));
+            std::memcpy(c1, n1, sizeof(c1));
+          }
         }
-        const bool prev_in = yy - 1 >= 0 && yy - 1 < H;
-        const uint32_t w0 = open_step(st0, b0, prev_in, colmask0);
-        const uint32_t w1 = open_step(st1, b1, prev_in, colmask1);
-        const int r = yy - 2;
-        if (r >= y0) {
-          bits[(1ll * t * H + r) * segs + seg0] = w0;
-          if (seg1 < segs) bits[(1ll * t * H + r) * segs + seg1] = w1;
+        for (int lane = 0; lane < 32; ++lane) {
+          uint64_t b0 = kWin36, b1 = kWin36;
+          if (row_in) {
+            uint32_t e = 0;
+            for (int j = 0; j < 4; ++j) e |= ((me[j] >> lane) & 1u) << j;
+            b0 = (static_cast<uint64_t>(c0[lane]) << 2) | (e & 3u) | (static_cast<uint64_t>(c1[lane] & 3u) << 34) | outcols0;
+            b1 = (static_cast<uint64_t>(c1[lane]) << 2) | (c0[lane] >> 30) | (static_cast<uint64_t>((e >> 2) & 3u) << 34) | outcols1;
+          }
+          const bool prev_in = yy - 1 >= 0 && yy - 1 < H;
+          const uint32_t w0 = open_step(st0[lane], b0, prev_in, colmask0);
+          const uint32_t w1 = open_step(st1[lane], b1, prev_in, colmask1);
+          const int r = yy - 2;
+          if (r >= y0 && lane < Tc) {
+            const long long plane = 32 * chunk + plane_of[lane];
+            bits[(plane * H + r) * segs + seg0] = w0;
+            if (seg1 < segs) bits[(plane * H + r) * segs + seg1] = w1;
+          }
         }
       }
     }

@@ -134,8 +134,10 @@ def test_mask_bits_equal_oracle_on_noisy_images(sw, h, w):
     rng = np.random.default_rng(h * 131 + w)
     aod = rng.random((h, w)).astype(np.float32)
     aod[rng.random((h, w)) < 0.02] = np.nan
-    thr = np.concatenate([[0.1, 0.25, 0.5, float(np.float32(0.3)), 0.3, 0.9, -1.0, 2.0], rng.random(33)])   # two chunks
-    ref = sweep_ref.threshold_masks_ref(aod, thr)
+    thr = np.concatenate([[0.1, 0.25, 0.5, float(np.float32(0.3)), 0.3, 0.9, -1.0, 2.0, 0.25, np.nan, np.inf, -np.inf],
+                          rng.random(29)])                                   # two chunks, unsorted, duplicates, non-finite
+    with np.errstate(invalid="ignore"):
+        ref = sweep_ref.threshold_masks_ref(aod, thr)
     assert np.array_equal(sw.unpack_bits(sw.mask_bits(aod, thr), w), ref)
     assert np.array_equal(sw.masks(aod, thr[:40]).cpu().numpy().astype(bool), ref[:40])
     blobs = (rng.random((h, w)) < 0.8).astype(np.float32)

@@ -72,8 +72,11 @@ def test_mask_bits_equal_oracle_on_noisy_images(emu, h, w):
     rng = np.random.default_rng(h * 131 + w)
     aod = rng.random((h, w)).astype(np.float32)
     aod[rng.random((h, w)) < 0.02] = np.nan
-    thr = np.array([0.1, 0.25, 0.5, float(np.float32(0.3)), 0.3, 0.9, -1.0, 2.0])
-    assert np.array_equal(unpack(mask_bits(emu, aod, thr), w), sweep_ref.threshold_masks_ref(aod, thr))
+    thr = np.array([0.1, 0.25, 0.5, float(np.float32(0.3)), 0.3, 0.9, -1.0, 2.0, 0.25, np.nan, np.inf, -np.inf])
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(unpack(mask_bits(emu, aod, thr), w), sweep_ref.threshold_masks_ref(aod, thr))
+    many = np.concatenate([thr[:9], rng.random(32), [0.5, 0.5]])            # two chunks, unsorted, duplicates
+    assert np.array_equal(unpack(mask_bits(emu, aod, many), w), sweep_ref.threshold_masks_ref(aod, many))
     blobs = (rng.random((h, w)) < 0.8).astype(np.float32)                    # large blobs: erosion leaves something
     assert np.array_equal(unpack(mask_bits(emu, blobs, [0.5]), w), sweep_ref.threshold_masks_ref(blobs, [0.5]))
     ones = np.ones((h, w), dtype=np.float32)
