@@ -190,19 +190,62 @@ def _sweep() -> ThresholdSweep:
     return _default
 
 
+class MaskDict(dict):
+    """What ``generate_mask_dict`` returns: a dict {threshold: bool mask [H, W]} whose masks stay on the device as bit
+    planes until somebody reads them.  ``masks[t]`` (and values() / items()) copies that one plane to the host and
+    unpacks it; ``find_plume_extents`` recognises the object and works on the resident planes, so the reference's call
+    sequence generate_mask_dict -> find_plume_extents -> find_threshold_index moves no mask across PCIe at all, and
+    ``extract_plume_roi`` (:243-303) only fetches the few planes it indexes.  Assigning to an entry turns it into an
+    ordinary host entry (and find_plume_extents then takes the host path)."""
+
+    def __init__(self, thresholds, bits: torch.Tensor, width: int):
+        super().__init__()
+        self._bits, self._width, self._plane, self._host_set = bits, width, {}, False
+        for i, t in enumerate(thresholds):                   # equal thresholds: one key, like the reference's dict
+            dict.__setitem__(self, t, None)
+            self._plane[t] = i
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if v is None:
+            v = ThresholdSweep.unpack_bits(self._bits[self._plane[key]:self._plane[key] + 1], self._width)[0]
+            dict.__setitem__(self, key, v)
+        return v
+
+    def __setitem__(self, key, value):
+        self._host_set = True
+        dict.__setitem__(self, key, value)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def values(self):
+        return [self[k] for k in self]
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def device_planes(self) -> Optional[torch.Tensor]:
+        """int32 [len(self), H, ceil(W / 32)] in key order, or None once an entry was assigned from the host."""
+        if self._host_set or any(k not in self._plane for k in self):
+            return None
+        return self._bits[torch.tensor([self._plane[k] for k in self], dtype=torch.long, device=self._bits.device)]
+
+
 def generate_mask_dict(aod, threshold_range) -> Dict[float, np.ndarray]:
-    """{threshold: bool mask [H, W]} -- aod > t with singleton pixels removed (erosion then dilation)."""
+    """{threshold: bool mask [H, W]} -- aod > t with singleton pixels removed (erosion then dilation); a MaskDict."""
     threshold_range = list(threshold_range)
-    s = _sweep()
-    m = s.unpack_bits(s.mask_bits(aod, threshold_range), np.shape(aod)[1])
-    return {t: m[i] for i, t in enumerate(threshold_range)}
+    return MaskDict(threshold_range, _sweep().mask_bits(aod, threshold_range), np.shape(aod)[1])
 
 
 def find_plume_extents(masks_dict, fire_rows, fire_cols) -> np.ndarray:
     """[len(masks_dict), len(fires)]: per threshold (dict order) and fire the pixel count of the labelled region
     nearest to the fire within its 31 x 31 window, 0 where there is none."""
-    stack = np.stack([np.asarray(masks_dict[k]) for k in masks_dict]) != 0
     s = _sweep()
+    planes = masks_dict.device_planes() if isinstance(masks_dict, MaskDict) else None
+    if planes is not None:
+        return s.extents_of_bits(planes.to(s.device), masks_dict._width, fire_rows, fire_cols)
+    stack = np.stack([np.asarray(masks_dict[k]) for k in masks_dict]) != 0
     return s.extents_of_bits(s.pack_bits_host(stack), stack.shape[2], fire_rows, fire_cols)
 
 

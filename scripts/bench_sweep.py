@@ -87,6 +87,17 @@ for _ in range(3):
 e2e_s = (time.perf_counter() - t0) / 3
 res = np.split(res_all, np.cumsum([len(t) for t in sweeps])[:-1])
 
+# the reference's own call sequence, one sweep at a time (identify(), gaussian_profile.py:489-503), host image in
+t0 = time.perf_counter()
+for _ in range(3):
+    named = []
+    for t in sweeps:
+        md = sweep.generate_mask_dict(aod, t)
+        named.append(sweep.find_plume_extents(md, rows, cols))
+        sweep.find_threshold_index(named[-1])
+named_s = (time.perf_counter() - t0) / 3
+agree = agree and all(bool(np.array_equal(a, b)) for a, b in zip(named, res))
+
 from oracle import c_ref, sweep_ref  # noqa: E402
 c_ref.label8(np.zeros((4, 4), dtype=np.uint8))                         # build / load outside the timed region
 t0 = time.perf_counter()
@@ -128,7 +139,9 @@ line = {
     "config": {"workload": f"{H}x{W} AOD, 3 sweeps x 25 thresholds = {n_thr} masks, components, 64 fires; one call"},
     "ms_per_timestamp_one_call_per_sweep": ms_per_sweep, "ms_per_timestamp_dense_planes": ms_dense,
     "e2e": {"value": 1.0 / e2e_s, "unit": "timestamps/s", "h2d_bytes_per_step": H * W * 4, "d2h_bytes_per_step": n_thr * 64 * 4,
-            "note": "ThresholdSweep.extents from a host image (75 thresholds in one call), extents copied back"},
+            "note": "ThresholdSweep.extents from a host image (75 thresholds in one call), extents copied back",
+            "reference_named_calls_ms": named_s * 1e3,
+            "reference_named_calls": "generate_mask_dict + find_plume_extents + find_threshold_index per sweep, three sweeps, host image in"},
     "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                  "bytes_definition": "dense formulation of round 1 (image + 10 B per pixel and threshold), for comparison across rounds",

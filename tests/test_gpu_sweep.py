@@ -46,8 +46,19 @@ def test_sweep_equals_reference_golden(sw, i):
 def test_reference_named_functions(sw):
     aod, fires, thr, masks, extents, _ = case(0)
     d = sweep.generate_mask_dict(aod, thr)
-    assert list(d.keys()) == list(thr) and all(np.array_equal(d[t], masks[k]) for k, t in enumerate(thr))
+    assert isinstance(d, dict) and len(d) == len(thr) and list(d.keys()) == list(thr) and list(d) == list(thr)
+    assert np.array_equal(sweep.find_plume_extents(d, fires[:, 0], fires[:, 1]), extents)      # resident bit planes
+    assert all(v is None for v in dict.values(d))                                              # ... nothing was fetched
+    assert all(np.array_equal(d[t], masks[k]) and d[t].dtype == bool for k, t in enumerate(thr))
+    assert np.array_equal(np.stack(d.values()), masks) and [k for k, _ in d.items()] == list(thr)
     assert np.array_equal(sweep.find_plume_extents(d, fires[:, 0], fires[:, 1]), extents)
+    plain = dict(d.items())                                                                    # an ordinary dict of host masks
+    assert np.array_equal(sweep.find_plume_extents(plain, fires[:, 0], fires[:, 1]), extents)
+    d[thr[3]] = np.zeros_like(masks[3])                                                        # a host edit is honoured
+    edited = sweep.find_plume_extents(d, fires[:, 0], fires[:, 1])
+    assert not edited[3].any() and np.array_equal(np.delete(edited, 3, 0), np.delete(extents, 3, 0))
+    dup = sweep.generate_mask_dict(aod, [0.3, 0.1, 0.3])                                       # equal thresholds: one key
+    assert list(dup) == [0.3, 0.1] and sweep.find_plume_extents(dup, fires[:, 0], fires[:, 1]).shape == (2, len(fires))
 
 
 @pytest.mark.parametrize("h,w,density", [(1, 1, 1.0), (7, 300, 0.5), (64, 64, 0.62), (257, 129, 0.4), (600, 800, 0.55)])

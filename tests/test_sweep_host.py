@@ -23,3 +23,28 @@ def test_reference_named_module_reexports():
     assert ref_named.generate_mask_dict is sweep.generate_mask_dict
     assert ref_named.find_plume_extents is sweep.find_plume_extents
     assert ref_named.cluster_fires is sweep.cluster_fires
+
+
+def test_mask_dict_is_a_lazy_dict_over_bit_planes():
+    """MaskDict without a GPU: bit planes in a CPU tensor; dict protocol, lazy unpacking, duplicate thresholds,
+    host edits."""
+    import torch
+    rng = np.random.default_rng(0)
+    h, w = 9, 70
+    masks = rng.random((4, h, w)) < 0.5
+    segs = (w + 31) // 32
+    padded = np.zeros((4, h, segs * 32), dtype=bool)
+    padded[:, :, :w] = masks
+    bits = torch.from_numpy(np.ascontiguousarray(np.packbits(padded, axis=2, bitorder="little").view("<u4").view(np.int32)))
+    thr = [0.5, 0.25, 0.5, 0.1]                                   # 0.5 twice: one key, the later plane (same mask in practice)
+    d = sweep.MaskDict(thr, bits, w)
+    assert isinstance(d, dict) and list(d) == [0.5, 0.25, 0.1] and len(d) == 3 and 0.25 in d
+    assert all(v is None for v in dict.values(d))
+    assert np.array_equal(d[0.25], masks[1]) and np.array_equal(d[0.5], masks[2]) and d.get(0.7) is None
+    assert np.array_equal(np.stack([d[k] for k in d]), masks[[2, 1, 3]])
+    assert np.array_equal(np.stack(d.values()), masks[[2, 1, 3]]) and [k for k, _ in d.items()] == [0.5, 0.25, 0.1]
+    planes = d.device_planes()
+    assert planes.shape == (3, h, segs) and torch.equal(planes, bits[[2, 1, 3]])
+    assert np.array_equal(sweep.ThresholdSweep.unpack_bits(planes, w), masks[[2, 1, 3]])
+    d[0.1] = np.zeros((h, w), dtype=bool)
+    assert d.device_planes() is None and not d[0.1].any()
