@@ -142,6 +142,10 @@ class UNetB200:
         # PLUME_GRAD_COMM=bf16: gradient buckets are rounded to bf16 for the all-reduce (half the bytes on the wire,
         # summed in bf16 by NCCL) and widened back into the fp32 gradient buffer; default fp32
         self.grad_comm_bf16 = os.environ.get("PLUME_GRAD_COMM", "fp32").lower() == "bf16" and self.world > 1
+        # PLUME_ADAM_PER_BUCKET=1: Adam per gradient bucket as its all-reduce completes instead of one launch after the
+        # last one (opt-in: measured at 2 GPUs, configs[1] 11.59 -> 11.52 ms, wide model 26.7 -> 26.3 ms, both inside
+        # the run-to-run spread; gpurun_out/r2ad)
+        self.adam_per_bucket = os.environ.get("PLUME_ADAM_PER_BUCKET", "0") == "1"
         self._comm_buf: Optional[torch.Tensor] = None
         self._tail_offset = min(s.offset for k, s in self.layout.slots.items() if k.startswith("enc0."))
 
@@ -692,12 +696,12 @@ class UNetB200:
                 break
             def reduce_bucket():
                 if not self.grad_comm_bf16:
-                    return dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True), None
+                    return dist.all_reduce(self.grads[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True), (a, e), False
                 if self._comm_buf is None:
                     self._comm_buf = torch.empty(self.layout.total, dtype=torch.bfloat16, device=self.device)
                 self.ops.cast_f32_bf16(self.grads[a:e], self._comm_buf[a:e])
                 return (dist.all_reduce(self._comm_buf[a:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True),
-                        (a, e))
+                        (a, e), True)
 
             if self.overlap_wgrad:
                 # the bucket's weight gradients are on the side stream, the rest on this one
@@ -709,11 +713,14 @@ class UNetB200:
             self._pending.append(wk)
             self._next_bucket += 1
 
+    def _wait_bucket(self, wk, rng, narrow) -> None:
+        wk.wait()                   # the current stream waits for this bucket's all-reduce (no host block under NCCL)
+        if narrow:                  # bf16 wire format: back into the fp32 gradient buffer
+            self.ops.cast_bf16_f32(self._comm_buf[rng[0]:rng[1]], self.grads[rng[0]:rng[1]])
+
     def wait_grads(self) -> None:
-        for wk, widen in self._pending:
-            wk.wait()
-            if widen is not None:   # bf16 wire format: back into the fp32 gradient buffer
-                self.ops.cast_bf16_f32(self._comm_buf[widen[0]:widen[1]], self.grads[widen[0]:widen[1]])
+        for wk, rng, narrow in self._pending:
+            self._wait_bucket(wk, rng, narrow)
         self._pending = []
 
     # ------------------------------------------------------------------ optimizer / step
@@ -729,6 +736,25 @@ class UNetB200:
         encoder block's weight gradients (the last ones the backward pass produces, at the end of the flat
         buffer) may still be running: everything before them is updated now, overlapping those kernels."""
         total = self.layout.total
+        if self._pending and self.adam_per_bucket:
+            # data parallel: the buckets' all-reduces finish front to back; each bucket is updated as soon as ITS
+            # all-reduce is done, under the all-reduces still in flight (the wide model's 2 GB of gradients take
+            # longer on the wire than Adam needs for them).  The last bucket's all-reduce was queued behind the
+            # tail weight gradients on the side stream, so waiting for it also joins that stream.
+            done = 0
+            for wk, rng, narrow in self._pending:
+                self._wait_bucket(wk, rng, narrow)
+                assert rng[0] == done
+                launch(rng[0], rng[1])
+                done = rng[1]
+            self._pending = []
+            if self._tail_open:
+                self._tail_open = False
+                torch.cuda.current_stream(self.device).wait_stream(self._side)
+            if done < total:
+                launch(done, total)
+            return
+        self.wait_grads()
         if self._tail_open:
             self._tail_open = False
             launch(0, self._tail_offset)
@@ -739,7 +765,6 @@ class UNetB200:
 
     def optimizer_step(self) -> None:
         spec = self.spec
-        self.wait_grads()
         self.step_count += 1
         self._adam_launch(lambda lo, hi: self.ops.adam(
             self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], spec.lr,
@@ -757,7 +782,6 @@ class UNetB200:
     def optimizer_step_dev(self, coef: torch.Tensor) -> None:
         """Adam with coefficients already in device memory (CUDA-graph capturable); the caller advances
         ``step_count`` and refreshes `coef` before every replay."""
-        self.wait_grads()
         self._adam_launch(lambda lo, hi: self.ops.adam_dev(
             self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], coef))
         self._param_version += 1
