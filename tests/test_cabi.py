@@ -66,3 +66,31 @@ def test_cuda_ops_refuse_to_run_without_gpu():
 
     with pytest.raises(plib.PlumeError):
         CudaOps()
+
+
+def test_label_generation_entry_points_plan_and_reject_without_gpu():
+    """Workspace planning of the sweep / fill calls is pure host code; null pointers and undersized workspaces are
+    rejected before anything touches the device."""
+    handle = plib.load()
+    h, w, t = 1200, 1200, 75
+    segs = (w + 31) // 32
+
+    def up(n):
+        return (n + 255) // 256 * 256
+
+    assert handle.plume_sweep_workspace_bytes(h, w, t) == up(t * h * 16 * segs * 8) + up(t * h * segs * 4)
+    assert handle.plume_sweep_workspace_bytes(0, w, t) == 0 and handle.plume_sweep_workspace_bytes(h, w, 0) == 0
+    assert handle.plume_fill_nearest_workspace_bytes(h, w) == up(h * segs * 4) + up(h * w * 4)
+    for name, args in (("plume_sweep_extents", (None, h, w, None, t, None, 4, 15, None, 0, None, None)),
+                       ("plume_sweep_extents_f64", (None, h, w, None, t, None, 4, 15, None, 0, None, None)),
+                       ("plume_bits_extents", (None, t, h, w, None, 4, 15, None, 0, None, None)),
+                       ("plume_threshold_mask_bits", (None, h, w, None, t, None, None)),
+                       ("plume_threshold_mask_bits_f64", (None, h, w, None, t, None, None)),
+                       ("plume_threshold_masks_f64", (None, h, w, None, t, None, None)),
+                       ("plume_pack_mask_bits", (None, t, h, w, None, None)),
+                       ("plume_fill_nearest", (None, h, w, -999.0, None, 0, None, None)),
+                       ("plume_fill_nearest_f64", (None, h, w, -999.0, None, 0, None, None))):
+        assert getattr(handle, name)(*args) != 0 and b"null" in handle.plume_last_error(), name
+    # nothing to do is not an error
+    assert handle.plume_sweep_extents(None, h, w, None, 0, None, 4, 15, None, 0, None, None) == 0
+    assert handle.plume_fill_nearest(None, 0, 0, -999.0, None, 0, None, None) == 0
