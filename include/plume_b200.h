@@ -358,6 +358,15 @@ int plume_threshold_mask_bits_f64(const double* aod, int H, int W, const double*
 int plume_pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, plume_stream_t stream);
 int plume_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_row_col, int n_fires, int win,
                        void* workspace, size_t workspace_bytes, int* extents, plume_stream_t stream);
+/* The component nearest to each fire in the plane chosen for it -- find_plume_mask (gaussian_profile.py:306-331:
+ * label(mask), extract_label, labelled_mask == label) without relabelling: component_bits[f] is a bit plane
+ * [H][ceil(W / 32)] holding the component nearest to fire f (same rule as plume_fire_extents) of plane plane_of_fire[f]
+ * (all zero when the window holds none or the plane index is negative); stats[f] = {area, min_row, min_col,
+ * max_row + 1, max_col + 1, root, 0, 0} int32.  workspace must be the one plume_bits_extents / plume_sweep_extents just
+ * used on the same bits: it holds the labelling. */
+int plume_fire_components(const uint32_t* bits, int T, int H, int W, const int* fire_row_col, const int* plane_of_fire,
+                          int n_fires, int win, const void* workspace, size_t workspace_bytes, uint32_t* component_bits,
+                          int* stats, plume_stream_t stream);
 int plume_sweep_extents(const float* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
                         int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
                         plume_stream_t stream);

@@ -637,6 +637,14 @@ int plume_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fir
   PLUME_CHECK(T <= 0 || n_fires <= 0 || (bits && fire_row_col && workspace && extents), "bits_extents: null pointer");
   return bits_extents(bits, T, H, W, fire_row_col, n_fires, win, workspace, workspace_bytes, extents, S(stream));
 }
+int plume_fire_components(const uint32_t* bits, int T, int H, int W, const int* fire_row_col, const int* plane_of_fire,
+                          int n_fires, int win, const void* workspace, size_t workspace_bytes, uint32_t* component_bits,
+                          int* stats, plume_stream_t stream) {
+  PLUME_CHECK(T <= 0 || n_fires <= 0 || (bits && fire_row_col && plane_of_fire && workspace && component_bits && stats),
+              "fire_components: null pointer");
+  return fire_components(bits, T, H, W, fire_row_col, plane_of_fire, n_fires, win, workspace, workspace_bytes,
+                         component_bits, stats, S(stream));
+}
 int plume_sweep_extents(const float* aod, int H, int W, const double* thresholds, int T, const int* fire_row_col,
                         int n_fires, int win, void* workspace, size_t workspace_bytes, int* extents,
                         plume_stream_t stream) {

@@ -100,6 +100,8 @@ int threshold_mask_bits(const void* aod, int f64, int H, int W, const double* th
 int pack_mask_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits, cudaStream_t s);
 int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
                  size_t workspace_bytes, int* extents, cudaStream_t s);
+int fire_components(const uint32_t* bits, int T, int H, int W, const int* fire_rc, const int* plane_of_fire, int n_fires,
+                    int win, const void* workspace, size_t workspace_bytes, uint32_t* comp, int* stats, cudaStream_t s);
 int sweep_extents(const void* aod, int f64, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,
                   void* workspace, size_t workspace_bytes, int* extents, cudaStream_t s);
 

@@ -557,6 +557,79 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) extents[t * n_fires + f] = extent_of_key(best, plane, ent_all + t * g.ent_per_plane, g, r, c, win);
 }
 
+// The component nearest to each fire in the plane chosen for it (find_plume_mask, gaussian_profile.py:306-331:
+// label(mask) -> extract_label -> labelled_mask == label), from planes that bits_extents has labelled: one block per
+// fire; warp 0 finds the nearest set pixel and its root, then every thread walks words of the plane and keeps the
+// runs that hang under that root.  stats[f] = {area, min_row, min_col, max_row + 1, max_col + 1, root, 0, 0}
+// (the bounding box as regionprops reports it; all zero and root = -1 when the fire has no component / no plane).
+__global__ void __launch_bounds__(256)
+    fire_components_kernel(const uint32_t* __restrict__ bits, const int2* __restrict__ ent_all, int T, Geom g,
+                           const int* __restrict__ fire_rc, const int* __restrict__ plane_of_fire, int win,
+                           uint32_t* __restrict__ comp, int* __restrict__ stats) {
+  __shared__ int s_root;
+  __shared__ int s_stat[5];
+  const int f = blockIdx.x, lane = threadIdx.x & 31;
+  const int p = plane_of_fire[f];
+  const bool has_plane = p >= 0 && p < T;
+  if (threadIdx.x == 0) {
+    s_root = -1;
+    s_stat[0] = 0, s_stat[1] = g.H, s_stat[2] = g.W, s_stat[3] = 0, s_stat[4] = 0;
+  }
+  __syncthreads();
+  const uint32_t* plane = bits + (has_plane ? p : 0) * g.words_per_plane;
+  const int2* ent = ent_all + (has_plane ? p : 0) * g.ent_per_plane;
+  if (has_plane && threadIdx.x < 32) {
+    const int r = fire_rc[2 * f], c = fire_rc[2 * f + 1];
+    unsigned long long best = kNoKey;
+    for (int dy = -win + lane; dy <= win; dy += 32) {
+      const int y = r + dy;
+      if (y < 0 || y >= g.H) continue;
+      const unsigned long long k = best_in_row(plane + 1ll * y * g.segs, g, c, dy, win);
+      best = k < best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    if (lane == 0) s_root = root_of_key(best, plane, ent, g, r, c, win);
+  }
+  __syncthreads();
+  const int root = s_root;
+  uint32_t* out = comp + f * g.words_per_plane;
+  int area = 0, y_min = g.H, x_min = g.W, y_max = 0, x_max = 0;
+  for (long long i = threadIdx.x; i < g.words_per_plane; i += blockDim.x) {
+    uint32_t o = 0;
+    if (root >= 0) {
+      const uint32_t w = plane[i];
+      if (w) {
+        const int y = static_cast<int>(i / g.segs), seg = static_cast<int>(i % g.segs);
+        o = component_word(w, ent, g, y, seg, root);
+        if (o) {
+          area += __popc(o);
+          y_min = min(y_min, y), y_max = max(y_max, y + 1);
+          x_min = min(x_min, 32 * seg + ctz32(o)), x_max = max(x_max, 32 * seg + 32 - clz32(o));
+        }
+      }
+    }
+    out[i] = o;
+  }
+  if (area) {
+    atomicAdd(&s_stat[0], area);
+    atomicMin(&s_stat[1], y_min);
+    atomicMin(&s_stat[2], x_min);
+    atomicMax(&s_stat[3], y_max);
+    atomicMax(&s_stat[4], x_max);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    int v = 0;
+    if (threadIdx.x < 5) v = s_stat[0] ? s_stat[threadIdx.x] : 0;
+    else if (threadIdx.x == 5) v = root;
+    stats[8 * f + threadIdx.x] = v;
+  }
+}
+
 namespace {
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 }  // namespace
@@ -604,6 +677,23 @@ int bits_extents_launch(const uint32_t* bits, int T, int H, int W, const int* fi
 int bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire_rc, int n_fires, int win, void* workspace,
                  size_t workspace_bytes, int* extents, cudaStream_t s) {
   return bits_extents_launch(bits, T, H, W, fire_rc, n_fires, win, workspace, workspace_bytes, extents, false, s);
+}
+
+int fire_components(const uint32_t* bits, int T, int H, int W, const int* fire_rc, const int* plane_of_fire, int n_fires,
+                    int win, const void* workspace, size_t workspace_bytes, uint32_t* comp, int* stats, cudaStream_t s) {
+  if (T <= 0 || H <= 0 || W <= 0 || n_fires <= 0) return 0;
+  const Geom g = make_geom(H, W);
+  if (g.ent_per_plane >= 0x7FFFFFFFll || win < 0 || win > 1000) {
+    set_error("fire_components: plane too large or bad window");
+    return -1;
+  }
+  if (workspace_bytes < sweep_workspace_bytes(H, W, T)) {
+    set_error("fire_components: workspace smaller than plume_sweep_workspace_bytes(H, W, T)");
+    return -1;
+  }
+  fire_components_kernel<<<static_cast<unsigned>(n_fires), 256, 0, s>>>(bits, static_cast<const int2*>(workspace), T, g,
+                                                                        fire_rc, plane_of_fire, win, comp, stats);
+  return check_launch_sweep("fire_components");
 }
 
 int sweep_extents(const void* aod, int f64, int H, int W, const double* thr, int T, const int* fire_rc, int n_fires, int win,

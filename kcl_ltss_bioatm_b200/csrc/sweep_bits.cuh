@@ -250,6 +250,21 @@ PLUME_HD int pop_run(uint32_t& rest, const Geom& g, int y, int seg, int& len) {
   return ent_index(g, y, 32 * seg + s);
 }
 
+// component extraction (after flatten: every run's parent is its root): the bits of word (y, seg) that belong to the
+// component `root`
+PLUME_HD uint32_t component_word(uint32_t w, const int2* ent, const Geom& g, int y, int seg, int root) {
+  uint32_t out = 0, rest = w;
+  while (rest) {
+    const int s = ctz32(rest);
+    const uint32_t from_s = rest >> s;
+    const int len = (~from_s) ? ctz32(~from_s) : 32;
+    const uint32_t run = low_mask32(len) << s;
+    rest &= ~run;
+    if (ent[ent_index(g, y, 32 * seg + s)].x == root) out |= run;
+  }
+  return out;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // extents: nearest set pixel to (r, c) in the (2 win + 1)^2 window; key = (squared distance << 32) | window index,
 // the minimum key is numpy's first minimum over the row-major window.
@@ -285,6 +300,17 @@ PLUME_HD unsigned long long best_in_row(const uint32_t* row_bits, const Geom& g,
     }
   }
   return best;
+}
+
+// root entry of the component of the pixel a key names (after flatten: a run's parent is its root), -1 for no key
+PLUME_HD int root_of_key(unsigned long long key, const uint32_t* plane_bits, const int2* ent, const Geom& g, int r, int c,
+                         int win) {
+  if (key == kNoKey) return -1;
+  const int side = 2 * win + 1;
+  const int k = static_cast<int>(key & 0xFFFFFFFFull);
+  const int y = r + k / side - win, x = c + k % side - win;
+  const uint32_t w = plane_bits[1ll * y * g.segs + (x >> 5)];
+  return ent[ent_index(g, y, (x & ~31) + run_start(w, x & 31))].x;
 }
 
 // size of the component of the pixel a key names (after flatten: a run's parent is its root)

@@ -86,6 +86,7 @@ SIGNATURES = {
     "plume_threshold_mask_bits_f64": (_I, [_P, _I, _I, _P, _I, _P, _P]),
     "plume_pack_mask_bits": (_I, [_P, _I, _I, _I, _P, _P]),
     "plume_bits_extents": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, c_size_t, _P, _P]),
+    "plume_fire_components": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, c_size_t, _P, _P, _P]),
     "plume_sweep_extents": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P, c_size_t, _P, _P]),
     "plume_sweep_extents_f64": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P, c_size_t, _P, _P]),
     "plume_maxpool2x2_bwd_bn": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),

@@ -528,6 +528,22 @@ class CudaOps:
               "plume_bits_extents")
         self.launches += 4 if n and t else 0
 
+    def fire_components(self, bits, w, fire_rc, plane_of_fire, win, workspace, comp, stats):
+        """After bits_extents / sweep_extents on the same bits and workspace: comp int32 [n, H, ceil(W / 32)] = the component
+        nearest to fire f in plane plane_of_fire[f] (int32 [n], negative = none), stats int32 [n, 8]."""
+        t, h, segs = bits.shape
+        n = fire_rc.shape[0]
+        if (segs != (w + 31) // 32 or tuple(comp.shape) != (n, h, segs) or tuple(stats.shape) != (n, 8)
+                or tuple(plane_of_fire.shape) != (n,) or fire_rc.dim() != 2 or fire_rc.shape[1] != 2):
+            raise ValueError("comp must be [n_fires, H, ceil(W / 32)], stats [n_fires, 8], plane_of_fire [n_fires]")
+        check(self.lib.plume_fire_components(self._dev(bits, torch.int32, "bits"), t, h, int(w),
+                                             self._dev(fire_rc, torch.int32, "fire_rc"),
+                                             self._dev(plane_of_fire, torch.int32, "plane_of_fire"), n, int(win),
+                                             self._dev(workspace, torch.uint8, "workspace"), workspace.numel(),
+                                             self._dev(comp, torch.int32, "comp"), self._dev(stats, torch.int32, "stats"),
+                                             current_stream()), "plume_fire_components")
+        self.launches += 1 if n and t else 0
+
     def sweep_extents(self, aod, thresholds, fire_rc, win, workspace, extents):
         """aod float32 / float64 [H, W], thresholds float64 [T], fire_rc int32 [n, 2] -> extents int32 [T, n]."""
         h, w = aod.shape

@@ -7,6 +7,7 @@ Reference-named functions (same arguments and results):
     generate_mask_dict(aod, threshold_range)                     gaussian_profile.py:142-154
     find_plume_extents(masks_dict, fire_rows, fire_cols)         gaussian_profile.py:157-179
     find_threshold_index(plume_extents_across_all_fires)         gaussian_profile.py:204-240  (host, numpy)
+    plume_masks(masks_dict, threshold_index_for_fires, rows, cols)   the label / extract_label / == part of find_plume_mask, :306-331
     cluster_fires(aod, fire_rows, fire_cols)                     gaussian_profile.py:126-139
     fire_cluster_centroids(fire_labels)                          gaussian_profile.py:474-477  (host, numpy)
     interpolate_aod_nearest(aod)                                 gaussian_profile.py:451-461
@@ -107,6 +108,26 @@ class ThresholdSweep:
         if len(rc) and t:
             self.ops.bits_extents(bits, w, rc, win, self._workspace(h, w, t), out)
         return out.cpu().numpy().astype(np.float64)
+
+    def fire_components(self, bits: torch.Tensor, w: int, plane_of_fire, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE):
+        """Per fire the connected component nearest to it in the plane chosen for it (``find_plume_mask``: label,
+        extract_label, ``labelled == label`` -- without a label plane).  bits: device bit planes [T, H, ceil(W / 32)];
+        plane_of_fire: plane index per fire, negative / None = no plane.  Returns (component bit planes on the device
+        int32 [n, H, ceil(W / 32)], stats int64 [n, 6] on the host = area, min_row, min_col, max_row + 1, max_col + 1,
+        root) -- area 0 where the fire's window holds no component."""
+        t, h, _ = bits.shape
+        rc = self._fires(fire_rows, fire_cols, h, w, win)
+        planes = np.array([-1 if p is None else int(p) for p in plane_of_fire], dtype=np.int64)
+        if len(planes) != len(rc) or (planes >= t).any():
+            raise ValueError("plane_of_fire needs one valid plane index (or None) per fire")
+        comp = torch.zeros(len(rc), h, (w + 31) // 32, dtype=torch.int32, device=bits.device)
+        stats = torch.zeros(len(rc), 8, dtype=torch.int32, device=bits.device)
+        if len(rc) and t:
+            ws = self._workspace(h, w, t)
+            scratch = torch.empty(t, len(rc), dtype=torch.int32, device=bits.device)
+            self.ops.bits_extents(bits, w, rc, win, ws, scratch)                    # labels the planes into ws
+            self.ops.fire_components(bits, w, rc, torch.tensor(planes, dtype=torch.int32).to(bits.device), win, ws, comp, stats)
+        return comp, stats[:, :6].cpu().numpy().astype(np.int64)
 
     def extents_of_masks(self, masks: torch.Tensor, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
         """uint8 masks [T, H, W] on the device -> float64 [T, n_fires] (find_plume_extents)."""
@@ -247,6 +268,24 @@ def find_plume_extents(masks_dict, fire_rows, fire_cols) -> np.ndarray:
         return s.extents_of_bits(planes.to(s.device), masks_dict._width, fire_rows, fire_cols)
     stack = np.stack([np.asarray(masks_dict[k]) for k in masks_dict]) != 0
     return s.extents_of_bits(s.pack_bits_host(stack), stack.shape[2], fire_rows, fire_cols)
+
+
+def plume_masks(masks_dict, threshold_index_for_fires, fire_rows, fire_cols):
+    """For every fire with a threshold index (``find_threshold_index``'s result; None = no plume) the bool mask [H, W] of
+    the labelled region nearest to the fire in that threshold's mask -- what ``find_plume_mask`` (:306-331) computes per
+    fire by relabelling the whole mask: ``labelled_mask == extract_label(labelled_mask, r, c)``.  None where there is no
+    index or the fire's window holds no region.  Also returns the regions' (area, bbox) rows."""
+    s = _sweep()
+    keys = list(masks_dict)
+    planes = masks_dict.device_planes() if isinstance(masks_dict, MaskDict) else None
+    if planes is not None:
+        w = masks_dict._width
+    else:
+        stack = np.stack([np.asarray(masks_dict[k]) for k in keys]) != 0
+        planes, w = s.pack_bits_host(stack), stack.shape[2]
+    comp, stats = s.fire_components(planes.to(s.device), w, threshold_index_for_fires, fire_rows, fire_cols)
+    host = s.unpack_bits(comp, w)
+    return [host[f] if stats[f, 0] > 0 else None for f in range(len(stats))], stats
 
 
 def find_threshold_index(plume_extents_across_all_fires) -> List[Optional[int]]:

@@ -137,3 +137,11 @@ def interpolate_aod_nearest_ref(aod: np.ndarray, null_value=NULL_VALUE, return_u
         out[by[lo:lo + 2048], bx[lo:lo + 2048]] = vals[k]
         unique[by[lo:lo + 2048], bx[lo:lo + 2048]] = (d2 == d2.min(axis=1, keepdims=True)).sum(axis=1) == 1
     return (out, unique) if return_unique else out
+
+
+def plume_mask_ref(mask: np.ndarray, r: int, c: int, win: int = P_ID_WIN_SIZE):
+    """gaussian_profile.py:306-331 (find_plume_mask up to assess_plume): label the mask, take the label nearest to the
+    fire, return ``labelled == label`` (None when the window holds no label)."""
+    lab = label_ref(mask)
+    l = extract_label_ref(lab, int(r), int(c), win)
+    return None if l is None else lab == l

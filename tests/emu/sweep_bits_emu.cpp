@@ -187,5 +187,48 @@ void emu_bits_extents(const uint32_t* bits, int T, int H, int W, const int* fire
     }
 }
 
+// fire_components_kernel after emu_bits_extents left the flattened entries in ent_all
+void emu_fire_components(const uint32_t* bits, int T, int H, int W, const int* fire_rc, const int* plane_of_fire,
+                         int n_fires, int win, const int2* ent_all, uint32_t* comp, int* stats) {
+  const Geom g = make_geom(H, W);
+  for (int f = 0; f < n_fires; ++f) {
+    const int p = plane_of_fire[f];
+    const bool has_plane = p >= 0 && p < T;
+    const uint32_t* plane = bits + (has_plane ? p : 0) * g.words_per_plane;
+    const int2* ent = ent_all + (has_plane ? p : 0) * g.ent_per_plane;
+    int root = -1;
+    if (has_plane) {
+      const int r = fire_rc[2 * f], c = fire_rc[2 * f + 1];
+      unsigned long long best = kNoKey;
+      for (int dy = -win; dy <= win; ++dy) {
+        const int y = r + dy;
+        if (y < 0 || y >= H) continue;
+        const unsigned long long k = best_in_row(plane + 1ll * y * g.segs, g, c, dy, win);
+        best = k < best ? k : best;
+      }
+      root = root_of_key(best, plane, ent, g, r, c, win);
+    }
+    int area = 0, y_min = H, x_min = W, y_max = 0, x_max = 0;
+    for (long long i = 0; i < g.words_per_plane; ++i) {
+      uint32_t o = 0;
+      if (root >= 0 && plane[i]) {
+        const int y = static_cast<int>(i / g.segs), seg = static_cast<int>(i % g.segs);
+        o = component_word(plane[i], ent, g, y, seg, root);
+        if (o) {
+          area += __builtin_popcount(o);
+          y_min = y < y_min ? y : y_min;
+          y_max = y + 1 > y_max ? y + 1 : y_max;
+          const int lo = 32 * seg + ctz32(o), hi = 32 * seg + 32 - clz32(o);
+          x_min = lo < x_min ? lo : x_min;
+          x_max = hi > x_max ? hi : x_max;
+        }
+      }
+      comp[f * g.words_per_plane + i] = o;
+    }
+    const int st[8] = {area, area ? y_min : 0, area ? x_min : 0, area ? y_max : 0, area ? x_max : 0, root, 0, 0};
+    std::memcpy(stats + 8 * f, st, sizeof(st));
+  }
+}
+
 long long emu_ent_count(int H, int W, int T) { return make_geom(H, W).ent_per_plane * T; }
 }

@@ -266,3 +266,49 @@ def test_nearest_fill_full_size_properties(sw):
         win = aod[y0:y + r + 1, x0:x + r + 1]
         wy, wx = np.nonzero(win == o[y, x])
         assert (np.round(dist[y, x] ** 2) == (wy + y0 - y) ** 2 + (wx + x0 - x) ** 2).any()
+
+
+@pytest.mark.parametrize("h,w,density", [(7, 300, 0.5), (64, 64, 0.62), (97, 129, 0.4), (257, 333, 0.55), (600, 800, 0.6)])
+def test_fire_components_equal_oracle_on_random_masks(sw, h, w, density):
+    """find_plume_mask's label / extract_label / == without a label plane: component masks and bounding boxes."""
+    rng = np.random.default_rng(h * 7 + w)
+    masks = rng.random((4, h, w)) < density
+    masks[1] = ~masks[1]
+    masks[3] = False
+    if h >= 8:
+        masks[2] = spiral(h, w)
+    win = min(sweep_ref.P_ID_WIN_SIZE, (h - 1) // 2, (w - 1) // 2)
+    n = 24
+    rows, cols = rng.integers(win, h - win, n), rng.integers(win, w - win, n)
+    planes = [None if p < 0 else int(p) for p in rng.integers(-1, 4, n)]
+    bits = sw.pack_bits_host(masks)
+    comp, stats = sw.fire_components(bits, w, planes, rows, cols, win)
+    got = sw.unpack_bits(comp, w)
+    for f, p in enumerate(planes):
+        ref = None if p is None else sweep_ref.plume_mask_ref(masks[p], rows[f], cols[f], win)
+        if ref is None:
+            assert not got[f].any() and stats[f, 0] == 0 and stats[f, 5] == -1
+        else:
+            ys, xs = np.nonzero(ref)
+            assert np.array_equal(got[f], ref)
+            assert stats[f, :5].tolist() == [ref.sum(), ys.min(), xs.min(), ys.max() + 1, xs.max() + 1]
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_plume_masks_follow_the_reference_call_sequence(sw, i):
+    """generate_mask_dict -> find_plume_extents -> find_threshold_index -> plume_masks on the golden cases: the mask
+    of every fire with a threshold index equals label / extract_label / == of the oracle on the reference's own mask."""
+    aod, fires, thr, masks, extents, index = case(i)
+    d = sweep.generate_mask_dict(aod, thr)
+    idx = sweep.find_threshold_index(sweep.find_plume_extents(d, fires[:, 0], fires[:, 1]))
+    assert [-1 if v is None else v for v in idx] == index.tolist()
+    got, stats = sweep.plume_masks(d, idx, fires[:, 0], fires[:, 1])
+    for f, k in enumerate(idx):
+        ref = None if k is None else sweep_ref.plume_mask_ref(masks[k], fires[f, 0], fires[f, 1])
+        if ref is None:
+            assert got[f] is None
+        else:
+            assert np.array_equal(got[f], ref) and stats[f, 0] == ref.sum() == extents[k, f]
+    plain = {t: masks[k] for k, t in enumerate(thr)}                                  # an ordinary dict of host masks
+    again, _ = sweep.plume_masks(plain, idx, fires[:, 0], fires[:, 1])
+    assert all((a is None and b is None) or np.array_equal(a, b) for a, b in zip(got, again))

@@ -50,7 +50,33 @@ def bits_extents(emu, bits, w, rows, cols, win=sweep_ref.P_ID_WIN_SIZE, seed=0):
     ent = np.full((emu.emu_ent_count(h, w, t), 2), 0x5A5A5A5A, dtype=np.int32)     # garbage: init must cover what is read
     out = np.full((t, len(rc)), -7, dtype=np.int32)
     emu.emu_bits_extents(P(bits), t, h, w, P(rc), len(rc), win, P(ent), P(out), seed)
+    bits_extents.last_entries = ent
     return out
+
+
+def fire_components(emu, bits, w, rows, cols, planes, win=sweep_ref.P_ID_WIN_SIZE):
+    """after bits_extents(...) on the same bits: (component masks bool [n, H, W], stats [n, 8])"""
+    t, h, segs = bits.shape
+    rc = np.ascontiguousarray(np.stack([rows, cols], 1), dtype=np.int32)
+    planes = np.ascontiguousarray(planes, dtype=np.int32)
+    comp = np.full((len(rc), h, segs), 0xDEADBEEF, dtype=np.uint32)
+    stats = np.full((len(rc), 8), -7, dtype=np.int32)
+    emu.emu_fire_components(P(bits), t, h, w, P(rc), P(planes), len(rc), win, P(bits_extents.last_entries), P(comp), P(stats))
+    return unpack(comp, w), stats
+
+
+def check_components(emu, bits, masks, w, rows, cols, win):
+    rng = np.random.default_rng(len(rows))
+    planes = rng.integers(-1, bits.shape[0], len(rows))
+    got, stats = fire_components(emu, bits, w, rows, cols, planes, win)
+    for f, p in enumerate(planes):
+        ref = None if p < 0 else sweep_ref.plume_mask_ref(masks[p], rows[f], cols[f], win)
+        if ref is None:
+            assert not got[f].any() and stats[f, 0] == 0 and stats[f, 5] == -1
+        else:
+            ys, xs = np.nonzero(ref)
+            assert np.array_equal(got[f], ref)
+            assert stats[f, :5].tolist() == [ref.sum(), ys.min(), xs.min(), ys.max() + 1, xs.max() + 1]
 
 
 @pytest.mark.parametrize("i", range(int(G["n_cases"])))
@@ -117,3 +143,4 @@ def test_extents_equal_oracle_on_random_masks(emu, h, w, density):
     ref = sweep_ref.find_plume_extents_ref(masks, rows, cols, win)
     for s in (0, 3, 11):
         assert np.array_equal(bits_extents(emu, bits, w, rows, cols, win, seed=s), ref)
+    check_components(emu, bits, masks, w, rows, cols, win)
