@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 namespace plume {
@@ -317,7 +318,7 @@ int fire_extents(const int* labels, const int* sizes, int T, int H, int W, const
 // ================================================================================================
 using namespace sweepbits;
 
-constexpr int kStripRows = 16;      // output rows per warp of mask_bits_kernel (+ 4 halo rows)
+constexpr int kStripRows = 16;      // output rows per warp of mask_bits_kernel (+ 4 halo rows); 8 when the grid is small
 constexpr int kMaskWarps = 4;
 
 // A warp takes two adjacent 32-column strips and kStripRows rows (the two extra window columns between the strips are
@@ -328,7 +329,7 @@ constexpr int kMaskWarps = 4;
 // (First version: one ballot per threshold and operand, 75 ballots per row instead of 14 shuffles: 69 vs 54 us.)
 template <typename V>
 __global__ void __launch_bounds__(kMaskWarps * 32)
-    mask_bits_kernel(const V* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T,
+    mask_bits_kernel(const V* __restrict__ aod, int H, int W, const double* __restrict__ thr, int T, int strip_rows,
                      uint32_t* __restrict__ bits, int2* __restrict__ ent_all) {
   __shared__ V s_thr[32];        // the chunk's thresholds, ascending, padded with +inf
   __shared__ V s_raw[32];
@@ -350,11 +351,11 @@ __global__ void __launch_bounds__(kMaskWarps * 32)
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int segs = (W + 31) / 32, pairs = (segs + 1) / 2;
-  const int strips = (H + kStripRows - 1) / kStripRows;
+  const int strips = (H + strip_rows - 1) / strip_rows;
   const long long wg = 1ll * blockIdx.x * kMaskWarps + (threadIdx.x >> 5);
   if (wg >= 1ll * pairs * strips) return;
-  const int sp = static_cast<int>(wg % pairs), y0 = static_cast<int>(wg / pairs) * kStripRows;
-  const int y_end = min(y0 + kStripRows, H);
+  const int sp = static_cast<int>(wg % pairs), y0 = static_cast<int>(wg / pairs) * strip_rows;
+  const int y_end = min(y0 + strip_rows, H);
   const int seg0 = 2 * sp, seg1 = 2 * sp + 1;
   const uint64_t colmask0 = window_colmask(seg0, W), colmask1 = window_colmask(seg1, W);
   const uint64_t outcols0 = ~colmask0 & kWin36, outcols1 = ~colmask1 & kWin36;
@@ -425,14 +426,24 @@ int mask_bits_launch(const void* aod, int f64, int H, int W, const double* thr, 
     set_error("threshold_mask_bits: plane too large");
     return -1;
   }
-  const long long warps = 1ll * ((g.segs + 1) / 2) * ((H + kStripRows - 1) / kStripRows);
-  const dim3 grid(static_cast<unsigned>((warps + kMaskWarps - 1) / kMaskWarps), static_cast<unsigned>((T + 31) / 32));
+  // 16 output rows per warp cost 4 halo rows (25 % extra work); a call with few thresholds does not fill the GPU with
+  // that (1200 x 1200 x 25: 9.6 warps per SM) and is latency bound, so it takes 8-row strips (twice the warps)
+  const long long chunks = (T + 31) / 32;
+  const long long warps16 = 1ll * ((g.segs + 1) / 2) * ((H + kStripRows - 1) / kStripRows);
+  static const int force_rows = [] {
+    const char* v = std::getenv("PLUME_SWEEP_STRIP_ROWS");
+    return v ? std::atoi(v) : 0;
+  }();
+  static const int sms = plume_num_sms() > 0 ? plume_num_sms() : 148;
+  const int strip_rows = force_rows > 0 ? force_rows : (warps16 * chunks < 16ll * sms ? kStripRows / 2 : kStripRows);
+  const long long warps = 1ll * ((g.segs + 1) / 2) * ((H + strip_rows - 1) / strip_rows);
+  const dim3 grid(static_cast<unsigned>((warps + kMaskWarps - 1) / kMaskWarps), static_cast<unsigned>(chunks));
   if (grid.y > 65535u) {
     set_error("threshold_mask_bits: too many thresholds");
     return -1;
   }
-  if (f64) mask_bits_kernel<double><<<grid, kMaskWarps * 32, 0, s>>>(static_cast<const double*>(aod), H, W, thr, T, bits, ent);
-  else mask_bits_kernel<float><<<grid, kMaskWarps * 32, 0, s>>>(static_cast<const float*>(aod), H, W, thr, T, bits, ent);
+  if (f64) mask_bits_kernel<double><<<grid, kMaskWarps * 32, 0, s>>>(static_cast<const double*>(aod), H, W, thr, T, strip_rows, bits, ent);
+  else mask_bits_kernel<float><<<grid, kMaskWarps * 32, 0, s>>>(static_cast<const float*>(aod), H, W, thr, T, strip_rows, bits, ent);
   return check_launch_sweep("threshold_mask_bits");
 }
 }  // namespace

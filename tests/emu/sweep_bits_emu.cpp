@@ -18,11 +18,10 @@ float round_down_to_float(double t) {          // __double2float_rd
   if (static_cast<double>(f) > t) f = std::nextafterf(f, -INFINITY);
   return f;
 }
-constexpr int kStripRows = 16;
 
 // mask_bits_kernel<float, true>: two adjacent strips per warp; per lane the count of thresholds below its pixel, a
 // 32 x 32 bit transpose across the "warp", lane r owns the r-th smallest threshold of the chunk
-void mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits) {
+void mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, int kStripRows) {
   const int segs = (W + 31) / 32, pairs = (segs + 1) / 2;
   const int strips = (H + kStripRows - 1) / kStripRows;
   for (int chunk = 0; chunk < (T + 31) / 32; ++chunk) {
@@ -112,8 +111,8 @@ std::vector<long long> order(long long n, unsigned seed) {
 
 extern "C" {
 
-void emu_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits) {
-  mask_bits(aod, H, W, thr, T, bits);
+void emu_mask_bits(const float* aod, int H, int W, const double* thr, int T, uint32_t* bits, int strip_rows) {
+  mask_bits(aod, H, W, thr, T, bits, strip_rows);
 }
 
 void emu_pack_bits(const uint8_t* masks, int T, int H, int W, uint32_t* bits) {

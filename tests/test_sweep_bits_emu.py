@@ -39,9 +39,13 @@ def mask_bits(emu, aod, thr):
     aod = np.ascontiguousarray(aod, dtype=np.float32)
     thr = np.ascontiguousarray(thr, dtype=np.float64)
     h, w = aod.shape
-    bits = np.full((len(thr), h, (w + 31) // 32), 0xDEADBEEF, dtype=np.uint32)
-    emu.emu_mask_bits(P(aod), h, w, P(thr), len(thr), P(bits))
-    return bits
+    out = []
+    for strip_rows in (16, 8, 5):                                 # the kernel takes 16- or 8-row strips; 5: ragged
+        bits = np.full((len(thr), h, (w + 31) // 32), 0xDEADBEEF, dtype=np.uint32)
+        emu.emu_mask_bits(P(aod), h, w, P(thr), len(thr), P(bits), strip_rows)
+        out.append(bits)
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+    return out[0]
 
 
 def bits_extents(emu, bits, w, rows, cols, win=sweep_ref.P_ID_WIN_SIZE, seed=0):
