@@ -240,6 +240,21 @@ class MaskDict(dict):
     def get(self, key, default=None):
         return self[key] if key in self else default
 
+    def __iter__(self):                 # an overridden __iter__ also makes dict(d) / d2.update(d) go through __getitem__
+        return super().__iter__()
+
+    def copy(self):
+        return dict(self.items())
+
+    def pop(self, key, *default):
+        if key in self:
+            v = self[key]
+            dict.pop(self, key)
+            return v
+        if default:
+            return default[0]
+        raise KeyError(key)
+
     def values(self):
         return [self[k] for k in self]
 

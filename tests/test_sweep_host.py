@@ -43,6 +43,14 @@ def test_mask_dict_is_a_lazy_dict_over_bit_planes():
     assert np.array_equal(d[0.25], masks[1]) and np.array_equal(d[0.5], masks[2]) and d.get(0.7) is None
     assert np.array_equal(np.stack([d[k] for k in d]), masks[[2, 1, 3]])
     assert np.array_equal(np.stack(d.values()), masks[[2, 1, 3]]) and [k for k, _ in d.items()] == [0.5, 0.25, 0.1]
+    fresh = sweep.MaskDict(thr, bits, w)
+    assert all(isinstance(v, np.ndarray) for v in dict(fresh).values()) and np.array_equal(fresh.copy()[0.25], masks[1])
+    merged = {}
+    merged.update(sweep.MaskDict(thr, bits, w))
+    assert np.array_equal(merged[0.1], masks[3])
+    popped = sweep.MaskDict(thr, bits, w)
+    assert np.array_equal(popped.pop(0.25), masks[1]) and list(popped) == [0.5, 0.1] and popped.pop(9.0, None) is None
+    assert popped.device_planes().shape == (2, h, segs)
     planes = d.device_planes()
     assert planes.shape == (3, h, segs) and torch.equal(planes, bits[[2, 1, 3]])
     assert np.array_equal(sweep.ThresholdSweep.unpack_bits(planes, w), masks[[2, 1, 3]])
