@@ -398,6 +398,12 @@ int plume_fill_nearest_f64(const double* aod, int H, int W, double null_value, v
  * plume_resample_workspace_bytes(...) bytes.  plume_gather_fill: out[i] = idx[i] >= 0 ? src[idx[i]] : fill_value,
  * elements of 4 (float32) or 8 (float64) bytes. */
 int plume_utm_zone_histogram(const double* lon, long long n, int* hist64, plume_stream_t stream);
+/* Geolocation half of read_modis_aod (tools.py:97-128): lat / lon (float64 [ny][nx], degrees) of the grid
+ * x = linspace(x_start, x_stop, nx), y = linspace(y_start, y_stop, ny) metres on the MODIS sinusoidal sphere of `radius`
+ * (6371007.181): latitude = y / R, longitude = x / (R cos(latitude)), wrapped into [-180, 180].  The HDF4 parsing of
+ * read_modis_aod (pyhdf) is not rebuilt. */
+int plume_sinusoidal_grid_latlon(double x_start, double x_stop, double y_start, double y_stop, int ny, int nx,
+                                 double radius, double* lat, double* lon, plume_stream_t stream);
 int plume_utm_forward(const double* lat, const double* lon, long long n, int zone, double* x, double* y,
                       plume_stream_t stream);
 int plume_utm_inverse(const double* x, const double* y, long long n, int zone, double* lat, double* lon,

@@ -678,6 +678,11 @@ int plume_utm_zone_histogram(const double* lon, long long n, int* hist64, plume_
   PLUME_CHECK(hist64 && (n <= 0 || lon), "utm_zone_histogram: null pointer");
   return utm_zone_histogram(lon, n, hist64, S(stream));
 }
+int plume_sinusoidal_grid_latlon(double x_start, double x_stop, double y_start, double y_stop, int ny, int nx,
+                                 double radius, double* lat, double* lon, plume_stream_t stream) {
+  PLUME_CHECK(ny <= 0 || nx <= 0 || (lat && lon), "sinusoidal_grid_latlon: null pointer");
+  return sinusoidal_grid_latlon(x_start, x_stop, y_start, y_stop, ny, nx, radius, lat, lon, S(stream));
+}
 int plume_utm_forward(const double* lat, const double* lon, long long n, int zone, double* x, double* y,
                       plume_stream_t stream) {
   PLUME_CHECK(n <= 0 || (lat && lon && x && y), "utm_forward: null pointer");

@@ -114,6 +114,8 @@ int fill_nearest(const void* aod, int f64, int H, int W, double null_value, void
 int utm_zone_histogram(const double* lon, long long n, int* hist64, cudaStream_t s);
 int utm_forward(const double* lat, const double* lon, long long n, int zone, double* x, double* y, cudaStream_t s);
 int utm_inverse(const double* x, const double* y, long long n, int zone, double* lat, double* lon, cudaStream_t s);
+int sinusoidal_grid_latlon(double x_start, double x_stop, double y_start, double y_stop, int ny, int nx, double radius,
+                           double* lat, double* lon, cudaStream_t s);
 size_t resample_workspace_bytes(int n_src, double min_x, double min_y, double max_x, double max_y, double radius);
 int resample_nearest_index(const double* src_lat, const double* src_lon, int n_src, int zone, double min_x,
                            double min_y, double max_x, double max_y, int x_size, int y_size, double radius,

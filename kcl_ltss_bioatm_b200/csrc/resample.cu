@@ -309,6 +309,49 @@ int utm_inverse(const double* x, const double* y, long long n, int zone, double*
   return check_launch_rs("utm_inverse");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Geolocation of a MODIS sinusoidal grid (read_modis_aod, tools.py:97-128): x = linspace(x_start, x_stop, nx),
+// y = linspace(y_start, y_stop, ny) in metres, meshgrid, inverse spherical sinusoidal projection
+// (+proj=sinu +R=6371007.181 +nadgrids=@null -> EPSG:4326: the null grid shift makes the sphere's latitude /
+// longitude the output, no datum step).  PROJ's operation order for the sphere: phi = y * (1 / R),
+// lam = (x * (1 / R)) / cos(phi), longitude wrapped into [-pi, pi], radians * (180 / pi).  numpy's linspace:
+// i * step + start with the last sample set to stop (both products and sums rounded separately: no FMA).
+// ------------------------------------------------------------------------------------------------
+__global__ void sinu_grid_kernel(double x_start, double x_stop, double x_step, double y_start, double y_stop,
+                                 double y_step, int ny, int nx, double inv_r, double* __restrict__ lat,
+                                 double* __restrict__ lon) {
+  const long long n = 1ll * ny * nx, step = 1ll * gridDim.x * blockDim.x;
+  constexpr double kPi = 3.14159265358979323846, kTwoPi = 6.28318530717958647693, kSpi = 3.14159265359;
+  constexpr double kRadToDeg = 57.295779513082321;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const int r = static_cast<int>(i / nx), c = static_cast<int>(i % nx);
+    const double x = (nx > 1 && c == nx - 1) ? x_stop : __dadd_rn(__dmul_rn(static_cast<double>(c), x_step), x_start);
+    const double y = (ny > 1 && r == ny - 1) ? y_stop : __dadd_rn(__dmul_rn(static_cast<double>(r), y_step), y_start);
+    const double phi = __dmul_rn(y, inv_r);
+    double lam = __ddiv_rn(__dmul_rn(x, inv_r), cos(phi));
+    if (fabs(lam) > kSpi) {                                  // PROJ adjlon
+      lam += kPi;
+      lam -= kTwoPi * floor(lam / kTwoPi);
+      lam -= kPi;
+    }
+    lat[i] = __dmul_rn(phi, kRadToDeg);
+    lon[i] = __dmul_rn(lam, kRadToDeg);
+  }
+}
+
+int sinusoidal_grid_latlon(double x_start, double x_stop, double y_start, double y_stop, int ny, int nx, double radius,
+                           double* lat, double* lon, cudaStream_t s) {
+  if (ny <= 0 || nx <= 0) return 0;
+  if (!(radius > 0)) {
+    set_error("sinusoidal_grid_latlon: radius must be positive");
+    return -1;
+  }
+  const double x_step = nx > 1 ? (x_stop - x_start) / (nx - 1) : 0.0, y_step = ny > 1 ? (y_stop - y_start) / (ny - 1) : 0.0;
+  sinu_grid_kernel<<<grid_1d(1ll * ny * nx, 256), 256, 0, s>>>(x_start, x_stop, x_step, y_start, y_stop, y_step, ny, nx,
+                                                               1.0 / radius, lat, lon);
+  return check_launch_rs("sinusoidal_grid_latlon");
+}
+
 size_t resample_workspace_bytes(int n_src, double min_x, double min_y, double max_x, double max_y, double radius) {
   if (n_src <= 0 || !(radius > 0) || !(max_x >= min_x) || !(max_y >= min_y)) return 0;
   const Buckets b = make_buckets(min_x, min_y, max_x, max_y, radius);

@@ -102,6 +102,7 @@ SIGNATURES = {
     "plume_set_deterministic": (None, [_I]),
     "plume_get_deterministic": (_I, []),
     "plume_utm_zone_histogram": (_I, [_P, _LL, _P, _P]),
+    "plume_sinusoidal_grid_latlon": (_I, [_D, _D, _D, _D, _I, _I, _D, _P, _P, _P]),
     "plume_utm_forward": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "plume_utm_inverse": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "plume_resample_workspace_bytes": (c_size_t, [_I, _D, _D, _D, _D, _D]),

@@ -580,6 +580,17 @@ class CudaOps:
               "plume_utm_zone_histogram")
         self.launches += 1
 
+    def sinusoidal_grid_latlon(self, x_start, x_stop, y_start, y_stop, radius, lat, lon):
+        """lat / lon float64 [ny, nx] (degrees) of the sinusoidal grid linspace(x_start, x_stop, nx) x linspace(y_start, y_stop, ny)."""
+        ny, nx = lat.shape
+        if lon.shape != lat.shape:
+            raise ValueError("lat and lon must have the same [ny, nx] shape")
+        check(self.lib.plume_sinusoidal_grid_latlon(float(x_start), float(x_stop), float(y_start), float(y_stop), ny, nx,
+                                                    float(radius), self._dev(lat, torch.float64, "lat"),
+                                                    self._dev(lon, torch.float64, "lon"), current_stream()),
+              "plume_sinusoidal_grid_latlon")
+        self.launches += 1
+
     def utm_forward(self, lats, lons, zone, x, y):
         check(self.lib.plume_utm_forward(self._dev(lats, torch.float64, "lats"), self._dev(lons, torch.float64, "lons"),
                                          lats.numel(), int(zone), self._dev(x, torch.float64, "x"),

@@ -9,7 +9,9 @@ CUDA kernels behind the C ABI (``csrc/resample.cu``); what the libraries compute
 ``oracle/resample_ref.py``.  numpy arrays in, numpy arrays out, like the reference; the neighbour INDEX map of the last
 swath geometry is cached on the device, so resampling further images on the same swath costs one gather.
 
-``read_modis_aod`` (``tools.py:67-130``) reads HDF4 through pyhdf, which is absent: not rebuilt.
+``read_modis_aod`` (``tools.py:67-130``) reads HDF4 through pyhdf, which is absent: the file parsing is not rebuilt
+(DESIGN.md section 7); its geolocation half (``:97-128``, the lat / lon arrays of the sinusoidal grid) is
+``modis_grid_latlon`` below.
 """
 from __future__ import annotations
 
@@ -19,6 +21,7 @@ import numpy as np
 import torch
 
 RADIUS_OF_INFLUENCE = 10000.0   # tools.py:57
+MODIS_SPHERE_RADIUS = 6371007.181   # tools.py:124 (+proj=sinu +R=6371007.181)
 
 
 class utm_resampler(object):
@@ -96,3 +99,20 @@ class utm_resampler(object):
         la, lo = torch.empty_like(x), torch.empty_like(x)
         self.ops.utm_inverse(x, y, self.zone, la, lo)
         return float(lo.item()), float(la.item())
+
+
+def modis_grid_latlon(x0, y0, x1, y1, ny, nx, device="cuda", ops=None):
+    """(lat, lon) float64 [ny, nx] device tensors of a MODIS sinusoidal grid from its corner coordinates in metres
+    (``UpperLeftPointMtrs`` = (x0, y0), ``LowerRightMtrs`` = (x1, y1) of StructMetadata.0) -- the second half of
+    ``read_modis_aod`` (tools.py:103-128): ``xinc = (x1 - x0) / nx``, ``x = linspace(x0, x0 + xinc * nx, nx)`` (likewise
+    y), meshgrid, ``pyproj.transform(sinu, wgs84, xv, yv)`` with ``+proj=sinu +R=6371007.181 +nadgrids=@null``."""
+    if ops is None:
+        from .ops import CudaOps
+
+        ops = CudaOps()
+    x0, y0, x1, y1 = float(x0), float(y0), float(x1), float(y1)
+    xinc, yinc = (x1 - x0) / nx, (y1 - y0) / ny                      # tools.py:115-116
+    lat = torch.empty(int(ny), int(nx), dtype=torch.float64, device=device)
+    lon = torch.empty_like(lat)
+    ops.sinusoidal_grid_latlon(x0, x0 + xinc * nx, y0, y0 + yinc * ny, MODIS_SPHERE_RADIUS, lat, lon)
+    return lat, lon

@@ -167,3 +167,24 @@ def resample_image_ref(image, image_lats, image_lons, zone, extent, x_size, y_si
     hit = idx >= 0
     out[hit] = flat[idx[hit]]
     return out
+
+
+MODIS_SPHERE_RADIUS = 6371007.181   # tools.py:124
+
+
+def modis_grid_latlon_ref(x0, y0, x1, y1, ny, nx):
+    """tools.py:103-128 with pyproj's spherical sinusoidal inverse written out (PARITY UNPINNED against pyproj, which is
+    absent: PROJ's gn_sinu spherical inverse is phi = y / R, lam = (x / R) / cos(phi); ``+nadgrids=@null`` suppresses
+    the datum step, so the sphere's latitude / longitude are the EPSG:4326 output; longitudes wrap into [-180, 180]).
+    Anchored on the published MODIS tile grid: tiles are 10 degrees = R * pi / 18 metres
+    (tests/test_resample_oracle.py)."""
+    xinc, yinc = (x1 - x0) / nx, (y1 - y0) / ny
+    x = np.linspace(x0, x0 + xinc * nx, nx)
+    y = np.linspace(y0, y0 + yinc * ny, ny)
+    xv, yv = np.meshgrid(x, y)
+    inv_r = 1.0 / MODIS_SPHERE_RADIUS
+    phi = yv * inv_r
+    lam = (xv * inv_r) / np.cos(phi)
+    wrap = np.abs(lam) > 3.14159265359
+    lam = np.where(wrap, (lam + np.pi) - 2 * np.pi * np.floor((lam + np.pi) / (2 * np.pi)) - np.pi, lam)
+    return phi * 57.295779513082321, lam * 57.295779513082321

@@ -84,3 +84,21 @@ def test_image_on_another_geometry_invalid_pixels_and_radius(ops):
     ref = rr.resample_image_ref(img, sub_lat, sub_lon, rs.zone, rs.extent, rs.x_size, rs.y_size, fill_value=-999)
     assert np.array_equal(got, ref)
     assert (got == -999).mean() > 0.3 and (got != -999).mean() > 0.2
+
+
+@pytest.mark.parametrize("h,v,ny,nx", [(18, 4, 1200, 1200), (0, 8, 64, 48), (35, 9, 1, 7), (17, 0, 33, 1), (20, 11, 240, 240)])
+def test_modis_grid_latlon_matches_the_oracle(ops, h, v, ny, nx):
+    """Geolocation half of read_modis_aod (tools.py:97-128) for MODIS tiles incl. the outermost ones (wrapped
+    longitudes) and degenerate shapes; fp64, operation order of the oracle; cos differs from libm's by an ulp."""
+    from kcl_ltss_bioatm_b200.resample import modis_grid_latlon
+    tile = rr.MODIS_SPHERE_RADIUS * np.pi / 18
+    x0, y0 = (h - 18) * tile, (9 - v) * tile
+    lat, lon = modis_grid_latlon(x0, y0, x0 + tile, y0 - tile, ny, nx, device="cuda", ops=ops)
+    rlat, rlon = rr.modis_grid_latlon_ref(x0, y0, x0 + tile, y0 - tile, ny, nx)
+    assert lat.dtype == torch.float64 and tuple(lat.shape) == (ny, nx)
+    assert np.array_equal(lat.cpu().numpy(), rlat)                                  # no transcendental: bit-equal
+    dlon = np.abs(lon.cpu().numpy() - rlon)
+    near_wrap = np.abs(np.abs(rlon) - 180.0) < 1e-6
+    assert (dlon[~near_wrap] <= 4e-13 * np.maximum(1.0, np.abs(rlon[~near_wrap]))).all()
+    from src.features import tools
+    assert tools.modis_grid_latlon is modis_grid_latlon

@@ -60,3 +60,22 @@ def test_nearest_resampling_of_a_grid_onto_itself_is_the_identity():
     out = rr.resample_image_ref(img[:, keep], tlat[:, keep], tlon[:, keep], zone, extent, xs, ys, fill_value=-999)
     assert np.array_equal(out[:, :5], img[:, :5])
     assert np.all(out[:, 15:] == -999) and np.all(out[:, 5:14] == img[:, 4:5])   # nearest column is the 5th
+
+
+def test_modis_sinusoidal_grid_against_the_published_tile_grid():
+    """MODIS sinusoidal tiles are 10 x 10 degrees at the equator: tile size = R * pi / 18 = 1111950.5197 m (published
+    grid constant), tile h18v04's upper-left corner is (0 m, 5559752.598 m) = (lon 0, lat 50 N), h17v03's lower-right
+    the same point.  The oracle must put the grid's first sample on the corner and follow x / (R cos(lat))."""
+    tile = rr.MODIS_SPHERE_RADIUS * np.pi / 18
+    assert abs(tile - 1111950.5197) < 1e-3
+    x0, y0 = 0.0, 5 * tile                                   # h18v04
+    lat, lon = rr.modis_grid_latlon_ref(x0, y0, x0 + tile, y0 - tile, 1200, 1200)
+    assert lat.shape == lon.shape == (1200, 1200)
+    assert abs(lat[0, 0] - 50.0) < 1e-9 and abs(lon[0, 0]) < 1e-12
+    assert abs(lat[-1, 0] - 40.0) < 1e-9                                          # linspace includes the far edge (tools.py:118-119)
+    assert abs(lon[-1, -1] - 10.0 / np.cos(np.radians(40.0))) < 1e-9             # 10 degrees of x at latitude 40
+    assert abs(lon[0, -1] - 10.0 / np.cos(np.radians(50.0))) < 1e-9
+    assert np.all(np.diff(lat[:, 0]) < 0) and np.all(np.diff(lon[0]) > 0)
+    # beyond the edge of the projection (fill area of the outermost tiles) longitudes wrap like PROJ's adjlon
+    lat2, lon2 = rr.modis_grid_latlon_ref(17 * tile, 8 * tile, 18 * tile, 7 * tile, 5, 5)
+    assert np.all(np.abs(lon2) <= 180.0 + 1e-9)
