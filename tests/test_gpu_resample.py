@@ -102,7 +102,7 @@ def test_modis_grid_latlon_matches_the_oracle(ops, h, v, ny, nx):
     xv = np.linspace(x0, x0 + tile, nx)[None, :] / rr.MODIS_SPHERE_RADIUS
     raw = np.degrees(np.abs(xv / np.cos(np.radians(rlat))))
     sane = (raw < 3600.0) & (np.abs(np.abs(rlon) - 180.0) > 1e-6)
-    assert sane.mean() > 0.9
+    assert sane.mean() > 0.8
     dlon = np.abs(lon.cpu().numpy() - rlon)
     assert (dlon[sane] <= 4e-13 * np.maximum(1.0, raw[sane])).all()
     from src.features import tools
