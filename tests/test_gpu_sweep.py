@@ -312,3 +312,27 @@ def test_plume_masks_follow_the_reference_call_sequence(sw, i):
     plain = {t: masks[k] for k, t in enumerate(thr)}                                  # an ordinary dict of host masks
     again, _ = sweep.plume_masks(plain, idx, fires[:, 0], fires[:, 1])
     assert all((a is None and b is None) or np.array_equal(a, b) for a, b in zip(got, again))
+
+
+def test_kernels_follow_scikit_image_documented_semantics(sw):
+    """tests/skimage_cases.py (docstring examples and border rules of the absent scikit-image) through the kernels."""
+    from tests import skimage_cases as C
+    for src, expect in ((C.ERODE_FULL, C.ERODE_FULL_EXPECT), (C.OPEN_IN, C.OPEN_EXPECT), (C.DILATE_DOT, np.zeros_like(C.DILATE_DOT))):
+        for dt in (np.float32, np.float64):
+            assert np.array_equal(sw.unpack_bits(sw.mask_bits(src.astype(dt), [0.5]), src.shape[1])[0], expect)
+            assert np.array_equal(sw.masks(src.astype(dt), [0.5]).cpu().numpy()[0].astype(bool), expect)
+    for mask, expect in ((C.LABEL_EYE, C.LABEL_EYE_EXPECT), (C.LABEL_ORDER, C.LABEL_ORDER_EXPECT)):
+        labels, sizes = sw.label(torch.from_numpy(mask.astype(np.uint8))[None].cuda())
+        lab = labels[0].cpu().numpy()
+        ids = np.unique(lab[lab >= 0])                          # canonical labels ascend in raster order of first pixels
+        got = np.zeros(mask.shape, dtype=np.int64)
+        for k, v in enumerate(ids):
+            got[lab == v] = k + 1
+        assert np.array_equal(got, expect)
+        assert sizes[0].cpu().numpy().sum() == mask.sum()
+    r, c = np.nonzero(C.RSO)
+    assert np.array_equal(sw.cluster_fires(C.RSO.shape, r, c, 7) > 0, C.RSO_MIN7_CONN2)
+    assert np.array_equal(sw.cluster_fires(C.RSO.shape, r, c, 8) > 0, C.RSO_MIN8_CONN2)
+    # 8-connectivity through the bit-plane path: the eye is one component of three pixels
+    ext = sw.extents_of_bits(sw.pack_bits_host(C.LABEL_EYE[None]), 3, [1], [1], win=1)
+    assert ext.tolist() == [[3.0]]

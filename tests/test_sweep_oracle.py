@@ -97,3 +97,34 @@ def test_nearest_fill_oracle_equals_reference_golden(i):
         d2 = (gy - y) ** 2 + (gx - x) ** 2
         tied = aod[gy[d2 == d2.min()], gx[d2 == d2.min()]].astype(np.float64)
         assert gold[y, x] in tied and np.float64(got[y, x]) == tied[0]
+
+
+def test_oracle_follows_scikit_image_documented_semantics():
+    """The three scikit-image primitives are not installed here; tests/skimage_cases.py writes their documented behaviour
+    down (docstring examples, border rules) and the oracle's restatements must reproduce it."""
+    from tests import skimage_cases as C
+
+    def rank_labels(mask):                      # label_ref's canonical labels -> scikit-image's 1..n raster-order numbers
+        lab = sweep_ref.label_ref(mask)
+        ids = np.unique(lab[lab > 0])
+        out = np.zeros_like(lab)
+        for k, v in enumerate(ids):
+            out[lab == v] = k + 1
+        return out
+
+    assert np.array_equal(rank_labels(C.LABEL_EYE), C.LABEL_EYE_EXPECT)
+    assert np.array_equal(rank_labels(C.LABEL_ORDER), C.LABEL_ORDER_EXPECT)
+    # remove_small_objects(label(a), min_size, connectivity=2) as cluster_fires uses it, on the docstring's array
+    for min_size, expect in ((7, C.RSO_MIN7_CONN2), (8, C.RSO_MIN8_CONN2)):
+        r, c = np.nonzero(C.RSO)
+        assert np.array_equal(sweep_ref.cluster_fires_ref(C.RSO.shape, r, c, min_size) > 0, expect)
+    # border rules and the erosion -> dilation pair of generate_mask_dict
+    for src, expect in ((C.ERODE_FULL, C.ERODE_FULL_EXPECT), (C.OPEN_IN, C.OPEN_EXPECT), (C.DILATE_DOT, np.zeros_like(C.DILATE_DOT))):
+        assert np.array_equal(sweep_ref.threshold_masks_ref(src.astype(np.float32), [0.5])[0], expect)
+    hole = sweep_ref.threshold_masks_ref(C.ERODE_HOLE.astype(np.float32), [0.5])[0]
+    assert np.array_equal(hole, ndi_dilate_cross(C.ERODE_HOLE_EXPECT))
+
+
+def ndi_dilate_cross(m):
+    p = np.pad(m, 1, constant_values=False)
+    return p[1:-1, 1:-1] | p[:-2, 1:-1] | p[2:, 1:-1] | p[1:-1, :-2] | p[1:-1, 2:]
