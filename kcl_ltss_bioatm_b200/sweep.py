@@ -28,6 +28,8 @@ from .ops import CudaOps
 
 P_ID_WIN_SIZE = 15  # gaussian_profile.py:37
 NULL_VALUE = -999   # gaussian_profile.py:41
+THRESHOLD_STEP_SIZES = [0.02, 0.03, 0.04]   # gaussian_profile.py:34
+THRESHOLD_MAX = [0.5, 0.75, 1]               # gaussian_profile.py:35
 
 
 class ThresholdSweep:
@@ -198,6 +200,45 @@ class ThresholdSweep:
         keep = size >= min_size
         r, c = rows.cpu().numpy()[keep], cols.cpu().numpy()[keep]
         out[r, c] = [ranks[v] for v in root[keep]]
+        return out
+
+
+    def timestamp(self, aod, fire_rows, fire_cols, fill: bool = True, win: int = P_ID_WIN_SIZE):
+        """The data-parallel front half of the reference's per-timestamp work in one go -- ``main`` :611-613 and
+        ``identify`` :478-499: nearest-valid fill of the AOD grid, fire clustering and centroids, then for each of the
+        three sweeps (THRESHOLD_STEP_SIZES / THRESHOLD_MAX) the masks, the plume extents of every fire cluster, the
+        threshold index per cluster (host) and, for the clusters that have one, the plume mask that
+        ``find_plume_mask`` would hand to ``assess_plume``.  The image crosses PCIe once; the 75 thresholds are
+        labelled in one call.  Returns a dict: ``aod_filled`` (device tensor), ``fire_rows`` / ``fire_cols`` (cluster
+        centroids), ``sweeps`` = list of {``thresholds``, ``extents`` [T, n], ``threshold_index`` [n],
+        ``plume_masks`` (list of bool [H, W] or None), ``regions`` int64 [n, 6]}."""
+        a = self._image(aod)
+        if fill:
+            a = self.fill_nearest(a)
+        h, w = a.shape
+        labels = self.cluster_fires((h, w), fire_rows, fire_cols)
+        rows, cols = fire_cluster_centroids(labels)
+        out = {"aod_filled": a, "fire_labels": labels, "fire_rows": rows, "fire_cols": cols, "sweeps": []}
+        ranges = [np.abs(np.arange(0, tmax, step) - tmax) for step, tmax in zip(THRESHOLD_STEP_SIZES, THRESHOLD_MAX)]
+        if len(rows) == 0:
+            return out
+        thr_all = np.concatenate(ranges)
+        bits = self.mask_bits(a, thr_all)
+        ext_all = self.extents_of_bits(bits, w, rows, cols, win)
+        lo = 0
+        for thr in ranges:
+            ext = ext_all[lo:lo + len(thr)]
+            index = find_threshold_index(ext)
+            planes = [None if k is None else lo + k for k in index]
+            if any(p is not None for p in planes):
+                comp, regions = self.fire_components(bits, w, planes, rows, cols, win)
+                host = self.unpack_bits(comp, w)
+                masks = [host[f] if regions[f, 0] > 0 else None for f in range(len(rows))]
+            else:
+                masks, regions = [None] * len(rows), np.zeros((len(rows), 6), dtype=np.int64)
+            out["sweeps"].append({"thresholds": thr, "extents": ext, "threshold_index": index, "plume_masks": masks,
+                                  "regions": regions})
+            lo += len(thr)
         return out
 
 

@@ -336,3 +336,42 @@ def test_kernels_follow_scikit_image_documented_semantics(sw):
     # 8-connectivity through the bit-plane path: the eye is one component of three pixels
     ext = sw.extents_of_bits(sw.pack_bits_host(C.LABEL_EYE[None]), 3, [1], [1], win=1)
     assert ext.tolist() == [[3.0]]
+
+
+def test_timestamp_front_half_equals_the_oracle_step_by_step(sw):
+    """ThresholdSweep.timestamp = main :611-613 + identify :478-499 up to find_plume_mask's labelling, against the same
+    steps made of oracle functions (fill, cluster_fires + centroids, three sweeps, threshold index, plume masks)."""
+    from tests.sweep_data import synthetic_fire_pixels
+    h, w = 150, 170
+    aod, _ = synthetic_aod(h, w, 2)
+    aod = (np.round(aod.astype(np.float64) * 1000) * 0.001)                 # MAIAC-like: multiples of 0.001 in float64
+    rng = np.random.default_rng(5)
+    aod[rng.random((h, w)) < 0.03] = sweep.NULL_VALUE
+    aod[60:70, 80:100] = sweep.NULL_VALUE
+    fr, fc = synthetic_fire_pixels(h, w, 3)
+    keep = (fr > 20) & (fr < h - 21) & (fc > 20) & (fc < w - 21)            # centroids must keep the window inside
+    fr, fc = fr[keep], fc[keep]
+    got = sw.timestamp(aod, fr, fc)
+    filled = sweep_ref.interpolate_aod_nearest_ref(aod)
+    assert np.array_equal(got["aod_filled"].cpu().numpy(), filled)
+    lab = sweep_ref.cluster_fires_ref((h, w), fr, fc)
+    rows, cols = sweep_ref.cluster_centroids_ref(lab)
+    assert np.array_equal(got["fire_labels"], lab) and np.array_equal(got["fire_rows"], rows) and np.array_equal(got["fire_cols"], cols)
+    assert len(rows) >= 3 and len(got["sweeps"]) == 3
+    n_masks = 0
+    for sweep_out, (step, tmax) in zip(got["sweeps"], zip(sweep.THRESHOLD_STEP_SIZES, sweep.THRESHOLD_MAX)):
+        thr = np.abs(np.arange(0, tmax, step) - tmax)
+        masks = sweep_ref.threshold_masks_ref(filled, thr)
+        ext = sweep_ref.find_plume_extents_ref(masks, rows, cols)
+        idx = sweep_ref.find_threshold_index_ref(ext)
+        assert np.array_equal(sweep_out["thresholds"], thr) and np.array_equal(sweep_out["extents"], ext)
+        assert sweep_out["threshold_index"] == idx
+        for f, k in enumerate(idx):
+            ref = None if k is None else sweep_ref.plume_mask_ref(masks[k], rows[f], cols[f])
+            if ref is None:
+                assert sweep_out["plume_masks"][f] is None
+            else:
+                n_masks += 1
+                assert np.array_equal(sweep_out["plume_masks"][f], ref) and sweep_out["regions"][f, 0] == ref.sum()
+    assert n_masks >= 1
+    assert sw.timestamp(aod, [], [])["sweeps"] == []
