@@ -114,22 +114,48 @@ class ThresholdSweep:
     def fire_components(self, bits: torch.Tensor, w: int, plane_of_fire, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE):
         """Per fire the connected component nearest to it in the plane chosen for it (``find_plume_mask``: label,
         extract_label, ``labelled == label`` -- without a label plane).  bits: device bit planes [T, H, ceil(W / 32)];
-        plane_of_fire: plane index per fire, negative / None = no plane.  Returns (component bit planes on the device
-        int32 [n, H, ceil(W / 32)], stats int64 [n, 6] on the host = area, min_row, min_col, max_row + 1, max_col + 1,
-        root) -- area 0 where the fire's window holds no component."""
-        t, h, _ = bits.shape
+        plane_of_fire: plane index per fire, negative / None = no plane.  Returns (crops, stats): stats int64 [n, 6] on
+        the host = area, min_row, min_col, max_row + 1, max_col + 1, root (area 0 where the fire has no plane or its
+        window holds no component); crops[f] = bool array of the component inside its bounding box
+        [min_row:max_row + 1, min_col:max_col + 1], None where area is 0.  Only fires with a plane get a component
+        plane on the device, and only bounding boxes are unpacked on the host."""
+        t, h, segs = bits.shape
         rc = self._fires(fire_rows, fire_cols, h, w, win)
         planes = np.array([-1 if p is None else int(p) for p in plane_of_fire], dtype=np.int64)
         if len(planes) != len(rc) or (planes >= t).any():
             raise ValueError("plane_of_fire needs one valid plane index (or None) per fire")
-        comp = torch.zeros(len(rc), h, (w + 31) // 32, dtype=torch.int32, device=bits.device)
-        stats = torch.zeros(len(rc), 8, dtype=torch.int32, device=bits.device)
-        if len(rc) and t:
-            ws = self._workspace(h, w, t)
-            scratch = torch.empty(t, len(rc), dtype=torch.int32, device=bits.device)
-            self.ops.bits_extents(bits, w, rc, win, ws, scratch)                    # labels the planes into ws
-            self.ops.fire_components(bits, w, rc, torch.tensor(planes, dtype=torch.int32).to(bits.device), win, ws, comp, stats)
-        return comp, stats[:, :6].cpu().numpy().astype(np.int64)
+        stats = np.zeros((len(rc), 6), dtype=np.int64)
+        stats[:, 5] = -1
+        crops = [None] * len(rc)
+        sel = np.nonzero(planes >= 0)[0]
+        if len(sel) == 0 or t == 0:
+            return crops, stats
+        sel_t = torch.from_numpy(sel).to(bits.device)
+        comp = torch.empty(len(sel), h, segs, dtype=torch.int32, device=bits.device)
+        st = torch.empty(len(sel), 8, dtype=torch.int32, device=bits.device)
+        ws = self._workspace(h, w, t)
+        scratch = torch.empty(t, len(sel), dtype=torch.int32, device=bits.device)
+        rc_sel = rc[sel_t].contiguous()
+        self.ops.bits_extents(bits, w, rc_sel, win, ws, scratch)                    # labels the planes into ws
+        self.ops.fire_components(bits, w, rc_sel, torch.from_numpy(planes[sel].astype(np.int32)).to(bits.device), win, ws,
+                                 comp, st)
+        stats[sel] = st[:, :6].cpu().numpy()
+        words = comp.cpu().numpy().view(np.uint32)
+        for j, f in enumerate(sel):
+            area, y0, x0, y1, x1 = stats[f, :5]
+            if area > 0:
+                s0, s1 = x0 >> 5, (x1 + 31) >> 5
+                sub = np.ascontiguousarray(words[j, y0:y1, s0:s1])
+                px = np.unpackbits(sub.view(np.uint8).reshape(y1 - y0, (s1 - s0) * 4), axis=1, bitorder="little")
+                crops[f] = px[:, x0 - 32 * s0:x1 - 32 * s0].astype(bool)
+        return crops, stats
+
+    @staticmethod
+    def full_mask(crop, stats_row, shape) -> np.ndarray:
+        """The [H, W] mask of a component from its bounding-box crop."""
+        out = np.zeros(shape, dtype=bool)
+        out[stats_row[1]:stats_row[3], stats_row[2]:stats_row[4]] = crop
+        return out
 
     def extents_of_masks(self, masks: torch.Tensor, fire_rows, fire_cols, win: int = P_ID_WIN_SIZE) -> np.ndarray:
         """uint8 masks [T, H, W] on the device -> float64 [T, n_fires] (find_plume_extents)."""
@@ -211,7 +237,8 @@ class ThresholdSweep:
         ``find_plume_mask`` would hand to ``assess_plume``.  The image crosses PCIe once; the 75 thresholds are
         labelled in one call.  Returns a dict: ``aod_filled`` (device tensor), ``fire_rows`` / ``fire_cols`` (cluster
         centroids), ``sweeps`` = list of {``thresholds``, ``extents`` [T, n], ``threshold_index`` [n],
-        ``plume_masks`` (list of bool [H, W] or None), ``regions`` int64 [n, 6]}."""
+        ``regions`` int64 [n, 6] = area, bounding box (min_row, min_col, max_row + 1, max_col + 1), root; ``plume_masks`` =
+        per cluster the bool mask INSIDE that bounding box, or None (``full_mask`` expands one to [H, W])}."""
         a = self._image(aod)
         if fill:
             a = self.fill_nearest(a)
@@ -230,12 +257,7 @@ class ThresholdSweep:
             ext = ext_all[lo:lo + len(thr)]
             index = find_threshold_index(ext)
             planes = [None if k is None else lo + k for k in index]
-            if any(p is not None for p in planes):
-                comp, regions = self.fire_components(bits, w, planes, rows, cols, win)
-                host = self.unpack_bits(comp, w)
-                masks = [host[f] if regions[f, 0] > 0 else None for f in range(len(rows))]
-            else:
-                masks, regions = [None] * len(rows), np.zeros((len(rows), 6), dtype=np.int64)
+            masks, regions = self.fire_components(bits, w, planes, rows, cols, win)
             out["sweeps"].append({"thresholds": thr, "extents": ext, "threshold_index": index, "plume_masks": masks,
                                   "regions": regions})
             lo += len(thr)
@@ -339,9 +361,9 @@ def plume_masks(masks_dict, threshold_index_for_fires, fire_rows, fire_cols):
     else:
         stack = np.stack([np.asarray(masks_dict[k]) for k in keys]) != 0
         planes, w = s.pack_bits_host(stack), stack.shape[2]
-    comp, stats = s.fire_components(planes.to(s.device), w, threshold_index_for_fires, fire_rows, fire_cols)
-    host = s.unpack_bits(comp, w)
-    return [host[f] if stats[f, 0] > 0 else None for f in range(len(stats))], stats
+    crops, stats = s.fire_components(planes.to(s.device), w, threshold_index_for_fires, fire_rows, fire_cols)
+    shape = (planes.shape[1], w)
+    return [None if c is None else s.full_mask(c, stats[f], shape) for f, c in enumerate(crops)], stats
 
 
 def find_threshold_index(plume_extents_across_all_fires) -> List[Optional[int]]:

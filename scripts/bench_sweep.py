@@ -128,6 +128,21 @@ scipy_filled = interpolate.NearestNDInterpolator(np.vstack((xx[good], yy[good]))
 fill_cpu_s = time.perf_counter() - t0
 fill_agree = float((fill_out.cpu().numpy() == scipy_filled).mean())          # < 1 only by distance ties
 
+# the whole data-parallel front half of a timestamp through ThresholdSweep.timestamp: host float64 image with nulls in
+ts_aod = np.round(aod.astype(np.float64) * 1000) * 0.001
+ts_aod[nul == -999] = -999
+fr = np.concatenate([rows + d for d in (0, 0, 1)])                  # 64 clusters of three touching fire pixels each
+fc = np.concatenate([cols + d for d in (0, 1, 1)])
+keep = (fr > 20) & (fr < H - 21) & (fc > 20) & (fc < W - 21)
+sw.timestamp(ts_aod, fr[keep], fc[keep])
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(3):
+    ts_out = sw.timestamp(ts_aod, fr[keep], fc[keep])
+torch.cuda.synchronize()
+timestamp_s = (time.perf_counter() - t0) / 3
+n_plume_masks = sum(m is not None for s_ in ts_out["sweeps"] for m in s_["plume_masks"])
+
 peaks = {}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(p):
@@ -149,6 +164,9 @@ line = {
     "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "timestamps/s", "cores": 1, "kind": "port",
                      "sample": f"plain-C oracle (two-pass union-find labelling), all three sweeps of the timestamp ({cpu_s:.2f} s)"},
     "parity_on_sample": ok,
+    "timestamp_front_half": {"ms": timestamp_s * 1e3, "fire_clusters": int(len(ts_out["fire_rows"])), "plume_masks_returned": int(n_plume_masks),
+                             "what": "ThresholdSweep.timestamp from a host float64 image with nulls: fill, fire clustering, 75 thresholds, "
+                                     "threshold index, plume masks unpacked on the host (main :611-613 + identify :478-499)"},
     "nearest_fill": {"ms": ms_fill, "ms_single_valid_pixel": ms_fill_worst, "null_fraction": float((~good).mean()), "dtype": "f64",
                      "gbps": (H * W * 8 * 2 + H * W * 4 * 2) / (ms_fill * 1e-3) / 1e9,
                      "bytes_definition": "image read + written (8 B each) and the row-offset plane written + read (4 B each)",

@@ -282,16 +282,16 @@ def test_fire_components_equal_oracle_on_random_masks(sw, h, w, density):
     rows, cols = rng.integers(win, h - win, n), rng.integers(win, w - win, n)
     planes = [None if p < 0 else int(p) for p in rng.integers(-1, 4, n)]
     bits = sw.pack_bits_host(masks)
-    comp, stats = sw.fire_components(bits, w, planes, rows, cols, win)
-    got = sw.unpack_bits(comp, w)
+    crops, stats = sw.fire_components(bits, w, planes, rows, cols, win)
     for f, p in enumerate(planes):
         ref = None if p is None else sweep_ref.plume_mask_ref(masks[p], rows[f], cols[f], win)
         if ref is None:
-            assert not got[f].any() and stats[f, 0] == 0 and stats[f, 5] == -1
+            assert crops[f] is None and stats[f, 0] == 0 and stats[f, 5] == -1
         else:
             ys, xs = np.nonzero(ref)
-            assert np.array_equal(got[f], ref)
             assert stats[f, :5].tolist() == [ref.sum(), ys.min(), xs.min(), ys.max() + 1, xs.max() + 1]
+            assert np.array_equal(crops[f], ref[ys.min():ys.max() + 1, xs.min():xs.max() + 1])
+            assert np.array_equal(sw.full_mask(crops[f], stats[f], ref.shape), ref)
 
 
 @pytest.mark.parametrize("i", range(N))
@@ -372,6 +372,7 @@ def test_timestamp_front_half_equals_the_oracle_step_by_step(sw):
                 assert sweep_out["plume_masks"][f] is None
             else:
                 n_masks += 1
-                assert np.array_equal(sweep_out["plume_masks"][f], ref) and sweep_out["regions"][f, 0] == ref.sum()
+                full = sw.full_mask(sweep_out["plume_masks"][f], sweep_out["regions"][f], ref.shape)
+                assert np.array_equal(full, ref) and sweep_out["regions"][f, 0] == ref.sum()
     assert n_masks >= 1
     assert sw.timestamp(aod, [], [])["sweeps"] == []
