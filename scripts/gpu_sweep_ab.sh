@@ -1,6 +1,8 @@
 #!/bin/bash
 # GPU box: sweep tests on the default build, then the sweep bench under every PLUME_SWEEP_VARIANT of interest
 # (bit 0 band-local phase, bit 1 path halving, bit 2 skip known stretches, bit 3 one-strip mask kernel), then ncu.
+# The variant switch existed in the build measured in profiles/r2_sweep_variants.txt (commit d2128d5^ .. d2128d5); the
+# kept variant is now the only code path, and VARIANTS=0 simply runs the bench once.
 cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out/${TAG:-r2ab}; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_sweep.py -x -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -5 $O/pytest.log

@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU box: sweep tests with both mask-kernel variants, A/B of the bench (PLUME_SWEEP_RANK=0 ballots, 1 rank + transpose),
+# GPU box: sweep tests with both mask-kernel variants, A/B of the bench (PLUME_SWEEP_RANK=0 ballots, 1 rank + transpose;
+# the switch existed in the build measured in profiles/r2_sweep_variants.txt, the rank variant is now the only one),
 # ncu launch list and one --set full capture of the mask and merge kernels.
 cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out/${TAG:-r2rk}; mkdir -p $O
