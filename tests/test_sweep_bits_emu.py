@@ -148,3 +148,44 @@ def test_extents_equal_oracle_on_random_masks(emu, h, w, density):
     for s in (0, 3, 11):
         assert np.array_equal(bits_extents(emu, bits, w, rows, cols, win, seed=s), ref)
     check_components(emu, bits, masks, w, rows, cols, win)
+
+
+def test_property_random_small_images(emu):
+    """Property test over many small random shapes (widths around the 32- and 64-column strip boundaries, heights
+    around the strip heights): masks, extents and component masks of the emulated kernel bodies equal the oracle."""
+    rng = np.random.default_rng(2024)
+    widths = [1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 128, 130]
+    heights = [1, 2, 3, 7, 8, 9, 15, 16, 17, 33]
+    for trial in range(60):
+        h, w = int(rng.choice(heights)), int(rng.choice(widths))
+        kind = trial % 4
+        if kind == 0:                                             # smooth blobs + noise
+            yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+            aod = (0.5 + 0.4 * np.sin(yy / 3.0 + trial) * np.cos(xx / 5.0)).astype(np.float32)
+            aod += (rng.random((h, w)) < 0.05) * rng.random((h, w)).astype(np.float32)
+        elif kind == 1:                                           # dense noise
+            aod = rng.random((h, w)).astype(np.float32)
+        elif kind == 2:                                           # long horizontal / vertical bars crossing word boundaries
+            aod = np.zeros((h, w), dtype=np.float32)
+            aod[::3, :] = 1.0
+            aod[:, ::7] = 1.0
+            aod[rng.random((h, w)) < 0.1] = 0.0
+        else:                                                     # everything set except a few holes
+            aod = np.ones((h, w), dtype=np.float32)
+            aod[rng.random((h, w)) < 0.08] = 0.0
+        thr = np.sort(rng.random(int(rng.integers(1, 6))))[::-1].copy()
+        ref_masks = sweep_ref.threshold_masks_ref(aod, thr)
+        bits = mask_bits(emu, aod, thr)
+        assert np.array_equal(unpack(bits, w), ref_masks), (trial, h, w)
+        raw = aod > 0.5                                           # un-opened masks: thin structures, diagonal contacts
+        stack = np.concatenate([ref_masks, raw[None], np.eye(h, w, dtype=bool)[None]])
+        pb = np.zeros((len(stack), h, (w + 31) // 32), dtype=np.uint32)
+        m8 = np.ascontiguousarray(stack.astype(np.uint8))
+        emu.emu_pack_bits(P(m8), len(stack), h, w, P(pb))
+        win = int(min(3, (h - 1) // 2, (w - 1) // 2))
+        n = 6
+        rows = rng.integers(win, h - win, n)
+        cols = rng.integers(win, w - win, n)
+        ref = sweep_ref.find_plume_extents_ref(stack, rows, cols, win)
+        assert np.array_equal(bits_extents(emu, pb, w, rows, cols, win, seed=trial), ref), (trial, h, w)
+        check_components(emu, pb, stack, w, rows, cols, win)
